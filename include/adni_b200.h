@@ -1,0 +1,206 @@
+/*
+ * adni_b200 — C-ABI of the B200-native training hot path for Liz490/multimodal_alzheimer.
+ *
+ * The reference has no FFI: its hot path is the torch.nn module graph executed by ATen/cuDNN
+ * (SURVEY.md §8b).  Each entry point below replaces one of those library dispatches; the comment on
+ * every declaration cites the reference call site (file:line under the reference repo) whose
+ * arithmetic it takes over.  The host-side mirror in multimodal_alzheimer_b200/ binds these symbols with
+ * ctypes (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host.
+ *   - activations: NDHWC, bf16 (uint16_t storage, "adni_bf16").  Weights for the tensor-core engine:
+ *     [Cout][kd][kh][kw][Cin] bf16 ("OTI") and [Cin][kd][kh][kw][Cout] bf16 ("ITO", for dgrad).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
+ *     persistent, and returns 0 or a negative ADNI_E* code; adni_last_error_string() explains.
+ *   - no CPU fallback exists: an unsupported shape is ADNI_ENOTSUP, never a silent slow path.
+ */
+#ifndef ADNI_B200_H
+#define ADNI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADNI_OK 0
+#define ADNI_EINVAL (-1)  /* bad argument                                    (reference: ValueError)      */
+#define ADNI_ENOTSUP (-2) /* shape/feature not supported by any CUDA engine  (no silent fallback)         */
+#define ADNI_ECUDA (-3)   /* wraps a cudaError_t                                                          */
+#define ADNI_ENOMEM (-4)  /* workspace too small / allocation failure -> torch.cuda.OutOfMemoryError      */
+
+typedef uint16_t adni_bf16;
+
+/* Conv engine selector (tests force one; product code passes AUTO). */
+#define ADNI_ENGINE_AUTO 0
+#define ADNI_ENGINE_TCGEN05 1 /* implicit GEMM on tcgen05/TMEM fed by TMA            */
+#define ADNI_ENGINE_DIRECT 2  /* CUDA-core direct convolution (small channel counts) */
+
+const char* adni_last_error_string(void);
+int adni_version(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
+long long adni_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conv3d.  Replaces torch.nn.Conv3d forward / autograd backward as used by
+ *   - MedicalNet ResNet (external; call sites pkg/models/mri_models/anat_cnn.py:18-31,
+ *     pkg/models/pet_models/pet_resnet_cnn.py:23-35): k in {7,3,1}, stride {1,2}, dilation {1,2,4},
+ *     padding = dilation*(k-1)/2, no bias;
+ *   - Small_PET_CNN / Anat_CNN head convs (pkg/models/pet_models/pet_cnn.py:21,
+ *     pkg/models/mri_models/anat_cnn.py:56): padding='same', bias.
+ * Geometry is isotropic (same k/stride/pad/dil on D,H,W), as everywhere in the reference.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, D, H, W; /* input batch and spatial extent */
+  int Cin, Cout;
+  int k, stride, pad, dil;
+} adni_conv3d_geom;
+
+/* out spatial extent for one axis */
+int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil);
+
+/* y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_oti) (+bias).  If stat_sum/stat_sqsum are non-null,
+ * per-channel sum(y) and sum(y*y) (fp64, from the fp32 accumulators) are ADDED into them: the
+ * BatchNorm3d batch statistics fused into the conv epilogue (MedicalNet bn1/bn2/bn3). */
+int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* w_oti, const float* bias,
+                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* stream);
+
+/* dx[N,D,H,W,Cin] = conv_transpose(dy[N,Do,Ho,Wo,Cout], w) (+ addend, same shape as dx, may be null).
+ * w_ito is the [Cin][taps][Cout] copy of the weights. */
+int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito,
+                      const adni_bf16* addend, adni_bf16* dx, int engine, void* stream);
+
+/* dw_oti[Cout][taps][Cin] (fp32) += sum over positions of dy^T * im2col(x).  The caller zeroes dw
+ * (the split-K partial sums are accumulated with red.global.add). dbias[Cout] (fp32, may be null) +=
+ * sum(dy). */
+int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* dy, float* dw_oti,
+                      float* dbias, int engine, void* stream);
+
+/* Weight layout conversions at the state_dict boundary (fp32 NCDHW nn.Parameter <-> kernel layouts).
+ * w_ncdhw: [Cout][Cin][taps] fp32.  Either output may be null. */
+int adni_weights_to_kernel_layout(const float* w_ncdhw, int Cout, int Cin, int taps, adni_bf16* w_oti,
+                                  adni_bf16* w_ito, void* stream);
+/* dw_oti [Cout][taps][Cin] fp32 -> grad_ncdhw [Cout][Cin][taps] fp32 (accumulate=1 adds into grad). */
+int adni_wgrad_to_param_layout(const float* dw_oti, int Cout, int Cin, int taps, float* grad_ncdhw, int accumulate,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm3d (train mode) + ReLU + residual add.  Replaces nn.BatchNorm3d / nn.ReLU / `out += residual`
+ * inside MedicalNet BasicBlock/Bottleneck and the "batchnorm_begin" layer (anat_cnn.py:49-50).
+ * ------------------------------------------------------------------------------------------- */
+/* From fp64 sum/sqsum over `count` elements per channel: mean, invstd (biased var, eps), and
+ * scale = gamma*invstd, shift = beta - mean*scale; running stats updated with momentum (unbiased var),
+ * exactly torch semantics.  running_* may be null. */
+int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double count, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+
+/* out = act( y*scale[c] + shift[c] + residual ), bf16 in/out, `rows` x C.  residual may be null;
+ * relu != 0 applies max(.,0).  If out_sum/out_sqsum non-null, per-channel fp64 sum / sum of squares of the
+ * (bf16-rounded) output are added into them (statistics for a following BatchNorm, e.g. batchnorm_begin). */
+int adni_bn_apply(const adni_bf16* y, const float* scale, const float* shift, const adni_bf16* residual,
+                  adni_bf16* out, long long rows, int C, int relu, double* out_sum, double* out_sqsum, void* stream);
+
+/* Backward, pass 1: g = dout * (relu ? out > 0 : 1);  red[0:C] += sum g, red[C:2C] += sum g*xhat with
+ * xhat = (y-mean)*invstd.  `out` is the forward output (needed only when relu). red is fp64[2C]. */
+int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
+                       const float* invstd, long long rows, int C, int relu, double* red, void* stream);
+
+/* Backward, pass 2: dy = gamma*invstd*( g - red_g/count - xhat*red_gx/count ) (bf16);
+ * dres (nullable) = g (the gradient flowing into the residual input); dgamma = red_gx, dbeta = red_g
+ * are written (fp32) when non-null.  `count` is the GLOBAL element count per channel (sync-BN). */
+int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
+                      const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
+                      int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream);
+
+/* Per-channel fp64 sum / sum of squares of a bf16 rows x C tensor (added into sum/sqsum). */
+int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, double* sqsum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling.  MaxPool3d(3,2,1) stem (MedicalNet), MaxPool3d(2) (pet_cnn.py:25, anat_cnn.py:62),
+ * AdaptiveAvgPool3d(1)+Flatten (anat_cnn.py:66-67, pet_cnn.py:32-33).
+ * ------------------------------------------------------------------------------------------- */
+/* floor-mode max pool, -inf padding, first maximum in (d,h,w) scan order wins (torch CPU tie rule);
+ * argmax (uint8 window slot kd*k*k+kh*k+kw) saved for backward. */
+int adni_maxpool3d_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, int k, int stride, int pad,
+                       adni_bf16* y, uint8_t* argmax, void* stream);
+int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D, int H, int W, int C, int k,
+                       int stride, int pad, adni_bf16* dx, void* stream);
+/* feat[N][C] (fp32) = mean over P positions of x[N][P][C]. */
+int adni_gap_fwd(const adni_bf16* x, int N, long long P, int C, float* feat, void* stream);
+/* dx[N][P][C] (bf16) = dfeat[N][C] / P. */
+int adni_gap_bwd(const float* dfeat, int N, long long P, int C, adni_bf16* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heads.  nn.Linear (+ReLU), nn.BatchNorm1d, torch.cat — anat_cnn.py:69-77, anat_pet_fusion.py:42-51,76,
+ * tabular_mri_fusion.py:33-42, pet_tabular_fusion.py:47-60, all_modalities_fusion.py:50-57.  fp32.
+ * ------------------------------------------------------------------------------------------- */
+/* y[B][out] = act(x[B][in] * W[out][in]^T + b).  ldx/ldy = row strides in elements (concat is expressed
+ * by writing into a column slice of a wider buffer). */
+int adni_linear_fwd(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int B, int in,
+                    int out, int relu, void* stream);
+/* Given dy (and y for the ReLU mask when relu): dx[B][in] (nullable; accumulate_dx adds),
+ * dW[out][in] += , db[out] += . */
+int adni_linear_bwd(const float* x, int ldx, const float* W, const float* y, int ldy, const float* dy, int lddy,
+                    float* dx, int lddx, int accumulate_dx, float* dW, float* db, int B, int in, int out, int relu,
+                    void* stream);
+/* BatchNorm1d train-mode over B rows, fp32 (anat_cnn.py:72-73).  Statistic sums are exposed so the
+ * host can all-reduce them for data parallelism: stats[0:C]=sum x, stats[C:2C]=sum x^2 (fp64). */
+int adni_rows_stats_f32(const float* x, int ldx, int B, int C, double* stats, void* stream);
+int adni_bn1d_apply(const float* x, int ldx, const float* scale, const float* shift, float* y, int ldy, int B, int C,
+                    int relu, void* stream);
+int adni_bn1d_bwd_reduce(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+                         const float* mean, const float* invstd, int B, int C, int relu, double* red, void* stream);
+int adni_bn1d_bwd_apply(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+                        const float* mean, const float* invstd, const float* gamma, const double* red, double count,
+                        int B, int C, int relu, float* dx, int lddx, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses, evaluated in fp64 on fp32 logits (reference casts logits .to(double): anat_cnn.py:104).
+ *   gamma > 0 : FocalLoss with DETACHED modulating factor (pkg/loss_functions/focalloss.py:20-40, :30);
+ *   gamma == 0: nn.CrossEntropyLoss(weight) (anat_cnn.py:84-85); class_weights may be null (all ones).
+ * partial[0] += sum_i numerator_i, partial[1] += sum_i normaliser_i (w[y_i] for CE, 1 for focal) so that the
+ * host can all-reduce them across ranks;  loss = partial[0]/partial[1].
+ * ------------------------------------------------------------------------------------------- */
+int adni_loss_fwd(const float* logits, int ld, const int64_t* target, int B, int C, double gamma,
+                  const double* class_weights, double* partial, double* per_sample_coeff, void* stream);
+/* dlogits[B][C] (fp32) = upstream * coeff_i * (softmax_i - onehot_i) / denom, where denom is the global
+ * normaliser (device scalar) and coeff_i = (1-pt)^gamma or w[y_i] saved by adni_loss_fwd. */
+int adni_loss_bwd(const float* logits, int ld, const int64_t* target, int B, int C, const double* per_sample_coeff,
+                  const double* denom, double upstream, float* dlogits, int lddl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input normalisation (pkg/utils/dataloader.py:213-215, 236-281; pkg/utils/standardization.py:34-55).
+ * ------------------------------------------------------------------------------------------- */
+/* Per-scan quantile min-max (dataloader.py:239-249,261-270) for `nscans` volumes of `nvox` voxels:
+ *   m = (x*mask)[x*mask != 0]; n = len(m); rank = q*(n-1) (fp64); lo=floor, hi=ceil, w = rank-lo;
+ *   Q = lerp(sorted[lo], sorted[hi], w) for q and for (1-q) computed as the fp64 expression 1-q;
+ *   out = clamp((x-Qmin)/(Qmax-Qmin), 0, 1) * mask.
+ * x: fp32 raw intensities, mask: uint8 (0/1).  out_f32 (nullable) fp32 and out_bf16 (nullable) bf16.
+ * info (nullable): per scan 8 int64 {n, lo_max, hi_max, lo_min, hi_min, 0,0,0}; qvals (nullable): per scan
+ * 2 fp64 {Qmax, Qmin}.  Order statistics are found by an exact radix select on the fp32 keys (no sort).
+ * workspace: adni_quantile_workspace_bytes(nscans) bytes. */
+size_t adni_quantile_workspace_bytes(int nscans);
+int adni_quantile_minmax_normalize(const float* x, const uint8_t* mask, int nscans, long long nvox, double q,
+                                   float* out_f32, adni_bf16* out_bf16, long long* info, double* qvals,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+/* out = ((double)x - mean)/std [* mask]  (torchvision Normalize in fp64, dataloader.py:213-215,:252-260,:274-278). */
+int adni_standardize(const float* x, const uint8_t* mask, long long n, double mean, double std, float* out_f32,
+                     adni_bf16* out_bf16, void* stream);
+/* Per-scan E[x], E[x^2] in fp64 (standardization.py:43-46): moments[2*s] += mean(x_s), moments[2*s+1] += mean(x_s^2). */
+int adni_scan_moments(const float* x, int nscans, long long nvox, double* moments, void* stream);
+/* Masked per-scan mean / unbiased std over non-zero masked voxels (dataloader.py:252-256 'normalize' variant):
+ * out[3*s] = n, out[3*s+1] = mean, out[3*s+2] = std (fp64). */
+int adni_masked_std_mean(const float* x, const uint8_t* mask, int nscans, long long nvox, double* out, void* stream);
+
+/* Casts between the module boundary (fp32 NCDHW with C==1, or fp64) and the kernel layout. */
+int adni_cast_f32_to_bf16(const float* x, adni_bf16* y, long long n, void* stream);
+int adni_cast_f64_to_bf16(const double* x, adni_bf16* y, long long n, void* stream);
+int adni_cast_bf16_to_f32(const adni_bf16* x, float* y, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADNI_B200_H */

@@ -1,0 +1,463 @@
+// Host-side planning + C-ABI entry points for Conv3d fprop / dgrad / wgrad.
+//
+// The planner turns a conv geometry into (tensor-map views, tap table, output view, box shape) for the
+// tcgen05 kernels in conv_igemm_kernels.cu, or dispatches to the CUDA-core direct engine
+// (conv_direct.cu) for the small-channel convolutions of Small_PET_CNN and the 1-channel stem.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "conv_igemm.cuh"
+
+namespace adni {
+
+int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
+
+int direct_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti,
+                      const float* bias, __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
+int direct_conv_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
+                      const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream);
+int direct_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
+                      float* dbias, cudaStream_t stream);
+
+namespace {
+
+struct View {  // a strided 5-D (N, D, H, W, C) view of an NDHWC bf16 tensor
+  const __nv_bfloat16* base;
+  int D, H, W;
+  long long sn, sd, sh, sw;
+};
+
+struct AxisTap {  // one kernel index along one axis: which parity view, box offset
+  int parity;
+  int off;
+};
+
+inline int out_extent(int in, int k, int stride, int pad, int dil) {
+  return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+}
+
+// forward-conv axis taps: input coordinate = o*stride + kk*dil - pad  -> (parity view, o + off)
+std::vector<AxisTap> fwd_axis_taps(int k, int stride, int pad, int dil) {
+  std::vector<AxisTap> v;
+  for (int kk = 0; kk < k; kk++) {
+    const int off = kk * dil - pad;
+    const int par = ((off % stride) + stride) % stride;
+    v.push_back({par, (off - par) / stride});
+  }
+  return v;
+}
+
+// number of (tile, tap) pairs along one axis whose shifted box intersects [0, ext_of_view)
+long long axis_score(int b, int out_ext, const std::vector<AxisTap>& taps, const std::vector<int>& view_ext) {
+  const int tiles = (out_ext + b - 1) / b;
+  long long s = 0;
+  for (int t = 0; t < tiles; t++)
+    for (const AxisTap& a : taps) {
+      const int lo = t * b + a.off;
+      if (lo + b > 0 && lo < view_ext[a.parity]) s++;
+    }
+  return s;
+}
+
+struct Box {
+  int bd, bh, bw;
+};
+
+// Choose the tile box. max_rows = 128 (fprop/dgrad, product <= 128) or exact 64 (wgrad K-block, product == 64).
+Box plan_box(int Do, int Ho, int Wo, int max_rows, bool exact, const std::vector<AxisTap>& td,
+             const std::vector<AxisTap>& th, const std::vector<AxisTap>& tw, const std::vector<int>& ext_d,
+             const std::vector<int>& ext_h, const std::vector<int>& ext_w) {
+  Box best{1, 1, 1};
+  double best_score = -1;
+  auto consider = [&](int bd, int bh, int bw) {
+    if (bd > 256 || bh > 256 || bw > 256) return;
+    const double s = double(axis_score(bd, Do, td, ext_d)) * double(axis_score(bh, Ho, th, ext_h)) *
+                     double(axis_score(bw, Wo, tw, ext_w));
+    // fewer MMA blocks first; then wider rows (longer contiguous TMA runs)
+    if (best_score < 0 || s < best_score ||
+        (s == best_score && (bw > best.bw || (bw == best.bw && bh > best.bh)))) {
+      best_score = s;
+      best = {bd, bh, bw};
+    }
+  };
+  if (exact) {
+    for (int bw = 1; bw <= max_rows; bw *= 2)
+      for (int bh = 1; bw * bh <= max_rows; bh *= 2) consider(max_rows / (bw * bh), bh, bw);
+  } else {
+    for (int bw = 1; bw <= std::min(Wo, max_rows); bw++)
+      for (int bh = 1; bh <= std::min(Ho, max_rows / bw); bh++) {
+        const int bd = std::min(Do, max_rows / (bw * bh));
+        if (bd >= 1) consider(bd, bh, bw);
+      }
+  }
+  return best;
+}
+
+int encode_view(CUtensorMap* m, const View& v, int C, const Box& b, int N) {
+  const uint64_t dims[5] = {uint64_t(C), uint64_t(v.W), uint64_t(v.H), uint64_t(v.D), uint64_t(N)};
+  const uint64_t strides[5] = {1, uint64_t(v.sw), uint64_t(v.sh), uint64_t(v.sd), uint64_t(v.sn)};
+  const uint32_t box[5] = {64, uint32_t(b.bw), uint32_t(b.bh), uint32_t(b.bd), 1};
+  return make_tmap_bf16(m, v.base, 5, dims, strides, box, true);
+}
+
+// Parity-class views of a dense NDHWC tensor for a given stride (stride^3 views).
+std::vector<View> parity_views(const __nv_bfloat16* base, int D, int H, int W, int C, int stride) {
+  std::vector<View> v;
+  const long long sw = C, sh = (long long)W * C, sd = (long long)H * W * C, sn = (long long)D * H * W * C;
+  for (int pd = 0; pd < stride; pd++)
+    for (int ph = 0; ph < stride; ph++)
+      for (int pw = 0; pw < stride; pw++) {
+        View x;
+        x.base = base + pd * sd + ph * sh + pw * sw;
+        x.D = (D - pd + stride - 1) / stride;
+        x.H = (H - ph + stride - 1) / stride;
+        x.W = (W - pw + stride - 1) / stride;
+        x.sn = sn;
+        x.sd = sd * stride;
+        x.sh = sh * stride;
+        x.sw = sw * stride;
+        v.push_back(x);
+      }
+  return v;
+}
+
+bool tc_supported(const adni_conv3d_geom& g) {
+  return g.Cin % 64 == 0 && g.Cout % 64 == 0 && (g.stride == 1 || g.stride == 2) && g.k * g.k * g.k <= kMaxTaps &&
+         g.pad <= 120 && g.dil * (g.k - 1) <= 120;
+}
+
+int pick_block_n(int n_total) { return n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64); }
+
+// ---------------------------------------------------------------------------------------------
+int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,
+             __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream) {
+  const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
+  const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
+  const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
+  const std::vector<View> views = parity_views(x, g.D, g.H, g.W, g.Cin, g.stride);
+  const std::vector<AxisTap> at = fwd_axis_taps(g.k, g.stride, g.pad, g.dil);
+  std::vector<int> ext_d, ext_h, ext_w;
+  for (int p = 0; p < g.stride; p++) {
+    ext_d.push_back((g.D - p + g.stride - 1) / g.stride);
+    ext_h.push_back((g.H - p + g.stride - 1) / g.stride);
+    ext_w.push_back((g.W - p + g.stride - 1) / g.stride);
+  }
+  const Box b = plan_box(Do, Ho, Wo, 128, false, at, at, at, ext_d, ext_h, ext_w);
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  for (size_t i = 0; i < views.size(); i++) {
+    int rc = encode_view(&p.a_maps[i], views[i], g.Cin, b, g.N);
+    if (rc) return rc;
+    p.a_ext[i][0] = views[i].D;
+    p.a_ext[i][1] = views[i].H;
+    p.a_ext[i][2] = views[i].W;
+  }
+  const int taps = g.k * g.k * g.k;
+  const int block_n = pick_block_n(g.Cout);
+  {
+    const uint64_t dims[2] = {uint64_t(taps) * g.Cin, uint64_t(g.Cout)};
+    const uint64_t strides[2] = {1, uint64_t(taps) * g.Cin};
+    const uint32_t box[2] = {64, uint32_t(block_n)};
+    int rc = make_tmap_bf16(&p.b_map, w_oti, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  int t = 0;
+  for (int kd = 0; kd < g.k; kd++)
+    for (int kh = 0; kh < g.k; kh++)
+      for (int kw = 0; kw < g.k; kw++, t++) {
+        ConvTap& tp = p.taps[t];
+        tp.map = int8_t((at[kd].parity * g.stride + at[kh].parity) * g.stride + at[kw].parity);
+        tp.dd = int8_t(at[kd].off);
+        tp.dh = int8_t(at[kh].off);
+        tp.dw = int8_t(at[kw].off);
+        tp.kofs = t * g.Cin;
+      }
+  p.ntaps = taps;
+  p.kc_blocks = g.Cin / 64;
+  p.N = g.N;
+  p.Do = Do;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.bd = b.bd;
+  p.bh = b.bh;
+  p.bw = b.bw;
+  p.tiles_d = (Do + b.bd - 1) / b.bd;
+  p.tiles_h = (Ho + b.bh - 1) / b.bh;
+  p.tiles_w = (Wo + b.bw - 1) / b.bw;
+  p.n_tiles = g.Cout / block_n;
+  p.n_total = g.Cout;
+  p.out_sw = g.Cout;
+  p.out_sh = (long long)Wo * g.Cout;
+  p.out_sd = (long long)Ho * Wo * g.Cout;
+  p.out_sn = (long long)Do * Ho * Wo * g.Cout;
+  p.out = y;
+  p.addend = nullptr;
+  p.bias = bias;
+  p.stat_sum = ssum;
+  p.stat_sq = ssq;
+  return launch_igemm(p, block_n, stream);
+}
+
+// dx = sum_k dy[(i + pad - k*dil)/stride] * w[k]^T, one launch per parity class of dx when stride > 1.
+int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
+             const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream) {
+  const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
+  const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
+  const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
+  const int taps = g.k * g.k * g.k;
+  const int block_n = pick_block_n(g.Cin);
+  View dyv;
+  dyv.base = dy;
+  dyv.D = Do;
+  dyv.H = Ho;
+  dyv.W = Wo;
+  dyv.sw = g.Cout;
+  dyv.sh = (long long)Wo * g.Cout;
+  dyv.sd = (long long)Ho * Wo * g.Cout;
+  dyv.sn = (long long)Do * Ho * Wo * g.Cout;
+  const std::vector<View> outs = parity_views(dx, g.D, g.H, g.W, g.Cin, g.stride);
+  const std::vector<View> adds =
+      addend ? parity_views(addend, g.D, g.H, g.W, g.Cin, g.stride) : std::vector<View>();
+  const std::vector<int> ext_d{Do}, ext_h{Ho}, ext_w{Wo};
+
+  int cls = 0;
+  for (int pd = 0; pd < g.stride; pd++)
+    for (int ph = 0; ph < g.stride; ph++)
+      for (int pw = 0; pw < g.stride; pw++, cls++) {
+        const View& ov = outs[cls];
+        if (ov.D <= 0 || ov.H <= 0 || ov.W <= 0) continue;
+        // per-axis taps contributing to this parity class
+        auto axis = [&](int par) {
+          std::vector<std::pair<int, AxisTap>> v;  // (kernel index, tap)
+          for (int kk = 0; kk < g.k; kk++) {
+            const int num = par + g.pad - kk * g.dil;
+            if (((num % g.stride) + g.stride) % g.stride != 0) continue;
+            v.push_back({kk, AxisTap{0, num / g.stride}});
+          }
+          return v;
+        };
+        const auto ad = axis(pd), ah = axis(ph), aw = axis(pw);
+        std::vector<AxisTap> td, th, tw;
+        for (auto& a : ad) td.push_back(a.second);
+        for (auto& a : ah) th.push_back(a.second);
+        for (auto& a : aw) tw.push_back(a.second);
+        // (an empty axis makes every score 0: any box works)
+        const Box b = plan_box(ov.D, ov.H, ov.W, 128, false, td, th, tw, ext_d, ext_h, ext_w);
+        IgemmParams p;
+        memset(&p, 0, sizeof(p));
+        int rc = encode_view(&p.a_maps[0], dyv, g.Cout, b, g.N);
+        if (rc) return rc;
+        p.a_ext[0][0] = Do;
+        p.a_ext[0][1] = Ho;
+        p.a_ext[0][2] = Wo;
+        {
+          const uint64_t dims[2] = {uint64_t(taps) * g.Cout, uint64_t(g.Cin)};
+          const uint64_t strides[2] = {1, uint64_t(taps) * g.Cout};
+          const uint32_t box[2] = {64, uint32_t(block_n)};
+          rc = make_tmap_bf16(&p.b_map, w_ito, 2, dims, strides, box, true);
+          if (rc) return rc;
+        }
+        int nt = 0;
+        for (auto& a : ad)
+          for (auto& bq : ah)
+            for (auto& cq : aw) {
+              ConvTap& tp = p.taps[nt++];
+              tp.map = 0;
+              tp.dd = int8_t(a.second.off);
+              tp.dh = int8_t(bq.second.off);
+              tp.dw = int8_t(cq.second.off);
+              tp.kofs = ((a.first * g.k + bq.first) * g.k + cq.first) * g.Cout;
+            }
+        p.ntaps = nt;
+        p.kc_blocks = g.Cout / 64;
+        p.N = g.N;
+        p.Do = ov.D;
+        p.Ho = ov.H;
+        p.Wo = ov.W;
+        p.bd = b.bd;
+        p.bh = b.bh;
+        p.bw = b.bw;
+        p.tiles_d = (ov.D + b.bd - 1) / b.bd;
+        p.tiles_h = (ov.H + b.bh - 1) / b.bh;
+        p.tiles_w = (ov.W + b.bw - 1) / b.bw;
+        p.n_tiles = g.Cin / block_n;
+        p.n_total = g.Cin;
+        p.out_sn = ov.sn;
+        p.out_sd = ov.sd;
+        p.out_sh = ov.sh;
+        p.out_sw = ov.sw;
+        p.out = const_cast<__nv_bfloat16*>(ov.base);
+        p.addend = addend ? adds[cls].base : nullptr;
+        rc = launch_igemm(p, block_n, stream);
+        if (rc) return rc;
+      }
+  return ADNI_OK;
+}
+
+int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
+             cudaStream_t stream) {
+  const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
+  const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
+  const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
+  const int taps = g.k * g.k * g.k;
+  const std::vector<View> views = parity_views(x, g.D, g.H, g.W, g.Cin, g.stride);
+  const std::vector<AxisTap> at = fwd_axis_taps(g.k, g.stride, g.pad, g.dil);
+  std::vector<int> ext_d, ext_h, ext_w;
+  for (int p = 0; p < g.stride; p++) {
+    ext_d.push_back((g.D - p + g.stride - 1) / g.stride);
+    ext_h.push_back((g.H - p + g.stride - 1) / g.stride);
+    ext_w.push_back((g.W - p + g.stride - 1) / g.stride);
+  }
+  const Box b = plan_box(Do, Ho, Wo, 64, true, at, at, at, ext_d, ext_h, ext_w);
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  View dyv;
+  dyv.base = dy;
+  dyv.D = Do;
+  dyv.H = Ho;
+  dyv.W = Wo;
+  dyv.sw = g.Cout;
+  dyv.sh = (long long)Wo * g.Cout;
+  dyv.sd = (long long)Ho * Wo * g.Cout;
+  dyv.sn = (long long)Do * Ho * Wo * g.Cout;
+  int rc = encode_view(&p.dy_map, dyv, g.Cout, b, g.N);
+  if (rc) return rc;
+  for (size_t i = 0; i < views.size(); i++) {
+    rc = encode_view(&p.x_maps[i], views[i], g.Cin, b, g.N);
+    if (rc) return rc;
+    p.x_ext[i][0] = views[i].D;
+    p.x_ext[i][1] = views[i].H;
+    p.x_ext[i][2] = views[i].W;
+  }
+  int t = 0;
+  for (int kd = 0; kd < g.k; kd++)
+    for (int kh = 0; kh < g.k; kh++)
+      for (int kw = 0; kw < g.k; kw++, t++) {
+        ConvTap& tp = p.taps[t];
+        tp.map = int8_t((at[kd].parity * g.stride + at[kh].parity) * g.stride + at[kw].parity);
+        tp.dd = int8_t(at[kd].off);
+        tp.dh = int8_t(at[kh].off);
+        tp.dw = int8_t(at[kw].off);
+        tp.kofs = t * g.Cin;
+      }
+  p.ntaps = taps;
+  p.cin_blocks = g.Cin / 64;
+  p.n_groups = taps * p.cin_blocks;
+  const int groups = p.n_groups >= 4 ? 4 : (p.n_groups >= 2 ? 2 : 1);
+  p.N = g.N;
+  p.Do = Do;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.bd = b.bd;
+  p.bh = b.bh;
+  p.bw = b.bw;
+  p.tiles_d = (Do + b.bd - 1) / b.bd;
+  p.tiles_h = (Ho + b.bh - 1) / b.bh;
+  p.tiles_w = (Wo + b.bw - 1) / b.bw;
+  p.pos_boxes = g.N * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.m_tiles = (g.Cout + 127) / 128;
+  p.n_tiles = (p.n_groups + groups - 1) / groups;
+  const int base_items = p.m_tiles * p.n_tiles;
+  int splits = (4 * num_sms() + base_items - 1) / base_items;
+  splits = std::min(splits, std::max(1, p.pos_boxes / 16));
+  splits = std::max(splits, 1);
+  p.boxes_per_split = (p.pos_boxes + splits - 1) / splits;
+  p.splits = (p.pos_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
+  p.cout = g.Cout;
+  p.k_total = p.n_groups * 64;
+  p.dw = dw;
+  return launch_wgrad(p, groups, stream);
+}
+
+int check_geom(const adni_conv3d_geom* g) {
+  ADNI_REQUIRE(g != nullptr, ADNI_EINVAL, "conv3d: null geometry");
+  ADNI_REQUIRE(g->N > 0 && g->D > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Cout > 0, ADNI_EINVAL,
+               "conv3d: non-positive extent");
+  ADNI_REQUIRE(g->k > 0 && g->stride > 0 && g->dil > 0 && g->pad >= 0, ADNI_EINVAL, "conv3d: bad k/stride/dil/pad");
+  ADNI_REQUIRE(out_extent(g->D, g->k, g->stride, g->pad, g->dil) > 0 &&
+                   out_extent(g->H, g->k, g->stride, g->pad, g->dil) > 0 &&
+                   out_extent(g->W, g->k, g->stride, g->pad, g->dil) > 0,
+               ADNI_EINVAL, "conv3d: empty output");
+  return ADNI_OK;
+}
+
+int resolve_engine(const adni_conv3d_geom& g, int engine, int* out) {
+  if (engine == ADNI_ENGINE_AUTO) engine = tc_supported(g) ? ADNI_ENGINE_TCGEN05 : ADNI_ENGINE_DIRECT;
+  if (engine == ADNI_ENGINE_TCGEN05 && !tc_supported(g)) {
+    set_error("conv3d: tcgen05 engine needs Cin,Cout multiples of 64, stride 1|2, k^3 <= 64 (Cin=%d Cout=%d k=%d s=%d)",
+              g.Cin, g.Cout, g.k, g.stride);
+    return ADNI_ENOTSUP;
+  }
+  if (engine != ADNI_ENGINE_TCGEN05 && engine != ADNI_ENGINE_DIRECT) {
+    set_error("conv3d: unknown engine %d", engine);
+    return ADNI_EINVAL;
+  }
+  *out = engine;
+  return ADNI_OK;
+}
+
+}  // namespace
+}  // namespace adni
+
+using namespace adni;
+
+extern "C" {
+
+int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil) { return out_extent(in, k, stride, pad, dil); }
+
+int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* w_oti, const float* bias,
+                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* stream) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(x && w_oti && y, ADNI_EINVAL, "conv3d_fprop: null pointer");
+  ADNI_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), ADNI_EINVAL, "conv3d_fprop: stats need both buffers");
+  int eng;
+  rc = resolve_engine(*g, engine, &eng);
+  if (rc) return rc;
+  auto xs = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto ws = reinterpret_cast<const __nv_bfloat16*>(w_oti);
+  auto ys = reinterpret_cast<__nv_bfloat16*>(y);
+  if (eng == ADNI_ENGINE_TCGEN05)
+    return tc_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
+  return direct_conv_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
+}
+
+int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
+                      adni_bf16* dx, int engine, void* stream) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(dy && w_ito && dx, ADNI_EINVAL, "conv3d_dgrad: null pointer");
+  int eng;
+  rc = resolve_engine(*g, engine, &eng);
+  if (rc) return rc;
+  auto dys = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto ws = reinterpret_cast<const __nv_bfloat16*>(w_ito);
+  auto as = reinterpret_cast<const __nv_bfloat16*>(addend);
+  auto dxs = reinterpret_cast<__nv_bfloat16*>(dx);
+  if (eng == ADNI_ENGINE_TCGEN05) return tc_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
+  return direct_conv_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
+}
+
+int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* dy, float* dw_oti, float* dbias,
+                      int engine, void* stream) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(x && dy && dw_oti, ADNI_EINVAL, "conv3d_wgrad: null pointer");
+  int eng;
+  rc = resolve_engine(*g, engine, &eng);
+  if (rc) return rc;
+  auto xs = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto dys = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (eng == ADNI_ENGINE_TCGEN05) {
+    ADNI_REQUIRE(dbias == nullptr, ADNI_ENOTSUP, "conv3d_wgrad: tcgen05 engine has no bias gradient (use channel_stats)");
+    return tc_wgrad(*g, xs, dys, dw_oti, static_cast<cudaStream_t>(stream));
+  }
+  return direct_conv_wgrad(*g, xs, dys, dw_oti, dbias, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// Parameter blocks shared by the tcgen05 implicit-GEMM conv kernels and their host-side planner.
+#pragma once
+#include "common.cuh"
+
+namespace adni {
+
+constexpr int kMaxTaps = 64;
+constexpr int kMaxMaps = 8;
+
+// One filter tap as seen by the TMA producer: which tensor map (stride-2 convs address the input through
+// 8 parity-class views), the box offset relative to the output-tile origin, and the column offset of the
+// tap's K-slice inside the weight matrix.
+struct ConvTap {
+  int8_t map, dd, dh, dw;
+  int32_t kofs;
+};
+
+// fprop / dgrad: D[M = output positions, N = out channels] = sum_taps A_tap[M, Kc] * B[N, tap*Kc..]^T
+struct IgemmParams {
+  CUtensorMap a_maps[kMaxMaps];  // 5-D (C, W, H, D, N) views of the activation tensor, box (64, bw, bh, bd, 1)
+  CUtensorMap b_map;             // 2-D (K_total, N_total) weight matrix, box (64, BLOCK_N)
+  ConvTap taps[kMaxTaps];
+  int a_ext[kMaxMaps][3];  // (D, H, W) extent of every A view, for the all-padding tap skip
+  int ntaps;
+  int kc_blocks;  // channels per tap / 64
+  int N, Do, Ho, Wo;
+  int bd, bh, bw;
+  int tiles_d, tiles_h, tiles_w;
+  int n_tiles;  // N_total / BLOCK_N
+  int n_total;
+  long long out_sn, out_sd, out_sh, out_sw;  // element strides of the output view (channel stride 1)
+  __nv_bfloat16* out;
+  const __nv_bfloat16* addend;  // same view as out, nullable
+  const float* bias;            // [N_total], nullable
+  double* stat_sum;             // [N_total], nullable
+  double* stat_sq;
+};
+
+// wgrad: D[M = Cout rows, N = K_total columns] += sum over position boxes of dY^T * X_tap
+struct WgradParams {
+  CUtensorMap dy_map;            // 5-D (Cout, Wo, Ho, Do, N), box (64, bw, bh, bd, 1), bw*bh*bd == 64
+  CUtensorMap x_maps[kMaxMaps];  // 5-D views of x, box (64, bw, bh, bd, 1)
+  ConvTap taps[kMaxTaps];
+  int x_ext[kMaxMaps][3];
+  int ntaps;
+  int cin_blocks;  // Cin / 64 (64-column groups per tap)
+  int n_groups;    // ntaps * cin_blocks
+  int N, Do, Ho, Wo;
+  int bd, bh, bw;
+  int tiles_d, tiles_h, tiles_w;
+  int pos_boxes;  // N * tiles_d * tiles_h * tiles_w
+  int m_tiles;    // ceil(Cout / 128)
+  int n_tiles;    // ceil(n_groups / GROUPS_PER_TILE)
+  int splits;
+  int boxes_per_split;
+  int cout;
+  int k_total;  // n_groups * 64
+  float* dw;    // [Cout][K_total] fp32, accumulated with red.add
+};
+
+}  // namespace adni

@@ -1,0 +1,592 @@
+// tcgen05 / TMEM implicit-GEMM Conv3d kernels (fprop, dgrad, wgrad) fed by TMA box loads.
+//
+// Replaces the cuDNN Conv3d forward/backward dispatched by MedicalNet's ResNet (SURVEY.md K1-K3;
+// reference call sites pkg/models/mri_models/anat_cnn.py:18-31,95).
+//
+// Formulation.  Activations are NDHWC bf16.  An output tile is a spatial BOX of <=128 output positions
+// (bw x bh x bd) of one sample times BLOCK_N output channels.  For every filter tap the A operand of the
+// GEMM is the same box shifted by (tap*dilation - pad): ONE tiled 5-D TMA load with the hardware
+// zero-filling the out-of-bounds halo.  The box lands in shared memory as 128 rows x 128 B (64 channels),
+// 128-byte swizzled: exactly the canonical K-major UMMA operand layout, so no thread ever touches operand
+// data.  Stride-2 convs address the input through 8 parity-class tensor maps (doubled strides), dgrad is
+// the same kernel on dY with the [Cin][tap][Cout] weight copy and mirrored tap offsets, and taps whose
+// shifted box lies entirely in the padding (up to 31 % of layer4's dilation-4 taps) are skipped.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
+// + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bf16 global, fused bias / residual-gradient
+// add / BatchNorm sum & sum-of-squares).  Two TMEM accumulators let the epilogue of tile i overlap the
+// mainloop of tile i+1.
+#include "conv_igemm.cuh"
+
+namespace adni {
+
+constexpr int kIgemmThreads = 192;
+
+struct TileCoord {
+  int n, d0, h0, w0, n0;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord c;
+  const int nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  const int tw = m % p.tiles_w;
+  m /= p.tiles_w;
+  const int th = m % p.tiles_h;
+  m /= p.tiles_h;
+  const int td = m % p.tiles_d;
+  c.n = m / p.tiles_d;
+  c.d0 = td * p.bd;
+  c.h0 = th * p.bh;
+  c.w0 = tw * p.bw;
+  c.n0 = nt * BLOCK_N;
+  return c;
+}
+
+__device__ __forceinline__ bool box_in_range(const int* ext, int d, int h, int w, int bd, int bh, int bw) {
+  return d + bd > 0 && d < ext[0] && h + bh > 0 && h < ext[1] && w + bw > 0 && w < ext[2];
+}
+
+template <int BLOCK_N, int STAGES>
+struct IgemmCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 4;
+  static constexpr int SMEM_BYTES = STAT_OFF + STAT_BYTES + 1024;  // + slack for manual 1024-B alignment
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < kMaxMaps && i < 1; i++) tma_prefetch_desc(&p.a_maps[i]);
+      tma_prefetch_desc(&p.b_map);
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bd) * 128u + Cfg::B_BYTES;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+        for (int t = 0; t < p.ntaps; t++) {
+          const ConvTap tap = p.taps[t];
+          const int d = c.d0 + tap.dd, h = c.h0 + tap.dh, w = c.w0 + tap.dw;
+          if (!box_in_range(p.a_ext[tap.map], d, h, w, p.bd, p.bh, p.bw)) continue;
+          for (int kb = 0; kb < p.kc_blocks; kb++) {
+            mbar_wait(&empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&full[st], tx_bytes);
+            tma_load_5d(smem_a + st * Cfg::A_BYTES, &p.a_maps[tap.map], &full[st], kb * 64, w, h, d, c.n);
+            tma_load_2d(smem_b + st * Cfg::B_BYTES, &p.b_map, &full[st], tap.kofs + kb * 64, c.n0);
+            if (++st == STAGES) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, false, false);
+      int st = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t accph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        uint32_t accum = 0;
+        for (int t = 0; t < p.ntaps; t++) {
+          const ConvTap tap = p.taps[t];
+          if (!box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw))
+            continue;
+          for (int kb = 0; kb < p.kc_blocks; kb++) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + st * Cfg::A_BYTES);
+            const uint32_t b_addr = smem_u32(smem_b + st * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(k));
+            }
+            accum = 1;
+            umma_commit(&empty[st]);  // frees the smem slot once these MMAs have read it
+            if (++st == STAGES) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          accph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== Epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;  // 0..127
+    const int row = q * 32 + lane;
+    const bool do_stats = p.stat_sum != nullptr;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+      bool has_k = false;
+      for (int t = 0; t < p.ntaps; t++) {
+        const ConvTap tap = p.taps[t];
+        has_k |= box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw);
+      }
+      const int rw = row % p.bw;
+      const int rh = (row / p.bw) % p.bh;
+      const int rd = row / (p.bw * p.bh);
+      const int od = c.d0 + rd, oh = c.h0 + rh, ow = c.w0 + rw;
+      const bool valid = rd < p.bd && od < p.Do && oh < p.Ho && ow < p.Wo;
+      const long long off = c.n * p.out_sn + od * p.out_sd + oh * p.out_sh + ow * p.out_sw + c.n0;
+
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
+        uint32_t v[32];
+        if (has_k) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(acc * BLOCK_N + chunk * 32),
+                        v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = 0u;
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] += __ldg(p.bias + c.n0 + chunk * 32 + j);
+        }
+        if (do_stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float x = valid ? f[j] : 0.f;
+            s1[j] = x;
+            s2[j] = x * x;
+          }
+          const float cs1 = warp_column_sums(s1, lane);
+          const float cs2 = warp_column_sums(s2, lane);
+          stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
+          stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
+        }
+        if (valid) {
+          if (p.addend != nullptr) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+              const uint4 a = __ldg(ap + j4);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                f[j4 * 8 + e * 2 + 0] += bf16_lo(aw[e]);
+                f[j4 * 8 + e * 2 + 1] += bf16_hi(aw[e]);
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            uint4 o;
+            o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+            o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+            o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+            o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+            op[j4] = o;
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        accph ^= 1;
+      }
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < BLOCK_N; col += 128) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; w4++) {
+            a += stat_smem[(w4 * 2 + 0) * BLOCK_N + col];
+            b += stat_smem[(w4 * 2 + 1) * BLOCK_N + col];
+          }
+          atomicAdd(p.stat_sum + c.n0 + col, static_cast<double>(a));
+          atomicAdd(p.stat_sq + c.n0 + col, static_cast<double>(b));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// wgrad:  dW[Cout][K_total] += sum over positions  dY[pos][Cout]^T * X[pos + tap][Cin]
+// Both operands are stored channel-contiguous, i.e. MN-major for this GEMM: the same TMA boxes as above
+// (64 positions x 64 channels, 128-B swizzle) are consumed through MN-major UMMA descriptors
+// (LBO = distance between 64-channel groups, SBO = 1024 between 8-position groups).
+// =================================================================================================
+template <int GROUPS, int STAGES>
+struct WgradCfg {
+  static constexpr int BLOCK_N = GROUPS * 64;
+  static constexpr int BOX_BYTES = 64 * 128;
+  static constexpr int A_BYTES = 2 * BOX_BYTES;
+  static constexpr int B_BYTES = GROUPS * BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+};
+
+struct WItem {
+  int mt, nt, ks;
+};
+__device__ __forceinline__ WItem decode_item(const WgradParams& p, int item) {
+  WItem w;
+  w.nt = item % p.n_tiles;
+  const int r = item / p.n_tiles;
+  w.mt = r % p.m_tiles;
+  w.ks = r / p.m_tiles;
+  return w;
+}
+struct PosBox {
+  int n, d0, h0, w0;
+};
+__device__ __forceinline__ PosBox decode_box(const WgradParams& p, int b) {
+  PosBox c;
+  const int tw = b % p.tiles_w;
+  b /= p.tiles_w;
+  const int th = b % p.tiles_h;
+  b /= p.tiles_h;
+  const int td = b % p.tiles_d;
+  c.n = b / p.tiles_d;
+  c.d0 = td * p.bd;
+  c.h0 = th * p.bh;
+  c.w0 = tw * p.bw;
+  return c;
+}
+
+template <int GROUPS>
+__device__ __forceinline__ bool wgrad_box_active(const WgradParams& p, const PosBox& c, int g0, int ng) {
+  // active if the X box of at least one of the tile's taps intersects the input
+  int last_tap = -1;
+  for (int g = 0; g < ng; g++) {
+    const int t = (g0 + g) / p.cin_blocks;
+    if (t == last_tap) continue;
+    last_tap = t;
+    const ConvTap tap = p.taps[t];
+    if (box_in_range(p.x_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw)) return true;
+  }
+  return false;
+}
+
+template <int GROUPS, int STAGES>
+__global__ void __launch_bounds__(kIgemmThreads, 1) wgrad_mnmajor_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<GROUPS, STAGES>;
+  constexpr int BLOCK_N = Cfg::BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = p.m_tiles * p.n_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.dy_map);
+      tma_prefetch_desc(&p.x_maps[0]);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const WItem it = decode_item(p, item);
+        const int g0 = it.nt * GROUPS;
+        const int ng = min(GROUPS, p.n_groups - g0);
+        const uint32_t tx_bytes = static_cast<uint32_t>(2 + ng) * Cfg::BOX_BYTES;
+        const int b_begin = it.ks * p.boxes_per_split;
+        const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
+        for (int b = b_begin; b < b_end; b++) {
+          const PosBox c = decode_box(p, b);
+          if (!wgrad_box_active<GROUPS>(p, c, g0, ng)) continue;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], tx_bytes);
+          uint8_t* a_dst = smem_a + st * Cfg::A_BYTES;
+          tma_load_5d(a_dst, &p.dy_map, &full[st], it.mt * 128, c.w0, c.h0, c.d0, c.n);
+          tma_load_5d(a_dst + Cfg::BOX_BYTES, &p.dy_map, &full[st], it.mt * 128 + 64, c.w0, c.h0, c.d0, c.n);
+          uint8_t* b_dst = smem_b + st * Cfg::B_BYTES;
+          for (int g = 0; g < ng; g++) {
+            const int t = (g0 + g) / p.cin_blocks;
+            const int c0 = ((g0 + g) % p.cin_blocks) * 64;
+            const ConvTap tap = p.taps[t];
+            tma_load_5d(b_dst + g * Cfg::BOX_BYTES, &p.x_maps[tap.map], &full[st], c0, c.w0 + tap.dw, c.h0 + tap.dh,
+                        c.d0 + tap.dd, c.n);
+          }
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, true, true);
+      int st = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t accph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const WItem it = decode_item(p, item);
+        const int g0 = it.nt * GROUPS;
+        const int ng = min(GROUPS, p.n_groups - g0);
+        const int b_begin = it.ks * p.boxes_per_split;
+        const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        uint32_t accum = 0;
+        for (int b = b_begin; b < b_end; b++) {
+          const PosBox c = decode_box(p, b);
+          if (!wgrad_box_active<GROUPS>(p, c, g0, ng)) continue;
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + st * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + st * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            // 16 positions per MMA = 2 groups of 8 rows (SBO 1024 B); channel groups Cfg::BOX_BYTES apart (LBO)
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, Cfg::BOX_BYTES, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, Cfg::BOX_BYTES, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(k));
+          }
+          accum = 1;
+          umma_commit(&empty[st]);
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          accph ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const WItem it = decode_item(p, item);
+      const int g0 = it.nt * GROUPS;
+      const int ng = min(GROUPS, p.n_groups - g0);
+      const int b_begin = it.ks * p.boxes_per_split;
+      const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
+      bool has_k = false;
+      for (int b = b_begin; b < b_end && !has_k; b++) {
+        const PosBox c = decode_box(p, b);
+        has_k = wgrad_box_active<GROUPS>(p, c, g0, ng);
+      }
+      const int co = it.mt * 128 + row;
+      float* dst = p.dw + static_cast<long long>(co) * p.k_total + static_cast<long long>(g0) * 64;
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      if (has_k) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < ng * 2; chunk++) {
+          uint32_t v[32];
+          tmem_ld_32x32(
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + chunk * 32), v);
+          tmem_ld_wait();
+          if (co < p.cout) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; j4++) {
+              float4 val;
+              val.x = __uint_as_float(v[j4 * 4 + 0]);
+              val.y = __uint_as_float(v[j4 * 4 + 1]);
+              val.z = __uint_as_float(v[j4 * 4 + 2]);
+              val.w = __uint_as_float(v[j4 * 4 + 3]);
+              atomicAdd(reinterpret_cast<float4*>(dst + chunk * 32 + j4 * 4), val);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        accph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// Launchers
+// =================================================================================================
+extern void count_launch();
+
+template <int BLOCK_N, int STAGES>
+static int launch_igemm_t(const IgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N, STAGES>;
+  auto kern = igemm_kmajor_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  ADNI_LAUNCH_CHECK("igemm_kmajor_kernel");
+  return ADNI_OK;
+}
+
+int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 64:
+      return launch_igemm_t<64, 8>(p, stream);
+    case 128:
+      return launch_igemm_t<128, 6>(p, stream);
+    case 256:
+      return launch_igemm_t<256, 4>(p, stream);
+    default:
+      set_error("igemm: unsupported BLOCK_N %d", block_n);
+      return ADNI_ENOTSUP;
+  }
+}
+
+template <int GROUPS, int STAGES>
+static int launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<GROUPS, STAGES>;
+  auto kern = wgrad_mnmajor_kernel<GROUPS, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  ADNI_LAUNCH_CHECK("wgrad_mnmajor_kernel");
+  return ADNI_OK;
+}
+
+int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream) {
+  switch (groups) {
+    case 1:
+      return launch_wgrad_t<1, 8>(p, stream);
+    case 2:
+      return launch_wgrad_t<2, 6>(p, stream);
+    case 4:
+      return launch_wgrad_t<4, 4>(p, stream);
+    default:
+      set_error("wgrad: unsupported group count %d", groups);
+      return ADNI_ENOTSUP;
+  }
+}
+
+}  // namespace adni

@@ -1,0 +1,609 @@
+// HBM-bound kernels around the convolutions: BatchNorm finalize / apply / backward, ReLU, residual add,
+// per-channel statistics, max / global-average pooling, casts and weight-layout transposes.
+// All activation tensors are [rows][C] views of NDHWC bf16 with C % 8 == 0: every thread moves 16-byte
+// vectors (8 channels), grids are sized in multiples of the SM count.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace adni {
+
+extern void count_launch();
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline int ew_grid(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+struct Vec8 {
+  float v[8];
+};
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  Vec8 o;
+  o.v[0] = bf16_lo(r.x);
+  o.v[1] = bf16_hi(r.x);
+  o.v[2] = bf16_lo(r.y);
+  o.v[3] = bf16_hi(r.y);
+  o.v[4] = bf16_lo(r.z);
+  o.v[5] = bf16_hi(r.z);
+  o.v[6] = bf16_lo(r.w);
+  o.v[7] = bf16_hi(r.w);
+  return o;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& a) {
+  uint4 o;
+  o.x = pack_bf16x2(a.v[0], a.v[1]);
+  o.y = pack_bf16x2(a.v[2], a.v[3]);
+  o.z = pack_bf16x2(a.v[4], a.v[5]);
+  o.w = pack_bf16x2(a.v[6], a.v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ Vec8 loadf8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  Vec8 o;
+  o.v[0] = a.x;
+  o.v[1] = a.y;
+  o.v[2] = a.z;
+  o.v[3] = a.w;
+  o.v[4] = b.x;
+  o.v[5] = b.y;
+  o.v[6] = b.z;
+  o.v[7] = b.w;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* ssum, const double* ssq, double count, int C, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* rmean, float* rvar,
+                                   float* mean, float* invstd, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = ssum[c] / count;
+  double var = ssq[c] / count - m * m;
+  if (var < 0) var = 0;
+  const float istd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  const float sc = g * istd;
+  if (mean) mean[c] = (float)m;
+  if (invstd) invstd[c] = istd;
+  if (scale) scale[c] = sc;
+  if (shift) shift[c] = b - (float)m * sc;
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+  if (rvar) {
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ y,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const __nv_bfloat16* __restrict__ res,
+                                                              __nv_bfloat16* __restrict__ out, long long nvec, int vpr,
+                                                              int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) * 8;
+    Vec8 a = load8(y + i * 8);
+    const Vec8 sc = loadf8(scale + c0), sh = loadf8(shift + c0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.v[j] = fmaf(a.v[j], sc.v[j], sh.v[j]);
+    if (res) {
+      const Vec8 r = load8(res + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a.v[j] += r.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) a.v[j] = fmaxf(a.v[j], 0.f);
+    }
+    store8(out + i * 8, a);
+  }
+}
+
+// Per-channel reductions over rows.  Block = 256 threads = (vpr channel vectors) x (rpp row lanes); a
+// block walks a slab of rows, reduces its row lanes through shared memory and issues one fp64 atomic per
+// channel.  MODE 0: sum x, sum x^2.  MODE 1: BatchNorm backward sums  sum g, sum g*xhat.
+constexpr int kRedSlabRows = 2048;
+
+template <int MODE>
+__global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,    // x | dout
+                                                                    const __nv_bfloat16* __restrict__ outp,  // - | out (relu mask)
+                                                                    const __nv_bfloat16* __restrict__ yraw,  // - | y
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd, long long rows,
+                                                                    int C, int relu, double* __restrict__ r0,
+                                                                    double* __restrict__ r1) {
+  __shared__ float sm[2][kEwThreads][8];
+  const int vpr = C / 8;
+  const int rpp = kEwThreads / vpr;  // row lanes per block (vpr <= 256)
+  const int cv = threadIdx.x % vpr;
+  const int rl = threadIdx.x / vpr;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+  const long long row_begin = (long long)blockIdx.x * kRedSlabRows;
+  const long long row_end = min(rows, row_begin + kRedSlabRows);
+  if (rl < rpp) {
+    Vec8 mu, is;
+    if (MODE == 1) {
+      mu = loadf8(mean + cv * 8);
+      is = loadf8(invstd + cv * 8);
+    }
+    for (long long r = row_begin + rl; r < row_end; r += rpp) {
+      const long long off = r * C + cv * 8;
+      const Vec8 x = load8(a + off);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += x.v[j];
+          s1[j] = fmaf(x.v[j], x.v[j], s1[j]);
+        }
+      } else {
+        Vec8 g = x;
+        if (relu) {
+          const Vec8 o = load8(outp + off);
+#pragma unroll
+          for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+        }
+        const Vec8 yv = load8(yraw + off);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
+          s0[j] += g.v[j];
+          s1[j] = fmaf(g.v[j], xh, s1[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sm[0][threadIdx.x][j] = s0[j];
+    sm[1][threadIdx.x][j] = s1[j];
+  }
+  __syncthreads();
+  // thread t < vpr*8 reduces channel (t/8 vector, t%8 lane) across the row lanes
+  for (int t = threadIdx.x; t < vpr * 8; t += kEwThreads) {
+    const int v = t / 8, j = t % 8;
+    float a0 = 0.f, a1 = 0.f;
+    for (int l = 0; l < rpp; l++) {
+      a0 += sm[0][l * vpr + v][j];
+      a1 += sm[1][l * vpr + v][j];
+    }
+    atomicAdd(r0 + v * 8 + j, (double)a0);
+    atomicAdd(r1 + v * 8 + j, (double)a1);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
+                        const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const double* __restrict__ red, double inv_count, long long nvec, int vpr, int C, int relu,
+                        __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) * 8;
+    Vec8 g = load8(dout + i * 8);
+    if (relu) {
+      const Vec8 o = load8(outp + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+    }
+    if (dres) store8(dres + i * 8, g);
+    const Vec8 yv = load8(yraw + i * 8);
+    const Vec8 mu = loadf8(mean + c0), is = loadf8(invstd + c0);
+    Vec8 r;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float gm = gamma ? __ldg(gamma + c0 + j) : 1.f;
+      const float mg = (float)(red[c0 + j] * inv_count);
+      const float mgx = (float)(red[C + c0 + j] * inv_count);
+      const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
+      r.v[j] = gm * is.v[j] * (g.v[j] - mg - xh * mgx);
+    }
+    store8(dy + i * 8, r);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)red[c];
+  if (dgamma) dgamma[c] = (float)red[C + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pooling
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+    maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int C, int k, int s, int pad,
+                       int Do, int Ho, int Wo, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ amax) {
+  const int vpr = C / 8;
+  const long long total = (long long)N * Do * Ho * Wo * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpr);
+    long long r = i / vpr;
+    const int ow = (int)(r % Wo);
+    r /= Wo;
+    const int oh = (int)(r % Ho);
+    r /= Ho;
+    const int od = (int)(r % Do);
+    const int n = (int)(r / Do);
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      best[j] = -INFINITY;
+      bidx[j] = -1;
+    }
+    for (int kd = 0; kd < k; kd++) {
+      const int id = od * s - pad + kd;
+      if (id < 0 || id >= D) continue;
+      for (int kh = 0; kh < k; kh++) {
+        const int ih = oh * s - pad + kh;
+        if (ih < 0 || ih >= H) continue;
+        for (int kw = 0; kw < k; kw++) {
+          const int iw = ow * s - pad + kw;
+          if (iw < 0 || iw >= W) continue;
+          const Vec8 v = load8(x + ((((long long)n * D + id) * H + ih) * W + iw) * C + cv * 8);
+          const int slot = (kd * k + kh) * k + kw;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (bidx[j] < 0 || v.v[j] > best[j]) {  // strict '>' : first maximum in scan order wins
+              best[j] = v.v[j];
+              bidx[j] = slot;
+            }
+          }
+        }
+      }
+    }
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = best[j];
+    store8(y + i * 8, o);
+    uint2 pk;
+    pk.x = (uint32_t)(bidx[0] & 255) | ((uint32_t)(bidx[1] & 255) << 8) | ((uint32_t)(bidx[2] & 255) << 16) |
+           ((uint32_t)(bidx[3] & 255) << 24);
+    pk.y = (uint32_t)(bidx[4] & 255) | ((uint32_t)(bidx[5] & 255) << 8) | ((uint32_t)(bidx[6] & 255) << 16) |
+           ((uint32_t)(bidx[7] & 255) << 24);
+    *reinterpret_cast<uint2*>(amax + i * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+    maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ amax, int N, int D, int H,
+                       int W, int C, int k, int s, int pad, int Do, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int vpr = C / 8;
+  const long long total = (long long)N * D * H * W * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpr);
+    long long r = i / vpr;
+    const int iw = (int)(r % W);
+    r /= W;
+    const int ih = (int)(r % H);
+    r /= H;
+    const int id = (int)(r % D);
+    const int n = (int)(r / D);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    // windows containing this input voxel: o*s - pad + kk == i  with 0 <= kk < k
+    const int od_lo = max(0, (id + pad - k + s) / s), od_hi = min(Do - 1, (id + pad) / s);
+    const int oh_lo = max(0, (ih + pad - k + s) / s), oh_hi = min(Ho - 1, (ih + pad) / s);
+    const int ow_lo = max(0, (iw + pad - k + s) / s), ow_hi = min(Wo - 1, (iw + pad) / s);
+    for (int od = od_lo; od <= od_hi; od++) {
+      const int kd = id + pad - od * s;
+      if (kd < 0 || kd >= k) continue;
+      for (int oh = oh_lo; oh <= oh_hi; oh++) {
+        const int kh = ih + pad - oh * s;
+        if (kh < 0 || kh >= k) continue;
+        for (int ow = ow_lo; ow <= ow_hi; ow++) {
+          const int kw = iw + pad - ow * s;
+          if (kw < 0 || kw >= k) continue;
+          const int slot = (kd * k + kh) * k + kw;
+          const long long o = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * vpr + cv;
+          const uint2 pk = __ldg(reinterpret_cast<const uint2*>(amax + o * 8));
+          const Vec8 g = load8(dy + o * 8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t word = j < 4 ? pk.x : pk.y;
+            const int a = (word >> ((j & 3) * 8)) & 255;
+            if (a == slot) acc[j] += g.v[j];
+          }
+        }
+      }
+    }
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = acc[j];
+    store8(dx + i * 8, o);
+  }
+}
+
+constexpr int kGapSplit = 8;
+__global__ void __launch_bounds__(kEwThreads)
+    gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, float inv_p, float* __restrict__ feat) {
+  // grid: (channel-vector blocks of 32, P splits, N); block = 32 channel vectors x 8 row lanes
+  __shared__ float sm[8][32][8];
+  const int vpr = C / 8;
+  const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int n = blockIdx.z;
+  const long long per = (P + gridDim.y - 1) / gridDim.y;
+  const long long p0 = (long long)blockIdx.y * per, p1 = min(P, p0 + per);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j] = 0.f;
+  if (cv < vpr) {
+    for (long long pp = p0 + rl; pp < p1; pp += 8) {
+      const Vec8 v = load8(x + ((long long)n * P + pp) * C + cv * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) s[j] += v.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) sm[rl][threadIdx.x & 31][j] = s[j];
+  __syncthreads();
+  const int t = threadIdx.x;  // 256 threads -> 32 vectors x 8 lanes
+  const int v = t >> 3, j = t & 7;
+  const int cvv = blockIdx.x * 32 + v;
+  if (cvv < vpr) {
+    float a = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; l++) a += sm[l][v][j];
+    atomicAdd(feat + (long long)n * C + cvv * 8 + j, a * inv_p);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+    gap_bwd_kernel(const float* __restrict__ dfeat, int N, long long P, int C, float inv_p,
+                   __nv_bfloat16* __restrict__ dx) {
+  const int vpr = C / 8;
+  const long long total = (long long)N * P * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpr);
+    const int n = (int)(i / ((long long)P * vpr));
+    Vec8 g = loadf8(dfeat + (long long)n * C + cv * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) g.v[j] *= inv_p;
+    store8(dx + i * 8, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Casts and batched transposes (weight layouts)
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void cast_to_bf16_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn((float)x[i]);
+}
+__global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+__device__ __forceinline__ void store_t(__nv_bfloat16* p, float v, bool) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_t(float* p, float v, bool acc) { *p = acc ? *p + v : v; }
+
+// in [batch][R][Cc] (fp32) -> out [batch][Cc][R]
+template <typename TOut>
+__global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict__ out, int R, int Cc, bool accumulate) {
+  __shared__ float tile[32][33];
+  const long long boff = (long long)blockIdx.z * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = in[boff + (long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) store_t(out + boff + (long long)c * R + r, tile[threadIdx.x][j], accumulate);
+  }
+}
+
+template <typename TOut>
+int launch_transpose(const float* in, TOut* out, int batch, int R, int Cc, bool accumulate, cudaStream_t stream) {
+  dim3 block(32, 8);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = std::min(batch - b0, 65535);
+    dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
+    transpose_kernel<TOut><<<grid, block, 0, stream>>>(in + (long long)b0 * R * Cc, out + (long long)b0 * R * Cc, R, Cc,
+                                                       accumulate);
+    count_launch();
+  }
+  ADNI_LAUNCH_CHECK("transpose_kernel");
+  return ADNI_OK;
+}
+
+}  // namespace
+}  // namespace adni
+
+using namespace adni;
+typedef __nv_bfloat16 bf16;
+#define BF(p) reinterpret_cast<bf16*>(p)
+#define CBF(p) reinterpret_cast<const bf16*>(p)
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double count, int C, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream) {
+  ADNI_REQUIRE(stat_sum && stat_sqsum && C > 0 && count > 0, ADNI_EINVAL, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stat_sum, stat_sqsum, count, C, gamma, beta, eps,
+                                                               momentum, running_mean, running_var, mean, invstd,
+                                                               scale, shift);
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_finalize_kernel");
+  return ADNI_OK;
+}
+
+int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, double* sqsum, void* stream) {
+  ADNI_REQUIRE(x && sum && sqsum && rows > 0, ADNI_EINVAL, "channel_stats: bad arguments");
+  ADNI_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, ADNI_ENOTSUP, "channel_stats: C=%d must be a multiple of 8 in [8,2048]",
+               C);
+  const int grid = (int)((rows + kRedSlabRows - 1) / kRedSlabRows);
+  channel_reduce_kernel<0><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr, rows, C, 0,
+                                                                 sum, sqsum);
+  count_launch();
+  ADNI_LAUNCH_CHECK("channel_reduce_kernel<0>");
+  return ADNI_OK;
+}
+
+int adni_bn_apply(const adni_bf16* y, const float* scale, const float* shift, const adni_bf16* residual, adni_bf16* out,
+                  long long rows, int C, int relu, double* out_sum, double* out_sqsum, void* stream) {
+  ADNI_REQUIRE(y && scale && shift && out && rows > 0, ADNI_EINVAL, "bn_apply: bad arguments");
+  ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_apply: C=%d must be a multiple of 8", C);
+  const long long nvec = rows * (C / 8);
+  bn_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(residual),
+                                                                                 BF(out), nvec, C / 8, relu);
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_apply_kernel");
+  if (out_sum && out_sqsum) return adni_channel_stats(out, rows, C, out_sum, out_sqsum, stream);
+  return ADNI_OK;
+}
+
+int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
+                       const float* invstd, long long rows, int C, int relu, double* red, void* stream) {
+  ADNI_REQUIRE(dout && y && mean && invstd && red && rows > 0, ADNI_EINVAL, "bn_bwd_reduce: bad arguments");
+  ADNI_REQUIRE(!relu || out, ADNI_EINVAL, "bn_bwd_reduce: relu mask needs the forward output");
+  ADNI_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, ADNI_ENOTSUP, "bn_bwd_reduce: C=%d must be a multiple of 8 in [8,2048]",
+               C);
+  const int grid = (int)((rows + kRedSlabRows - 1) / kRedSlabRows);
+  channel_reduce_kernel<1><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, rows, C,
+                                                                 relu, red, red + C);
+  count_launch();
+  ADNI_LAUNCH_CHECK("channel_reduce_kernel<1>");
+  return ADNI_OK;
+}
+
+int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
+                      const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
+                      int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream) {
+  ADNI_REQUIRE(dout && y && mean && invstd && red && dy && rows > 0 && count > 0, ADNI_EINVAL,
+               "bn_bwd_apply: bad arguments");
+  ADNI_REQUIRE(!relu || out, ADNI_EINVAL, "bn_bwd_apply: relu mask needs the forward output");
+  ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long nvec = rows * (C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(
+      CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy), BF(dres));
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  if (dgamma || dbeta) {
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(red, C, dgamma, dbeta);
+    count_launch();
+    ADNI_LAUNCH_CHECK("bn_param_grads_kernel");
+  }
+  return ADNI_OK;
+}
+
+int adni_maxpool3d_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, int k, int stride, int pad, adni_bf16* y,
+                       uint8_t* argmax, void* stream) {
+  ADNI_REQUIRE(x && y && argmax, ADNI_EINVAL, "maxpool3d_fwd: null pointer");
+  ADNI_REQUIRE(C % 8 == 0 && k >= 1 && k * k * k <= 255 && stride >= 1 && 2 * pad <= k, ADNI_ENOTSUP,
+               "maxpool3d_fwd: unsupported C=%d k=%d stride=%d pad=%d", C, k, stride, pad);
+  const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  ADNI_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, ADNI_EINVAL, "maxpool3d_fwd: empty output");
+  const long long total = (long long)N * Do * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(x), N, D, H, W, C, k, stride, pad,
+                                                                                 Do, Ho, Wo, BF(y), argmax);
+  count_launch();
+  ADNI_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return ADNI_OK;
+}
+
+int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D, int H, int W, int C, int k, int stride,
+                       int pad, adni_bf16* dx, void* stream) {
+  ADNI_REQUIRE(dy && dx && argmax, ADNI_EINVAL, "maxpool3d_bwd: null pointer");
+  ADNI_REQUIRE(C % 8 == 0 && k >= 1 && k * k * k <= 255 && stride >= 1 && 2 * pad <= k, ADNI_ENOTSUP,
+               "maxpool3d_bwd: unsupported C=%d k=%d stride=%d pad=%d", C, k, stride, pad);
+  const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = (long long)N * D * H * W * (C / 8);
+  maxpool_bwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k,
+                                                                                 stride, pad, Do, Ho, Wo, BF(dx));
+  count_launch();
+  ADNI_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return ADNI_OK;
+}
+
+int adni_gap_fwd(const adni_bf16* x, int N, long long P, int C, float* feat, void* stream) {
+  ADNI_REQUIRE(x && feat && N > 0 && P > 0, ADNI_EINVAL, "gap_fwd: bad arguments");
+  ADNI_REQUIRE(C % 8 == 0 && N <= 65535, ADNI_ENOTSUP, "gap_fwd: C=%d must be a multiple of 8", C);
+  ADNI_CUDA_OK(cudaMemsetAsync(feat, 0, sizeof(float) * (size_t)N * C, ST(stream)));
+  const int split = (int)std::min<long long>(kGapSplit, (P + 63) / 64);
+  dim3 grid((C / 8 + 31) / 32, split, N);
+  gap_fwd_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), P, C, 1.0f / (float)P, feat);
+  count_launch();
+  ADNI_LAUNCH_CHECK("gap_fwd_kernel");
+  return ADNI_OK;
+}
+
+int adni_gap_bwd(const float* dfeat, int N, long long P, int C, adni_bf16* dx, void* stream) {
+  ADNI_REQUIRE(dfeat && dx && N > 0 && P > 0, ADNI_EINVAL, "gap_bwd: bad arguments");
+  ADNI_REQUIRE(C % 8 == 0, ADNI_ENOTSUP, "gap_bwd: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * P * (C / 8);
+  gap_bwd_kernel<<<ew_grid(total, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(dfeat, N, P, C, 1.0f / (float)P,
+                                                                                 BF(dx));
+  count_launch();
+  ADNI_LAUNCH_CHECK("gap_bwd_kernel");
+  return ADNI_OK;
+}
+
+int adni_cast_f32_to_bf16(const float* x, adni_bf16* y, long long n, void* stream) {
+  ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
+  cast_to_bf16_kernel<float><<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(x, BF(y), n);
+  count_launch();
+  ADNI_LAUNCH_CHECK("cast_to_bf16_kernel");
+  return ADNI_OK;
+}
+int adni_cast_f64_to_bf16(const double* x, adni_bf16* y, long long n, void* stream) {
+  ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
+  cast_to_bf16_kernel<double><<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(x, BF(y), n);
+  count_launch();
+  ADNI_LAUNCH_CHECK("cast_to_bf16_kernel");
+  return ADNI_OK;
+}
+int adni_cast_bf16_to_f32(const adni_bf16* x, float* y, long long n, void* stream) {
+  ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
+  cast_bf16_to_f32_kernel<<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(CBF(x), y, n);
+  count_launch();
+  ADNI_LAUNCH_CHECK("cast_bf16_to_f32_kernel");
+  return ADNI_OK;
+}
+
+int adni_weights_to_kernel_layout(const float* w_ncdhw, int Cout, int Cin, int taps, adni_bf16* w_oti, adni_bf16* w_ito,
+                                  void* stream) {
+  ADNI_REQUIRE(w_ncdhw && Cout > 0 && Cin > 0 && taps > 0, ADNI_EINVAL, "weights_to_kernel_layout: bad arguments");
+  int rc = ADNI_OK;
+  // OTI: per output channel, [Cin][taps] -> [taps][Cin]
+  if (w_oti) rc = launch_transpose<bf16>(w_ncdhw, BF(w_oti), Cout, Cin, taps, false, ST(stream));
+  // ITO: [Cout][Cin*taps] -> [Cin*taps][Cout]
+  if (rc == ADNI_OK && w_ito) rc = launch_transpose<bf16>(w_ncdhw, BF(w_ito), 1, Cout, Cin * taps, false, ST(stream));
+  return rc;
+}
+
+int adni_wgrad_to_param_layout(const float* dw_oti, int Cout, int Cin, int taps, float* grad_ncdhw, int accumulate,
+                               void* stream) {
+  ADNI_REQUIRE(dw_oti && grad_ncdhw && Cout > 0 && Cin > 0 && taps > 0, ADNI_EINVAL,
+               "wgrad_to_param_layout: bad arguments");
+  // per output channel, [taps][Cin] -> [Cin][taps]
+  return launch_transpose<float>(dw_oti, grad_ncdhw, Cout, taps, Cin, accumulate != 0, ST(stream));
+}
+
+}  // extern "C"
