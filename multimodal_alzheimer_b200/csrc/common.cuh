@@ -107,11 +107,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a dead pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the GPU box.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("adni_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+    if ((++spins & 255u) == 0 && global_timer_ns() - t0 > 4000000000ull) {  // 4 s: the pipeline is dead
+      printf("adni_b200: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }

@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C-ABI (one Python function per kernel family).
+
+All activation tensors are bf16 NDHWC (shape [N, D, H, W, C], contiguous).  These wrappers only allocate
+outputs with torch (PyTorch owns device memory and streams — plumbing) and pass raw pointers to
+libadni_b200.so; no arithmetic happens in Python and nothing here falls back to torch ops.
+"""
+import torch
+
+from . import _lib
+from ._lib import ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05, call, geom, out_extent, ptr, stream_ptr  # noqa: F401
+
+BF16 = torch.bfloat16
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+# --------------------------------------------------------------------------------------------- conv
+def weights_to_kernel_layout(w, want_ito=True):
+    """fp32 [Cout, Cin, kd, kh, kw] parameter -> (bf16 [Cout, taps, Cin], bf16 [Cin, taps, Cout])."""
+    w = _chk(w.detach(), torch.float32, "weight")
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    oti = torch.empty((cout, taps, cin), dtype=BF16, device=w.device)
+    ito = torch.empty((cin, taps, cout), dtype=BF16, device=w.device) if want_ito else None
+    call("adni_weights_to_kernel_layout", ptr(w), cout, cin, taps, ptr(oti), ptr(ito), stream_ptr())
+    return oti, ito
+
+
+def wgrad_to_param_layout(dw_oti, shape, out=None):
+    """fp32 [Cout, taps, Cin] -> fp32 parameter-shaped gradient [Cout, Cin, kd, kh, kw]."""
+    cout, cin = shape[0], shape[1]
+    taps = dw_oti.shape[1]
+    accumulate = out is not None
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dw_oti.device)
+    call("adni_wgrad_to_param_layout", ptr(dw_oti), cout, cin, taps, ptr(out), int(accumulate), stream_ptr())
+    return out
+
+
+def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE_AUTO):
+    _chk(x, BF16, "x")
+    _chk(w_oti, BF16, "w_oti")
+    N, D, H, W, Cin = x.shape
+    Cout = w_oti.shape[0]
+    g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
+    Do, Ho, Wo = (out_extent(v, k, stride, pad, dil) for v in (D, H, W))
+    y = torch.empty((N, Do, Ho, Wo, Cout), dtype=BF16, device=x.device)
+    st = torch.zeros((2, Cout), dtype=torch.float64, device=x.device) if stats else None
+    call("adni_conv3d_fprop", g, ptr(x), ptr(w_oti), ptr(bias), ptr(y), ptr(st[0]) if stats else None,
+         ptr(st[1]) if stats else None, engine, stream_ptr())
+    return y, st
+
+
+def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=ENGINE_AUTO):
+    _chk(dy, BF16, "dy")
+    _chk(w_ito, BF16, "w_ito")
+    N, D, H, W, Cin = in_shape
+    Cout = dy.shape[-1]
+    g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    if addend is not None:
+        _chk(addend, BF16, "addend")
+    call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, stream_ptr())
+    return dx
+
+
+def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUTO):
+    _chk(x, BF16, "x")
+    _chk(dy, BF16, "dy")
+    N, D, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
+    dw = torch.zeros((Cout, k * k * k, Cin), dtype=torch.float32, device=x.device)
+    db = None
+    if want_dbias:
+        if engine == ENGINE_DIRECT or (Cin % 64 != 0 or Cout % 64 != 0):
+            db = torch.zeros((Cout,), dtype=torch.float32, device=x.device)
+            call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), ptr(db), ENGINE_DIRECT, stream_ptr())
+            return dw, db
+        s = channel_stats(dy.view(-1, Cout))
+        db = s[0].to(torch.float32)
+    call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, engine, stream_ptr())
+    return dw, db
+
+
+# --------------------------------------------------------------------------------------------- BN
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
+    """stats: fp64 [2, C] (sum, sum of squares).  Returns (mean, invstd, scale, shift), fp32 [C] each."""
+    C = stats.shape[1]
+    out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
+    call("adni_bn_finalize", ptr(stats[0]), ptr(stats[1]), float(count), C, ptr(gamma), ptr(beta), float(eps),
+         float(momentum), ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+         stream_ptr())
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_apply(y, scale, shift, residual=None, relu=True):
+    _chk(y, BF16, "y")
+    C = y.shape[-1]
+    rows = y.numel() // C
+    out = torch.empty_like(y)
+    call("adni_bn_apply", ptr(y), ptr(scale), ptr(shift), ptr(residual), ptr(out), rows, C, int(relu), None, None,
+         stream_ptr())
+    return out
+
+
+def channel_stats(x2d):
+    """bf16 [rows, C] -> fp64 [2, C] (sum, sum of squares)."""
+    _chk(x2d, BF16, "x")
+    C = x2d.shape[-1]
+    rows = x2d.numel() // C
+    st = torch.zeros((2, C), dtype=torch.float64, device=x2d.device)
+    call("adni_channel_stats", ptr(x2d), rows, C, ptr(st[0]), ptr(st[1]), stream_ptr())
+    return st
+
+
+def bn_bwd_reduce(dout, out, y, mean, invstd, relu):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    red = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+    call("adni_bn_bwd_reduce", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), rows, C,
+         int(relu), ptr(red), stream_ptr())
+    return red
+
+
+def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_param_grads=True):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_dres else None
+    pg = torch.empty((2, C), dtype=torch.float32, device=y.device) if want_param_grads else None
+    call("adni_bn_bwd_apply", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
+         ptr(red), float(count), rows, C, int(relu), ptr(dy), ptr(dres),
+         ptr(pg[0]) if want_param_grads else None, ptr(pg[1]) if want_param_grads else None, stream_ptr())
+    if want_param_grads:
+        return dy, dres, pg[0], pg[1]
+    return dy, dres, None, None
+
+
+# --------------------------------------------------------------------------------------------- pooling
+def maxpool3d_fwd(x, k, stride, pad):
+    _chk(x, BF16, "x")
+    N, D, H, W, C = x.shape
+    Do, Ho, Wo = ((v + 2 * pad - k) // stride + 1 for v in (D, H, W))
+    y = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=x.device)
+    am = torch.empty((N, Do, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+    call("adni_maxpool3d_fwd", ptr(x), N, D, H, W, C, k, stride, pad, ptr(y), ptr(am), stream_ptr())
+    return y, am
+
+
+def maxpool3d_bwd(dy, argmax, in_shape, k, stride, pad):
+    N, D, H, W, C = in_shape
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    call("adni_maxpool3d_bwd", ptr(dy), ptr(argmax), N, D, H, W, C, k, stride, pad, ptr(dx), stream_ptr())
+    return dx
+
+
+def gap_fwd(x):
+    _chk(x, BF16, "x")
+    N, C = x.shape[0], x.shape[-1]
+    P = x.numel() // (N * C)
+    feat = torch.empty((N, C), dtype=torch.float32, device=x.device)
+    call("adni_gap_fwd", ptr(x), N, P, C, ptr(feat), stream_ptr())
+    return feat
+
+
+def gap_bwd(dfeat, shape):
+    N, C = shape[0], shape[-1]
+    P = 1
+    for v in shape[1:-1]:
+        P *= v
+    dfeat = _chk(dfeat, torch.float32, "dfeat")
+    dx = torch.empty(shape, dtype=BF16, device=dfeat.device)
+    call("adni_gap_bwd", ptr(dfeat), N, P, C, ptr(dx), stream_ptr())
+    return dx
+
+
+# --------------------------------------------------------------------------------------------- heads
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D tensor with unit column stride")
+    return t.stride(0)
+
+
+def linear_fwd(x, W, b, relu, out=None):
+    """x fp32 [B, in] (row-strided view allowed), W fp32 [out, in]; `out` may be a column slice (concat)."""
+    B, nin = x.shape
+    nout = W.shape[0]
+    if out is None:
+        out = torch.empty((B, nout), dtype=torch.float32, device=x.device)
+    call("adni_linear_fwd", ptr(x), _ld(x), ptr(W), ptr(b), ptr(out), _ld(out), B, nin, nout, int(relu), stream_ptr())
+    return out
+
+
+def linear_bwd(x, W, y, dy, relu, need_dx=True, need_dw=True, has_bias=True):
+    B, nin = x.shape
+    nout = W.shape[0]
+    dx = torch.empty((B, nin), dtype=torch.float32, device=x.device) if need_dx else None
+    dW = torch.zeros_like(W) if need_dw else None
+    db = torch.zeros((nout,), dtype=torch.float32, device=x.device) if (need_dw and has_bias) else None
+    call("adni_linear_bwd", ptr(x), _ld(x), ptr(W), ptr(y), _ld(y) if y is not None else 0, ptr(dy), _ld(dy), ptr(dx),
+         _ld(dx) if need_dx else 0, 0, ptr(dW), ptr(db), B, nin, nout, int(relu), stream_ptr())
+    return dx, dW, db
+
+
+def rows_stats_f32(x):
+    B, C = x.shape
+    st = torch.zeros((2, C), dtype=torch.float64, device=x.device)
+    call("adni_rows_stats_f32", ptr(x), _ld(x), B, C, ptr(st), stream_ptr())
+    return st
+
+
+def bn1d_apply(x, scale, shift, relu):
+    B, C = x.shape
+    y = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    call("adni_bn1d_apply", ptr(x), _ld(x), ptr(scale), ptr(shift), ptr(y), _ld(y), B, C, int(relu), stream_ptr())
+    return y
+
+
+def bn1d_bwd_reduce(dy, y, x, mean, invstd, relu):
+    B, C = x.shape
+    red = torch.zeros((2, C), dtype=torch.float64, device=x.device)
+    call("adni_bn1d_bwd_reduce", ptr(dy), _ld(dy), ptr(y), _ld(y), ptr(x), _ld(x), ptr(mean), ptr(invstd), B, C,
+         int(relu), ptr(red), stream_ptr())
+    return red
+
+
+def bn1d_bwd_apply(dy, y, x, mean, invstd, gamma, red, count, relu):
+    B, C = x.shape
+    dx = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    pg = torch.empty((2, C), dtype=torch.float32, device=x.device)
+    call("adni_bn1d_bwd_apply", ptr(dy), _ld(dy), ptr(y), _ld(y), ptr(x), _ld(x), ptr(mean), ptr(invstd), ptr(gamma),
+         ptr(red), float(count), B, C, int(relu), ptr(dx), _ld(dx), ptr(pg[0]), ptr(pg[1]), stream_ptr())
+    return dx, pg[0], pg[1]
+
+
+# --------------------------------------------------------------------------------------------- loss
+def loss_fwd(logits, target, gamma, class_weights):
+    """Returns (partial fp64[2] = [numerator, normaliser], per-sample coefficient fp64[B])."""
+    B, C = logits.shape
+    _chk(target, torch.int64, "target")
+    partial = torch.zeros((2,), dtype=torch.float64, device=logits.device)
+    coeff = torch.empty((B,), dtype=torch.float64, device=logits.device)
+    call("adni_loss_fwd", ptr(logits), _ld(logits), ptr(target), B, C, float(gamma or 0.0), ptr(class_weights),
+         ptr(partial), ptr(coeff), stream_ptr())
+    return partial, coeff
+
+
+def loss_bwd(logits, target, coeff, denom, upstream=1.0):
+    B, C = logits.shape
+    dl = torch.empty((B, C), dtype=torch.float32, device=logits.device)
+    call("adni_loss_bwd", ptr(logits), _ld(logits), ptr(target), B, C, ptr(coeff), ptr(denom), float(upstream), ptr(dl),
+         _ld(dl), stream_ptr())
+    return dl
+
+
+# --------------------------------------------------------------------------------------------- normalisation
+def quantile_minmax_normalize(x, mask, q, out_dtype=torch.float32, want_info=False):
+    """x fp32 [S, ...], mask uint8 same shape.  Returns normalised volumes (and (info, qvals) if asked)."""
+    _chk(x, torch.float32, "x")
+    _chk(mask, torch.uint8, "mask")
+    S = x.shape[0]
+    nvox = x[0].numel()
+    ws_bytes = int(_lib.load().adni_quantile_workspace_bytes(S))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    of = torch.empty_like(x) if out_dtype == torch.float32 else None
+    ob = torch.empty(x.shape, dtype=BF16, device=x.device) if out_dtype == BF16 else None
+    info = torch.empty((S, 8), dtype=torch.int64, device=x.device) if want_info else None
+    qv = torch.empty((S, 2), dtype=torch.float64, device=x.device) if want_info else None
+    call("adni_quantile_minmax_normalize", ptr(x), ptr(mask), S, nvox, float(q), ptr(of), ptr(ob), ptr(info), ptr(qv),
+         ptr(ws), ws_bytes, stream_ptr())
+    out = of if of is not None else ob
+    if want_info:
+        return out, info, qv
+    return out
+
+
+def standardize(x, mean, std, mask=None, out_dtype=torch.float32):
+    _chk(x, torch.float32, "x")
+    of = torch.empty_like(x) if out_dtype == torch.float32 else None
+    ob = torch.empty(x.shape, dtype=BF16, device=x.device) if out_dtype == BF16 else None
+    call("adni_standardize", ptr(x), ptr(mask), x.numel(), float(mean), float(std), ptr(of), ptr(ob), stream_ptr())
+    return of if of is not None else ob
+
+
+def scan_moments(x):
+    _chk(x, torch.float32, "x")
+    S = x.shape[0]
+    m = torch.zeros((S, 2), dtype=torch.float64, device=x.device)
+    call("adni_scan_moments", ptr(x), S, x[0].numel(), ptr(m), stream_ptr())
+    return m
+
+
+def masked_std_mean(x, mask):
+    _chk(x, torch.float32, "x")
+    _chk(mask, torch.uint8, "mask")
+    S = x.shape[0]
+    out = torch.empty((S, 3), dtype=torch.float64, device=x.device)
+    call("adni_masked_std_mean", ptr(x), ptr(mask), S, x[0].numel(), ptr(out), stream_ptr())
+    return out
+
+
+def cast_to_bf16(x):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    if x.dtype == torch.float32:
+        call("adni_cast_f32_to_bf16", ptr(x), ptr(y), x.numel(), stream_ptr())
+    elif x.dtype == torch.float64:
+        call("adni_cast_f64_to_bf16", ptr(x), ptr(y), x.numel(), stream_ptr())
+    else:
+        raise ValueError(f"cast_to_bf16: unsupported dtype {x.dtype}")
+    return y
+
+
+def cast_to_f32(x):
+    _chk(x, BF16, "x")
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("adni_cast_bf16_to_f32", ptr(x), ptr(y), x.numel(), stream_ptr())
+    return y

@@ -1,0 +1,125 @@
+"""Parity of the CUDA Conv3d engines (tcgen05 implicit GEMM and direct) against torch fp32 conv on the
+same bf16-rounded operands.  Tolerances: outputs are bf16-rounded fp32 accumulations, so rel-L2 <= 6e-3
+(bf16 has 8 mantissa bits: half-ulp relative error 2^-9 = 2e-3 per element); wgrad is fp32: <= 2e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._util import assert_close, to_ncdhw_f32, to_ndhwc_bf16
+
+pytestmark = pytest.mark.gpu
+
+TC, DIRECT = 1, 2
+
+# (N, D, H, W, Cin, Cout, k, stride, pad, dil)
+TC_SHAPES = [
+    (1, 8, 8, 16, 64, 64, 1, 1, 0, 1),      # 1x1x1 = plain GEMM, one tile
+    (1, 16, 16, 16, 64, 64, 3, 1, 1, 1),    # layer1-like
+    (2, 16, 16, 16, 128, 256, 3, 1, 2, 2),  # layer3.0.conv1 (dilation 2)
+    (1, 16, 16, 16, 256, 512, 3, 1, 4, 4),  # layer4.0.conv1 (dilation 4, tap skipping)
+    (2, 16, 16, 16, 64, 128, 3, 2, 1, 1),   # layer2.0.conv1 (stride 2, parity views)
+    (2, 16, 16, 16, 64, 128, 1, 2, 0, 1),   # layer2.0.downsample
+    (1, 12, 14, 12, 128, 128, 3, 1, 1, 1),  # ragged extents (91x109x91 input family)
+    (1, 11, 13, 9, 64, 64, 3, 2, 1, 1),     # odd extents with stride 2
+    (3, 8, 8, 8, 192, 64, 3, 1, 1, 1),      # Cin not a power of two
+]
+
+
+def _mk(shape, dev, seed=0):
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((N, Cin, D, H, W), generator=g).to(dev)
+    w = (torch.randn((Cout, Cin, k, k, k), generator=g) / (Cin * k ** 3) ** 0.5).to(dev)
+    x_b = to_ndhwc_bf16(x)
+    x_ref = to_ncdhw_f32(x_b)
+    w_ref = w.to(torch.bfloat16).float()
+    return x_b, x_ref, w, w_ref
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_fprop(cuda_dev, shape):
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    oti, _ = K.weights_to_kernel_layout(w)
+    y, st = K.conv3d_fprop(x_b, oti, None, k, s, p, d, stats=True, engine=TC)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x_ref, w_ref, None, s, p, d)
+    assert_close(to_ncdhw_f32(y), ref, 6e-3, f"fprop {shape}")
+    ssum = ref.sum(dim=(0, 2, 3, 4)).double()
+    ssq = (ref.double() ** 2).sum(dim=(0, 2, 3, 4))
+    assert_close(st[0], ssum, 1e-3, f"fprop stats sum {shape}") if float(ssum.norm()) > 1 else None
+    assert_close(st[1], ssq, 1e-4, f"fprop stats sqsum {shape}")
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_dgrad(cuda_dev, shape):
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    _, ito = K.weights_to_kernel_layout(w)
+    x_ref.requires_grad_(True)
+    ref_y = F.conv3d(x_ref, w_ref, None, s, p, d)
+    dy = torch.randn_like(ref_y)
+    dy_b = to_ndhwc_bf16(dy)
+    ref_y.backward(to_ncdhw_f32(dy_b))
+    add = to_ndhwc_bf16(torch.randn_like(x_ref))
+    dx = K.conv3d_dgrad(dy_b, ito, tuple(x_b.shape), k, s, p, d, addend=add, engine=TC)
+    torch.cuda.synchronize()
+    assert_close(to_ncdhw_f32(dx), x_ref.grad + to_ncdhw_f32(add), 6e-3, f"dgrad {shape}")
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_wgrad(cuda_dev, shape):
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    w_ref.requires_grad_(True)
+    ref_y = F.conv3d(x_ref, w_ref, None, s, p, d)
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref_y))
+    ref_y.backward(to_ncdhw_f32(dy_b))
+    dw, _ = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, engine=TC)
+    g = K.wgrad_to_param_layout(dw, tuple(w.shape))
+    torch.cuda.synchronize()
+    assert_close(g, w_ref.grad, 2e-4, f"wgrad {shape}")
+
+
+DIRECT_SHAPES = [
+    (2, 16, 16, 16, 1, 8, 5, 1, 2, 1),    # Small_PET_CNN conv1
+    (2, 8, 8, 8, 8, 16, 5, 1, 2, 1),      # conv2
+    (1, 8, 8, 8, 16, 32, 3, 1, 1, 1),     # conv3
+    (1, 8, 8, 8, 32, 64, 3, 1, 1, 1),     # conv4
+    (1, 18, 20, 22, 1, 64, 7, 2, 3, 1),   # ResNet stem
+    (1, 9, 9, 9, 24, 40, 3, 2, 1, 2),     # odd everything
+]
+
+
+@pytest.mark.parametrize("shape", DIRECT_SHAPES)
+def test_direct_conv(cuda_dev, shape):
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    bias = torch.randn(Cout, device=cuda_dev)
+    oti, ito = K.weights_to_kernel_layout(w)
+    x_ref.requires_grad_(True)
+    w_ref.requires_grad_(True)
+    b_ref = bias.clone().requires_grad_(True)
+    ref = F.conv3d(x_ref, w_ref, b_ref, s, p, d)
+    y, st = K.conv3d_fprop(x_b, oti, bias, k, s, p, d, stats=True, engine=DIRECT)
+    assert_close(to_ncdhw_f32(y), ref.detach(), 6e-3, f"direct fprop {shape}")
+    assert_close(st[1], (ref.detach().double() ** 2).sum(dim=(0, 2, 3, 4)), 1e-4, f"direct stats {shape}")
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref))
+    ref.backward(to_ncdhw_f32(dy_b))
+    dx = K.conv3d_dgrad(dy_b, ito, tuple(x_b.shape), k, s, p, d, engine=DIRECT)
+    assert_close(to_ncdhw_f32(dx), x_ref.grad, 6e-3, f"direct dgrad {shape}")
+    dw, db = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, want_dbias=True, engine=DIRECT)
+    assert_close(K.wgrad_to_param_layout(dw, tuple(w.shape)), w_ref.grad, 2e-4, f"direct wgrad {shape}")
+    assert_close(db, b_ref.grad, 2e-4, f"direct dbias {shape}")
+
+
+def test_engine_rejects_unsupported(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    x = torch.zeros((1, 4, 4, 4, 8), dtype=torch.bfloat16, device=cuda_dev)
+    w = torch.zeros((8, 27, 8), dtype=torch.bfloat16, device=cuda_dev)
+    with pytest.raises(NotImplementedError):
+        K.conv3d_fprop(x, w, None, 3, 1, 1, 1, engine=TC)

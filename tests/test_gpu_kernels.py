@@ -1,0 +1,260 @@
+"""Parity of the HBM-/latency-bound CUDA kernels against torch on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._util import assert_close, to_ncdhw_f32, to_ndhwc_bf16
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _rand_act(shape, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dev).to(BF)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (1, 3, 5, 7, 24), (3, 8, 8, 8, 512), (1, 40, 16, 16, 8)])
+def test_channel_stats_and_bn_forward(cuda_dev, shape):
+    from multimodal_alzheimer_b200 import kernels as K
+    y = _rand_act(shape, cuda_dev) * 3 + 1
+    C = shape[-1]
+    rows = y.numel() // C
+    st = K.channel_stats(y.view(-1, C))
+    yf = y.float().view(-1, C).double()
+    assert_close(st[0], yf.sum(0), 1e-5, "sum")
+    assert_close(st[1], (yf * yf).sum(0), 1e-5, "sqsum")
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    beta = torch.randn(C, device=cuda_dev)
+    rm = torch.zeros(C, device=cuda_dev)
+    rv = torch.ones(C, device=cuda_dev)
+    mean, invstd, scale, shift = K.bn_finalize(st, rows, gamma, beta, 1e-5, 0.1, rm, rv)
+    bn = torch.nn.BatchNorm1d(C).to(cuda_dev)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    ref = bn(y.float().view(-1, C))
+    assert_close(rm, bn.running_mean, 1e-5, "running_mean")
+    assert_close(rv, bn.running_var, 1e-5, "running_var")
+    res = _rand_act(shape, cuda_dev, 1)
+    out = K.bn_apply(y, scale, shift, residual=res, relu=True)
+    ref_out = F.relu(ref + res.float().view(-1, C)).detach()
+    assert_close(out.float().view(-1, C), ref_out, 5e-3, "bn_apply+res+relu")
+    out2 = K.bn_apply(y, scale, shift, residual=None, relu=False)
+    assert_close(out2.float().view(-1, C), ref.detach(), 5e-3, "bn_apply")
+
+
+@pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False)])
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (2, 8, 8, 8, 256)])
+def test_bn_backward(cuda_dev, shape, relu, with_res):
+    from multimodal_alzheimer_b200 import kernels as K
+    C = shape[-1]
+    y = _rand_act(shape, cuda_dev) * 2 + 0.5
+    res = _rand_act(shape, cuda_dev, 1) if with_res else None
+    dout = _rand_act(shape, cuda_dev, 2)
+    rows = y.numel() // C
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    beta = torch.randn(C, device=cuda_dev) * 0.1
+    st = K.channel_stats(y.view(-1, C))
+    mean, invstd, scale, shift = K.bn_finalize(st, rows, gamma, beta, 1e-5, 0.1, None, None)
+    out = K.bn_apply(y, scale, shift, residual=res, relu=relu)
+    red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu)
+    dy, dres, dgamma, dbeta = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, rows, relu, with_res)
+    # torch reference in fp32 on the same bf16-rounded inputs, using the relu mask of the kernel's own output
+    yr = y.float().view(-1, C).requires_grad_(True)
+    g_ = gamma.clone().requires_grad_(True)
+    b_ = beta.clone().requires_grad_(True)
+    z = F.batch_norm(yr, None, None, g_, b_, True, 0.1, 1e-5)
+    rr = res.float().view(-1, C).requires_grad_(True) if with_res else None
+    if with_res:
+        z = z + rr
+    g_up = dout.float().view(-1, C)
+    if relu:
+        g_up = g_up * (out.float().view(-1, C) > 0)
+    z.backward(g_up)
+    assert_close(dy.float().view(-1, C), yr.grad, 8e-3, "dy")
+    assert_close(dgamma, g_.grad, 2e-3, "dgamma")
+    assert_close(dbeta, b_.grad, 2e-3, "dbeta")
+    if with_res:
+        assert_close(dres.float().view(-1, C), rr.grad, 1e-6, "dres")
+
+
+@pytest.mark.parametrize("cfg", [((2, 16, 16, 16, 64), 3, 2, 1), ((1, 9, 11, 13, 16), 3, 2, 1), ((2, 8, 8, 8, 8), 2, 2, 0)])
+def test_maxpool(cuda_dev, cfg):
+    from multimodal_alzheimer_b200 import kernels as K
+    shape, k, s, p = cfg
+    # quantise to few distinct values so that ties occur and the first-max rule is exercised
+    x = (torch.randint(0, 6, shape, generator=torch.Generator().manual_seed(3)).float() - 1).to(cuda_dev).to(BF)
+    y, am = K.maxpool3d_fwd(x, k, s, p)
+    xr = to_ncdhw_f32(x).cpu().requires_grad_(True)   # CPU max_pool3d defines the tie rule of the oracle
+    ref = F.max_pool3d(xr, k, s, p)
+    assert torch.equal(to_ncdhw_f32(y).cpu(), ref.detach())
+    dy = torch.randint(-3, 4, ref.shape, generator=torch.Generator().manual_seed(4)).float()
+    ref.backward(dy)
+    dx = K.maxpool3d_bwd(to_ndhwc_bf16(dy).to(cuda_dev), am, tuple(x.shape), k, s, p)
+    assert torch.equal(to_ncdhw_f32(dx).cpu(), xr.grad)
+
+
+def test_gap(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    x = _rand_act((3, 5, 6, 7, 512), cuda_dev)
+    feat = K.gap_fwd(x)
+    ref = x.float().mean(dim=(1, 2, 3))
+    assert_close(feat, ref, 1e-5, "gap fwd")
+    df = torch.randn((3, 512), device=cuda_dev)
+    dx = K.gap_bwd(df, tuple(x.shape))
+    refdx = (df / (5 * 6 * 7))[:, None, None, None, :].expand(x.shape)
+    assert_close(dx.float(), refdx, 4e-3, "gap bwd")
+
+
+@pytest.mark.parametrize("cfg", [(5, 512, 3, True), (4, 128, 64, True), (7, 1024, 512, False), (2, 64, 3, False)])
+def test_linear(cuda_dev, cfg):
+    from multimodal_alzheimer_b200 import kernels as K
+    B, nin, nout, relu = cfg
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((B, nin), generator=g).to(cuda_dev)
+    W = (torch.randn((nout, nin), generator=g) / nin ** 0.5).to(cuda_dev)
+    b = torch.randn((nout,), generator=g).to(cuda_dev)
+    dy = torch.randn((B, nout), generator=g).to(cuda_dev)
+    y = K.linear_fwd(x, W, b, relu)
+    xr, Wr, br = (t.clone().requires_grad_(True) for t in (x, W, b))
+    ref = F.linear(xr, Wr, br)
+    if relu:
+        ref = F.relu(ref)
+    assert_close(y, ref.detach(), 1e-5, "linear fwd")
+    ref.backward(dy)
+    dx, dW, db = K.linear_bwd(x, W, y, dy, relu)
+    assert_close(dx, xr.grad, 1e-5, "linear dx")
+    assert_close(dW, Wr.grad, 1e-5, "linear dW")
+    assert_close(db, br.grad, 1e-5, "linear db")
+    # concat expressed as a column slice of a wider buffer
+    wide = torch.zeros((B, nout + 5), device=cuda_dev)
+    K.linear_fwd(x, W, b, relu, out=wide[:, 5:])
+    assert_close(wide[:, 5:], ref.detach(), 1e-5, "linear fwd into slice")
+    assert float(wide[:, :5].abs().sum()) == 0
+
+
+def test_bn1d(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    B, C = 6, 40
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((B, C), generator=g).to(cuda_dev) * 2 + 1
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_dev)
+    beta = torch.randn(C, generator=g).to(cuda_dev)
+    dy = torch.randn((B, C), generator=g).to(cuda_dev)
+    st = K.rows_stats_f32(x)
+    mean, invstd, scale, shift = K.bn_finalize(st, B, gamma, beta, 1e-5, 0.1, None, None)
+    y = K.bn1d_apply(x, scale, shift, True)
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, gamma, beta))
+    ref = F.relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5))
+    assert_close(y, ref.detach(), 1e-5, "bn1d fwd")
+    ref.backward(dy)
+    red = K.bn1d_bwd_reduce(dy, y, x, mean, invstd, True)
+    dx, dgamma, dbeta = K.bn1d_bwd_apply(dy, y, x, mean, invstd, gamma, red, B, True)
+    assert_close(dx, xr.grad, 1e-4, "bn1d dx")
+    assert_close(dgamma, gr.grad, 1e-4, "bn1d dgamma")
+    assert_close(dbeta, br.grad, 1e-4, "bn1d dbeta")
+
+
+@pytest.mark.parametrize("gamma", [0.0, 1.0, 2.0, 5.0])
+@pytest.mark.parametrize("C", [2, 3])
+def test_loss(cuda_dev, gamma, C):
+    """focal (detached pt, pkg/loss_functions/focalloss.py:30) / weighted CE, fp64, tolerance 1e-12."""
+    from multimodal_alzheimer_b200 import kernels as K
+    from oracle.losses import FocalLossOracle
+    B = 9
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn((B, C), generator=g) * 3).to(cuda_dev)
+    target = torch.randint(0, C, (B,), generator=g).to(cuda_dev)
+    cw = torch.tensor([0.4651162790697675, 0.6712473572938689, 0.8636363636363636][:C], dtype=torch.float64,
+                      device=cuda_dev)
+    partial, coeff = K.loss_fwd(logits, target, gamma, cw if gamma == 0 else None)
+    loss = partial[0] / partial[1]
+    dl = K.loss_bwd(logits, target, coeff, partial[1:2])
+    zr = logits.double().clone().requires_grad_(True)
+    if gamma > 0:
+        ref = FocalLossOracle(gamma=gamma)(zr, target)
+    else:
+        ref = F.cross_entropy(zr, target, weight=cw)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-12 * max(1.0, abs(float(ref)))
+    assert_close(dl, zr.grad.float(), 1e-6, "dlogits")
+
+
+def _synthetic_scans(S, shape, dev, seed=15):
+    g = torch.Generator().manual_seed(seed)
+    v = 400 * torch.randn((S,) + shape, generator=g).abs() + 50 * torch.rand((S,) + shape, generator=g)
+    D, H, W = shape
+    zz, yy, xx = torch.meshgrid(torch.arange(D), torch.arange(H), torch.arange(W), indexing="ij")
+    ell = (((zz - (D - 1) / 2) / (0.42 * D)) ** 2 + ((yy - (H - 1) / 2) / (0.42 * H)) ** 2 +
+           ((xx - (W - 1) / 2) / (0.42 * W)) ** 2) <= 1
+    mask = ell[None].expand(S, -1, -1, -1).clone()
+    zero = torch.rand((S,) + shape, generator=g) < 0.005
+    v[zero & mask] = 0.0
+    return v.float().to(dev).contiguous(), mask.to(torch.uint8).to(dev).contiguous()
+
+
+@pytest.mark.parametrize("q", [0.95, 0.98, 0.99, 1.0])
+def test_quantile_normalize(cuda_dev, q):
+    """Order-statistic indices bit-exact; Qmin/Qmax bit-exact (fp64); normalised volume bit-exact in fp32."""
+    from multimodal_alzheimer_b200 import kernels as K
+    from oracle.normalization import quantile_minmax_oracle
+    x, mask = _synthetic_scans(3, (24, 28, 20), cuda_dev)
+    out, info, qv = K.quantile_minmax_normalize(x, mask, q, want_info=True)
+    torch.cuda.synchronize()
+    for s in range(x.shape[0]):
+        ref, meta = quantile_minmax_oracle(x[s].cpu().double(), mask[s].cpu().double(), q)
+        assert int(info[s, 0]) == meta["n"]
+        assert [int(v) for v in info[s, 1:5]] == [meta["lo_max"], meta["hi_max"], meta["lo_min"], meta["hi_min"]]
+        assert float(qv[s, 0]) == meta["qmax"] and float(qv[s, 1]) == meta["qmin"]
+        assert torch.equal(out[s].cpu(), ref.float())
+
+
+def test_quantile_negative_and_ties(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    from oracle.normalization import quantile_minmax_oracle
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(-50, 50, (2, 10, 12, 8), generator=g).float().to(cuda_dev)   # many ties, negatives, zeros
+    mask = (torch.rand((2, 10, 12, 8), generator=g) < 0.7).to(torch.uint8).to(cuda_dev)
+    out, info, qv = K.quantile_minmax_normalize(x, mask, 0.9, want_info=True)
+    for s in range(2):
+        ref, meta = quantile_minmax_oracle(x[s].cpu().double(), mask[s].cpu().double(), 0.9)
+        assert int(info[s, 0]) == meta["n"]
+        assert float(qv[s, 0]) == meta["qmax"] and float(qv[s, 1]) == meta["qmin"]
+        assert torch.equal(out[s].cpu(), ref.float())
+
+
+def test_standardize_and_moments(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    from oracle.normalization import masked_std_mean_oracle, pet_standardize_oracle, split_moments_oracle
+    x, mask = _synthetic_scans(2, (16, 12, 20), cuda_dev, seed=3)
+    out = K.standardize(x, 0.5145, 0.5383)
+    ref = pet_standardize_oracle(x.cpu().double(), 0.5145, 0.5383).float()
+    assert torch.equal(out.cpu(), ref)
+    m = K.scan_moments(x)
+    mean, std, per_scan = split_moments_oracle([x[s].cpu().double() for s in range(2)])
+    assert_close(m.cpu(), per_scan, 1e-12, "scan moments")
+    sm = K.masked_std_mean(x, mask).cpu()
+    for s in range(2):
+        n, mu, sd = masked_std_mean_oracle(x[s].cpu().double(), mask[s].cpu().double())
+        assert int(sm[s, 0]) == n
+        assert abs(float(sm[s, 1]) - mu) <= 1e-12 * abs(mu) and abs(float(sm[s, 2]) - sd) <= 1e-12 * sd
+
+
+def test_weight_layout_roundtrip(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    w = torch.randn((40, 24, 3, 3, 3), device=cuda_dev)
+    oti, ito = K.weights_to_kernel_layout(w)
+    wb = w.to(BF)
+    assert torch.equal(oti, wb.view(40, 24, 27).permute(0, 2, 1).contiguous())
+    assert torch.equal(ito, wb.view(40, 24, 27).permute(1, 2, 0).contiguous())
+    dw = torch.randn((40, 27, 24), device=cuda_dev)
+    g = K.wgrad_to_param_layout(dw, tuple(w.shape))
+    assert torch.equal(g, dw.permute(0, 2, 1).contiguous().view(w.shape))
+
+
+def test_casts(cuda_dev):
+    from multimodal_alzheimer_b200 import kernels as K
+    x = torch.randn(1000, device=cuda_dev, dtype=torch.float64)
+    assert torch.equal(K.cast_to_bf16(x), x.float().to(BF))
+    assert torch.equal(K.cast_to_f32(K.cast_to_bf16(x.float())), x.float().to(BF).float())
