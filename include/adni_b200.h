@@ -115,6 +115,15 @@ int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf
                       const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
                       int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream);
 
+/* Eval-mode BatchNorm (module.eval()): scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale. */
+int adni_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                        float eps, int C, float* scale, float* shift, void* stream);
+
+/* Stand-alone nn.ReLU on bf16 activations (pet_cnn.py:24 when no BatchNorm precedes it): y = max(x,0);
+ * dx = dy * (y > 0). n = number of elements (multiple of 8). */
+int adni_relu_fwd(const adni_bf16* x, adni_bf16* y, long long n, void* stream);
+int adni_relu_bwd(const adni_bf16* dy, const adni_bf16* y, adni_bf16* dx, long long n, void* stream);
+
 /* Per-channel fp64 sum / sum of squares of a bf16 rows x C tensor (added into sum/sqsum). */
 int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, double* sqsum, void* stream);
 
@@ -146,6 +155,9 @@ int adni_linear_fwd(const float* x, int ldx, const float* W, const float* b, flo
 int adni_linear_bwd(const float* x, int ldx, const float* W, const float* y, int ldy, const float* dy, int lddy,
                     float* dx, int lddx, int accumulate_dx, float* dW, float* db, int B, int in, int out, int relu,
                     void* stream);
+/* Stand-alone nn.ReLU on fp32 features: dy == NULL -> out = max(x,0); else out = dy * (x > 0) with x the forward
+ * output (backward). */
+int adni_relu_f32(const float* x, const float* dy, float* out, long long n, void* stream);
 /* BatchNorm1d train-mode over B rows, fp32 (anat_cnn.py:72-73).  Statistic sums are exposed so the
  * host can all-reduce them for data parallelism: stats[0:C]=sum x, stats[C:2C]=sum x^2 (fp64). */
 int adni_rows_stats_f32(const float* x, int ldx, int B, int C, double* stats, void* stream);
@@ -158,18 +170,21 @@ int adni_bn1d_bwd_apply(const float* dy, int lddy, const float* y, int ldy, cons
                         int B, int C, int relu, float* dx, int lddx, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Losses, evaluated in fp64 on fp32 logits (reference casts logits .to(double): anat_cnn.py:104).
+ * Losses, evaluated in fp64 (reference casts logits .to(double): anat_cnn.py:104).  logits_f64 selects the
+ * storage type of `logits` (and of `dlogits`): 0 = fp32, 1 = fp64.
  *   gamma > 0 : FocalLoss with DETACHED modulating factor (pkg/loss_functions/focalloss.py:20-40, :30);
  *   gamma == 0: nn.CrossEntropyLoss(weight) (anat_cnn.py:84-85); class_weights may be null (all ones).
  * partial[0] += sum_i numerator_i, partial[1] += sum_i normaliser_i (w[y_i] for CE, 1 for focal) so that the
  * host can all-reduce them across ranks;  loss = partial[0]/partial[1].
  * ------------------------------------------------------------------------------------------- */
-int adni_loss_fwd(const float* logits, int ld, const int64_t* target, int B, int C, double gamma,
+int adni_loss_fwd(const void* logits, int logits_f64, int ld, const int64_t* target, int B, int C, double gamma,
                   const double* class_weights, double* partial, double* per_sample_coeff, void* stream);
-/* dlogits[B][C] (fp32) = upstream * coeff_i * (softmax_i - onehot_i) / denom, where denom is the global
- * normaliser (device scalar) and coeff_i = (1-pt)^gamma or w[y_i] saved by adni_loss_fwd. */
-int adni_loss_bwd(const float* logits, int ld, const int64_t* target, int B, int C, const double* per_sample_coeff,
-                  const double* denom, double upstream, float* dlogits, int lddl, void* stream);
+/* dlogits[B][C] = upstream * coeff_i * (softmax_i - onehot_i) / denom, where denom is the global normaliser
+ * and upstream the incoming gradient (both DEVICE fp64 scalars), coeff_i = (1-pt)^gamma or w[y_i] saved by
+ * adni_loss_fwd. */
+int adni_loss_bwd(const void* logits, int logits_f64, int ld, const int64_t* target, int B, int C,
+                  const double* per_sample_coeff, const double* denom, const double* upstream, void* dlogits, int lddl,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input normalisation (pkg/utils/dataloader.py:213-215, 236-281; pkg/utils/standardization.py:34-55).

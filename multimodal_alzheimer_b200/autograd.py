@@ -1,0 +1,403 @@
+"""torch.autograd.Function wrappers that sequence the CUDA kernels of the hot path.
+
+Tensor convention inside the encoder: activations are bf16, shape [N, D, H, W, C] (NDHWC, contiguous).
+Parameters stay torch fp32 nn.Parameters in the reference layout (Conv3d weight [Cout, Cin, kd, kh, kw]);
+each Function converts them to the kernel layouts on the fly and returns gradients in parameter layout.
+
+Residual blocks are ONE Function each (not a chain of small ones) so that the backward pass can fuse the
+residual-branch gradient into the dgrad epilogue instead of letting autograd add bf16 tensors with a torch
+kernel, and so that every intermediate is freed as soon as its consumer has run.
+
+Data parallelism: when torch.distributed is initialised with world_size > 1 the BatchNorm
+statistic sums (forward: sum x, sum x^2; backward: sum g, sum g*xhat) and the loss normaliser are
+all-reduced so that N ranks on shards of a batch reproduce the single-process full-batch step.
+"""
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+BF16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------- DP helpers
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def _allreduce_(t):
+    if _world() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+class BNState:
+    """Non-tensor BatchNorm configuration handed to the Functions (running buffers are updated in place)."""
+
+    def __init__(self, module):
+        self.eps = module.eps
+        self.momentum = module.momentum
+        self.running_mean = module.running_mean
+        self.running_var = module.running_var
+        self.training = module.training
+        self.module = module
+
+
+def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
+    """Shared BN forward. Returns (out, mean, invstd, count). stats may be None (computed with a reduction pass)."""
+    C = y.shape[-1]
+    rows = y.numel() // C
+    if bn.training:
+        if stats is None:
+            stats = K.channel_stats(y.view(-1, C))
+        _allreduce_(stats)
+        count = rows * _world()
+        mean, invstd, scale, shift = K.bn_finalize(stats, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean,
+                                                   bn.running_var)
+        if bn.module is not None and bn.module.num_batches_tracked is not None:
+            bn.module.num_batches_tracked += 1
+    else:
+        scale, shift = K.bn_eval_params(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
+        mean = invstd = None
+        count = rows
+    out = K.bn_apply(y, scale, shift, residual=residual, relu=relu)
+    return out, mean, invstd, count
+
+
+def _bn_backward(dout, out, y, mean, invstd, gamma, count, relu, want_dres, want_pg):
+    red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu)
+    _allreduce_(red)
+    return K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_pg)
+
+
+class ConvCfg:
+    def __init__(self, k, stride, pad, dil):
+        self.k, self.stride, self.pad, self.dil = k, stride, pad, dil
+
+
+def _conv_fwd(x, w, cfg, bias=None, stats=True, need_ito=True):
+    oti, ito = K.weights_to_kernel_layout(w, want_ito=need_ito)
+    y, st = K.conv3d_fprop(x, oti, bias, cfg.k, cfg.stride, cfg.pad, cfg.dil, stats=stats)
+    return y, st, ito
+
+
+def _conv_wgrad(x, dy, cfg, wshape, want_dbias=False):
+    dw, db = K.conv3d_wgrad(x, dy, cfg.k, cfg.stride, cfg.pad, cfg.dil, want_dbias=want_dbias)
+    return K.wgrad_to_param_layout(dw, tuple(wshape)), db
+
+
+# --------------------------------------------------------------------------------------------- input cast
+class InputToVolume(torch.autograd.Function):
+    """(B,1,D,H,W) fp32/fp64 NCDHW module input -> bf16 NDHWC (same memory order because C == 1)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise NotImplementedError("encoder inputs must be (B, 1, D, H, W); multi-channel input volumes are "
+                                      "outside the supported path")
+        N, _, D, H, W = x.shape
+        return K.cast_to_bf16(x.contiguous()).view(N, D, H, W, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None
+
+
+# --------------------------------------------------------------------------------------------- stem
+class StemFn(torch.autograd.Function):
+    """conv1 (7x7x7, s2) -> bn1 -> ReLU -> MaxPool3d(3,2,1)  (MedicalNet ResNet.forward, first line)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, bn, cfg, pool):
+        y, st, _ = _conv_fwd(x, w, cfg, need_ito=False)
+        a, mean, invstd, count = _bn_forward(y, st, gamma, beta, bn, None, True)
+        p, am = K.maxpool3d_fwd(a, *pool)
+        ctx.save_for_backward(x, y, a, am, mean, invstd, gamma)
+        ctx.cfg, ctx.pool, ctx.count, ctx.wshape = cfg, pool, count, w.shape
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        x, y, a, am, mean, invstd, gamma = ctx.saved_tensors
+        da = K.maxpool3d_bwd(dp.contiguous(), am, tuple(a.shape), *ctx.pool)
+        dy, _, dgamma, dbeta = _bn_backward(da, a, y, mean, invstd, gamma, ctx.count, True, False, True)
+        del da
+        dw, _ = _conv_wgrad(x, dy, ctx.cfg, ctx.wshape)
+        return None, dw, dgamma, dbeta, None, None, None
+
+
+# --------------------------------------------------------------------------------------------- residual blocks
+class BasicBlockFn(torch.autograd.Function):
+    """MedicalNet BasicBlock: conv3-bn-relu-conv3-bn (+ downsample(x) | x) - relu."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, bn1, bn2, bnd, c1, c2, cd):
+        need_dx = ctx.needs_input_grad[0]
+        y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
+        a1, m1, is1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
+        y2, st2, w2_ito = _conv_fwd(a1, w2, c2)
+        if wd is not None:
+            yd, std, wd_ito = _conv_fwd(x, wd, cd, need_ito=need_dx)
+            r, md, isd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
+        else:
+            yd = wd_ito = md = isd = None
+            nd = 0
+            r = x
+        out, m2, is2, n2 = _bn_forward(y2, st2, g2, b2, bn2, r, True)
+        ctx.save_for_backward(x, y1, a1, y2, out, yd, m1, is1, m2, is2, md, isd, g1, g2, gd, w1_ito, w2_ito, wd_ito)
+        ctx.cfg = (c1, c2, cd, n1, n2, nd, w1.shape, w2.shape, None if wd is None else wd.shape, need_dx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, a1, y2, out, yd, m1, is1, m2, is2, md, isd, g1, g2, gd, w1_ito, w2_ito, wd_ito = ctx.saved_tensors
+        c1, c2, cd, n1, n2, nd, ws1, ws2, wsd, need_dx = ctx.cfg
+        dout = dout.contiguous()
+        dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, m2, is2, g2, n2, True, True, True)
+        dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
+        da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
+        del dy2
+        dy1, _, dg1, db1 = _bn_backward(da1, a1, y1, m1, is1, g1, n1, True, False, True)
+        del da1
+        dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
+        dwd = dgd = dbd = None
+        dx = None
+        if yd is not None:
+            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, md, isd, gd, nd, False, False, True)
+            dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
+            if need_dx:
+                dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
+                dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dxd)
+        elif need_dx:
+            dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dres)
+        return (dx, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd) + (None,) * 6
+
+
+class BottleneckFn(torch.autograd.Function):
+    """MedicalNet Bottleneck: 1x1-bn-relu, 3x3(stride,dil)-bn-relu, 1x1-bn (+ downsample(x) | x) - relu."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, wd, gd, bd, bn1, bn2, bn3, bnd, c1, c2, c3, cd):
+        need_dx = ctx.needs_input_grad[0]
+        y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
+        a1, m1, is1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
+        y2, st2, w2_ito = _conv_fwd(a1, w2, c2)
+        a2, m2, is2, n2 = _bn_forward(y2, st2, g2, b2, bn2, None, True)
+        y3, st3, w3_ito = _conv_fwd(a2, w3, c3)
+        if wd is not None:
+            yd, std, wd_ito = _conv_fwd(x, wd, cd, need_ito=need_dx)
+            r, md, isd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
+        else:
+            yd = wd_ito = md = isd = None
+            nd = 0
+            r = x
+        out, m3, is3, n3 = _bn_forward(y3, st3, g3, b3, bn3, r, True)
+        ctx.save_for_backward(x, y1, a1, y2, a2, y3, out, yd, m1, is1, m2, is2, m3, is3, md, isd, g1, g2, g3, gd,
+                              w1_ito, w2_ito, w3_ito, wd_ito)
+        ctx.cfg = (c1, c2, c3, cd, n1, n2, n3, nd, w1.shape, w2.shape, w3.shape, None if wd is None else wd.shape,
+                   need_dx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, y1, a1, y2, a2, y3, out, yd, m1, is1, m2, is2, m3, is3, md, isd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
+         wd_ito) = ctx.saved_tensors
+        c1, c2, c3, cd, n1, n2, n3, nd, ws1, ws2, ws3, wsd, need_dx = ctx.cfg
+        dout = dout.contiguous()
+        dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, m3, is3, g3, n3, True, True, True)
+        dw3, _ = _conv_wgrad(a2, dy3, c3, ws3)
+        da2 = K.conv3d_dgrad(dy3, w3_ito, tuple(a2.shape), c3.k, c3.stride, c3.pad, c3.dil)
+        del dy3
+        dy2, _, dg2, db2 = _bn_backward(da2, a2, y2, m2, is2, g2, n2, True, False, True)
+        del da2
+        dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
+        da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
+        del dy2
+        dy1, _, dg1, db1 = _bn_backward(da1, a1, y1, m1, is1, g1, n1, True, False, True)
+        del da1
+        dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
+        dwd = dgd = dbd = None
+        dx = None
+        if yd is not None:
+            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, md, isd, gd, nd, False, False, True)
+            dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
+            if need_dx:
+                dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
+                dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dxd)
+        elif need_dx:
+            dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dres)
+        return (dx, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dwd, dgd, dbd) + (None,) * 8
+
+
+# --------------------------------------------------------------------------------------------- stand-alone ops
+class Conv3dFn(torch.autograd.Function):
+    """Conv3d (+bias). Returns (y, stats) where stats (fp64 [2,Cout]) feeds a following BatchNorm3d."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, cfg, want_stats):
+        need_dx = ctx.needs_input_grad[0]
+        y, st, ito = _conv_fwd(x, w, cfg, bias=bias, stats=want_stats, need_ito=need_dx)
+        ctx.save_for_backward(x, ito)
+        ctx.cfg = (cfg, w.shape, bias is not None, need_dx)
+        if st is None:
+            st = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(st)
+        return y, st
+
+    @staticmethod
+    def backward(ctx, dy, _dst):
+        x, ito = ctx.saved_tensors
+        cfg, wshape, has_bias, need_dx = ctx.cfg
+        dy = dy.contiguous()
+        dw, db = _conv_wgrad(x, dy, cfg, wshape, want_dbias=has_bias)
+        dx = K.conv3d_dgrad(dy, ito, tuple(x.shape), cfg.k, cfg.stride, cfg.pad, cfg.dil) if need_dx else None
+        return dx, dw, db, None, None
+
+
+class BatchNormActFn(torch.autograd.Function):
+    """BatchNorm3d (batch statistics) [+ residual] [+ ReLU] on a bf16 NDHWC tensor."""
+
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, residual, bn, relu):
+        st = stats if (stats is not None and stats.numel() > 0) else None
+        out, mean, invstd, count = _bn_forward(y, st, gamma, beta, bn, residual, relu)
+        ctx.save_for_backward(y, out, mean, invstd, gamma)
+        ctx.cfg = (count, relu, residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, out, mean, invstd, gamma = ctx.saved_tensors
+        count, relu, has_res = ctx.cfg
+        if mean is None:
+            raise NotImplementedError("BatchNorm backward in eval mode is outside the training hot path")
+        dy, dres, dgamma, dbeta = _bn_backward(dout.contiguous(), out if relu else None, y, mean, invstd, gamma, count,
+                                               relu, has_res, True)
+        return dy, None, dgamma, dbeta, dres, None, None
+
+
+class ReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.relu_fwd(x.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.relu_bwd(dy.contiguous(), y)
+
+
+class ReluF32Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.relu_f32(x.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.relu_f32(y, dy.contiguous())
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        y, am = K.maxpool3d_fwd(x.contiguous(), k, stride, pad)
+        ctx.save_for_backward(am)
+        ctx.cfg = (tuple(x.shape), k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (am,) = ctx.saved_tensors
+        shape, k, stride, pad = ctx.cfg
+        return K.maxpool3d_bwd(dy.contiguous(), am, shape, k, stride, pad), None, None, None
+
+
+class GapFn(torch.autograd.Function):
+    """AdaptiveAvgPool3d(1): bf16 [N,D,H,W,C] -> fp32 [N,C,1,1,1]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return K.gap_fwd(x.contiguous()).view(x.shape[0], x.shape[-1], 1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, df):
+        N, C = ctx.shape[0], ctx.shape[-1]
+        return K.gap_bwd(df.reshape(N, C).contiguous(), ctx.shape)
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        x = x.contiguous()
+        y = K.linear_fwd(x, W, b, relu)
+        ctx.save_for_backward(x, W, y)
+        ctx.cfg = (relu, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        relu, has_bias = ctx.cfg
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
+        dx, dW, db = K.linear_bwd(x, W, y, dy.contiguous(), relu, need_dx=need_dx, need_dw=need_dw, has_bias=has_bias)
+        return dx, dW, db if has_bias else None, None
+
+
+class BatchNorm1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu):
+        x = x.contiguous()
+        B, C = x.shape
+        if bn.training:
+            st = _allreduce_(K.rows_stats_f32(x))
+            count = B * _world()
+            mean, invstd, scale, shift = K.bn_finalize(st, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean,
+                                                       bn.running_var)
+            if bn.module is not None and bn.module.num_batches_tracked is not None:
+                bn.module.num_batches_tracked += 1
+        else:
+            scale, shift = K.bn_eval_params(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
+            mean = invstd = None
+            count = B
+        y = K.bn1d_apply(x, scale, shift, relu)
+        ctx.save_for_backward(x, y, mean, invstd, gamma)
+        ctx.cfg = (count, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, invstd, gamma = ctx.saved_tensors
+        count, relu = ctx.cfg
+        dy = dy.contiguous()
+        red = _allreduce_(K.bn1d_bwd_reduce(dy, y, x, mean, invstd, relu))
+        dx, dgamma, dbeta = K.bn1d_bwd_apply(dy, y, x, mean, invstd, gamma, red, count, relu)
+        return dx, dgamma, dbeta, None, None
+
+
+class LossFn(torch.autograd.Function):
+    """Focal (detached modulating factor) / weighted cross entropy in fp64 with the GLOBAL-batch normaliser."""
+
+    @staticmethod
+    def forward(ctx, logits, target, gamma, class_weights, mean=True):
+        logits = logits.contiguous()
+        partial, coeff = K.loss_fwd(logits, target.contiguous(), gamma, class_weights)
+        _allreduce_(partial)
+        if not mean:  # size_average=False: plain sum, normaliser 1
+            partial[1] = 1.0
+        ctx.save_for_backward(logits, target, coeff, partial)
+        return partial[0] / partial[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, coeff, partial = ctx.saved_tensors
+        up = g.reshape(1).to(torch.float64).contiguous()
+        return K.loss_bwd(logits, target, coeff, partial[1:2], up), None, None, None, None

@@ -216,6 +216,38 @@ __global__ void __launch_bounds__(kEwThreads)
   }
 }
 
+__global__ void bn_eval_params_kernel(const float* rm, const float* rv, const float* gamma, const float* beta, float eps,
+                                      int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+__global__ void __launch_bounds__(kEwThreads) relu_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ y, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    Vec8 a = load8(x + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.v[j] = fmaxf(a.v[j], 0.f);
+    store8(y + i * 8, a);
+  }
+}
+__global__ void __launch_bounds__(kEwThreads) relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                              const __nv_bfloat16* __restrict__ y,
+                                                              __nv_bfloat16* __restrict__ dx, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    Vec8 g = load8(dy + i * 8);
+    const Vec8 o = load8(y + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+    store8(dx + i * 8, g);
+  }
+}
+
 __global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -451,6 +483,31 @@ int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double co
                                                                scale, shift);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_finalize_kernel");
+  return ADNI_OK;
+}
+
+int adni_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                        float eps, int C, float* scale, float* shift, void* stream) {
+  ADNI_REQUIRE(running_mean && running_var && scale && shift && C > 0, ADNI_EINVAL, "bn_eval_params: bad arguments");
+  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(running_mean, running_var, gamma, beta, eps, C, scale,
+                                                                  shift);
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_eval_params_kernel");
+  return ADNI_OK;
+}
+
+int adni_relu_fwd(const adni_bf16* x, adni_bf16* y, long long n, void* stream) {
+  ADNI_REQUIRE(x && y && n > 0 && n % 8 == 0, ADNI_EINVAL, "relu_fwd: bad arguments");
+  relu_fwd_kernel<<<ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(y), n / 8);
+  count_launch();
+  ADNI_LAUNCH_CHECK("relu_fwd_kernel");
+  return ADNI_OK;
+}
+int adni_relu_bwd(const adni_bf16* dy, const adni_bf16* y, adni_bf16* dx, long long n, void* stream) {
+  ADNI_REQUIRE(dy && y && dx && n > 0 && n % 8 == 0, ADNI_EINVAL, "relu_bwd: bad arguments");
+  relu_bwd_kernel<<<ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(dx), n / 8);
+  count_launch();
+  ADNI_LAUNCH_CHECK("relu_bwd_kernel");
   return ADNI_OK;
 }
 

@@ -62,6 +62,13 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, int ldx, const
   }
 }
 
+__global__ void relu_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out,
+                                long long n) {
+  // dy == nullptr: out = max(x, 0);  else: out = dy * (x > 0)   (x is the forward OUTPUT in the backward case)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dy ? (x[i] > 0.f ? dy[i] : 0.f) : fmaxf(x[i], 0.f);
+}
+
 __global__ void rows_stats_kernel(const float* __restrict__ x, int ldx, int B, int C, double* __restrict__ stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -134,14 +141,15 @@ __device__ __forceinline__ double pow_gamma(double base, double gamma) {
   return pow(base, gamma);
 }
 
-__global__ void loss_fwd_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
+template <typename T>
+__global__ void loss_fwd_kernel(const T* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
                                 int C, double gamma, const double* __restrict__ cw, double* __restrict__ partial,
                                 double* __restrict__ coeff) {
   __shared__ double sm[2][32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double num = 0, nrm = 0;
   if (i < B) {
-    const float* z = logits + (long long)i * ld;
+    const T* z = logits + (long long)i * ld;
     double m = (double)z[0];
     for (int c = 1; c < C; c++) m = fmax(m, (double)z[c]);
     double se = 0;
@@ -180,21 +188,22 @@ __global__ void loss_fwd_kernel(const float* __restrict__ logits, int ld, const 
   }
 }
 
-__global__ void loss_bwd_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
+template <typename T>
+__global__ void loss_bwd_kernel(const T* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
                                 int C, const double* __restrict__ coeff, const double* __restrict__ denom,
-                                double upstream, float* __restrict__ dl, int lddl) {
+                                const double* __restrict__ upstream, T* __restrict__ dl, int lddl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
-  const float* z = logits + (long long)i * ld;
+  const T* z = logits + (long long)i * ld;
   double m = (double)z[0];
   for (int c = 1; c < C; c++) m = fmax(m, (double)z[c]);
   double se = 0;
   for (int c = 0; c < C; c++) se += exp((double)z[c] - m);
   const int t = (int)target[i];
-  const double k = upstream * coeff[i] / denom[0];
+  const double k = upstream[0] * coeff[i] / denom[0];
   for (int c = 0; c < C; c++) {
     const double p = exp((double)z[c] - m) / se;
-    dl[(long long)i * lddl + c] = (float)(k * (p - (c == t ? 1.0 : 0.0)));
+    dl[(long long)i * lddl + c] = (T)(k * (p - (c == t ? 1.0 : 0.0)));
   }
 }
 
@@ -235,6 +244,14 @@ int adni_linear_bwd(const float* x, int ldx, const float* W, const float* y, int
     count_launch();
     ADNI_LAUNCH_CHECK("linear_bwd_dw_kernel");
   }
+  return ADNI_OK;
+}
+
+int adni_relu_f32(const float* x, const float* dy, float* out, long long n, void* stream) {
+  ADNI_REQUIRE(x && out && n > 0, ADNI_EINVAL, "relu_f32: bad arguments");
+  relu_f32_kernel<<<(unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, ST(stream)>>>(x, dy, out, n);
+  count_launch();
+  ADNI_LAUNCH_CHECK("relu_f32_kernel");
   return ADNI_OK;
 }
 
@@ -279,25 +296,37 @@ int adni_bn1d_bwd_apply(const float* dy, int lddy, const float* y, int ldy, cons
   return ADNI_OK;
 }
 
-int adni_loss_fwd(const float* logits, int ld, const int64_t* target, int B, int C, double gamma,
+int adni_loss_fwd(const void* logits, int logits_f64, int ld, const int64_t* target, int B, int C, double gamma,
                   const double* class_weights, double* partial, double* per_sample_coeff, void* stream) {
   ADNI_REQUIRE(logits && target && partial && per_sample_coeff && B > 0, ADNI_EINVAL, "loss_fwd: bad arguments");
   ADNI_REQUIRE(C >= 2 && C <= kMaxClasses && ld >= C, ADNI_ENOTSUP, "loss_fwd: C=%d outside [2,%d]", C, kMaxClasses);
   ADNI_REQUIRE(gamma >= 0, ADNI_EINVAL, "loss_fwd: negative focal gamma");
-  loss_fwd_kernel<<<(B + 127) / 128, 128, 0, ST(stream)>>>(logits, ld, target, B, C, gamma, class_weights, partial,
-                                                            per_sample_coeff);
+  if (logits_f64)
+    loss_fwd_kernel<double><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const double*>(logits), ld, target, B,
+                                                                    C, gamma, class_weights, partial,
+                                                                    per_sample_coeff);
+  else
+    loss_fwd_kernel<float><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(logits), ld, target, B,
+                                                                   C, gamma, class_weights, partial, per_sample_coeff);
   count_launch();
   ADNI_LAUNCH_CHECK("loss_fwd_kernel");
   return ADNI_OK;
 }
 
-int adni_loss_bwd(const float* logits, int ld, const int64_t* target, int B, int C, const double* per_sample_coeff,
-                  const double* denom, double upstream, float* dlogits, int lddl, void* stream) {
-  ADNI_REQUIRE(logits && target && per_sample_coeff && denom && dlogits && B > 0, ADNI_EINVAL,
+int adni_loss_bwd(const void* logits, int logits_f64, int ld, const int64_t* target, int B, int C,
+                  const double* per_sample_coeff, const double* denom, const double* upstream, void* dlogits, int lddl,
+                  void* stream) {
+  ADNI_REQUIRE(logits && target && per_sample_coeff && denom && upstream && dlogits && B > 0, ADNI_EINVAL,
                "loss_bwd: bad arguments");
   ADNI_REQUIRE(C >= 2 && C <= kMaxClasses, ADNI_ENOTSUP, "loss_bwd: C=%d outside [2,%d]", C, kMaxClasses);
-  loss_bwd_kernel<<<(B + 127) / 128, 128, 0, ST(stream)>>>(logits, ld, target, B, C, per_sample_coeff, denom, upstream,
-                                                            dlogits, lddl);
+  if (logits_f64)
+    loss_bwd_kernel<double><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const double*>(logits), ld, target, B,
+                                                                    C, per_sample_coeff, denom, upstream,
+                                                                    static_cast<double*>(dlogits), lddl);
+  else
+    loss_bwd_kernel<float><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(logits), ld, target, B, C,
+                                                                   per_sample_coeff, denom, upstream,
+                                                                   static_cast<float*>(dlogits), lddl);
   count_launch();
   ADNI_LAUNCH_CHECK("loss_bwd_kernel");
   return ADNI_OK;

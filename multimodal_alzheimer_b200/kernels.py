@@ -12,6 +12,56 @@ from ._lib import ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05, call, geom, out_ex
 BF16 = torch.bfloat16
 
 
+class _Profile:
+    """Optional per-kernel timing of the conv launches (bench.py's roofline): CUDA events recorded on the launching
+    stream around each call, tagged with the kernel family and the call's algorithmic FLOPs."""
+
+    def __init__(self):
+        self.on = False
+        self.records = []
+
+    def enable(self):
+        self.on = True
+        self.records = []
+
+    def disable_and_collect(self):
+        self.on = False
+        torch.cuda.synchronize()
+        out = {}
+        for tag, flops, e0, e1 in self.records:
+            d = out.setdefault(tag, {"flops": 0, "ms": 0.0, "n": 0})
+            d["flops"] += flops
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+        self.records = []
+        return out
+
+    def begin(self):
+        if not self.on:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, tag, flops):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((tag, flops, e0, e1))
+
+
+PROFILE = _Profile()
+
+
+def _engine_tag(Cin, Cout, k, stride, engine, wgrad=False):
+    tc = engine == ENGINE_TCGEN05 or (engine == ENGINE_AUTO and Cin % 64 == 0 and Cout % 64 == 0 and
+                                      stride in (1, 2) and k ** 3 <= 64)
+    if not tc:
+        return "direct"
+    return "tc_wgrad" if wgrad else "tc_kmajor"
+
+
 def _chk(t, dtype, name):
     if t.dtype != dtype:
         raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
@@ -52,8 +102,10 @@ def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE
     Do, Ho, Wo = (out_extent(v, k, stride, pad, dil) for v in (D, H, W))
     y = torch.empty((N, Do, Ho, Wo, Cout), dtype=BF16, device=x.device)
     st = torch.zeros((2, Cout), dtype=torch.float64, device=x.device) if stats else None
+    ev = PROFILE.begin()
     call("adni_conv3d_fprop", g, ptr(x), ptr(w_oti), ptr(bias), ptr(y), ptr(st[0]) if stats else None,
          ptr(st[1]) if stats else None, engine, stream_ptr())
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3)
     return y, st
 
 
@@ -66,7 +118,9 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
     dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
     if addend is not None:
         _chk(addend, BF16, "addend")
+    ev = PROFILE.begin()
     call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, stream_ptr())
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * dy.numel() * Cin * k ** 3)
     return dx
 
 
@@ -81,11 +135,15 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
     if want_dbias:
         if engine == ENGINE_DIRECT or (Cin % 64 != 0 or Cout % 64 != 0):
             db = torch.zeros((Cout,), dtype=torch.float32, device=x.device)
+            ev = PROFILE.begin()
             call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), ptr(db), ENGINE_DIRECT, stream_ptr())
+            PROFILE.end(ev, "direct", 2 * dy.numel() * Cin * k ** 3)
             return dw, db
         s = channel_stats(dy.view(-1, Cout))
         db = s[0].to(torch.float32)
+    ev = PROFILE.begin()
     call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, engine, stream_ptr())
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine, wgrad=True), 2 * dy.numel() * Cin * k ** 3)
     return dw, db
 
 
@@ -107,6 +165,35 @@ def bn_apply(y, scale, shift, residual=None, relu=True):
     out = torch.empty_like(y)
     call("adni_bn_apply", ptr(y), ptr(scale), ptr(shift), ptr(residual), ptr(out), rows, C, int(relu), None, None,
          stream_ptr())
+    return out
+
+
+def bn_eval_params(running_mean, running_var, gamma, beta, eps):
+    C = running_mean.shape[0]
+    out = torch.empty((2, C), dtype=torch.float32, device=running_mean.device)
+    call("adni_bn_eval_params", ptr(running_mean), ptr(running_var), ptr(gamma), ptr(beta), float(eps), C, ptr(out[0]),
+         ptr(out[1]), stream_ptr())
+    return out[0], out[1]
+
+
+def relu_fwd(x):
+    _chk(x, BF16, "x")
+    y = torch.empty_like(x)
+    call("adni_relu_fwd", ptr(x), ptr(y), x.numel(), stream_ptr())
+    return y
+
+
+def relu_bwd(dy, y):
+    dx = torch.empty_like(y)
+    call("adni_relu_bwd", ptr(dy), ptr(y), ptr(dx), y.numel(), stream_ptr())
+    return dx
+
+
+def relu_f32(x, dy=None):
+    """dy None: max(x, 0); else dy * (x > 0) with x the forward output."""
+    x = _chk(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    call("adni_relu_f32", ptr(x), ptr(dy), ptr(out), x.numel(), stream_ptr())
     return out
 
 
@@ -247,16 +334,19 @@ def loss_fwd(logits, target, gamma, class_weights):
     _chk(target, torch.int64, "target")
     partial = torch.zeros((2,), dtype=torch.float64, device=logits.device)
     coeff = torch.empty((B,), dtype=torch.float64, device=logits.device)
-    call("adni_loss_fwd", ptr(logits), _ld(logits), ptr(target), B, C, float(gamma or 0.0), ptr(class_weights),
-         ptr(partial), ptr(coeff), stream_ptr())
+    call("adni_loss_fwd", ptr(logits), int(logits.dtype == torch.float64), _ld(logits), ptr(target), B, C,
+         float(gamma or 0.0), ptr(class_weights), ptr(partial), ptr(coeff), stream_ptr())
     return partial, coeff
 
 
-def loss_bwd(logits, target, coeff, denom, upstream=1.0):
+def loss_bwd(logits, target, coeff, denom, upstream=None):
+    """denom / upstream: fp64 device scalars (1-element tensors); dlogits has the dtype of logits."""
     B, C = logits.shape
-    dl = torch.empty((B, C), dtype=torch.float32, device=logits.device)
-    call("adni_loss_bwd", ptr(logits), _ld(logits), ptr(target), B, C, ptr(coeff), ptr(denom), float(upstream), ptr(dl),
-         _ld(dl), stream_ptr())
+    if upstream is None:
+        upstream = torch.ones((1,), dtype=torch.float64, device=logits.device)
+    dl = torch.empty((B, C), dtype=logits.dtype, device=logits.device)
+    call("adni_loss_bwd", ptr(logits), int(logits.dtype == torch.float64), _ld(logits), ptr(target), B, C, ptr(coeff),
+         ptr(denom), ptr(upstream), ptr(dl), _ld(dl), stream_ptr())
     return dl
 
 

@@ -1,0 +1,129 @@
+"""Base_Model: the LightningModule surface of the path (reference pkg/models/base_model.py:11-89).
+
+Keeps `__init__(hparams)`, `forward`, `general_step(batch, idx, mode) -> {'loss','outputs','labels'}`,
+`training_step/validation_step/test_step/predict_step`, `configure_optimizers`, `hparams`, `save`.
+The torchmetrics F1 bookkeeping and confusion-matrix plotting of the reference are logging, not path arithmetic
+ and are not reproduced.  When pytorch_lightning is importable the class derives from
+pl.LightningModule; otherwise from a small stand-in with the same few methods.
+"""
+from abc import ABC, abstractmethod
+
+import torch
+import torch.nn as nn
+
+try:  # pragma: no cover - pytorch_lightning is not in the build image
+    import pytorch_lightning as pl
+
+    _LightningBase = pl.LightningModule
+except Exception:  # noqa: BLE001
+    pl = None
+
+    class _Hparams(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError as e:
+                raise AttributeError(k) from e
+
+    class _LightningBase(nn.Module):
+        """Minimal stand-in for pl.LightningModule (save_hyperparameters / hparams / log / load_from_checkpoint)."""
+
+        def __init__(self):
+            super().__init__()
+            self._hparams = _Hparams()
+            self.logged = {}
+
+        def save_hyperparameters(self, hparams=None, ignore=None):
+            hp = dict(hparams or {})
+            for k in (ignore or []):
+                hp.pop(k, None)
+            self._hparams = _Hparams(hp)
+
+        @property
+        def hparams(self):
+            return self._hparams
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def log(self, name, value, **kwargs):
+            self.logged[name] = value
+
+        def log_dict(self, d, **kwargs):
+            self.logged.update(d)
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs):
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            model = cls(ckpt["hyper_parameters"], **kwargs)
+            model.load_state_dict(ckpt["state_dict"])
+            return model
+
+        def save_checkpoint(self, path):
+            torch.save({"state_dict": self.state_dict(), "hyper_parameters": dict(self.hparams)}, path)
+
+
+class Base_Model(_LightningBase, ABC):
+    def __init__(self, hparams, gpu_id=None):
+        super().__init__()
+        self.save_hyperparameters(hparams, ignore=["gpu_id"])
+        if hparams["n_classes"] == 3:
+            self.label_ind_by_names = {"CN": 0, "MCI": 1, "AD": 2}
+        else:
+            self.label_ind_by_names = {"CN": 0, "AD": 1}
+
+    @abstractmethod
+    def forward(self, x):
+        pass
+
+    @property
+    def is_cuda(self):
+        return next(self.parameters()).is_cuda
+
+    def save(self, path):
+        print("Saving model... %s" % path)
+        torch.save(self, path)
+
+    @abstractmethod
+    def general_step(self, batch, batch_idx, mode) -> dict:
+        pass
+
+    def training_step(self, batch, batch_idx):
+        return self.general_step(batch, batch_idx, "train")
+
+    def validation_step(self, batch, batch_idx):
+        return self.general_step(batch, batch_idx, "val")
+
+    def test_step(self, batch, batch_idx):
+        return self.general_step(batch, batch_idx, "test")
+
+    def predict_step(self, batch, batch_idx):
+        return self.general_step(batch, batch_idx, "pred")
+
+    @abstractmethod
+    def configure_optimizers(self):
+        pass
+
+
+def volume_input(x):
+    """batch['mri'] / batch['pet1451'] (B, D, H, W), fp64 or fp32 -> (B, 1, D, H, W).  The reference then casts
+    `.to(float32)` on the device (anat_cnn.py:100-103); here the cast (fp64 -> fp32 -> bf16) happens inside the
+    first CUDA kernel of the encoder.  bf16 volumes produced by pkg/utils/normalization.py (already the encoder's
+    input type) become NDHWC (B, D, H, W, 1)."""
+    if x.dtype == torch.bfloat16:
+        return x.unsqueeze(-1)
+    return x.unsqueeze(1)
+
+
+def adam_or_plateau(hparams, parameters_optim, **adam_kwargs):
+    """Adam (+ optional ReduceLROnPlateau on val_loss_epoch), as every configure_optimizers of the path ends
+    (anat_cnn.py:127-136)."""
+    optimizer = torch.optim.Adam(parameters_optim, **adam_kwargs)
+    if hparams.get("reduce_factor_lr_schedule"):
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=hparams["reduce_factor_lr_schedule"])
+        return {"optimizer": optimizer, "lr_scheduler": scheduler, "monitor": "val_loss_epoch"}
+    return optimizer

@@ -13,7 +13,11 @@ from .medicalnet import feature_width, generate_model
 
 
 class _Hparams(dict):
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
 
 
 class LightningStandIn(nn.Module):

@@ -1,0 +1,190 @@
+"""Builders shared by the model-level parity tests: the same hparams build the oracle (CPU, torch.nn) and the
+product (CUDA kernels); weights are copied oracle -> product through state_dict (identical keys)."""
+import copy
+
+import torch
+
+CW3 = torch.tensor([0.4651162790697675, 0.6712473572938689, 0.8636363636363636], dtype=torch.float64)  # test_tab.py:36-40
+
+
+def hp_anat(depth=10, n_classes=3, fl_gamma=None, bn_begin=False, bn_dense=False, linear_out=()):
+    return dict(n_classes=n_classes, resnet_depth=depth, batchnorm_begin=bn_begin, batchnorm_dense=bn_dense,
+                linear_out=list(linear_out), fl_gamma=fl_gamma, loss_class_weights=CW3[:n_classes].clone(), lr=1e-3,
+                lr_pretrained=1e-4, l2_reg=0.0, reduce_factor_lr_schedule=None, norm_percentile=0.98)
+
+
+def hp_pet(n_classes=3, batchnorm=False, conv_out=(8, 16, 32, 64), filter_size=(5, 5, 3, 3), linear_out=64):
+    return dict(n_classes=n_classes, conv_out=list(conv_out), filter_size=list(filter_size), linear_out=linear_out,
+                batchnorm=batchnorm, loss_class_weights=CW3[:n_classes].clone(), lr=1e-3,
+                reduce_factor_lr_schedule=None)
+
+
+def hp_fusion(n_classes=3, fl_gamma=1, simple_dim_red=False):
+    return dict(n_classes=n_classes, fl_gamma=fl_gamma, loss_class_weights=CW3[:n_classes].clone(), lr=1e-3,
+                lr_pretrained=1e-4, l2_reg=0.0, reduce_factor_lr_schedule=None, simple_dim_red=simple_dim_red,
+                ensemble_size=4)
+
+
+def build_pair(kind, seed=15, **kw):
+    """Returns (oracle_model_cpu, product_model) with identical weights. kind in
+    {'anat','pet_resnet','small_pet','anat_pet','anat_pet_2resnet','mri_tab','pet_tab','all'}."""
+    import oracle.models as O
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import all_modalities_fusion as P_all
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import anat_pet_fusion as P_ap
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import pet_tabular_fusion as P_pt
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import tabular_mri_fusion as P_mt
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_cnn import Small_PET_CNN
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_resnet_cnn import PET_CNN_ResNet
+
+    torch.manual_seed(seed)
+    depth = kw.get("depth", 10)
+    nc = kw.get("n_classes", 3)
+
+    class OracleResNetPETTrunk(torch.nn.Module):
+        def __init__(self, enc):
+            super().__init__()
+            self.encoder = enc
+            self.encoder.model.conv_seg = self.encoder.model.conv_seg[:2]
+            self.relu = torch.nn.ReLU()
+            self.reduce_dim_pet = torch.nn.Sequential(torch.nn.Linear(512, 64), self.relu)
+
+        def forward(self, x):
+            out = self.encoder(x)
+            return self.reduce_dim_pet(out.view(out.shape[0], -1))
+
+    def anat(o):
+        hp = hp_anat(depth, nc, kw.get("fl_gamma"), kw.get("bn_begin", False), kw.get("bn_dense", False),
+                     kw.get("linear_out", ()))
+        return (O.Anat_CNN if o else Anat_CNN)(hp)
+
+    def petres(o):
+        hp = hp_anat(depth, nc, kw.get("fl_gamma"), kw.get("bn_begin", False), kw.get("bn_dense", False),
+                     kw.get("linear_out", ()))
+        return (O.PET_CNN_ResNet if o else PET_CNN_ResNet)(hp)
+
+    def smallpet(o):
+        hp = hp_pet(nc, kw.get("pet_batchnorm", False), kw.get("conv_out", (8, 16, 32, 64)),
+                    kw.get("filter_size", (5, 5, 3, 3)))
+        return (O.Small_PET_CNN if o else Small_PET_CNN)(hp)
+
+    def anat_pet(o, two_resnet):
+        hp = hp_fusion(nc, kw.get("fl_gamma", 1))
+        if two_resnet:
+            trunk = (OracleResNetPETTrunk if o else P_ap.ResNet_PET_Trunk)(petres(o))
+            return (O.Anat_PET_CNN if o else P_ap.Anat_PET_CNN)(hp, model_mri=anat(o), pet_trunk=trunk)
+        return (O.Anat_PET_CNN if o else P_ap.Anat_PET_CNN)(hp, model_pet=smallpet(o), model_mri=anat(o))
+
+    def mri_tab(o):
+        return (O.Tabular_MRT_Model if o else P_mt.Tabular_MRT_Model)(hp_fusion(nc, kw.get("fl_gamma", 1)),
+                                                                      model_mri=anat(o))
+
+    def pet_tab(o):
+        return (O.PET_TABULAR_CNN if o else P_pt.PET_TABULAR_CNN)(
+            hp_fusion(nc, kw.get("fl_gamma", 1), kw.get("simple_dim_red", False)), model_pet=smallpet(o))
+
+    def build(o):
+        if kind == "anat":
+            return anat(o)
+        if kind == "pet_resnet":
+            return petres(o)
+        if kind == "small_pet":
+            return smallpet(o)
+        if kind == "anat_pet":
+            return anat_pet(o, False)
+        if kind == "anat_pet_2resnet":
+            return anat_pet(o, True)
+        if kind == "mri_tab":
+            return mri_tab(o)
+        if kind == "pet_tab":
+            return pet_tab(o)
+        if kind == "all":
+            hp = hp_fusion(nc, kw.get("fl_gamma", 1))
+            cls = O.All_Modalities_Fusion if o else P_all.All_Modalities_Fusion
+            return cls(hp, model_anat_pet=anat_pet(o, False), model_anat_tab=mri_tab(o), model_pet_tab=pet_tab(o))
+        raise ValueError(kind)
+
+    oracle = build(True)
+    product = build(False)
+    missing = product.load_state_dict(copy.deepcopy(oracle.state_dict()), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return oracle, product
+
+
+def synthetic_batch(B, shape, n_classes=3, seed=15, modalities=("mri",)):
+    g = torch.Generator().manual_seed(seed)
+    batch = {}
+    if "mri" in modalities:
+        batch["mri"] = torch.rand((B,) + tuple(shape), generator=g, dtype=torch.float64)
+    if "pet1451" in modalities:
+        pet = torch.randn((B,) + tuple(shape), generator=g, dtype=torch.float64) * 0.5383 + 0.5145
+        batch["pet1451"] = (pet.clamp_min(0) - 0.5145) / 0.5383
+    if "tabular" in modalities:
+        batch["tabular"] = torch.randn((B, 1024), generator=g, dtype=torch.float32)
+    batch["label"] = torch.randint(0, n_classes, (B,), generator=g)
+    batch["label"][0] = 0
+    batch["label"][-1] = n_classes - 1
+    return batch
+
+
+def oracle_step(model, batch):
+    """One fwd+bwd of the oracle on the CPU. Works for every model kind (tabular key naming differs)."""
+    model.train()
+    b = dict(batch)
+    if "tabular" in b:
+        b["tabular_features"] = b["tabular"]
+    if hasattr(model, "general_step"):
+        try:
+            out = model.general_step(b, 0, "train")
+        except (KeyError, AttributeError, TypeError):
+            out = None
+    else:
+        out = None
+    if out is None:  # stage-2 tabular models of the oracle expose forward only
+        y = b["label"]
+        if model.__class__.__name__ == "Tabular_MRT_Model":
+            yh = model(b["tabular"], b["mri"].unsqueeze(1).float()).double()
+        else:
+            yh = model(b["pet1451"].unsqueeze(1).float(), b["tabular"]).double()
+        out = {"loss": model.criterion(yh, y), "outputs": yh, "labels": y}
+    out["loss"].backward()
+    return out
+
+
+def product_step(model, batch, dev):
+    model.to(dev).train()
+    b = {k: v.to(dev) for k, v in batch.items()}
+    out = model.general_step(b, 0, "train")
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    return out
+
+
+def autocast_step(model, batch, dev):
+    """The oracle itself executed by PyTorch under bf16 autocast on the GPU: the noise floor of bf16 operands with
+    fp32 accumulation on this input (SURVEY.md §8c 'bracketed by a torch-autocast-bf16 oracle run')."""
+    model = copy.deepcopy(model).to(dev)
+    model.zero_grad(set_to_none=True)
+    model.train()
+    b = {k: v.to(dev) for k, v in batch.items()}
+    if "tabular" in b:
+        b["tabular_features"] = b["tabular"]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = b["label"]
+        name = model.__class__.__name__
+        if name == "Tabular_MRT_Model":
+            yh = model(b["tabular"], b["mri"].unsqueeze(1).float())
+        elif name == "PET_TABULAR_CNN":
+            yh = model(b["pet1451"].unsqueeze(1).float(), b["tabular"])
+        elif name == "All_Modalities_Fusion":
+            yh = model(b["pet1451"].unsqueeze(1).float(), b["mri"].unsqueeze(1).float(), b["tabular"])
+        elif name == "Anat_PET_CNN":
+            yh = model(b["pet1451"].unsqueeze(1).float(), b["mri"].unsqueeze(1).float())
+        elif name in ("Small_PET_CNN", "PET_CNN_ResNet"):
+            yh = model(b["pet1451"].unsqueeze(1).float())
+        else:
+            yh = model(b["mri"].unsqueeze(1).float())
+    loss = model.criterion(yh.double(), y)
+    loss.backward()
+    torch.cuda.synchronize()
+    return model, {"loss": loss, "outputs": yh.double(), "labels": y}

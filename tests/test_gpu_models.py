@@ -1,0 +1,120 @@
+"""Module-level parity: one training step (forward, loss, backward) of every model of the path on the CUDA
+kernels vs the CPU oracle with identical weights and inputs.
+
+Tolerances (bf16 operands / fp32 accumulation vs the fp32 CPU oracle): logits rel-L2 <= 2e-2,
+loss abs <= 2e-2, BatchNorm running statistics rel-L2 <= 1e-2, parameter gradients rel-L2 <= 3e-2 — each OR within 2x
+of the error that PyTorch's own bf16-autocast execution of the oracle makes on the same inputs (tiny batches make
+the last BatchNorm's backward cancel catastrophically in bf16 — for torch exactly as for these kernels — so the
+autocast run is the honest noise floor; the bracket is measured, not assumed)."""
+import pytest
+import torch
+
+from tests._models import autocast_step, build_pair, oracle_step, product_step, synthetic_batch
+from tests._util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def _compare(oracle, product, out_o, out_p, check_grads=True, bracket=None, out_a=None):
+    lo, lp = out_o["outputs"].detach(), out_p["outputs"].detach().cpu()
+    assert lp.dtype == torch.float64 and out_p["loss"].dtype == torch.float64
+    la = rel_l2(out_a["outputs"].detach().cpu(), lo) if out_a is not None else 0.0
+    assert rel_l2(lp, lo) <= max(2e-2, 2 * la), f"logits rel_l2 {rel_l2(lp, lo):.3e} (autocast {la:.3e})\n{lp}\n{lo}"
+    assert abs(float(out_p["loss"]) - float(out_o["loss"])) <= 2e-2, (float(out_p["loss"]), float(out_o["loss"]))
+    po = dict(oracle.named_parameters())
+    pa = dict(bracket.named_parameters()) if bracket is not None else {}
+    worst = []
+    for name, p in product.named_parameters():
+        q = po[name]
+        if q.grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0, f"{name}: unexpected gradient"
+            continue
+        assert p.grad is not None, f"{name}: missing gradient"
+        g, r = p.grad.detach().cpu(), q.grad.detach()
+        if float(r.norm()) < 1e-12:
+            continue
+        c, e = _cos(g, r), rel_l2(g, r)
+        ea = rel_l2(pa[name].grad.detach().float().cpu(), r) if name in pa and pa[name].grad is not None else 0.0
+        worst.append((e - 2 * ea, c, e, ea, name))
+    worst.sort(reverse=True)
+    report = "\n".join(f"  cos={c:.5f} rel={e:.3e} autocast_rel={ea:.3e} {n}" for _, c, e, ea, n in worst[:8])
+    if check_grads:
+        for _, c, e, ea, n in worst:
+            assert e <= max(3e-2, 2 * ea), "gradient mismatch:\n" + report
+    bo = dict(oracle.named_buffers())
+    for name, b in product.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            assert rel_l2(b.detach().cpu(), bo[name]) <= 1e-2, f"{name}: {rel_l2(b.detach().cpu(), bo[name]):.3e}"
+        elif name.endswith("num_batches_tracked"):
+            assert int(b) == int(bo[name]), name
+    return report
+
+
+CASES = [
+    # kind, kwargs, batch, volume shape, modalities
+    ("anat", dict(depth=10), 2, (64, 64, 64), ("mri",)),                                   # config 1 (reduced size)
+    ("anat", dict(depth=18, bn_begin=True, bn_dense=True, linear_out=(32,), fl_gamma=2), 3, (48, 56, 48), ("mri",)),
+    ("anat", dict(depth=50, fl_gamma=1), 2, (40, 48, 40), ("mri",)),                       # Bottleneck path
+    ("pet_resnet", dict(depth=10, n_classes=2), 2, (48, 48, 48), ("pet1451",)),
+    ("small_pet", dict(), 2, (32, 32, 32), ("pet1451",)),
+    ("small_pet", dict(pet_batchnorm=True, n_classes=2), 3, (32, 40, 32), ("pet1451",)),
+    ("anat_pet", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451")),                     # faithful config 3
+    ("anat_pet_2resnet", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451")),             # north-star config 3
+    ("mri_tab", dict(depth=10), 2, (48, 48, 48), ("mri", "tabular")),
+    ("pet_tab", dict(simple_dim_red=True), 2, (32, 32, 32), ("pet1451", "tabular")),
+    ("all", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451", "tabular")),               # config 4
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
+def test_training_step_parity(cuda_dev, case):
+    kind, kw, B, shape, mods = case
+    oracle, product = build_pair(kind, **kw)
+    batch = synthetic_batch(B, shape, kw.get("n_classes", 3), modalities=mods)
+    bracket, out_a = autocast_step(oracle, batch, cuda_dev)
+    out_o = oracle_step(oracle, batch)
+    out_p = product_step(product, batch, cuda_dev)
+    report = _compare(oracle, product, out_o, out_p, bracket=bracket, out_a=out_a)
+    print(report)
+
+
+def test_config1_full_size(cuda_dev):
+    """BASELINE.json configs[0]: ResNet-10 MRI-only 3-class, batch 2 of 1x128^3, weighted CE, fwd+bwd."""
+    oracle, product = build_pair("anat", depth=10)
+    batch = synthetic_batch(2, (128, 128, 128), 3, modalities=("mri",))
+    batch["label"] = torch.tensor([0, 2])
+    bracket, out_a = autocast_step(oracle, batch, cuda_dev)
+    out_o = oracle_step(oracle, batch)
+    out_p = product_step(product, batch, cuda_dev)
+    _compare(oracle, product, out_o, out_p, bracket=bracket, out_a=out_a)
+
+
+def test_frozen_encoder_has_no_grads(cuda_dev):
+    """anat_cnn.py:118-120: without lr_pretrained the encoder is frozen (BN still uses batch statistics)."""
+    _, product = build_pair("anat", depth=10)
+    product.hparams["lr_pretrained"] = None
+    product.to(cuda_dev)
+    opt = product.configure_optimizers()
+    assert len(opt.param_groups) == len(list(product.model.parameters()))
+    batch = synthetic_batch(2, (32, 32, 32), 3, modalities=("mri",))
+    out = product_step(product, batch, cuda_dev)
+    for n, p in product.model.named_parameters():
+        assert (p.grad is not None) == ("conv_seg" in n), n
+    assert int(product.model.bn1.num_batches_tracked) == 1
+    assert torch.isfinite(out["loss"])
+
+
+def test_eval_mode_uses_running_stats(cuda_dev):
+    oracle, product = build_pair("anat", depth=10)
+    batch = synthetic_batch(2, (32, 32, 32), 3, modalities=("mri",))
+    oracle.eval()
+    product.to(cuda_dev).eval()
+    with torch.no_grad():
+        lo = oracle(batch["mri"].unsqueeze(1).float())
+        lp = product(batch["mri"].unsqueeze(1).float().to(cuda_dev)).cpu()
+    assert rel_l2(lp, lo) <= 3e-2 or float((lp - lo).abs().max()) <= 3e-2
