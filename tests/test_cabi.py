@@ -1,0 +1,70 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/adni_b200.h declares, and
+rejects bad arguments with the documented error codes before touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from multimodal_alzheimer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "adni_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(adni_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/adni_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS), set(declared) ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_version_and_launch_counter(lib):
+    assert lib.adni_version() >= 100
+    assert lib.adni_launch_count() >= 0
+
+
+def test_out_extent_matches_torch_formula(lib):
+    for n, k, s, p, d in [(128, 7, 2, 3, 1), (64, 3, 2, 1, 1), (16, 3, 1, 4, 4), (91, 7, 2, 3, 1), (23, 3, 2, 1, 1)]:
+        y = torch.nn.functional.conv1d(torch.zeros(1, 1, n), torch.zeros(1, 1, k), stride=s, padding=p, dilation=d)
+        assert lib.adni_conv3d_out_extent(n, k, s, p, d) == y.shape[-1]
+
+
+def test_bad_arguments_return_einval_without_a_gpu(lib):
+    g = _lib.geom(1, 8, 8, 8, 64, 64, 3, 1, 1, 1)
+    assert lib.adni_conv3d_fprop(ctypes.byref(g), None, None, None, None, None, None, 0, None) == -1
+    assert b"null" in lib.adni_last_error_string()
+    bad = _lib.geom(1, 8, 8, 8, 64, 64, 3, 0, 1, 1)  # stride 0
+    assert lib.adni_conv3d_fprop(ctypes.byref(bad), None, None, None, None, None, None, 0, None) == -1
+    assert lib.adni_quantile_workspace_bytes(3) == 3 * lib.adni_quantile_workspace_bytes(1) > 0
+    assert lib.adni_loss_fwd(None, 0, 3, None, 4, 3, 1.0, None, None, None, None) == -1
+
+
+def test_unsupported_engine_is_enotsup_not_a_fallback(lib):
+    g = _lib.geom(1, 8, 8, 8, 8, 8, 3, 1, 1, 1)
+    one = ctypes.c_void_p(16)  # never dereferenced: the engine check happens first
+    assert lib.adni_conv3d_fprop(ctypes.byref(g), one, one, None, one, None, None, _lib.ENGINE_TCGEN05, None) == -2
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    with pytest.raises(_lib.AdniError):
+        _lib.ptr(torch.zeros(4))
+    from multimodal_alzheimer_b200 import kernels as K
+    with pytest.raises(_lib.AdniError):
+        K.relu_f32(torch.zeros(8))
