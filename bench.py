@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1)
+    ap.add_argument("--shape-profile", default=None, help="write the per-conv-shape timing table to this JSON file")
     return ap.parse_args()
 
 
@@ -283,6 +284,12 @@ def run_b200(args):
     barrier()
     launches = _lib.launch_count() - launches0
     prof = K.PROFILE.disable_and_collect()
+    if args.shape_profile and rank == 0:
+        table = {k: {"ms_per_step": v["ms"] / args.steps, "n_per_step": v["n"] / args.steps,
+                     "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else None}
+                 for k, v in sorted(K.PROFILE.shapes.items(), key=lambda kv: -kv[1]["ms"])}
+        with open(args.shape_profile, "w") as f:
+            json.dump(table, f, indent=1)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -360,7 +367,10 @@ def run_b200(args):
         "other_kernels": {
             "wgrad_mnmajor_kernel": {"achieved": tf(wg), "frac": (tf(wg) / peaks["bf16_tflops_sustained"]) if tf(wg) else None,
                                      "kernel_ms_per_step": wg["ms"] / args.steps},
-            "direct_conv (stem, CUDA cores)": {"achieved": tf(dr), "kernel_ms_per_step": dr["ms"] / args.steps},
+            "stem_fprop/stem_wgrad_kernel (tcgen05, 1-channel stem)": {
+                "achieved": tf(prof.get("tc_stem", {"flops": 0, "ms": 0.0})),
+                "kernel_ms_per_step": prof.get("tc_stem", {"ms": 0.0})["ms"] / args.steps},
+            "direct_conv (CUDA cores)": {"achieved": tf(dr), "kernel_ms_per_step": dr["ms"] / args.steps},
         },
         "whole_step_tensor_frac": step_flops / (ms_total / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
     }

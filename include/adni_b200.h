@@ -78,6 +78,22 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
 int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* dy, float* dw_oti,
                       float* dbias, int engine, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core path of the 1-channel stem  conv1 = Conv3d(1, 64, k=7, stride=2, pad=3, bias=False)  (MedicalNet
+ * ResNet; call site anat_cnn.py:18-31).  x is the bf16 volume [N][D][H][W]; adni_stem_expand writes the 16-byte
+ * "filter-window pixels" X8[n][d][h][w'][j] = x[n][d][h][2w'-3+j] that TMA + tcgen05 consume.
+ * ------------------------------------------------------------------------------------------- */
+long long adni_stem_x8_elems(int N, int D, int H, int W);
+int adni_stem_expand(const adni_bf16* x, int N, int D, int H, int W, adni_bf16* x8, void* stream);
+/* w_ncdhw fp32 [64][1][7][7][7] -> w2g bf16 [56][64][8] (kd*8+kh taps, zero padded). */
+int adni_stem_weights(const float* w_ncdhw, adni_bf16* w2g, void* stream);
+/* y[N][Do][Ho][Wo][64] (+ fused BatchNorm sum / sum-of-squares, fp64, added into stat_*; may be null). */
+int adni_stem_fprop(const adni_bf16* x8, int N, int D, int H, int W, const adni_bf16* w2g, adni_bf16* y,
+                    double* stat_sum, double* stat_sqsum, void* stream);
+/* grad_ncdhw fp32 [64][1][7][7][7] = dy^T * window(x).  workspace: 512*64 floats (overwritten). */
+int adni_stem_wgrad(const adni_bf16* x8, const adni_bf16* dy, int N, int D, int H, int W, float* workspace,
+                    float* grad_ncdhw, void* stream);
+
 /* Weight layout conversions at the state_dict boundary (fp32 NCDHW nn.Parameter <-> kernel layouts).
  * w_ncdhw: [Cout][Cin][taps] fp32.  Either output may be null. */
 int adni_weights_to_kernel_layout(const float* w_ncdhw, int Cout, int Cin, int taps, adni_bf16* w_oti,

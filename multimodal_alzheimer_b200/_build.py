@@ -14,8 +14,10 @@ LIB = os.path.join(CSRC, "libadni_b200.so")
 SOURCES = [
     "runtime.cu",
     "conv_igemm_kernels.cu",
+    "conv_wgrad2.cu",
     "conv_api.cu",
     "conv_direct.cu",
+    "conv_stem.cu",
     "elementwise.cu",
     "head_loss.cu",
     "normalize.cu",

@@ -38,6 +38,11 @@ _SIGNATURES = {
     "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P],
     "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
     "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
+    "adni_stem_x8_elems": [_I, _I, _I, _I],
+    "adni_stem_expand": [_P, _I, _I, _I, _I, _P, _P],
+    "adni_stem_weights": [_P, _P, _P],
+    "adni_stem_fprop": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "adni_stem_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "adni_weights_to_kernel_layout": [_P, _I, _I, _I, _P, _P, _P],
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
@@ -76,6 +81,7 @@ _SIGNATURES = {
 _RESTYPES = {
     "adni_last_error_string": ctypes.c_char_p,
     "adni_launch_count": ctypes.c_longlong,
+    "adni_stem_x8_elems": ctypes.c_longlong,
     "adni_quantile_workspace_bytes": ctypes.c_size_t,
 }
 

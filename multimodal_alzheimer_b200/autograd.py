@@ -111,11 +111,17 @@ class StemFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, bn, cfg, pool):
-        y, st, _ = _conv_fwd(x, w, cfg, need_ito=False)
+        tc = K.stem_supported(x.shape[-1], w.shape[0], cfg.k, cfg.stride, cfg.pad, cfg.dil)
+        if tc:  # tcgen05 path: the W-axis filter window becomes a 16-byte pixel (csrc/conv_stem.cu)
+            xs = K.stem_expand(x)
+            y, st = K.stem_fprop(xs, tuple(x.shape), w)
+        else:
+            xs = x
+            y, st, _ = _conv_fwd(x, w, cfg, need_ito=False)
         a, mean, invstd, count = _bn_forward(y, st, gamma, beta, bn, None, True)
         p, am = K.maxpool3d_fwd(a, *pool)
-        ctx.save_for_backward(x, y, a, am, mean, invstd, gamma)
-        ctx.cfg, ctx.pool, ctx.count, ctx.wshape = cfg, pool, count, w.shape
+        ctx.save_for_backward(xs, y, a, am, mean, invstd, gamma)
+        ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, w.shape, tc, tuple(x.shape)
         return p
 
     @staticmethod
@@ -124,7 +130,10 @@ class StemFn(torch.autograd.Function):
         da = K.maxpool3d_bwd(dp.contiguous(), am, tuple(a.shape), *ctx.pool)
         dy, _, dgamma, dbeta = _bn_backward(da, a, y, mean, invstd, gamma, ctx.count, True, False, True)
         del da
-        dw, _ = _conv_wgrad(x, dy, ctx.cfg, ctx.wshape)
+        if ctx.tc:
+            dw = K.stem_wgrad(x, dy, ctx.xshape)
+        else:
+            dw, _ = _conv_wgrad(x, dy, ctx.cfg, ctx.wshape)
         return None, dw, dgamma, dbeta, None, None, None
 
 

@@ -14,6 +14,7 @@ namespace adni {
 
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
+int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
 
 int direct_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti,
                       const float* bias, __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
@@ -312,7 +313,7 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     ext_h.push_back((g.H - p + g.stride - 1) / g.stride);
     ext_w.push_back((g.W - p + g.stride - 1) / g.stride);
   }
-  const Box b = plan_box(Do, Ho, Wo, 64, true, at, at, at, ext_d, ext_h, ext_w);
+  const Box b = plan_box(Do, Ho, Wo, 32, true, at, at, at, ext_d, ext_h, ext_w);
 
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -348,7 +349,9 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.ntaps = taps;
   p.cin_blocks = g.Cin / 64;
   p.n_groups = taps * p.cin_blocks;
-  const int groups = p.n_groups >= 4 ? 4 : (p.n_groups >= 2 ? 2 : 1);
+  // one CTA owns all 512 TMEM columns: mt_cfg accumulators of 128 Cout rows x (512/mt_cfg) K_total columns
+  const int mt_cfg = g.Cout >= 512 ? 4 : (g.Cout >= 256 ? 2 : 1);
+  const int groups = 8 / mt_cfg;
   p.N = g.N;
   p.Do = Do;
   p.Ho = Ho;
@@ -360,18 +363,18 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.tiles_h = (Ho + b.bh - 1) / b.bh;
   p.tiles_w = (Wo + b.bw - 1) / b.bw;
   p.pos_boxes = g.N * p.tiles_d * p.tiles_h * p.tiles_w;
-  p.m_tiles = (g.Cout + 127) / 128;
+  p.m_tiles = (g.Cout + 128 * mt_cfg - 1) / (128 * mt_cfg);
   p.n_tiles = (p.n_groups + groups - 1) / groups;
   const int base_items = p.m_tiles * p.n_tiles;
   int splits = (4 * num_sms() + base_items - 1) / base_items;
-  splits = std::min(splits, std::max(1, p.pos_boxes / 16));
+  splits = std::min(splits, std::max(1, p.pos_boxes / 32));
   splits = std::max(splits, 1);
   p.boxes_per_split = (p.pos_boxes + splits - 1) / splits;
   p.splits = (p.pos_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = g.Cout;
   p.k_total = p.n_groups * 64;
   p.dw = dw;
-  return launch_wgrad(p, groups, stream);
+  return launch_wgrad2(p, mt_cfg, stream);
 }
 
 int check_geom(const adni_conv3d_geom* g) {

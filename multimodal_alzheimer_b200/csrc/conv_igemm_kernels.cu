@@ -98,75 +98,92 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // 64-bit mask of the taps whose shifted box intersects the input for this tile (lane t tests taps t, t+32)
+  auto tap_mask = [&](const TileCoord& c) -> unsigned long long {
+    bool v0 = false, v1 = false;
+    if (lane < p.ntaps) {
+      const ConvTap tap = p.taps[lane];
+      v0 = box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw);
+    }
+    if (lane + 32 < p.ntaps) {
+      const ConvTap tap = p.taps[lane + 32];
+      v1 = box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw);
+    }
+    const unsigned long long lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+    return lo | (hi << 32);
+  };
+
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (lane 0: A box, lane 1: weight tile) =====================
     if (lane == 0) {
-      for (int i = 0; i < kMaxMaps && i < 1; i++) tma_prefetch_desc(&p.a_maps[i]);
+      tma_prefetch_desc(&p.a_maps[0]);
       tma_prefetch_desc(&p.b_map);
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bd) * 128u + Cfg::B_BYTES;
-      int st = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile<BLOCK_N>(p, tile);
-        for (int t = 0; t < p.ntaps; t++) {
-          const ConvTap tap = p.taps[t];
-          const int d = c.d0 + tap.dd, h = c.h0 + tap.dh, w = c.w0 + tap.dw;
-          if (!box_in_range(p.a_ext[tap.map], d, h, w, p.bd, p.bh, p.bw)) continue;
-          for (int kb = 0; kb < p.kc_blocks; kb++) {
+    }
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bd) * 128u + Cfg::B_BYTES;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+      unsigned long long mask = tap_mask(c);
+      while (mask) {
+        const int t = __ffsll(static_cast<long long>(mask)) - 1;
+        mask &= mask - 1;
+        const ConvTap tap = p.taps[t];
+        const int d = c.d0 + tap.dd, h = c.h0 + tap.dh, w = c.w0 + tap.dw;
+        const CUtensorMap* amap = &p.a_maps[tap.map];
+        for (int kb = 0; kb < p.kc_blocks; kb++) {
+          if (lane == 0) {
             mbar_wait(&empty[st], ph ^ 1);
             mbar_arrive_expect_tx(&full[st], tx_bytes);
-            tma_load_5d(smem_a + st * Cfg::A_BYTES, &p.a_maps[tap.map], &full[st], kb * 64, w, h, d, c.n);
-            tma_load_2d(smem_b + st * Cfg::B_BYTES, &p.b_map, &full[st], tap.kofs + kb * 64, c.n0);
-            if (++st == STAGES) {
-              st = 0;
-              ph ^= 1;
-            }
+          }
+          __syncwarp();
+          if (lane == 0) tma_load_5d(smem_a + st * Cfg::A_BYTES, amap, &full[st], kb * 64, w, h, d, c.n);
+          if (lane == 1) tma_load_2d(smem_b + st * Cfg::B_BYTES, &p.b_map, &full[st], tap.kofs + kb * 64, c.n0);
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, false, false);
-      int st = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t accph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+    // ===================== MMA issuer (lane 0 issues; the warp computes the tap mask) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, false, false);
+    const uint64_t desc_hi = umma_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFFull);
+    int st = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile<BLOCK_N>(p, tile);
+      const int nkb = __popcll(tap_mask(c)) * p.kc_blocks;
+      if (lane == 0) {
         mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        uint32_t accum = 0;
-        for (int t = 0; t < p.ntaps; t++) {
-          const ConvTap tap = p.taps[t];
-          if (!box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw))
-            continue;
-          for (int kb = 0; kb < p.kc_blocks; kb++) {
-            mbar_wait(&full[st], ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + st * Cfg::A_BYTES);
-            const uint32_t b_addr = smem_u32(smem_b + st * Cfg::B_BYTES);
+        for (int i = 0; i < nkb; i++) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo0 + ((smem_u32(smem_a + st * Cfg::A_BYTES) & 0x3FFFFu) >> 4);
+          const uint32_t b_lo = desc_lo0 + ((smem_u32(smem_b + st * Cfg::B_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(k));
-            }
-            accum = 1;
-            umma_commit(&empty[st]);  // frees the smem slot once these MMAs have read it
-            if (++st == STAGES) {
-              st = 0;
-              ph ^= 1;
-            }
+          for (int k = 0; k < 4; k++)
+            umma_bf16(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                      static_cast<uint32_t>(i | k));
+          umma_commit(&empty[st]);  // frees the smem slot once these MMAs have read it
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
           }
         }
         umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1;
-        }
+      }
+      st = __shfl_sync(0xffffffffu, st, 0);
+      ph = __shfl_sync(0xffffffffu, ph, 0);
+      if (++acc == 2) {
+        acc = 0;
+        accph ^= 1;
       }
     }
   } else {
@@ -180,11 +197,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
     uint32_t accph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile<BLOCK_N>(p, tile);
-      bool has_k = false;
-      for (int t = 0; t < p.ntaps; t++) {
-        const ConvTap tap = p.taps[t];
-        has_k |= box_in_range(p.a_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw);
-      }
+      const bool has_k = tap_mask(c) != 0ull;
       const int rw = row % p.bw;
       const int rh = (row / p.bw) % p.bh;
       const int rd = row / (p.bw * p.bh);
@@ -331,18 +344,70 @@ __device__ __forceinline__ PosBox decode_box(const WgradParams& p, int b) {
   return c;
 }
 
+// Per-item constants: the (tensor map, box offset, channel slice) of each 64-column group of the output tile,
+// resolved once per item so that the per-K-block loops contain no divisions.
 template <int GROUPS>
-__device__ __forceinline__ bool wgrad_box_active(const WgradParams& p, const PosBox& c, int g0, int ng) {
-  // active if the X box of at least one of the tile's taps intersects the input
-  int last_tap = -1;
-  for (int g = 0; g < ng; g++) {
-    const int t = (g0 + g) / p.cin_blocks;
-    if (t == last_tap) continue;
-    last_tap = t;
+struct WItemCtx {
+  int map[GROUPS], dd[GROUPS], dh[GROUPS], dw[GROUPS], c0[GROUPS];
+  int ng;
+  int b_begin, b_end;
+  int mt, g0;
+};
+template <int GROUPS>
+__device__ __forceinline__ WItemCtx<GROUPS> make_item_ctx(const WgradParams& p, int item) {
+  WItemCtx<GROUPS> x;
+  const WItem it = decode_item(p, item);
+  x.mt = it.mt;
+  x.g0 = it.nt * GROUPS;
+  x.ng = min(GROUPS, p.n_groups - x.g0);
+  x.b_begin = it.ks * p.boxes_per_split;
+  x.b_end = min(x.b_begin + p.boxes_per_split, p.pos_boxes);
+#pragma unroll
+  for (int g = 0; g < GROUPS; g++) {
+    const int gg = min(x.g0 + g, p.n_groups - 1);
+    const int t = gg / p.cin_blocks;
     const ConvTap tap = p.taps[t];
-    if (box_in_range(p.x_ext[tap.map], c.d0 + tap.dd, c.h0 + tap.dh, c.w0 + tap.dw, p.bd, p.bh, p.bw)) return true;
+    x.map[g] = tap.map;
+    x.dd[g] = tap.dd;
+    x.dh[g] = tap.dh;
+    x.dw[g] = tap.dw;
+    x.c0[g] = (gg - t * p.cin_blocks) * 64;
   }
-  return false;
+  return x;
+}
+// Position-box iterator without div/mod in the loop.
+struct BoxIter {
+  int n, td, th, tw;
+  __device__ __forceinline__ void init(const WgradParams& p, int b) {
+    tw = b % p.tiles_w;
+    b /= p.tiles_w;
+    th = b % p.tiles_h;
+    b /= p.tiles_h;
+    td = b % p.tiles_d;
+    n = b / p.tiles_d;
+  }
+  __device__ __forceinline__ void next(const WgradParams& p) {
+    if (++tw == p.tiles_w) {
+      tw = 0;
+      if (++th == p.tiles_h) {
+        th = 0;
+        if (++td == p.tiles_d) {
+          td = 0;
+          ++n;
+        }
+      }
+    }
+  }
+};
+template <int GROUPS>
+__device__ __forceinline__ bool wgrad_box_active(const WgradParams& p, const WItemCtx<GROUPS>& x, int d0, int h0,
+                                                 int w0) {
+  bool any = false;
+#pragma unroll
+  for (int g = 0; g < GROUPS; g++)
+    any |= (g < x.ng) &&
+           box_in_range(p.x_ext[x.map[g]], d0 + x.dd[g], h0 + x.dh[g], w0 + x.dw[g], p.bd, p.bh, p.bw);
+  return any;
 }
 
 template <int GROUPS, int STAGES>
@@ -384,38 +449,48 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) wgrad_mnmajor_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===================== TMA producer: the whole warp walks the loop, lane l issues box l =====================
     if (lane == 0) {
       tma_prefetch_desc(&p.dy_map);
       tma_prefetch_desc(&p.x_maps[0]);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const WItem it = decode_item(p, item);
-        const int g0 = it.nt * GROUPS;
-        const int ng = min(GROUPS, p.n_groups - g0);
-        const uint32_t tx_bytes = static_cast<uint32_t>(2 + ng) * Cfg::BOX_BYTES;
-        const int b_begin = it.ks * p.boxes_per_split;
-        const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
-        for (int b = b_begin; b < b_end; b++) {
-          const PosBox c = decode_box(p, b);
-          if (!wgrad_box_active<GROUPS>(p, c, g0, ng)) continue;
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
+      const uint32_t tx_bytes = static_cast<uint32_t>(2 + x.ng) * Cfg::BOX_BYTES;
+      // this lane's box: lanes 0,1 = dY channel halves, lanes 2.. = X groups
+      const int g = lane - 2;
+      int my_map = 0, my_dd = 0, my_dh = 0, my_dw = 0, my_c0 = 0;
+#pragma unroll
+      for (int gi = 0; gi < GROUPS; gi++)
+        if (g == gi) {
+          my_map = x.map[gi];
+          my_dd = x.dd[gi];
+          my_dh = x.dh[gi];
+          my_dw = x.dw[gi];
+          my_c0 = x.c0[gi];
+        }
+      BoxIter bi;
+      bi.init(p, x.b_begin);
+      for (int b = x.b_begin; b < x.b_end; b++, bi.next(p)) {
+        const int d0 = bi.td * p.bd, h0 = bi.th * p.bh, w0 = bi.tw * p.bw;
+        if (!wgrad_box_active<GROUPS>(p, x, d0, h0, w0)) continue;
+        if (lane == 0) {
           mbar_wait(&empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&full[st], tx_bytes);
-          uint8_t* a_dst = smem_a + st * Cfg::A_BYTES;
-          tma_load_5d(a_dst, &p.dy_map, &full[st], it.mt * 128, c.w0, c.h0, c.d0, c.n);
-          tma_load_5d(a_dst + Cfg::BOX_BYTES, &p.dy_map, &full[st], it.mt * 128 + 64, c.w0, c.h0, c.d0, c.n);
-          uint8_t* b_dst = smem_b + st * Cfg::B_BYTES;
-          for (int g = 0; g < ng; g++) {
-            const int t = (g0 + g) / p.cin_blocks;
-            const int c0 = ((g0 + g) % p.cin_blocks) * 64;
-            const ConvTap tap = p.taps[t];
-            tma_load_5d(b_dst + g * Cfg::BOX_BYTES, &p.x_maps[tap.map], &full[st], c0, c.w0 + tap.dw, c.h0 + tap.dh,
-                        c.d0 + tap.dd, c.n);
-          }
-          if (++st == STAGES) {
-            st = 0;
-            ph ^= 1;
-          }
+        }
+        __syncwarp();
+        if (lane < 2) {
+          tma_load_5d(smem_a + st * Cfg::A_BYTES + lane * Cfg::BOX_BYTES, &p.dy_map, &full[st], x.mt * 128 + lane * 64,
+                      w0, h0, d0, bi.n);
+        } else if (g < x.ng) {
+          tma_load_5d(smem_b + st * Cfg::B_BYTES + g * Cfg::BOX_BYTES, &p.x_maps[my_map], &full[st], my_c0, w0 + my_dw,
+                      h0 + my_dh, d0 + my_dd, bi.n);
+        }
+        if (++st == STAGES) {
+          st = 0;
+          ph ^= 1;
         }
       }
     }
@@ -427,18 +502,15 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) wgrad_mnmajor_kernel(const _
       int acc = 0;
       uint32_t accph = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const WItem it = decode_item(p, item);
-        const int g0 = it.nt * GROUPS;
-        const int ng = min(GROUPS, p.n_groups - g0);
-        const int b_begin = it.ks * p.boxes_per_split;
-        const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
+        const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
         mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         uint32_t accum = 0;
-        for (int b = b_begin; b < b_end; b++) {
-          const PosBox c = decode_box(p, b);
-          if (!wgrad_box_active<GROUPS>(p, c, g0, ng)) continue;
+        BoxIter bi;
+        bi.init(p, x.b_begin);
+        for (int b = x.b_begin; b < x.b_end; b++, bi.next(p)) {
+          if (!wgrad_box_active<GROUPS>(p, x, bi.td * p.bd, bi.th * p.bh, bi.tw * p.bw)) continue;
           mbar_wait(&full[st], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + st * Cfg::A_BYTES);
@@ -470,17 +542,16 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) wgrad_mnmajor_kernel(const _
     int acc = 0;
     uint32_t accph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WItem it = decode_item(p, item);
-      const int g0 = it.nt * GROUPS;
-      const int ng = min(GROUPS, p.n_groups - g0);
-      const int b_begin = it.ks * p.boxes_per_split;
-      const int b_end = min(b_begin + p.boxes_per_split, p.pos_boxes);
+      const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
+      const int g0 = x.g0, ng = x.ng;
       bool has_k = false;
-      for (int b = b_begin; b < b_end && !has_k; b++) {
-        const PosBox c = decode_box(p, b);
-        has_k = wgrad_box_active<GROUPS>(p, c, g0, ng);
+      {
+        BoxIter bi;
+        bi.init(p, x.b_begin);
+        for (int b = x.b_begin; b < x.b_end && !has_k; b++, bi.next(p))
+          has_k = wgrad_box_active<GROUPS>(p, x, bi.td * p.bd, bi.th * p.bh, bi.tw * p.bw);
       }
-      const int co = it.mt * 128 + row;
+      const int co = x.mt * 128 + row;
       float* dst = p.dw + static_cast<long long>(co) * p.k_total + static_cast<long long>(g0) * 64;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();

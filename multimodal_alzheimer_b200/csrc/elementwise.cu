@@ -114,7 +114,15 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat1
 // Per-channel reductions over rows.  Block = 256 threads = (vpr channel vectors) x (rpp row lanes); a
 // block walks a slab of rows, reduces its row lanes through shared memory and issues one fp64 atomic per
 // channel.  MODE 0: sum x, sum x^2.  MODE 1: BatchNorm backward sums  sum g, sum g*xhat.
-constexpr int kRedSlabRows = 2048;
+// rows per block: sized on the host so that the grid is >= 4 blocks per SM (small-spatial layers have few rows).
+inline int red_slab_rows(long long rows, int C) {
+  const int rpp = kEwThreads / (C / 8);
+  long long slab = (rows + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4);
+  const long long min_slab = (long long)rpp * 8;  // >= 8 rows per thread keeps the atomic tail small
+  if (slab < min_slab) slab = min_slab;
+  if (slab > 4096) slab = 4096;
+  return (int)slab;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,    // x | dout
@@ -122,7 +130,8 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
                                                                     const __nv_bfloat16* __restrict__ yraw,  // - | y
                                                                     const float* __restrict__ mean,
                                                                     const float* __restrict__ invstd, long long rows,
-                                                                    int C, int relu, double* __restrict__ r0,
+                                                                    int C, int relu, int slab_rows,
+                                                                    double* __restrict__ r0,
                                                                     double* __restrict__ r1) {
   __shared__ float sm[2][kEwThreads][8];
   const int vpr = C / 8;
@@ -132,8 +141,8 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
-  const long long row_begin = (long long)blockIdx.x * kRedSlabRows;
-  const long long row_end = min(rows, row_begin + kRedSlabRows);
+  const long long row_begin = (long long)blockIdx.x * slab_rows;
+  const long long row_end = min(rows, row_begin + slab_rows);
   if (rl < rpp) {
     Vec8 mu, is;
     if (MODE == 1) {
@@ -515,9 +524,10 @@ int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, d
   ADNI_REQUIRE(x && sum && sqsum && rows > 0, ADNI_EINVAL, "channel_stats: bad arguments");
   ADNI_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, ADNI_ENOTSUP, "channel_stats: C=%d must be a multiple of 8 in [8,2048]",
                C);
-  const int grid = (int)((rows + kRedSlabRows - 1) / kRedSlabRows);
+  const int slab = red_slab_rows(rows, C);
+  const int grid = (int)((rows + slab - 1) / slab);
   channel_reduce_kernel<0><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr, rows, C, 0,
-                                                                 sum, sqsum);
+                                                                 slab, sum, sqsum);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<0>");
   return ADNI_OK;
@@ -542,9 +552,10 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
   ADNI_REQUIRE(!relu || out, ADNI_EINVAL, "bn_bwd_reduce: relu mask needs the forward output");
   ADNI_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, ADNI_ENOTSUP, "bn_bwd_reduce: C=%d must be a multiple of 8 in [8,2048]",
                C);
-  const int grid = (int)((rows + kRedSlabRows - 1) / kRedSlabRows);
+  const int slab = red_slab_rows(rows, C);
+  const int grid = (int)((rows + slab - 1) / slab);
   channel_reduce_kernel<1><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, rows, C,
-                                                                 relu, red, red + C);
+                                                                 relu, slab, red, red + C);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<1>");
   return ADNI_OK;

@@ -28,11 +28,15 @@ class _Profile:
         self.on = False
         torch.cuda.synchronize()
         out = {}
-        for tag, flops, e0, e1 in self.records:
-            d = out.setdefault(tag, {"flops": 0, "ms": 0.0, "n": 0})
-            d["flops"] += flops
-            d["ms"] += e0.elapsed_time(e1)
-            d["n"] += 1
+        shapes = {}
+        for tag, flops, e0, e1, shape in self.records:
+            ms = e0.elapsed_time(e1)
+            for dd, key in ((out, tag), (shapes, f"{tag} {shape}")):
+                d = dd.setdefault(key, {"flops": 0, "ms": 0.0, "n": 0})
+                d["flops"] += flops
+                d["ms"] += ms
+                d["n"] += 1
+        self.shapes = shapes
         self.records = []
         return out
 
@@ -43,12 +47,12 @@ class _Profile:
         e.record()
         return e
 
-    def end(self, e0, tag, flops):
+    def end(self, e0, tag, flops, shape=""):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.records.append((tag, flops, e0, e1))
+        self.records.append((tag, flops, e0, e1, shape))
 
 
 PROFILE = _Profile()
@@ -105,7 +109,8 @@ def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE
     ev = PROFILE.begin()
     call("adni_conv3d_fprop", g, ptr(x), ptr(w_oti), ptr(bias), ptr(y), ptr(st[0]) if stats else None,
          ptr(st[1]) if stats else None, engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3)
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3,
+                f"fprop N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
     return y, st
 
 
@@ -120,7 +125,8 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
         _chk(addend, BF16, "addend")
     ev = PROFILE.begin()
     call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * dy.numel() * Cin * k ** 3)
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * dy.numel() * Cin * k ** 3,
+                f"dgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
     return dx
 
 
@@ -143,8 +149,51 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
         db = s[0].to(torch.float32)
     ev = PROFILE.begin()
     call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine, wgrad=True), 2 * dy.numel() * Cin * k ** 3)
+    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine, wgrad=True), 2 * dy.numel() * Cin * k ** 3,
+                f"wgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
     return dw, db
+
+
+# --------------------------------------------------------------------------------------------- stem (tcgen05)
+def stem_supported(Cin, Cout, k, stride, pad, dil):
+    return Cin == 1 and Cout == 64 and k == 7 and stride == 2 and pad == 3 and dil == 1
+
+
+def stem_expand(x):
+    """bf16 [N, D, H, W, 1] -> X8 bf16 [N, D, H, W', 8] (filter-window pixels)."""
+    _chk(x, BF16, "x")
+    N, D, H, W = x.shape[:4]
+    Wo = (W - 1) // 2 + 1
+    x8 = torch.empty((N, D, H, Wo, 8), dtype=BF16, device=x.device)
+    call("adni_stem_expand", ptr(x), N, D, H, W, ptr(x8), stream_ptr())
+    return x8
+
+
+def stem_fprop(x8, in_shape, w, stats=True):
+    """x8 from stem_expand, w fp32 [64,1,7,7,7]. Returns (y bf16 [N,Do,Ho,Wo,64], stats fp64 [2,64])."""
+    N, D, H, W = in_shape[:4]
+    w2g = torch.empty((56, 64, 8), dtype=BF16, device=x8.device)
+    call("adni_stem_weights", ptr(_chk(w.detach(), torch.float32, "weight")), ptr(w2g), stream_ptr())
+    Do, Ho, Wo = ((v - 1) // 2 + 1 for v in (D, H, W))
+    y = torch.empty((N, Do, Ho, Wo, 64), dtype=BF16, device=x8.device)
+    st = torch.zeros((2, 64), dtype=torch.float64, device=x8.device) if stats else None
+    ev = PROFILE.begin()
+    call("adni_stem_fprop", ptr(x8), N, D, H, W, ptr(w2g), ptr(y), ptr(st[0]) if stats else None,
+         ptr(st[1]) if stats else None, stream_ptr())
+    PROFILE.end(ev, "tc_stem", 2 * N * Do * Ho * Wo * 64 * 343)
+    return y, st
+
+
+def stem_wgrad(x8, dy, in_shape):
+    """Returns the fp32 parameter-layout gradient [64, 1, 7, 7, 7]."""
+    _chk(dy, BF16, "dy")
+    N, D, H, W = in_shape[:4]
+    ws = torch.empty((512 * 64,), dtype=torch.float32, device=x8.device)
+    grad = torch.empty((64, 1, 7, 7, 7), dtype=torch.float32, device=x8.device)
+    ev = PROFILE.begin()
+    call("adni_stem_wgrad", ptr(x8), ptr(dy), N, D, H, W, ptr(ws), ptr(grad), stream_ptr())
+    PROFILE.end(ev, "tc_stem", 2 * dy.numel() * 343)
+    return grad
 
 
 # --------------------------------------------------------------------------------------------- BN

@@ -123,3 +123,30 @@ def test_engine_rejects_unsupported(cuda_dev):
     w = torch.zeros((8, 27, 8), dtype=torch.bfloat16, device=cuda_dev)
     with pytest.raises(NotImplementedError):
         K.conv3d_fprop(x, w, None, 3, 1, 1, 1, engine=TC)
+
+
+STEM_SHAPES = [(2, 16, 16, 16), (1, 32, 24, 40), (1, 18, 20, 22), (3, 9, 11, 13), (1, 128, 128, 128)]
+
+
+@pytest.mark.parametrize("shape", STEM_SHAPES)
+def test_tc_stem(cuda_dev, shape):
+    """Conv3d(1,64,k=7,s=2,p=3) on tcgen05 through the W-window ("X8") expansion: fprop + BN sums + wgrad."""
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((N, 1, D, H, W), generator=g).to(cuda_dev)
+    w = (torch.randn((64, 1, 7, 7, 7), generator=g) / 343 ** 0.5).to(cuda_dev)
+    x_b = x.to(torch.bfloat16).view(N, D, H, W, 1).contiguous()
+    x_ref = x_b.view(N, 1, D, H, W).float()
+    w_ref = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv3d(x_ref, w_ref, None, 2, 3, 1)
+    x8 = K.stem_expand(x_b)
+    y, st = K.stem_fprop(x8, tuple(x_b.shape), w)
+    torch.cuda.synchronize()
+    assert_close(to_ncdhw_f32(y), ref.detach(), 6e-3, f"stem fprop {shape}")
+    assert_close(st[1], (ref.detach().double() ** 2).sum(dim=(0, 2, 3, 4)), 1e-4, f"stem stats {shape}")
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref))
+    ref.backward(to_ncdhw_f32(dy_b))
+    gw = K.stem_wgrad(x8, dy_b, tuple(x_b.shape))
+    torch.cuda.synchronize()
+    assert_close(gw, w_ref.grad, 2e-4, f"stem wgrad {shape}")
