@@ -131,6 +131,10 @@ int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf
                       const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
                       int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream);
 
+/* dgamma[c] = red[C+c], dbeta[c] = red[c] (fp64 -> fp32): BatchNorm parameter gradients from the LOCAL backward
+ * sums (under data parallelism the gradient all-reduce adds the ranks' contributions). */
+int adni_bn_param_grads(const double* red, int C, float* dgamma, float* dbeta, void* stream);
+
 /* Eval-mode BatchNorm (module.eval()): scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale. */
 int adni_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
                         float eps, int C, float* scale, float* shift, void* stream);

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "adni_bn1d_bwd_apply": [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _D, _I, _I, _I, _P, _I, _P, _P, _P],
     "adni_loss_fwd": [_P, _I, _I, _P, _I, _I, _D, _P, _P, _P, _P],
     "adni_loss_bwd": [_P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
+    "adni_bn_param_grads": [_P, _I, _P, _P, _P],
     "adni_bn_eval_params": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "adni_relu_fwd": [_P, _P, _LL, _P],
     "adni_relu_f32": [_P, _P, _P, _LL, _P],

@@ -68,8 +68,12 @@ def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
 
 def _bn_backward(dout, out, y, mean, invstd, gamma, count, relu, want_dres, want_pg):
     red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu)
+    # dgamma / dbeta are the LOCAL sums: the gradient all-reduce that follows the backward pass makes them global
+    # (taking them from the all-reduced statistics would count every rank's contribution world_size times).
+    dgamma, dbeta = K.bn_param_grads(red) if want_pg else (None, None)
     _allreduce_(red)
-    return K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_pg)
+    dy, dres, _, _ = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, False)
+    return dy, dres, dgamma, dbeta
 
 
 class ConvCfg:
@@ -387,8 +391,10 @@ class BatchNorm1dFn(torch.autograd.Function):
         x, y, mean, invstd, gamma = ctx.saved_tensors
         count, relu = ctx.cfg
         dy = dy.contiguous()
-        red = _allreduce_(K.bn1d_bwd_reduce(dy, y, x, mean, invstd, relu))
-        dx, dgamma, dbeta = K.bn1d_bwd_apply(dy, y, x, mean, invstd, gamma, red, count, relu)
+        red = K.bn1d_bwd_reduce(dy, y, x, mean, invstd, relu)
+        dgamma, dbeta = K.bn_param_grads(red)  # local sums; the gradient all-reduce makes them global
+        _allreduce_(red)
+        dx, _, _ = K.bn1d_bwd_apply(dy, y, x, mean, invstd, gamma, red, count, relu)
         return dx, dgamma, dbeta, None, None
 
 

@@ -495,6 +495,14 @@ int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double co
   return ADNI_OK;
 }
 
+int adni_bn_param_grads(const double* red, int C, float* dgamma, float* dbeta, void* stream) {
+  ADNI_REQUIRE(red && C > 0 && (dgamma || dbeta), ADNI_EINVAL, "bn_param_grads: bad arguments");
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(red, C, dgamma, dbeta);
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_param_grads_kernel");
+  return ADNI_OK;
+}
+
 int adni_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
                         float eps, int C, float* scale, float* shift, void* stream) {
   ADNI_REQUIRE(running_mean && running_var && scale && shift && C > 0, ADNI_EINVAL, "bn_eval_params: bad arguments");

@@ -217,6 +217,14 @@ def bn_apply(y, scale, shift, residual=None, relu=True):
     return out
 
 
+def bn_param_grads(red):
+    """fp64 [2, C] backward sums (sum g, sum g*xhat) -> (dgamma, dbeta) fp32 [C]."""
+    C = red.shape[1]
+    pg = torch.empty((2, C), dtype=torch.float32, device=red.device)
+    call("adni_bn_param_grads", ptr(red), C, ptr(pg[0]), ptr(pg[1]), stream_ptr())
+    return pg[0], pg[1]
+
+
 def bn_eval_params(running_mean, running_var, gamma, beta, eps):
     C = running_mean.shape[0]
     out = torch.empty((2, C), dtype=torch.float32, device=running_mean.device)

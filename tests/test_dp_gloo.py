@@ -1,0 +1,93 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: sharding, bucketed gradient all-reduce, and the
+statistic / loss-normaliser exchange that makes N shards equal the single-process full batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    r, lr, w = dp.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+def _bucket_fn(rank, world):
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 1000, 3, 70000, 11)]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    params[2].grad = None  # a frozen / unused parameter must be skipped, not crash
+    b = dp.GradientBuckets(params, bucket_mb=0.2)
+    assert len(b.buckets) >= 2
+    b.all_reduce()
+    return [None if p.grad is None else float(p.grad[0]) for p in params]
+
+
+def test_gradient_buckets_sum_across_ranks():
+    out = _run(_bucket_fn)
+    tot = sum(r + 1 for r in range(2))
+    for rank in range(2):
+        assert out[rank] == [tot * 1.0, tot * 2.0, None, tot * 4.0, tot * 5.0]
+
+
+def _syncbn_fn(rank, world):
+    """The reductions the autograd Functions perform (sum x, sum x^2 | loss numerator, normaliser) reproduce the
+    full-batch BatchNorm statistics and weighted-CE loss when every rank holds a shard."""
+    from multimodal_alzheimer_b200 import autograd as A
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 5, generator=g, dtype=torch.float64)          # full batch (identical on every rank)
+    lo, hi = dp.shard_bounds(8, rank, world)
+    xs = x[lo:hi]
+    stats = torch.stack([xs.sum(0), (xs * xs).sum(0)])
+    A._allreduce_(stats)
+    count = xs.shape[0] * A._world()
+    mean = stats[0] / count
+    var = stats[1] / count - mean * mean
+    ok_bn = torch.allclose(mean, x.mean(0)) and torch.allclose(var, x.var(0, unbiased=False))
+    # weighted CE: numerator and sum of target weights are both global sums
+    w = torch.tensor([0.4651162790697675, 0.6712473572938689, 0.8636363636363636], dtype=torch.float64)
+    z = torch.randn(8, 3, generator=g, dtype=torch.float64)
+    t = torch.randint(0, 3, (8,), generator=g)
+    nll = -torch.log_softmax(z[lo:hi], 1).gather(1, t[lo:hi, None]).squeeze(1)
+    partial = torch.stack([(w[t[lo:hi]] * nll).sum(), w[t[lo:hi]].sum()])
+    A._allreduce_(partial)
+    ref = torch.nn.functional.cross_entropy(z, t, weight=w)
+    return bool(ok_bn), abs(float(partial[0] / partial[1]) - float(ref)) < 1e-14
+
+
+def test_sharded_statistics_equal_full_batch():
+    out = _run(_syncbn_fn)
+    assert all(out[r] == (True, True) for r in range(2))
+
+
+def test_shard_bounds():
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    assert [dp.shard_bounds(32, r, 8) for r in range(8)] == [(4 * r, 4 * r + 4) for r in range(8)]
+    assert dp.shard_bounds(16, 0, 1) == (0, 16)
+    with pytest.raises(ValueError):
+        dp.shard_bounds(10, 0, 4)
