@@ -275,6 +275,8 @@ def run_b200(args):
     if sampler:
         sampler.start()
     K.PROFILE.enable()
+    if args.shape_profile:
+        _lib.CALL_TIMING = {}
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -284,10 +286,13 @@ def run_b200(args):
     barrier()
     launches = _lib.launch_count() - launches0
     prof = K.PROFILE.disable_and_collect()
+    call_ms = _lib.collect_call_timing() if args.shape_profile else {}
     if args.shape_profile and rank == 0:
         table = {k: {"ms_per_step": v["ms"] / args.steps, "n_per_step": v["n"] / args.steps,
                      "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else None}
                  for k, v in sorted(K.PROFILE.shapes.items(), key=lambda kv: -kv[1]["ms"])}
+        table["__entry_points__"] = {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps}
+                                     for k, (n, ms) in sorted(call_ms.items(), key=lambda kv: -kv[1][1])}
         with open(args.shape_profile, "w") as f:
             json.dump(table, f, indent=1)
     clocks = sampler.stop() if sampler else None

@@ -120,16 +120,19 @@ int adni_bn_apply(const adni_bf16* y, const float* scale, const float* shift, co
                   adni_bf16* out, long long rows, int C, int relu, double* out_sum, double* out_sqsum, void* stream);
 
 /* Backward, pass 1: g = dout * (relu ? out > 0 : 1);  red[0:C] += sum g, red[C:2C] += sum g*xhat with
- * xhat = (y-mean)*invstd.  `out` is the forward output (needed only when relu). red is fp64[2C]. */
+ * xhat = (y-mean)*invstd.  The ReLU mask comes from `out` (the forward output) or, when out is NULL and there was
+ * no residual, is recomputed as y*scale+shift > 0 (saves one tensor read). red is fp64[2C]. */
 int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
-                       const float* invstd, long long rows, int C, int relu, double* red, void* stream);
+                       const float* invstd, const float* scale, const float* shift, long long rows, int C, int relu,
+                       double* red, void* stream);
 
 /* Backward, pass 2: dy = gamma*invstd*( g - red_g/count - xhat*red_gx/count ) (bf16);
  * dres (nullable) = g (the gradient flowing into the residual input); dgamma = red_gx, dbeta = red_g
  * are written (fp32) when non-null.  `count` is the GLOBAL element count per channel (sync-BN). */
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
-                      const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
-                      int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream);
+                      const float* invstd, const float* gamma, const float* scale, const float* shift,
+                      const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
+                      float* dgamma, float* dbeta, void* stream);
 
 /* dgamma[c] = red[C+c], dbeta[c] = red[c] (fp64 -> fp32): BatchNorm parameter gradients from the LOCAL backward
  * sums (under data parallelism the gradient all-reduce adds the ranks' contributions). */

@@ -47,8 +47,8 @@ _SIGNATURES = {
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "adni_bn_apply": [_P, _P, _P, _P, _P, _LL, _I, _I, _P, _P, _P],
-    "adni_bn_bwd_reduce": [_P, _P, _P, _P, _P, _LL, _I, _I, _P, _P],
-    "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _P],
+    "adni_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P],
+    "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _P],
     "adni_channel_stats": [_P, _LL, _I, _P, _P, _P],
     "adni_maxpool3d_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "adni_maxpool3d_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
@@ -137,10 +137,29 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# optional per-entry-point device timing (bench.py --shape-profile): name -> [n, list of (start, end) events]
+CALL_TIMING = None
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if CALL_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        CALL_TIMING.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     _check(rc, name)
+
+
+def collect_call_timing():
+    """Returns {entry point: (calls, total ms)} and resets the recorder."""
+    global CALL_TIMING
+    rec, CALL_TIMING = CALL_TIMING, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
 
 
 def geom(N, D, H, W, Cin, Cout, k, stride, pad, dil):

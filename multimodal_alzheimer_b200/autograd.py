@@ -46,7 +46,8 @@ class BNState:
 
 
 def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
-    """Shared BN forward. Returns (out, mean, invstd, count). stats may be None (computed with a reduction pass)."""
+    """Shared BN forward. Returns (out, bnp, count) with bnp = fp32 [4, C] rows (mean, invstd, scale, shift);
+    stats may be None (computed with a reduction pass)."""
     C = y.shape[-1]
     rows = y.numel() // C
     if bn.training:
@@ -54,25 +55,31 @@ def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
             stats = K.channel_stats(y.view(-1, C))
         _allreduce_(stats)
         count = rows * _world()
-        mean, invstd, scale, shift = K.bn_finalize(stats, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean,
-                                                   bn.running_var)
+        bnp = K.bn_finalize(stats, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+        scale, shift = bnp[2], bnp[3]
         if bn.module is not None and bn.module.num_batches_tracked is not None:
             bn.module.num_batches_tracked += 1
     else:
         scale, shift = K.bn_eval_params(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
-        mean = invstd = None
+        bnp = None
         count = rows
     out = K.bn_apply(y, scale, shift, residual=residual, relu=relu)
-    return out, mean, invstd, count
+    return out, bnp, count
 
 
-def _bn_backward(dout, out, y, mean, invstd, gamma, count, relu, want_dres, want_pg):
-    red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu)
+def _bn_backward(dout, out, y, bnp, gamma, count, relu, want_dres, want_pg):
+    """out=None with relu=True: the forward had no residual, the ReLU mask is recomputed from y*scale+shift."""
+    if bnp is None:
+        raise NotImplementedError("BatchNorm backward in eval mode is outside the training hot path")
+    mean, invstd, scale, shift = bnp[0], bnp[1], bnp[2], bnp[3]
+    if not relu or out is not None:
+        scale = shift = None
+    red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale, shift)
     # dgamma / dbeta are the LOCAL sums: the gradient all-reduce that follows the backward pass makes them global
     # (taking them from the all-reduced statistics would count every rank's contribution world_size times).
     dgamma, dbeta = K.bn_param_grads(red) if want_pg else (None, None)
     _allreduce_(red)
-    dy, dres, _, _ = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, False)
+    dy, dres, _, _ = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, False, scale, shift)
     return dy, dres, dgamma, dbeta
 
 
@@ -122,17 +129,18 @@ class StemFn(torch.autograd.Function):
         else:
             xs = x
             y, st, _ = _conv_fwd(x, w, cfg, need_ito=False)
-        a, mean, invstd, count = _bn_forward(y, st, gamma, beta, bn, None, True)
+        a, bnp, count = _bn_forward(y, st, gamma, beta, bn, None, True)
         p, am = K.maxpool3d_fwd(a, *pool)
-        ctx.save_for_backward(xs, y, a, am, mean, invstd, gamma)
+        ctx.save_for_backward(xs, y, am, bnp, gamma)
+        ctx.a_shape = tuple(a.shape)
         ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, w.shape, tc, tuple(x.shape)
         return p
 
     @staticmethod
     def backward(ctx, dp):
-        x, y, a, am, mean, invstd, gamma = ctx.saved_tensors
-        da = K.maxpool3d_bwd(dp.contiguous(), am, tuple(a.shape), *ctx.pool)
-        dy, _, dgamma, dbeta = _bn_backward(da, a, y, mean, invstd, gamma, ctx.count, True, False, True)
+        x, y, am, bnp, gamma = ctx.saved_tensors
+        da = K.maxpool3d_bwd(dp.contiguous(), am, ctx.a_shape, *ctx.pool)
+        dy, _, dgamma, dbeta = _bn_backward(da, None, y, bnp, gamma, ctx.count, True, False, True)
         del da
         if ctx.tc:
             dw = K.stem_wgrad(x, dy, ctx.xshape)
@@ -149,36 +157,36 @@ class BasicBlockFn(torch.autograd.Function):
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, bn1, bn2, bnd, c1, c2, cd):
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
-        a1, m1, is1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
+        a1, p1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
         y2, st2, w2_ito = _conv_fwd(a1, w2, c2)
         if wd is not None:
             yd, std, wd_ito = _conv_fwd(x, wd, cd, need_ito=need_dx)
-            r, md, isd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
+            r, pd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
         else:
-            yd = wd_ito = md = isd = None
+            yd = wd_ito = pd = None
             nd = 0
             r = x
-        out, m2, is2, n2 = _bn_forward(y2, st2, g2, b2, bn2, r, True)
-        ctx.save_for_backward(x, y1, a1, y2, out, yd, m1, is1, m2, is2, md, isd, g1, g2, gd, w1_ito, w2_ito, wd_ito)
+        out, p2, n2 = _bn_forward(y2, st2, g2, b2, bn2, r, True)
+        ctx.save_for_backward(x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito)
         ctx.cfg = (c1, c2, cd, n1, n2, nd, w1.shape, w2.shape, None if wd is None else wd.shape, need_dx)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y1, a1, y2, out, yd, m1, is1, m2, is2, md, isd, g1, g2, gd, w1_ito, w2_ito, wd_ito = ctx.saved_tensors
+        x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito = ctx.saved_tensors
         c1, c2, cd, n1, n2, nd, ws1, ws2, wsd, need_dx = ctx.cfg
         dout = dout.contiguous()
-        dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, m2, is2, g2, n2, True, True, True)
+        dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, p2, g2, n2, True, True, True)
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
         da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
         del dy2
-        dy1, _, dg1, db1 = _bn_backward(da1, a1, y1, m1, is1, g1, n1, True, False, True)
+        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True)
         del da1
         dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
         dwd = dgd = dbd = None
         dx = None
         if yd is not None:
-            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, md, isd, gd, nd, False, False, True)
+            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, pd, gd, nd, False, False, True)
             dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
             if need_dx:
                 dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
@@ -195,46 +203,46 @@ class BottleneckFn(torch.autograd.Function):
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, wd, gd, bd, bn1, bn2, bn3, bnd, c1, c2, c3, cd):
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
-        a1, m1, is1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
+        a1, p1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
         y2, st2, w2_ito = _conv_fwd(a1, w2, c2)
-        a2, m2, is2, n2 = _bn_forward(y2, st2, g2, b2, bn2, None, True)
+        a2, p2, n2 = _bn_forward(y2, st2, g2, b2, bn2, None, True)
         y3, st3, w3_ito = _conv_fwd(a2, w3, c3)
         if wd is not None:
             yd, std, wd_ito = _conv_fwd(x, wd, cd, need_ito=need_dx)
-            r, md, isd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
+            r, pd, nd = _bn_forward(yd, std, gd, bd, bnd, None, False)
         else:
-            yd = wd_ito = md = isd = None
+            yd = wd_ito = pd = None
             nd = 0
             r = x
-        out, m3, is3, n3 = _bn_forward(y3, st3, g3, b3, bn3, r, True)
-        ctx.save_for_backward(x, y1, a1, y2, a2, y3, out, yd, m1, is1, m2, is2, m3, is3, md, isd, g1, g2, g3, gd,
-                              w1_ito, w2_ito, w3_ito, wd_ito)
+        out, p3, n3 = _bn_forward(y3, st3, g3, b3, bn3, r, True)
+        ctx.save_for_backward(x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
+                              wd_ito)
         ctx.cfg = (c1, c2, c3, cd, n1, n2, n3, nd, w1.shape, w2.shape, w3.shape, None if wd is None else wd.shape,
                    need_dx)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (x, y1, a1, y2, a2, y3, out, yd, m1, is1, m2, is2, m3, is3, md, isd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
+        (x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
          wd_ito) = ctx.saved_tensors
         c1, c2, c3, cd, n1, n2, n3, nd, ws1, ws2, ws3, wsd, need_dx = ctx.cfg
         dout = dout.contiguous()
-        dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, m3, is3, g3, n3, True, True, True)
+        dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, p3, g3, n3, True, True, True)
         dw3, _ = _conv_wgrad(a2, dy3, c3, ws3)
         da2 = K.conv3d_dgrad(dy3, w3_ito, tuple(a2.shape), c3.k, c3.stride, c3.pad, c3.dil)
         del dy3
-        dy2, _, dg2, db2 = _bn_backward(da2, a2, y2, m2, is2, g2, n2, True, False, True)
+        dy2, _, dg2, db2 = _bn_backward(da2, None, y2, p2, g2, n2, True, False, True)
         del da2
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
         da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
         del dy2
-        dy1, _, dg1, db1 = _bn_backward(da1, a1, y1, m1, is1, g1, n1, True, False, True)
+        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True)
         del da1
         dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
         dwd = dgd = dbd = None
         dx = None
         if yd is not None:
-            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, md, isd, gd, nd, False, False, True)
+            dyd, _, dgd, dbd = _bn_backward(dres, None, yd, pd, gd, nd, False, False, True)
             dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
             if need_dx:
                 dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
@@ -275,19 +283,16 @@ class BatchNormActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, stats, gamma, beta, residual, bn, relu):
         st = stats if (stats is not None and stats.numel() > 0) else None
-        out, mean, invstd, count = _bn_forward(y, st, gamma, beta, bn, residual, relu)
-        ctx.save_for_backward(y, out, mean, invstd, gamma)
+        out, bnp, count = _bn_forward(y, st, gamma, beta, bn, residual, relu)
+        ctx.save_for_backward(y, out if (relu and residual is not None) else None, bnp, gamma)
         ctx.cfg = (count, relu, residual is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, out, mean, invstd, gamma = ctx.saved_tensors
+        y, out, bnp, gamma = ctx.saved_tensors
         count, relu, has_res = ctx.cfg
-        if mean is None:
-            raise NotImplementedError("BatchNorm backward in eval mode is outside the training hot path")
-        dy, dres, dgamma, dbeta = _bn_backward(dout.contiguous(), out if relu else None, y, mean, invstd, gamma, count,
-                                               relu, has_res, True)
+        dy, dres, dgamma, dbeta = _bn_backward(dout.contiguous(), out, y, bnp, gamma, count, relu, has_res, True)
         return dy, None, dgamma, dbeta, dres, None, None
 
 
@@ -374,7 +379,7 @@ class BatchNorm1dFn(torch.autograd.Function):
             st = _allreduce_(K.rows_stats_f32(x))
             count = B * _world()
             mean, invstd, scale, shift = K.bn_finalize(st, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean,
-                                                       bn.running_var)
+                                                       bn.running_var).unbind(0)
             if bn.module is not None and bn.module.num_batches_tracked is not None:
                 bn.module.num_batches_tracked += 1
         else:

@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
                                                                     const __nv_bfloat16* __restrict__ outp,  // - | out (relu mask)
                                                                     const __nv_bfloat16* __restrict__ yraw,  // - | y
                                                                     const float* __restrict__ mean,
-                                                                    const float* __restrict__ invstd, long long rows,
+                                                                    const float* __restrict__ invstd,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift, long long rows,
                                                                     int C, int relu, int slab_rows,
                                                                     double* __restrict__ r0,
                                                                     double* __restrict__ r1) {
@@ -144,10 +146,14 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
   const long long row_begin = (long long)blockIdx.x * slab_rows;
   const long long row_end = min(rows, row_begin + slab_rows);
   if (rl < rpp) {
-    Vec8 mu, is;
+    Vec8 mu, is, sc, sh;
     if (MODE == 1) {
       mu = loadf8(mean + cv * 8);
       is = loadf8(invstd + cv * 8);
+      if (relu == 2) {  // ReLU mask recomputed from y (no residual): out > 0  <=>  y*scale + shift > 0
+        sc = loadf8(scale + cv * 8);
+        sh = loadf8(shift + cv * 8);
+      }
     }
     for (long long r = row_begin + rl; r < row_end; r += rpp) {
       const long long off = r * C + cv * 8;
@@ -160,12 +166,15 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
         }
       } else {
         Vec8 g = x;
-        if (relu) {
+        const Vec8 yv = load8(yraw + off);
+        if (relu == 1) {
           const Vec8 o = load8(outp + off);
 #pragma unroll
           for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+        } else if (relu == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) g.v[j] = fmaf(yv.v[j], sc.v[j], sh.v[j]) > 0.f ? g.v[j] : 0.f;
         }
-        const Vec8 yv = load8(yraw + off);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
@@ -194,33 +203,49 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
   }
 }
 
+// dy = gamma*invstd*(g - mean_g - xhat*mean_gx) rewritten as  dy = A[c]*g + B[c]*y + K[c]:  the per-channel
+// coefficients are computed once per block into shared memory (fp64 sums -> fp32), so the streaming loop issues only
+// the tensor loads plus 6 shared-memory vector loads instead of ~28 scalar parameter loads per 8 elements.
 __global__ void __launch_bounds__(kEwThreads)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
                         const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
                         const double* __restrict__ red, double inv_count, long long nvec, int vpr, int C, int relu,
                         __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres) {
+  extern __shared__ float coef[];  // [5][C]: A, B, K, scale, shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gm = gamma ? gamma[c] : 1.f;
+    const float is = invstd[c], mu = mean[c];
+    const float mg = (float)(red[c] * inv_count);
+    const float mgx = (float)(red[C + c] * inv_count);
+    const float a = gm * is;
+    const float b = -a * is * mgx;
+    coef[c] = a;
+    coef[C + c] = b;
+    coef[2 * C + c] = -a * mg - b * mu;
+    coef[3 * C + c] = relu == 2 ? scale[c] : 0.f;
+    coef[4 * C + c] = relu == 2 ? shift[c] : 0.f;
+  }
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % vpr) * 8;
     Vec8 g = load8(dout + i * 8);
-    if (relu) {
+    const Vec8 yv = load8(yraw + i * 8);
+    if (relu == 1) {
       const Vec8 o = load8(outp + i * 8);
 #pragma unroll
       for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+    } else if (relu == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = fmaf(yv.v[j], coef[3 * C + c0 + j], coef[4 * C + c0 + j]) > 0.f ? g.v[j] : 0.f;
     }
     if (dres) store8(dres + i * 8, g);
-    const Vec8 yv = load8(yraw + i * 8);
-    const Vec8 mu = loadf8(mean + c0), is = loadf8(invstd + c0);
     Vec8 r;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const float gm = gamma ? __ldg(gamma + c0 + j) : 1.f;
-      const float mg = (float)(red[c0 + j] * inv_count);
-      const float mgx = (float)(red[C + c0 + j] * inv_count);
-      const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
-      r.v[j] = gm * is.v[j] * (g.v[j] - mg - xh * mgx);
-    }
+    for (int j = 0; j < 8; j++)
+      r.v[j] = fmaf(coef[c0 + j], g.v[j], fmaf(coef[C + c0 + j], yv.v[j], coef[2 * C + c0 + j]));
     store8(dy + i * 8, r);
   }
 }
@@ -371,6 +396,84 @@ __global__ void __launch_bounds__(kEwThreads)
 #pragma unroll
     for (int j = 0; j < 8; j++) o.v[j] = acc[j];
     store8(dx + i * 8, o);
+  }
+}
+
+// Tiled max-pool backward: a block owns an 8x8x8 input tile (x 64 channels) and first stages the <= 6^3 pooled
+// windows that can point into it (dy + arg-max) in shared memory, so global traffic is ~1x instead of the up to
+// 8 window probes per voxel of the straightforward gather above.
+constexpr int kMpT = 8;
+constexpr int kMpWMax = 6;
+__global__ void __launch_bounds__(kEwThreads)
+    maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ amax, int N, int D, int H,
+                             int W, int C, int k, int s, int pad, int Do, int Ho, int Wo, int tiles_d, int tiles_h,
+                             int tiles_w, __nv_bfloat16* __restrict__ dx) {
+  __shared__ uint4 s_dy[kMpWMax * kMpWMax * kMpWMax * 8];   // [window][cv] 8 channels bf16
+  __shared__ uint2 s_am[kMpWMax * kMpWMax * kMpWMax * 8];   // [window][cv] 8 arg-max bytes
+  const int vpr = C / 8;
+  const int cv0 = blockIdx.y * 8;  // 64-channel chunk
+  int t = blockIdx.x;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  t /= tiles_h;
+  const int td = t % tiles_d;
+  const int n = t / tiles_d;
+  const int i0d = td * kMpT, i0h = th * kMpT, i0w = tw * kMpT;
+  auto lo = [&](int i0) {
+    const int num = i0 + pad - k + 1;
+    return num <= 0 ? 0 : (num + s - 1) / s;
+  };
+  const int od0 = lo(i0d), oh0 = lo(i0h), ow0 = lo(i0w);
+  const int nd = min(Do - 1, (i0d + kMpT - 1 + pad) / s) - od0 + 1;
+  const int nh = min(Ho - 1, (i0h + kMpT - 1 + pad) / s) - oh0 + 1;
+  const int nw = min(Wo - 1, (i0w + kMpT - 1 + pad) / s) - ow0 + 1;
+  const int nwin = nd * nh * nw;
+  for (int i = threadIdx.x; i < nwin * 8; i += kEwThreads) {
+    const int cv = i & 7, wdx = i >> 3;
+    const int ww = wdx % nw, wh = (wdx / nw) % nh, wd = wdx / (nw * nh);
+    if (cv0 + cv < vpr) {
+      const long long o = ((((long long)n * Do + od0 + wd) * Ho + oh0 + wh) * Wo + ow0 + ww) * vpr + cv0 + cv;
+      s_dy[i] = __ldg(reinterpret_cast<const uint4*>(dy + o * 8));
+      s_am[i] = __ldg(reinterpret_cast<const uint2*>(amax + o * 8));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMpT * kMpT * kMpT * 8; i += kEwThreads) {
+    const int cv = i & 7, v = i >> 3;
+    const int iw = i0w + (v % kMpT), ih = i0h + ((v / kMpT) % kMpT), id = i0d + v / (kMpT * kMpT);
+    if (iw >= W || ih >= H || id >= D || cv0 + cv >= vpr) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    const int a_lo = max(od0, lo(id)), a_hi = min(od0 + nd - 1, (id + pad) / s);
+    const int b_lo = max(oh0, lo(ih)), b_hi = min(oh0 + nh - 1, (ih + pad) / s);
+    const int c_lo = max(ow0, lo(iw)), c_hi = min(ow0 + nw - 1, (iw + pad) / s);
+    for (int od = a_lo; od <= a_hi; od++) {
+      const int kd = id + pad - od * s;
+      for (int oh = b_lo; oh <= b_hi; oh++) {
+        const int kh = ih + pad - oh * s;
+        for (int ow = c_lo; ow <= c_hi; ow++) {
+          const int kw = iw + pad - ow * s;
+          const int slot = (kd * k + kh) * k + kw;
+          const int wdx = ((od - od0) * nh + (oh - oh0)) * nw + (ow - ow0);
+          const uint2 pk = s_am[wdx * 8 + cv];
+          const uint4 g = s_dy[wdx * 8 + cv];
+          const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t word = j < 4 ? pk.x : pk.y;
+            const int a = (word >> ((j & 3) * 8)) & 255;
+            const float gv = (j & 1) ? bf16_hi(gw[j >> 1]) : bf16_lo(gw[j >> 1]);
+            if (a == slot) acc[j] += gv;
+          }
+        }
+      }
+    }
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = acc[j];
+    store8(dx + (((((long long)n * D + id) * H + ih) * W + iw) * vpr + cv0 + cv) * 8, o);
   }
 }
 
@@ -534,8 +637,8 @@ int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, d
                C);
   const int slab = red_slab_rows(rows, C);
   const int grid = (int)((rows + slab - 1) / slab);
-  channel_reduce_kernel<0><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr, rows, C, 0,
-                                                                 slab, sum, sqsum);
+  channel_reduce_kernel<0><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                 nullptr, rows, C, 0, slab, sum, sqsum);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<0>");
   return ADNI_OK;
@@ -555,30 +658,38 @@ int adni_bn_apply(const adni_bf16* y, const float* scale, const float* shift, co
 }
 
 int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
-                       const float* invstd, long long rows, int C, int relu, double* red, void* stream) {
+                       const float* invstd, const float* scale, const float* shift, long long rows, int C, int relu,
+                       double* red, void* stream) {
   ADNI_REQUIRE(dout && y && mean && invstd && red && rows > 0, ADNI_EINVAL, "bn_bwd_reduce: bad arguments");
-  ADNI_REQUIRE(!relu || out, ADNI_EINVAL, "bn_bwd_reduce: relu mask needs the forward output");
+  ADNI_REQUIRE(!relu || out || (scale && shift), ADNI_EINVAL,
+               "bn_bwd_reduce: relu mask needs the forward output or scale/shift");
+  if (relu) relu = out ? 1 : 2;
   ADNI_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, ADNI_ENOTSUP, "bn_bwd_reduce: C=%d must be a multiple of 8 in [8,2048]",
                C);
   const int slab = red_slab_rows(rows, C);
   const int grid = (int)((rows + slab - 1) / slab);
-  channel_reduce_kernel<1><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, rows, C,
-                                                                 relu, slab, red, red + C);
+  channel_reduce_kernel<1><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale, shift,
+                                                                 rows, C, relu, slab, red, red + C);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<1>");
   return ADNI_OK;
 }
 
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
-                      const float* invstd, const float* gamma, const double* red, double count, long long rows, int C,
-                      int relu, adni_bf16* dy, adni_bf16* dres, float* dgamma, float* dbeta, void* stream) {
+                      const float* invstd, const float* gamma, const float* scale, const float* shift,
+                      const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
+                      float* dgamma, float* dbeta, void* stream) {
   ADNI_REQUIRE(dout && y && mean && invstd && red && dy && rows > 0 && count > 0, ADNI_EINVAL,
                "bn_bwd_apply: bad arguments");
-  ADNI_REQUIRE(!relu || out, ADNI_EINVAL, "bn_bwd_apply: relu mask needs the forward output");
+  ADNI_REQUIRE(!relu || out || (scale && shift), ADNI_EINVAL,
+               "bn_bwd_apply: relu mask needs the forward output or scale/shift");
+  if (relu) relu = out ? 1 : 2;
   ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   const long long nvec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(
-      CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy), BF(dres));
+  ADNI_REQUIRE(C <= 2048, ADNI_ENOTSUP, "bn_bwd_apply: C=%d > 2048", C);
+  bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 5 * C * sizeof(float), ST(stream)>>>(
+      CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, scale, shift, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy),
+      BF(dres));
   count_launch();
   ADNI_LAUNCH_CHECK("bn_bwd_apply_kernel");
   if (dgamma || dbeta) {
@@ -611,8 +722,17 @@ int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D,
                "maxpool3d_bwd: unsupported C=%d k=%d stride=%d pad=%d", C, k, stride, pad);
   const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long total = (long long)N * D * H * W * (C / 8);
-  maxpool_bwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k,
-                                                                                 stride, pad, Do, Ho, Wo, BF(dx));
+  // windows that can touch an 8-voxel tile edge: (8 + k - 2)/s + 1 (+1 for unaligned tiles when s does not divide 8)
+  const int wmax = (kMpT + k - 2) / stride + 1 + ((kMpT % stride) ? 1 : 0);
+  if (wmax <= kMpWMax) {
+    const int td = (D + kMpT - 1) / kMpT, th = (H + kMpT - 1) / kMpT, tw = (W + kMpT - 1) / kMpT;
+    dim3 grid((unsigned)((long long)N * td * th * tw), (unsigned)((C / 8 + 7) / 8));
+    maxpool_bwd_tiled_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k, stride, pad, Do, Ho,
+                                                                  Wo, td, th, tw, BF(dx));
+  } else {
+    maxpool_bwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k,
+                                                                                   stride, pad, Do, Ho, Wo, BF(dx));
+  }
   count_launch();
   ADNI_LAUNCH_CHECK("maxpool_bwd_kernel");
   return ADNI_OK;

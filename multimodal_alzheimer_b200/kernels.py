@@ -198,13 +198,13 @@ def stem_wgrad(x8, dy, in_shape):
 
 # --------------------------------------------------------------------------------------------- BN
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
-    """stats: fp64 [2, C] (sum, sum of squares).  Returns (mean, invstd, scale, shift), fp32 [C] each."""
+    """stats: fp64 [2, C] (sum, sum of squares).  Returns fp32 [4, C]: rows mean, invstd, scale, shift."""
     C = stats.shape[1]
     out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
     call("adni_bn_finalize", ptr(stats[0]), ptr(stats[1]), float(count), C, ptr(gamma), ptr(beta), float(eps),
          float(momentum), ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
          stream_ptr())
-    return out[0], out[1], out[2], out[3]
+    return out
 
 
 def bn_apply(y, scale, shift, residual=None, relu=True):
@@ -264,23 +264,25 @@ def channel_stats(x2d):
     return st
 
 
-def bn_bwd_reduce(dout, out, y, mean, invstd, relu):
+def bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale=None, shift=None):
+    """relu mask: from `out`, or (out None, no residual in the forward) recomputed from y*scale+shift."""
     C = y.shape[-1]
     rows = y.numel() // C
     red = torch.zeros((2, C), dtype=torch.float64, device=y.device)
-    call("adni_bn_bwd_reduce", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), rows, C,
-         int(relu), ptr(red), stream_ptr())
+    call("adni_bn_bwd_reduce", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(scale),
+         ptr(shift), rows, C, int(relu), ptr(red), stream_ptr())
     return red
 
 
-def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_param_grads=True):
+def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_param_grads=True, scale=None,
+                 shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     pg = torch.empty((2, C), dtype=torch.float32, device=y.device) if want_param_grads else None
     call("adni_bn_bwd_apply", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
-         ptr(red), float(count), rows, C, int(relu), ptr(dy), ptr(dres),
+         ptr(scale), ptr(shift), ptr(red), float(count), rows, C, int(relu), ptr(dy), ptr(dres),
          ptr(pg[0]) if want_param_grads else None, ptr(pg[1]) if want_param_grads else None, stream_ptr())
     if want_param_grads:
         return dy, dres, pg[0], pg[1]
