@@ -1,0 +1,140 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels run): construction from hparams,
+state_dict compatibility with the oracle/reference key names, truncation/slicing semantics of the fusion stages,
+optimizer grouping and freezing, Sequential fusion dispatch, error behaviour, checkpoint round trip."""
+import pytest
+import torch
+
+from tests._models import build_pair, hp_anat, hp_fusion, hp_pet
+
+
+ALL_KINDS = ["anat", "pet_resnet", "small_pet", "anat_pet", "anat_pet_2resnet", "mri_tab", "pet_tab", "all"]
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
+def test_state_dict_keys_and_shapes_match_oracle(kind):
+    oracle, product = build_pair(kind, depth=10)   # build_pair load_state_dict(strict=True)s oracle -> product
+    so, sp = oracle.state_dict(), product.state_dict()
+    assert list(so.keys()) == list(sp.keys())
+    assert all(so[k].shape == sp[k].shape and so[k].dtype == sp[k].dtype for k in so)
+    assert all(torch.equal(so[k], sp[k]) for k in so)
+
+
+def test_resnet18_checkpoint_key_names():
+    """model.conv1.weight, model.layer{1-4}.{i}.{conv,bn}{1,2}.*, downsample.{0,1}.*, conv_seg.*"""
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    m = Anat_CNN(hp_anat(18, bn_begin=True))
+    keys = list(m.state_dict().keys())
+    assert len(keys) == 128 and keys[0] == "model.conv1.weight"
+    for k in ("model.bn1.running_var", "model.layer2.0.downsample.0.weight", "model.layer2.0.downsample.1.running_mean",
+              "model.layer4.1.bn2.num_batches_tracked", "model.conv_seg.0.weight", "model.conv_seg.3.bias",
+              "criterion.weight"):
+        assert k in keys, k
+    assert tuple(m.model.conv1.weight.shape) == (64, 1, 7, 7, 7)
+    assert m.model.layer3[0].conv1.cfg.dil == 2 and m.model.layer4[1].conv2.cfg.dil == 4
+    assert m.model.layer2[0].conv1.cfg.stride == 2 and m.model.layer3[0].conv1.cfg.stride == 1
+
+
+def test_bad_depth_raises_value_error():
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    with pytest.raises(ValueError):
+        Anat_CNN(hp_anat(34))       # anat_cnn.py:44-46: heads exist only for 10/18/50
+    with pytest.raises(ValueError):
+        Anat_CNN(hp_anat(42))
+
+
+def test_fusion_truncations():
+    """anat_pet_fusion.py:28-32, all_modalities_fusion.py:29-31."""
+    from multimodal_alzheimer_b200 import nn as bnn
+    _, m3 = build_pair("anat_pet", depth=10, n_classes=3)
+    assert isinstance(m3.model_pet[-1], bnn.ReLU) and isinstance(m3.model_pet[-2], bnn.Linear)   # model[:-1]
+    _, m2 = build_pair("anat_pet", depth=10, n_classes=2)
+    assert isinstance(m2.model_pet[-1], bnn.Flatten)                                              # model[:-3]
+    assert len(m3.model_mri.model.conv_seg) == 2 and isinstance(m3.model_mri.model.conv_seg[0], bnn.AdaptiveAvgPool3d)
+    _, mb = build_pair("anat_pet", depth=10, bn_begin=True)
+    assert isinstance(mb.model_mri.model.conv_seg[0], bnn.BatchNorm3d)                            # conv_seg[:2]
+    _, ma = build_pair("all", depth=10)
+    for sub in (ma.model_anat_pet, ma.model_anat_tab, ma.model_pet_tab):
+        assert len(sub.model_fuse) == 1 and sub.model_fuse[0] is sub.stage2out                    # model_fuse[:-2]
+    assert type(ma.model_anat_pet.model_fuse).__name__ == "Sequential"
+
+
+def test_freezing_and_optimizer_groups():
+    _, m = build_pair("anat", depth=10)
+    m.hparams["lr_pretrained"] = None
+    opt = m.configure_optimizers()                                   # anat_cnn.py:111-128
+    n_params = len(list(m.model.parameters()))
+    assert len(opt.param_groups) == n_params                         # one group per tensor, frozen ones included
+    for name, p in m.model.named_parameters():
+        assert p.requires_grad == ("conv_seg" in name)
+    m.hparams["lr_pretrained"] = 1e-5
+    opt = m.configure_optimizers()
+    lrs = {g["lr"] for g in opt.param_groups}
+    assert lrs == {1e-3, 1e-5} and all(p.requires_grad for p in m.model.parameters())
+    m.hparams["reduce_factor_lr_schedule"] = 0.5
+    out = m.configure_optimizers()
+    assert out["monitor"] == "val_loss_epoch" and "lr_scheduler" in out
+    # fusion: stage-1 frozen unless lr_pretrained (anat_pet_fusion.py:35-40)
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.anat_pet_fusion import Anat_PET_CNN
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_cnn import Small_PET_CNN
+    hp = hp_fusion()
+    hp["lr_pretrained"] = None
+    f = Anat_PET_CNN(hp, model_pet=Small_PET_CNN(hp_pet()), model_mri=Anat_CNN(hp_anat(10)))
+    assert not any(p.requires_grad for p in f.model_mri.parameters())
+    assert not any(p.requires_grad for p in f.model_pet.parameters())
+    assert all(p.requires_grad for p in f.model_fuse.parameters())
+
+
+def test_sequential_fuses_reference_patterns(monkeypatch):
+    """Conv3d->BN3d->ReLU, BN3d->ReLU, Linear->BN1d->ReLU and Linear->ReLU run as single fused calls."""
+    from multimodal_alzheimer_b200 import nn as bnn
+    calls = []
+    monkeypatch.setattr(bnn.Conv3d, "forward_with_stats", lambda self, x, want=True: (calls.append("conv+stats") or x, "st"))
+    monkeypatch.setattr(bnn.Conv3d, "forward", lambda self, x: calls.append("conv") or x)
+    monkeypatch.setattr(bnn.BatchNorm3d, "forward",
+                        lambda self, x, stats=None, residual=None, relu=False: calls.append(f"bn3d(stats={stats is not None},relu={relu})") or x)
+    monkeypatch.setattr(bnn.BatchNorm1d, "forward", lambda self, x, relu=False: calls.append(f"bn1d(relu={relu})") or x)
+    monkeypatch.setattr(bnn.Linear, "forward", lambda self, x, relu=False: calls.append(f"linear(relu={relu})") or x)
+    monkeypatch.setattr(bnn.ReLU, "forward", lambda self, x: calls.append("relu") or x)
+    monkeypatch.setattr(bnn.MaxPool3d, "forward", lambda self, x: calls.append("pool") or x)
+    seq = bnn.Sequential(bnn.Conv3d(1, 8, 3, padding="same"), bnn.BatchNorm3d(8), bnn.ReLU(), bnn.MaxPool3d(2),
+                         bnn.Conv3d(8, 8, 3, padding="same"), bnn.ReLU(), bnn.BatchNorm3d(8), bnn.ReLU(),
+                         bnn.Linear(8, 8), bnn.BatchNorm1d(8), bnn.ReLU(), bnn.Linear(8, 4), bnn.ReLU(),
+                         bnn.Linear(4, 2))
+    seq(torch.zeros(1))
+    assert calls == ["conv+stats", "bn3d(stats=True,relu=True)", "pool", "conv", "relu", "bn3d(stats=False,relu=True)",
+                     "linear(relu=False)", "bn1d(relu=True)", "linear(relu=True)", "linear(relu=False)"]
+    assert isinstance(seq[:-1], bnn.Sequential) and len(seq[:-3]) == 11
+
+
+def test_conv_same_padding_and_geometry():
+    from multimodal_alzheimer_b200 import nn as bnn
+    c = bnn.Conv3d(1, 8, 5, padding="same")
+    assert (c.cfg.k, c.cfg.stride, c.cfg.pad, c.cfg.dil) == (5, 1, 2, 1) and c.bias is not None
+    with pytest.raises(NotImplementedError):
+        bnn.Conv3d(1, 8, 4, padding="same")
+    with pytest.raises(ValueError):
+        bnn.Conv3d(1, 8, (3, 5, 3))
+
+
+def test_checkpoint_round_trip(tmp_path):
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    m = Anat_CNN(hp_anat(10, bn_begin=True))
+    path = str(tmp_path / "anat.ckpt")
+    m.save_checkpoint(path)                      # {'state_dict', 'hyper_parameters'}: the Lightning .ckpt fields
+    m2 = Anat_CNN.load_from_checkpoint(path)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m2.hparams["resnet_depth"] == 10
+
+
+def test_loss_modules_follow_reference_selection():
+    from multimodal_alzheimer_b200.pkg.loss_functions.focalloss import CrossEntropyLoss, FocalLoss, make_criterion
+    assert isinstance(make_criterion({"fl_gamma": 2, "loss_class_weights": None}), FocalLoss)
+    ce = make_criterion({"fl_gamma": None, "loss_class_weights": torch.tensor([0.5, 0.5], dtype=torch.float64)})
+    assert isinstance(ce, CrossEntropyLoss) and "weight" in dict(ce.named_buffers())
+    with pytest.raises(NotImplementedError):
+        FocalLoss(gamma=1, alpha=0.25)
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_cnn import Small_PET_CNN
+    hp = hp_pet()
+    hp["fl_gamma"] = 5
+    assert isinstance(Small_PET_CNN(hp).criterion, CrossEntropyLoss)     # pet_cnn.py:47-48 ignores fl_gamma
