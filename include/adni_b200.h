@@ -160,6 +160,19 @@ int adni_maxpool3d_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, in
                        adni_bf16* y, uint8_t* argmax, void* stream);
 int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D, int H, int W, int C, int k,
                        int stride, int pad, adni_bf16* dx, void* stream);
+/* Fused stem tail  bn1 -> ReLU -> MaxPool3d(3,2,1)  (MedicalNet ResNet.forward) and its backward, without
+ * materialising the activated 64-channel tensor or its gradient:
+ *   fwd   : p, argmax = maxpool(relu(y*scale + shift))            y: raw conv1 output [N][D][H][W][C]
+ *   reduce: g = relu_mask(y) * maxpool_bwd(dp, argmax);  red[0:C] += sum g, red[C:2C] += sum g*xhat
+ *   apply : dy = gamma*invstd*(g - red_g/count - xhat*red_gx/count)
+ * bnp is the fp32 [4][C] block (mean, invstd, scale, shift) written by adni_bn_finalize. */
+int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float* shift, int N, int D, int H, int W,
+                             int C, int k, int stride, int pad, adni_bf16* p, uint8_t* argmax, void* stream);
+int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const adni_bf16* y, const float* bnp, int N,
+                               int D, int H, int W, int C, int k, int stride, int pad, double* red, void* stream);
+int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const adni_bf16* y, const float* bnp,
+                              const float* gamma, const double* red, double count, int N, int D, int H, int W, int C,
+                              int k, int stride, int pad, adni_bf16* dy, void* stream);
 /* feat[N][C] (fp32) = mean over P positions of x[N][P][C]. */
 int adni_gap_fwd(const adni_bf16* x, int N, long long P, int C, float* feat, void* stream);
 /* dx[N][P][C] (bf16) = dfeat[N][C] / P. */

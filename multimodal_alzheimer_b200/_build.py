@@ -18,6 +18,7 @@ SOURCES = [
     "conv_api.cu",
     "conv_direct.cu",
     "conv_stem.cu",
+    "stem_fused.cu",
     "elementwise.cu",
     "head_loss.cu",
     "normalize.cu",

@@ -129,19 +129,39 @@ class StemFn(torch.autograd.Function):
         else:
             xs = x
             y, st, _ = _conv_fwd(x, w, cfg, need_ito=False)
-        a, bnp, count = _bn_forward(y, st, gamma, beta, bn, None, True)
-        p, am = K.maxpool3d_fwd(a, *pool)
+        fused = bn.training and K.fused_pool_supported(*pool)
+        if fused:  # bn1 -> ReLU -> max-pool in one pass over y (csrc/stem_fused.cu); `a` never exists
+            C = y.shape[-1]
+            _allreduce_(st)
+            count = (y.numel() // C) * _world()
+            bnp = K.bn_finalize(st, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+            if bn.module is not None and bn.module.num_batches_tracked is not None:
+                bn.module.num_batches_tracked += 1
+            p, am = K.bn_relu_maxpool_fwd(y, bnp, *pool)
+            a_shape = tuple(y.shape)
+        else:
+            a, bnp, count = _bn_forward(y, st, gamma, beta, bn, None, True)
+            p, am = K.maxpool3d_fwd(a, *pool)
+            a_shape = tuple(a.shape)
         ctx.save_for_backward(xs, y, am, bnp, gamma)
-        ctx.a_shape = tuple(a.shape)
+        ctx.a_shape = a_shape
         ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, w.shape, tc, tuple(x.shape)
+        ctx.fused = fused
         return p
 
     @staticmethod
     def backward(ctx, dp):
         x, y, am, bnp, gamma = ctx.saved_tensors
-        da = K.maxpool3d_bwd(dp.contiguous(), am, ctx.a_shape, *ctx.pool)
-        dy, _, dgamma, dbeta = _bn_backward(da, None, y, bnp, gamma, ctx.count, True, False, True)
-        del da
+        dp = dp.contiguous()
+        if ctx.fused:
+            red = K.maxpool_bn_bwd_reduce(dp, am, y, bnp, *ctx.pool)
+            dgamma, dbeta = K.bn_param_grads(red)
+            _allreduce_(red)
+            dy = K.maxpool_bn_bwd_apply(dp, am, y, bnp, gamma, red, ctx.count, *ctx.pool)
+        else:
+            da = K.maxpool3d_bwd(dp, am, ctx.a_shape, *ctx.pool)
+            dy, _, dgamma, dbeta = _bn_backward(da, None, y, bnp, gamma, ctx.count, True, False, True)
+            del da
         if ctx.tc:
             dw = K.stem_wgrad(x, dy, ctx.xshape)
         else:

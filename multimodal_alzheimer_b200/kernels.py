@@ -307,6 +307,38 @@ def maxpool3d_bwd(dy, argmax, in_shape, k, stride, pad):
     return dx
 
 
+def fused_pool_supported(k, stride, pad):
+    return (k, stride, pad) == (3, 2, 1)
+
+
+def bn_relu_maxpool_fwd(y, bnp, k, stride, pad):
+    """maxpool(relu(y*scale+shift)) without materialising the activation. bnp: fp32 [4, C] from bn_finalize."""
+    _chk(y, BF16, "y")
+    N, D, H, W, C = y.shape
+    Do, Ho, Wo = ((v + 2 * pad - k) // stride + 1 for v in (D, H, W))
+    p = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=y.device)
+    am = torch.empty((N, Do, Ho, Wo, C), dtype=torch.uint8, device=y.device)
+    call("adni_bn_relu_maxpool_fwd", ptr(y), ptr(bnp[2]), ptr(bnp[3]), N, D, H, W, C, k, stride, pad, ptr(p), ptr(am),
+         stream_ptr())
+    return p, am
+
+
+def maxpool_bn_bwd_reduce(dp, argmax, y, bnp, k, stride, pad):
+    N, D, H, W, C = y.shape
+    red = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+    call("adni_maxpool_bn_bwd_reduce", ptr(dp), ptr(argmax), ptr(y), ptr(bnp), N, D, H, W, C, k, stride, pad, ptr(red),
+         stream_ptr())
+    return red
+
+
+def maxpool_bn_bwd_apply(dp, argmax, y, bnp, gamma, red, count, k, stride, pad):
+    N, D, H, W, C = y.shape
+    dy = torch.empty_like(y)
+    call("adni_maxpool_bn_bwd_apply", ptr(dp), ptr(argmax), ptr(y), ptr(bnp), ptr(gamma), ptr(red), float(count), N, D,
+         H, W, C, k, stride, pad, ptr(dy), stream_ptr())
+    return dy
+
+
 def gap_fwd(x):
     _chk(x, BF16, "x")
     N, C = x.shape[0], x.shape[-1]

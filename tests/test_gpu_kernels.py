@@ -258,3 +258,36 @@ def test_casts(cuda_dev):
     x = torch.randn(1000, device=cuda_dev, dtype=torch.float64)
     assert torch.equal(K.cast_to_bf16(x), x.float().to(BF))
     assert torch.equal(K.cast_to_f32(K.cast_to_bf16(x.float())), x.float().to(BF).float())
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 16, 64), (1, 9, 11, 13, 64), (1, 32, 20, 24, 16)])
+def test_fused_stem_tail_matches_unfused_kernels(cuda_dev, shape):
+    """bn1 -> ReLU -> MaxPool3d(3,2,1) fused (stem_fused.cu) vs bn_apply + maxpool3d + bn_bwd_* kernels."""
+    from multimodal_alzheimer_b200 import kernels as K
+    C = shape[-1]
+    y = _rand_act(shape, cuda_dev) * 2 + 0.3
+    rows = y.numel() // C
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    beta = torch.randn(C, device=cuda_dev) * 0.2
+    bnp = K.bn_finalize(K.channel_stats(y.view(-1, C)), rows, gamma, beta, 1e-5, 0.1, None, None)
+    a = K.bn_apply(y, bnp[2], bnp[3], residual=None, relu=True)
+    p_ref, am_ref = K.maxpool3d_fwd(a, 3, 2, 1)
+    p, am = K.bn_relu_maxpool_fwd(y, bnp, 3, 2, 1)
+    assert torch.equal(p, p_ref) and torch.equal(am, am_ref)
+    dp = _rand_act(tuple(p.shape), cuda_dev, 5)
+    da = K.maxpool3d_bwd(dp, am_ref, tuple(a.shape), 3, 2, 1)
+    red_ref = K.bn_bwd_reduce(da, a, y, bnp[0], bnp[1], True)
+    dy_ref, _, _, _ = K.bn_bwd_apply(da, a, y, bnp[0], bnp[1], gamma, red_ref, rows, True, False)
+    red = K.maxpool_bn_bwd_reduce(dp, am, y, bnp, 3, 2, 1)
+    # the unfused path rounds the pooled gradient to bf16 before reducing; the fused one keeps it in fp32
+    assert_close(red, red_ref, 6e-3, "fused reduce")
+    dy = K.maxpool_bn_bwd_apply(dp, am, y, bnp, gamma, red, rows, 3, 2, 1)
+    assert_close(dy.float(), dy_ref.float(), 1e-2, "fused apply")
+    # fp32 torch reference of the same chain on the bf16-rounded activation
+    af = a.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    pf = F.max_pool3d(af, 3, 2, 1)
+    pf.backward(dp.float().permute(0, 4, 1, 2, 3).contiguous())
+    g = (af.grad * (af > 0)).permute(0, 2, 3, 4, 1).reshape(-1, C).double()
+    xh = ((y.float().view(-1, C) - bnp[0]) * bnp[1]).double()
+    assert_close(red[0], g.sum(0), 1e-5, "fused reduce vs fp32 reference (sum g)")
+    assert_close(red[1], (g * xh).sum(0), 1e-5, "fused reduce vs fp32 reference (sum g*xhat)")
