@@ -3,6 +3,7 @@
 // The planner turns a conv geometry into (tensor-map views, tap table, output view, box shape) for the
 // tcgen05 kernels in conv_igemm_kernels.cu, or dispatches to the CUDA-core direct engine
 // (conv_direct.cu) for the small-channel convolutions of Small_PET_CNN and the 1-channel stem.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -200,6 +201,10 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.bias = bias;
   p.stat_sum = ssum;
   p.stat_sq = ssq;
+  {
+    const char* dbg = getenv("ADNI_DEBUG_MODE");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   return launch_igemm(p, block_n, stream);
 }
 
@@ -350,7 +355,11 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.cin_blocks = g.Cin / 64;
   p.n_groups = taps * p.cin_blocks;
   // one CTA owns all 512 TMEM columns: mt_cfg accumulators of 128 Cout rows x (512/mt_cfg) K_total columns
-  const int mt_cfg = g.Cout >= 512 ? 4 : (g.Cout >= 256 ? 2 : 1);
+  int mt_cfg = g.Cout >= 256 ? 2 : 1;  // measured best on B200 (tools/wgrad_probe.py)
+  if (const char* e = getenv("ADNI_WGRAD_MT")) {  // tuning / diagnostics override
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) mt_cfg = v;
+  }
   const int groups = 8 / mt_cfg;
   p.N = g.N;
   p.Do = Do;

@@ -34,6 +34,7 @@ struct IgemmParams {
   const float* bias;            // [N_total], nullable
   double* stat_sum;             // [N_total], nullable
   double* stat_sq;
+  int debug;  // diagnostics only (ADNI_DEBUG_MODE): 1 = no MMA issue, 2 = no TMA loads, 3 = no epilogue stores
 };
 
 // wgrad: D[M = Cout rows, N = K_total columns] += sum over position boxes of dY^T * X_tap

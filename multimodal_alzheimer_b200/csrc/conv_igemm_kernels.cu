@@ -134,11 +134,16 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
         for (int kb = 0; kb < p.kc_blocks; kb++) {
           if (lane == 0) {
             mbar_wait(&empty[st], ph ^ 1);
-            mbar_arrive_expect_tx(&full[st], tx_bytes);
+            if (p.debug == 2)
+              mbar_arrive(&full[st]);
+            else
+              mbar_arrive_expect_tx(&full[st], tx_bytes);
           }
           __syncwarp();
-          if (lane == 0) tma_load_5d(smem_a + st * Cfg::A_BYTES, amap, &full[st], kb * 64, w, h, d, c.n);
-          if (lane == 1) tma_load_2d(smem_b + st * Cfg::B_BYTES, &p.b_map, &full[st], tap.kofs + kb * 64, c.n0);
+          if (p.debug != 2) {
+            if (lane == 0) tma_load_5d(smem_a + st * Cfg::A_BYTES, amap, &full[st], kb * 64, w, h, d, c.n);
+            if (lane == 1) tma_load_2d(smem_b + st * Cfg::B_BYTES, &p.b_map, &full[st], tap.kofs + kb * 64, c.n0);
+          }
           if (++st == STAGES) {
             st = 0;
             ph ^= 1;
@@ -158,29 +163,33 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile<BLOCK_N>(p, tile);
       const int nkb = __popcll(tap_mask(c)) * p.kc_blocks;
-      if (lane == 0) {
-        mbar_wait(&tempty[acc], accph ^ 1);
+      // The whole warp walks the loop with warp-uniform state (so ptxas keeps stage / descriptor arithmetic on the
+      // uniform datapath instead of ELECT + R2UR per operand); one elected lane issues the tcgen05 instructions.
+      mbar_wait(&tempty[acc], accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+      for (int i = 0; i < nkb; i++) {
+        mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int i = 0; i < nkb; i++) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t a_lo = desc_lo0 + ((smem_u32(smem_a + st * Cfg::A_BYTES) & 0x3FFFFu) >> 4);
-          const uint32_t b_lo = desc_lo0 + ((smem_u32(smem_b + st * Cfg::B_BYTES) & 0x3FFFFu) >> 4);
+        const uint32_t a_lo = desc_lo0 + ((smem_u32(smem_a + st * Cfg::A_BYTES) & 0x3FFFFu) >> 4);
+        const uint32_t b_lo = desc_lo0 + ((smem_u32(smem_b + st * Cfg::B_BYTES) & 0x3FFFFu) >> 4);
+        if (elect_one_sync()) {
+          if (p.debug != 1) {
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
-                      static_cast<uint32_t>(i | k));
-          umma_commit(&empty[st]);  // frees the smem slot once these MMAs have read it
-          if (++st == STAGES) {
-            st = 0;
-            ph ^= 1;
+            for (int k = 0; k < 4; k++)
+              umma_bf16(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                        static_cast<uint32_t>(i | k));
           }
+          umma_commit(&empty[st]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++st == STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
       }
-      st = __shfl_sync(0xffffffffu, st, 0);
-      ph = __shfl_sync(0xffffffffu, ph, 0);
+      if (elect_one_sync()) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
       if (++acc == 2) {
         acc = 0;
         accph ^= 1;
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
           stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
           stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
         }
-        if (valid) {
+        if (valid && p.debug != 3) {
           if (p.addend != nullptr) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
 #pragma unroll
