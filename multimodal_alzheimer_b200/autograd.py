@@ -27,10 +27,36 @@ def _world():
     return 1
 
 
+# The process group used by the collectives inside the Functions.  Fusion models run their two encoder branches on
+# two CUDA streams; giving each branch its own NCCL communicator keeps one branch's (compute-dependent) reductions
+# from queueing behind the other's.  Forward code selects it with `dp_group(...)`; every Function remembers the
+# group of its forward pass for its backward pass.
+_GROUP = [None]
+
+
+class dp_group:
+    def __init__(self, group):
+        self.group = group
+
+    def __enter__(self):
+        self.prev, _GROUP[0] = _GROUP[0], self.group
+
+    def __exit__(self, *exc):
+        _GROUP[0] = self.prev
+
+
 def _allreduce_(t):
     if _world() > 1:
-        dist.all_reduce(t)
+        dist.all_reduce(t, group=_GROUP[0])
     return t
+
+
+def _with_forward_group(backward):
+    """Decorator for Function.backward: run the backward collectives on the group the forward used."""
+    def wrapped(ctx, *grads):
+        with dp_group(getattr(ctx, "dp_group", None)):
+            return backward(ctx, *grads)
+    return wrapped
 
 
 class BNState:
@@ -122,6 +148,7 @@ class StemFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, bn, cfg, pool):
+        ctx.dp_group = _GROUP[0]
         tc = K.stem_supported(x.shape[-1], w.shape[0], cfg.k, cfg.stride, cfg.pad, cfg.dil)
         if tc:  # tcgen05 path: the W-axis filter window becomes a 16-byte pixel (csrc/conv_stem.cu)
             xs = K.stem_expand(x)
@@ -150,6 +177,7 @@ class StemFn(torch.autograd.Function):
         return p
 
     @staticmethod
+    @_with_forward_group
     def backward(ctx, dp):
         x, y, am, bnp, gamma = ctx.saved_tensors
         dp = dp.contiguous()
@@ -175,6 +203,7 @@ class BasicBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, bn1, bn2, bnd, c1, c2, cd):
+        ctx.dp_group = _GROUP[0]
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
         a1, p1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
@@ -192,6 +221,7 @@ class BasicBlockFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_with_forward_group
     def backward(ctx, dout):
         x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito = ctx.saved_tensors
         c1, c2, cd, n1, n2, nd, ws1, ws2, wsd, need_dx = ctx.cfg
@@ -221,6 +251,7 @@ class BottleneckFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, wd, gd, bd, bn1, bn2, bn3, bnd, c1, c2, c3, cd):
+        ctx.dp_group = _GROUP[0]
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
         a1, p1, n1 = _bn_forward(y1, st1, g1, b1, bn1, None, True)
@@ -242,6 +273,7 @@ class BottleneckFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_with_forward_group
     def backward(ctx, dout):
         (x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
          wd_ito) = ctx.saved_tensors
@@ -302,6 +334,7 @@ class BatchNormActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, stats, gamma, beta, residual, bn, relu):
+        ctx.dp_group = _GROUP[0]
         st = stats if (stats is not None and stats.numel() > 0) else None
         out, bnp, count = _bn_forward(y, st, gamma, beta, bn, residual, relu)
         ctx.save_for_backward(y, out if (relu and residual is not None) else None, bnp, gamma)
@@ -309,6 +342,7 @@ class BatchNormActFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_with_forward_group
     def backward(ctx, dout):
         y, out, bnp, gamma = ctx.saved_tensors
         count, relu, has_res = ctx.cfg
@@ -393,6 +427,7 @@ class LinearFn(torch.autograd.Function):
 class BatchNorm1dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, bn, relu):
+        ctx.dp_group = _GROUP[0]
         x = x.contiguous()
         B, C = x.shape
         if bn.training:
@@ -412,6 +447,7 @@ class BatchNorm1dFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_with_forward_group
     def backward(ctx, dy):
         x, y, mean, invstd, gamma = ctx.saved_tensors
         count, relu = ctx.cfg

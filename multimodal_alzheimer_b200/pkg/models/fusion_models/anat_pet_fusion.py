@@ -8,6 +8,7 @@ mapping (B,1,D,H,W) -> (B,64): `ResNet_PET_Trunk` gives BASELINE.json's two-bran
 import torch
 
 from .... import nn as bnn
+from ....branches import run_two
 from ...loss_functions.focalloss import make_criterion
 from ..base_model import Base_Model, adam_or_plateau, volume_input
 from ..mri_models.anat_cnn import Anat_CNN
@@ -62,8 +63,8 @@ class Anat_PET_CNN(Base_Model):
 
     def forward(self, x_pet, x_mri):
         bs = x_mri.shape[0]
-        out_pet = self.model_pet(x_pet)
-        out_mri = self.model_mri(x_mri)
+        # the two stage-1 trunks are independent: they run on two CUDA streams (multimodal_alzheimer_b200/branches.py)
+        out_pet, out_mri = run_two(lambda: self.model_pet(x_pet), lambda: self.model_mri(x_mri), x_pet)
         out_mri = out_mri.view(bs, -1)
         out_mri = self.reduce_dim_mri(out_mri)
         out = torch.cat((out_pet, out_mri), dim=1)
