@@ -162,7 +162,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, args.cpu_sample_pairs),
+        "config": workload_config(args, args.gpus, args.global_batch or (32 if args.workload == "pet_mri_fusion_r18" else 16)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -420,6 +420,12 @@ def run_b200(args):
         },
         "whole_step_tensor_frac": step_flops / (ms_total / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
     }
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if fusion and vol == 128 and args.depth == 18 and world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:  # DRAM bytes per launch of this kernel on this workload, from the committed ncu capture
+            tr = json.load(f)
+        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get("source")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cstep, cvols, threads = cpu_reference_step_fn(args.workload, args.depth, vol, args.cpu_sample_pairs)

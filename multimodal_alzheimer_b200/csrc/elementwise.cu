@@ -85,29 +85,57 @@ __global__ void bn_finalize_kernel(const double* ssum, const double* ssq, double
   }
 }
 
+__device__ __forceinline__ Vec8 unpack_vec8(const uint4& r) {
+  Vec8 o;
+  o.v[0] = bf16_lo(r.x);
+  o.v[1] = bf16_hi(r.x);
+  o.v[2] = bf16_lo(r.y);
+  o.v[3] = bf16_hi(r.y);
+  o.v[4] = bf16_lo(r.z);
+  o.v[5] = bf16_hi(r.z);
+  o.v[6] = bf16_lo(r.w);
+  o.v[7] = bf16_hi(r.w);
+  return o;
+}
+constexpr int kEwUnroll = 4;  // independent 16-byte loads in flight per thread and tensor
+
 __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ y,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const __nv_bfloat16* __restrict__ res,
                                                               __nv_bfloat16* __restrict__ out, long long nvec, int vpr,
                                                               int relu) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vpr) * 8;
-    Vec8 a = load8(y + i * 8);
-    const Vec8 sc = loadf8(scale + c0), sh = loadf8(shift + c0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kEwUnroll) {
+    uint4 ry[kEwUnroll], rr[kEwUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; j++) a.v[j] = fmaf(a.v[j], sc.v[j], sh.v[j]);
-    if (res) {
-      const Vec8 r = load8(res + i * 8);
-#pragma unroll
-      for (int j = 0; j < 8; j++) a.v[j] += r.v[j];
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        ry[u] = __ldg(reinterpret_cast<const uint4*>(y + i * 8));
+        if (res) rr[u] = __ldg(reinterpret_cast<const uint4*>(res + i * 8));
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) a.v[j] = fmaxf(a.v[j], 0.f);
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) break;
+      const int c0 = (int)(i % vpr) * 8;
+      Vec8 a = unpack_vec8(ry[u]);
+      const Vec8 sc = loadf8(scale + c0), sh = loadf8(shift + c0);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a.v[j] = fmaf(a.v[j], sc.v[j], sh.v[j]);
+      if (res) {
+        const Vec8 r = unpack_vec8(rr[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.v[j] += r.v[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.v[j] = fmaxf(a.v[j], 0.f);
+      }
+      store8(out + i * 8, a);
     }
-    store8(out + i * 8, a);
   }
 }
 
@@ -155,31 +183,48 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
         sh = loadf8(shift + cv * 8);
       }
     }
-    for (long long r = row_begin + rl; r < row_end; r += rpp) {
-      const long long off = r * C + cv * 8;
-      const Vec8 x = load8(a + off);
-      if (MODE == 0) {
+    for (long long r0 = row_begin + rl; r0 < row_end; r0 += (long long)rpp * kEwUnroll) {
+      uint4 ra[kEwUnroll], ry[kEwUnroll], ro[kEwUnroll];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          s0[j] += x.v[j];
-          s1[j] = fmaf(x.v[j], x.v[j], s1[j]);
+      for (int u = 0; u < kEwUnroll; u++) {  // all loads of the batch are issued before the first use
+        const long long r = r0 + (long long)u * rpp;
+        if (r < row_end) {
+          const long long off = r * C + cv * 8;
+          ra[u] = __ldg(reinterpret_cast<const uint4*>(a + off));
+          if (MODE == 1) {
+            ry[u] = __ldg(reinterpret_cast<const uint4*>(yraw + off));
+            if (relu == 1) ro[u] = __ldg(reinterpret_cast<const uint4*>(outp + off));
+          }
         }
-      } else {
-        Vec8 g = x;
-        const Vec8 yv = load8(yraw + off);
-        if (relu == 1) {
-          const Vec8 o = load8(outp + off);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
-        } else if (relu == 2) {
+      for (int u = 0; u < kEwUnroll; u++) {
+        const long long r = r0 + (long long)u * rpp;
+        if (r >= row_end) break;
+        const Vec8 x = unpack_vec8(ra[u]);
+        if (MODE == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) g.v[j] = fmaf(yv.v[j], sc.v[j], sh.v[j]) > 0.f ? g.v[j] : 0.f;
-        }
+          for (int j = 0; j < 8; j++) {
+            s0[j] += x.v[j];
+            s1[j] = fmaf(x.v[j], x.v[j], s1[j]);
+          }
+        } else {
+          Vec8 g = x;
+          const Vec8 yv = unpack_vec8(ry[u]);
+          if (relu == 1) {
+            const Vec8 o = unpack_vec8(ro[u]);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
-          s0[j] += g.v[j];
-          s1[j] = fmaf(g.v[j], xh, s1[j]);
+            for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+          } else if (relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) g.v[j] = fmaf(yv.v[j], sc.v[j], sh.v[j]) > 0.f ? g.v[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float xh = (yv.v[j] - mu.v[j]) * is.v[j];
+            s0[j] += g.v[j];
+            s1[j] = fmaf(g.v[j], xh, s1[j]);
+          }
         }
       }
     }
@@ -228,25 +273,41 @@ __global__ void __launch_bounds__(kEwThreads)
     coef[4 * C + c] = relu == 2 ? shift[c] : 0.f;
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vpr) * 8;
-    Vec8 g = load8(dout + i * 8);
-    const Vec8 yv = load8(yraw + i * 8);
-    if (relu == 1) {
-      const Vec8 o = load8(outp + i * 8);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kEwUnroll) {
+    uint4 rg[kEwUnroll], ry[kEwUnroll], ro[kEwUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
-    } else if (relu == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) g.v[j] = fmaf(yv.v[j], coef[3 * C + c0 + j], coef[4 * C + c0 + j]) > 0.f ? g.v[j] : 0.f;
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        rg[u] = __ldg(reinterpret_cast<const uint4*>(dout + i * 8));
+        ry[u] = __ldg(reinterpret_cast<const uint4*>(yraw + i * 8));
+        if (relu == 1) ro[u] = __ldg(reinterpret_cast<const uint4*>(outp + i * 8));
+      }
     }
-    if (dres) store8(dres + i * 8, g);
-    Vec8 r;
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      r.v[j] = fmaf(coef[c0 + j], g.v[j], fmaf(coef[C + c0 + j], yv.v[j], coef[2 * C + c0 + j]));
-    store8(dy + i * 8, r);
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) break;
+      const int c0 = (int)(i % vpr) * 8;
+      Vec8 g = unpack_vec8(rg[u]);
+      const Vec8 yv = unpack_vec8(ry[u]);
+      if (relu == 1) {
+        const Vec8 o = unpack_vec8(ro[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = o.v[j] > 0.f ? g.v[j] : 0.f;
+      } else if (relu == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          g.v[j] = fmaf(yv.v[j], coef[3 * C + c0 + j], coef[4 * C + c0 + j]) > 0.f ? g.v[j] : 0.f;
+      }
+      if (dres) store8(dres + i * 8, g);
+      Vec8 r;
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        r.v[j] = fmaf(coef[c0 + j], g.v[j], fmaf(coef[C + c0 + j], yv.v[j], coef[2 * C + c0 + j]));
+      store8(dy + i * 8, r);
+    }
   }
 }
 

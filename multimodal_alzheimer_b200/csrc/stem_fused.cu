@@ -46,8 +46,11 @@ __global__ void __launch_bounds__(kThreads)
                             uint8_t* __restrict__ amax) {
   __shared__ uint4 s_a[kFI * kFI * kFI * kFCv];
   const int vpr = C / 8;
-  const int cv0 = blockIdx.y * kFCv;
-  int t = blockIdx.x;
+  // channel chunks are the fastest-varying block index: the blocks sharing a voxel tile (and its 128-byte lines)
+  // run at the same time, so the second half of every line is an L2 hit instead of a second DRAM read
+  const int n_chunks = (vpr + kFCv - 1) / kFCv;
+  const int cv0 = (blockIdx.x % n_chunks) * kFCv;
+  int t = blockIdx.x / n_chunks;
   const int tw = t % tiles_w;
   t /= tiles_w;
   const int th = t % tiles_h;
@@ -142,8 +145,9 @@ __global__ void __launch_bounds__(kThreads, 3)
   extern __shared__ float s_g[];  // [512 voxels][kBCv][8]
   __shared__ float s_red[2][kThreads / kBCv][kBCv * 8 + 1];
   const int vpr = C / 8;
-  const int cv0 = blockIdx.y * kBCv;
-  int t = blockIdx.x;
+  const int n_chunks = (vpr + kBCv - 1) / kBCv;  // fastest-varying: see bn_relu_pool_fwd_kernel
+  const int cv0 = (blockIdx.x % n_chunks) * kBCv;
+  int t = blockIdx.x / n_chunks;
   const int tw = t % tiles_w;
   t /= tiles_w;
   const int th = t % tiles_h;
@@ -292,7 +296,7 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int td = (Do + kFT - 1) / kFT, th = (Ho + kFT - 1) / kFT, tw = (Wo + kFT - 1) / kFT;
-  dim3 grid((unsigned)((long long)N * td * th * tw), (unsigned)((C / 8 + kFCv - 1) / kFCv));
+  dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kFCv - 1) / kFCv)));
   bn_relu_pool_fwd_kernel<<<grid, kThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift, N, D, H, W,
                                                              C, Do, Ho, Wo, td, th, tw, reinterpret_cast<bf16*>(p),
                                                              argmax);
@@ -308,7 +312,7 @@ int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int td = (D + kBT - 1) / kBT, th = (H + kBT - 1) / kBT, tw = (W + kBT - 1) / kBT;
-  dim3 grid((unsigned)((long long)N * td * th * tw), (unsigned)((C / 8 + kBCv - 1) / kBCv));
+  dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kBCv - 1) / kBCv)));
   static bool attr0 = false;
   if (!attr0) {
     ADNI_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -332,7 +336,7 @@ int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const 
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int td = (D + kBT - 1) / kBT, th = (H + kBT - 1) / kBT, tw = (W + kBT - 1) / kBT;
-  dim3 grid((unsigned)((long long)N * td * th * tw), (unsigned)((C / 8 + kBCv - 1) / kBCv));
+  dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kBCv - 1) / kBCv)));
   static bool attr1 = false;
   if (!attr1) {
     ADNI_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -3,5 +3,8 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/tests.log 2>&1
 echo "tests exit $?"; tail -n 2 gpurun_out/tests.log
-timeout 1200 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --shape-profile gpurun_out/shapes.json > gpurun_out/bench_full.log 2>&1
-echo "bench full exit $?"; tail -n 1 gpurun_out/bench_full.log | cut -c1-200
+timeout 1200 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --shape-profile gpurun_out/shapes.json > gpurun_out/bench_full.log 2>&1
+echo "bench full exit $?"; tail -n 1 gpurun_out/bench_full.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:d[k] for k in ('value','ms_per_step','launch_mode')}, d['eager']['ms_per_step'], d['roofline']['frac'])"
