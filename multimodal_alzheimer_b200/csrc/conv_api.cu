@@ -16,6 +16,8 @@ namespace adni {
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
+int halo_plan_smem(HaloParams* p, int block_n);
+int launch_igemm_halo(const HaloParams& p, int block_n, int smem_bytes, cudaStream_t stream);
 
 int direct_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti,
                       const float* bias, __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
@@ -134,8 +136,78 @@ bool tc_supported(const adni_conv3d_geom& g) {
 int pick_block_n(int n_total) { return n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64); }
 
 // ---------------------------------------------------------------------------------------------
+// Halo-resident engine (conv_halo.cu): 3x3x3 / stride 1 / dilation 1 / pad 1, Cin == Cout in {64, 128}.
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+bool halo_supported(const adni_conv3d_geom& g) {
+  return g.k == 3 && g.stride == 1 && g.dil == 1 && g.pad == 1 && g.Cin == g.Cout && (g.Cin == 64 || g.Cin == 128) &&
+         env_int("ADNI_HALO", 1) != 0;
+}
+
+// `a` is the tensor the taps slide over (x for fprop, dy for dgrad), `w` the matching K-major weight copy
+// (OTI / ITO), `mirror` selects dgrad's flipped tap order.  Returns ADNI_ENOTSUP when the tile set does not fit.
+int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat16* w, bool mirror, const float* bias,
+            const __nv_bfloat16* addend, __nv_bfloat16* out, double* ssum, double* ssq, cudaStream_t stream) {
+  const int C = g.Cin;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.pitch = env_int("ADNI_HALO_PITCH", 10);
+  p.debug = env_int("ADNI_HALO_DEBUG", 0);
+  p.kb = C / 64;
+  if (p.pitch < 10 || p.pitch > 16) return ADNI_ENOTSUP;
+  const int smem_bytes = halo_plan_smem(&p, C);
+  if (smem_bytes == 0) return ADNI_ENOTSUP;
+  {
+    const uint64_t dims[5] = {uint64_t(C), uint64_t(g.W), uint64_t(g.H), uint64_t(g.D), uint64_t(g.N)};
+    const uint64_t strides[5] = {1, uint64_t(C), uint64_t(g.W) * C, uint64_t(g.H) * g.W * C,
+                                 uint64_t(g.D) * g.H * g.W * C};
+    const uint32_t box[5] = {64, uint32_t(p.pitch), 18, 1, 1};
+    int rc = make_tmap_bf16(&p.a_map, a, 5, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(27) * C, uint64_t(C)};
+    const uint64_t strides[2] = {1, uint64_t(27) * C};
+    const uint32_t box[2] = {64, uint32_t(C)};
+    int rc = make_tmap_bf16(&p.b_map, w, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  for (int od = 0; od < 3; od++)
+    for (int oh = 0; oh < 3; oh++)
+      for (int ow = 0; ow < 3; ow++) {
+        const int t = mirror ? ((2 - od) * 3 + (2 - oh)) * 3 + (2 - ow) : (od * 3 + oh) * 3 + ow;
+        p.kofs[(od * 3 + oh) * 3 + ow] = t * C;
+      }
+  p.N = g.N;
+  p.D = g.D;
+  p.H = g.H;
+  p.W = g.W;
+  p.tiles_h = (g.H + 15) / 16;
+  p.tiles_w = (g.W + 7) / 8;
+  const long long total = (long long)g.N * p.tiles_h * p.tiles_w * g.D;
+  if (total > 0x7fffffffLL) return ADNI_ENOTSUP;
+  p.total = int(total);
+  p.out_sw = C;
+  p.out_sh = (long long)g.W * C;
+  p.out_sd = (long long)g.H * g.W * C;
+  p.out_sn = (long long)g.D * g.H * g.W * C;
+  p.out = out;
+  p.addend = addend;
+  p.bias = bias;
+  p.stat_sum = ssum;
+  p.stat_sq = ssq;
+  return launch_igemm_halo(p, C, smem_bytes, stream);
+}
+
 int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,
              __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream) {
+  if (halo_supported(g)) {
+    const int rc = tc_halo(g, x, w_oti, false, bias, nullptr, y, ssum, ssq, stream);
+    if (rc != ADNI_ENOTSUP) return rc;
+  }
   const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
   const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
   const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
@@ -211,6 +283,10 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
 // dx = sum_k dy[(i + pad - k*dil)/stride] * w[k]^T, one launch per parity class of dx when stride > 1.
 int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
              const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream) {
+  if (halo_supported(g)) {
+    const int rc = tc_halo(g, dy, w_ito, true, nullptr, addend, dx, nullptr, nullptr, stream);
+    if (rc != ADNI_ENOTSUP) return rc;
+  }
   const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
   const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
   const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
