@@ -113,9 +113,23 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // Hot path: poll only.  %globaltimer is a slow system-level read (hundreds of cycles); touching it on every
-  // wait that is not satisfied at once serialised the TMA producers at one pipeline stage per ~650-800 cycles.
-  // It is sampled once per 4096 failed polls, only to turn a dead pipeline into a trap instead of a hang.
+  // NOTE (measured, tools/ubench + wgrad shape profile): the %globaltimer read after the first failed poll acts as a
+  // back-off.  Polling try_wait in a tight loop from the first failure on made every tcgen05 kernel slower (wgrad
+  // -35 %, fprop -5 %): the polls compete with the TMA complete_tx / tcgen05.commit updates of the same barrier.
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0 && global_timer_ns() - t0 > 4000000000ull) {  // 4 s: the pipeline is dead
+      printf("adni_b200: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// Tight polling variant.  Measured better for the producer / MMA-issuer threads of the igemm and halo conv kernels
+// (short stages, double-buffered accumulators: fprop+dgrad 27.4 -> 26.3 ms per step) and worse for wgrad2 / stem.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -124,11 +138,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       if (t0 == 0) {
         t0 = t;
       } else if (t - t0 > 4000000000ull) {  // 4 s: the pipeline is dead
-        printf("adni_b200: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+        printf("adni_b200: mbarrier timeout (spin) block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
         __trap();
       }
     }
   }
+}
+
+// Whole-warp wait for warps that are NOT on the critical path (epilogue warps waiting for an accumulator): lane 0
+// polls with a back-off sleep, the other lanes park on the warp barrier.  128 threads spinning on try_wait for a whole
+// main loop take issue slots and shared-memory bandwidth from the single TMA / MMA issuing threads (wgrad: -35 %).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(64);
+      if ((++spins & 4095u) == 0) {
+        const uint64_t t = global_timer_ns();
+        if (t0 == 0) {
+          t0 = t;
+        } else if (t - t0 > 4000000000ull) {
+          printf("adni_b200: mbarrier timeout (parked) block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
         const HaloSeg s = halo_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
           const uint32_t slot = seq % ring, par = (seq / ring) & 1u;
-          mbar_wait(&empty_p[slot], par ^ 1u);
+          mbar_wait_spin(&empty_p[slot], par ^ 1u);
           if (p.debug & 4) {
             mbar_arrive(&full_p[slot]);
             continue;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
             for (int kh = 0; kh < 3; kh++) {
               for (int kw0 = 0; kw0 < 3; kw0 += p.tps) {
                 for (int kb = 0; kb < p.kb; kb++) {
-                  mbar_wait(&empty_b[st], ph ^ 1u);
+                  mbar_wait_spin(&empty_b[st], ph ^ 1u);
                   if (p.debug & 2) {
                     mbar_arrive(&full_b[st]);
                   } else {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     for (int i = begin; i < end;) {
       const HaloSeg s = halo_segment(p, i, end);
       for (int d = s.dA; d < s.dB; d++) {
-        mbar_wait(&tempty[acc], accph ^ 1u);
+        mbar_wait_spin(&tempty[acc], accph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (mw * 2u + static_cast<uint32_t>(acc)) * BLOCK_N;
         uint32_t accum = 0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
           const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
           const uint32_t slot = sq % ring;
           while (waited <= sq) {  // planes become visible in load order; each is waited for exactly once
-            mbar_wait(&full_p[waited % ring], (waited / ring) & 1u);
+            mbar_wait_spin(&full_p[waited % ring], (waited / ring) & 1u);
             waited++;
           }
           const uint32_t plane_addr = smem_p_u32 + slot * plane_bytes;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
             for (int kw0 = 0; kw0 < 3; kw0 += p.tps) {
               for (int kb = 0; kb < p.kb; kb++, gs++) {
                 if ((gs & 1u) == mw) {
-                  mbar_wait(&full_b[st], ph);
+                  mbar_wait_spin(&full_b[st], ph);
                   tc_fence_after();
                   const uint32_t a_lo =
                       ((plane_addr + kb * p.plane_kb_bytes + static_cast<uint32_t>(kh * p.pitch + kw0) * 128u) & 0x3FFFFu) >> 4;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       const bool valid = oh < p.H && ow < p.W;
       for (int d = s.dA; d < s.dB; d++) {
         const long long off = s.n * p.out_sn + d * p.out_sd + oh * p.out_sh + ow * p.out_sw;
-        mbar_wait(&tfull[acc], accph);
+        mbar_wait_parked(&tfull[acc], accph);
         tc_fence_after();
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {

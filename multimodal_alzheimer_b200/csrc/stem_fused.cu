@@ -3,6 +3,8 @@
 // its gradient (33.5 MB per volume each).  HBM traffic per volume: forward reads y once; backward reads y twice
 // (reduction pass, apply pass) and writes dy once.
 //   MedicalNet ResNet.forward: x = maxpool(relu(bn1(conv1(x))))   (call site pkg/models/mri_models/anat_cnn.py:95)
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -273,6 +275,287 @@ __global__ void __launch_bounds__(kThreads, 3)
   }
 }
 
+
+// ================================================================================================
+// Streaming variants (default).  No shared-memory staging, no block-wide phases: every thread keeps its loads in
+// flight while it computes, and every 128-byte line of y is requested as a whole line by 8 neighbouring lanes.
+// ================================================================================================
+
+// Forward.  Thread = one pooled (oh, ow) column x 8 channels, marching along od.  Max-pooling is separable with the
+// first-maximum tie rule intact: the in-plane winner is the first maximum in (kh, kw) order, planes are compared in
+// kd order with a strict '>'.  The odd input plane 2*od+1 is shared by outputs od and od+1: its in-plane result is
+// carried in registers, so every input plane is read (and BN+ReLU'd) once per thread.
+constexpr int kSFh = 2, kSFw = 8, kSFThreads = kSFh * kSFw * 8;  // 2 x 8 pooled columns x 8 channel vectors
+
+struct PlaneMax {
+  float v[8];
+  uint32_t idx;  // 8 nibbles: kh*3 + kw of the winner of every channel
+};
+
+__device__ __forceinline__ PlaneMax plane_max(const __nv_bfloat16* __restrict__ yplane, int H, int W, int C, int oh, int ow,
+                                              int coff, const float* __restrict__ sc, const float* __restrict__ sh) {
+  uint4 raw[9];
+  bool ok[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++) {
+      const int ih = oh * kS - kPad + kh, iw = ow * kS - kPad + kw;
+      const bool v = ih >= 0 && ih < H && iw >= 0 && iw < W;
+      ok[kh * 3 + kw] = v;
+      raw[kh * 3 + kw] = v ? __ldg(reinterpret_cast<const uint4*>(yplane + ((long long)ih * W + iw) * C + coff))
+                           : make_uint4(0, 0, 0, 0);
+    }
+  }
+  PlaneMax m;
+#pragma unroll
+  for (int j = 0; j < 8; j++) m.v[j] = -INFINITY;
+  m.idx = 0;
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    if (!ok[t]) continue;
+    float f[8];
+    unpack8(raw[t], f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    float r[8];
+    unpack8(pack8(f), r);  // compare what bn_apply would have stored: the bf16-rounded activation
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (r[j] > m.v[j]) {  // first maximum in (kh, kw) order wins
+        m.v[j] = r[j];
+        m.idx = (m.idx & ~(0xFu << (4 * j))) | (static_cast<uint32_t>(t) << (4 * j));
+      }
+    }
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(kSFThreads)
+    bn_relu_pool_fwd_stream_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho, int Wo,
+                                   int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
+                                   uint8_t* __restrict__ amax) {
+  const int vpr = C / 8;
+  __shared__ float s_sc[64], s_sh[64];  // the block's 64 channels
+  if (threadIdx.x < 64) {
+    const int c = min(blockIdx.y * 64 + (int)threadIdx.x, C - 1);
+    s_sc[threadIdx.x] = scale[c];
+    s_sh[threadIdx.x] = shift[c];
+  }
+  __syncthreads();
+  const int cv = blockIdx.y * 8 + (threadIdx.x & 7);
+  const int lw = (threadIdx.x >> 3) % kSFw, lh = threadIdx.x / (8 * kSFw);
+  int t = blockIdx.x;
+  const int ds = t % dsplit;
+  t /= dsplit;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  const int n = t / tiles_h;
+  const int oh = th * kSFh + lh, ow = tw * kSFw + lw;
+  if (oh >= Ho || ow >= Wo || cv >= vpr) return;
+  const int per = (Do + dsplit - 1) / dsplit;
+  const int od_begin = ds * per, od_end = min(Do, od_begin + per);
+  if (od_begin >= od_end) return;
+  const int coff = cv * 8;
+  const float* sc = s_sc + (threadIdx.x & 7) * 8;
+  const float* sh = s_sh + (threadIdx.x & 7) * 8;
+  const long long plane = (long long)H * W * C;
+  const __nv_bfloat16* ys = y + (long long)n * D * plane;
+  PlaneMax carry;
+  bool have_carry = false;
+  if (od_begin * kS - kPad >= 0) {  // the plane below the first output of this d-range
+    carry = plane_max(ys + (long long)(od_begin * kS - kPad) * plane, H, W, C, oh, ow, coff, sc, sh);
+    have_carry = true;
+  }
+  for (int od = od_begin; od < od_end; od++) {
+    float best[8];
+    uint32_t bidx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      best[j] = have_carry ? carry.v[j] : -INFINITY;
+      bidx[j] = have_carry ? ((carry.idx >> (4 * j)) & 0xFu) : 0xFFu;
+    }
+    const PlaneMax mid = plane_max(ys + (long long)(od * kS) * plane, H, W, C, oh, ow, coff, sc, sh);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (mid.v[j] > best[j]) {
+        best[j] = mid.v[j];
+        bidx[j] = 9u + ((mid.idx >> (4 * j)) & 0xFu);
+      }
+    }
+    have_carry = od * kS + 1 < D;
+    if (have_carry) {
+      carry = plane_max(ys + (long long)(od * kS + 1) * plane, H, W, C, oh, ow, coff, sc, sh);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (carry.v[j] > best[j]) {
+          best[j] = carry.v[j];
+          bidx[j] = 18u + ((carry.idx >> (4 * j)) & 0xFu);
+        }
+      }
+    }
+    const long long oi = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * vpr + cv;
+    *reinterpret_cast<uint4*>(p + oi * 8) = pack8(best);
+    uint2 pk;
+    pk.x = (bidx[0] & 255u) | ((bidx[1] & 255u) << 8) | ((bidx[2] & 255u) << 16) | ((bidx[3] & 255u) << 24);
+    pk.y = (bidx[4] & 255u) | ((bidx[5] & 255u) << 8) | ((bidx[6] & 255u) << 16) | ((bidx[7] & 255u) << 24);
+    *reinterpret_cast<uint2*>(amax + oi * 8) = pk;
+  }
+}
+
+// Backward as a GATHER over 2x2x2 input cells.  Thread = the 8 voxels (2cd+ed, 2ch+eh, 2cw+ew), e in {0,1}, of one
+// cell x 8 channels.  Along every axis a voxel with an even coordinate is the centre tap of window c, an odd one the
+// last tap of window c and the first tap of window c+1, so the cell only ever receives gradient from the 2x2x2
+// windows (c + a), a in {0,1}: the thread loads those 8 (dp, arg-max) vectors once, and every voxel adds dp where the
+// recorded arg-max slot is its own tap (fixed order: deterministic, no atomics, no shared-memory staging).  Then the
+// ReLU mask recomputed from y and
+//   MODE 0: sum g, sum g*xhat per channel (block reduction, fp64 atomics per block);
+//   MODE 1: dy = A*g + B*y + K.
+constexpr int kGThreads = 128;
+
+__device__ __forceinline__ constexpr int pool_tap(int e, int a) { return e == 0 ? 1 : (a == 0 ? 2 : 0); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kGThreads, 3)
+    pool_bn_bwd_cell_kernel(const __nv_bfloat16* __restrict__ dp, const uint8_t* __restrict__ amax,
+                            const __nv_bfloat16* __restrict__ y, const float* __restrict__ bnp /* [4][C] */,
+                            const float* __restrict__ gamma, const double* __restrict__ red_in, double inv_count, int N,
+                            int D, int H, int W, int C, int Do, int Ho, int Wo, double* __restrict__ red_out,
+                            __nv_bfloat16* __restrict__ dy) {
+  const int vpr = C / 8;  // power of two <= 32 (checked by the launcher): a thread's channel vector never changes
+  const int cv = threadIdx.x & (vpr - 1);
+  const int coff = cv * 8;
+  // per-channel constants live in shared memory (7 x 8 registers per thread otherwise): mu, is, sc, sh, A, B, K
+  __shared__ float s_c[7][256];
+  for (int c = threadIdx.x; c < C; c += kGThreads) {
+    const float mu = bnp[c], is = bnp[C + c];
+    s_c[0][c] = mu;
+    s_c[1][c] = is;
+    s_c[2][c] = bnp[2 * C + c];
+    s_c[3][c] = bnp[3 * C + c];
+    if (MODE == 1) {
+      const float gm = gamma ? gamma[c] : 1.f;
+      const float mg = (float)(red_in[c] * inv_count), mgx = (float)(red_in[C + c] * inv_count);
+      const float a = gm * is, b = -a * is * mgx;
+      s_c[4][c] = a;
+      s_c[5][c] = b;
+      s_c[6][c] = -a * mg - b * mu;
+    }
+  }
+  __syncthreads();
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) a0[j] = a1[j] = 0.f;
+
+  const int Cd = (D + 1) / 2, Ch = (H + 1) / 2, Cw = (W + 1) / 2;
+  const long long items = (long long)N * Cd * Ch * Cw * vpr;
+  const long long stride = (long long)gridDim.x * kGThreads;
+  const long long sW = C, sH = (long long)W * C, sD = (long long)H * W * C;
+  for (long long it = (long long)blockIdx.x * kGThreads + threadIdx.x; it < items; it += stride) {
+    long long r = it / vpr;
+    const int cw = (int)(r % Cw);
+    r /= Cw;
+    const int ch = (int)(r % Ch);
+    r /= Ch;
+    const int cd = (int)(r % Cd);
+    const int n = (int)(r / Cd);
+    const bool vd1 = 2 * cd + 1 < D, vh1 = 2 * ch + 1 < H, vw1 = 2 * cw + 1 < W;
+    const long long ybase = ((((long long)n * D + 2 * cd) * H + 2 * ch) * W + 2 * cw) * C + coff;
+    // all loads of the item are issued before the first use: 8 y vectors, 8 windows
+    uint4 yr[8];
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+      const int ed = v >> 2, eh = (v >> 1) & 1, ew = v & 1;
+      const bool ok = (!ed || vd1) && (!eh || vh1) && (!ew || vw1);
+      yr[v] = ok ? __ldg(reinterpret_cast<const uint4*>(y + ybase + ed * sD + eh * sH + ew * sW)) : make_uint4(0, 0, 0, 0);
+    }
+    uint4 wd[8];
+    uint2 wm[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const int ad = w >> 2, ah = (w >> 1) & 1, aw = w & 1;
+      const bool ok = cd + ad < Do && ch + ah < Ho && cw + aw < Wo;
+      const long long o = ((((long long)n * Do + cd + ad) * Ho + ch + ah) * Wo + cw + aw) * vpr + cv;
+      wd[w] = ok ? __ldg(reinterpret_cast<const uint4*>(dp + o * 8)) : make_uint4(0, 0, 0, 0);
+      wm[w] = ok ? __ldg(reinterpret_cast<const uint2*>(amax + o * 8)) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+      const int ed = v >> 2, eh = (v >> 1) & 1, ew = v & 1;
+      const bool ok = (!ed || vd1) && (!eh || vh1) && (!ew || vw1);
+      if (!ok) continue;  // warp-uniform except at the ragged W edge
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) g[j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        const int ad = w >> 2, ah = (w >> 1) & 1, aw = w & 1;
+        if (ad > ed || ah > eh || aw > ew) continue;  // compile-time: an even coordinate only sees window c
+        const uint32_t slot = static_cast<uint32_t>((pool_tap(ed, ad) * 3 + pool_tap(eh, ah)) * 3 + pool_tap(ew, aw));
+        const uint32_t eq_lo = __vcmpeq4(wm[w].x, slot * 0x01010101u), eq_hi = __vcmpeq4(wm[w].y, slot * 0x01010101u);
+        float f[8];
+        unpack8(wd[w], f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t m = (j < 4 ? eq_lo : eq_hi) & (0xFFu << ((j & 3) * 8));
+          g[j] += m ? f[j] : 0.f;
+        }
+      }
+      float yv[8];
+      unpack8(yr[v], yv);
+#pragma unroll
+      for (int j = 0; j < 8; j++) g[j] = fmaf(yv[j], s_c[2][coff + j], s_c[3][coff + j]) > 0.f ? g[j] : 0.f;  // ReLU mask
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          a0[j] += g[j];
+          a1[j] = fmaf(g[j], (yv[j] - s_c[0][coff + j]) * s_c[1][coff + j], a1[j]);
+        }
+      } else {
+        float rr[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) rr[j] = fmaf(s_c[4][coff + j], g[j], fmaf(s_c[5][coff + j], yv[j], s_c[6][coff + j]));
+        *reinterpret_cast<uint4*>(dy + ybase + ed * sD + eh * sH + ew * sW) = pack8(rr);
+      }
+    }
+  }
+  if (MODE == 0) {
+    __shared__ float s_part[2][kGThreads / 32][32 * 8 + 8];
+    // lanes with the same (lane mod vpr) hold the same channels: fold them with shuffles, then across warps in smem
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      for (int o = 16; o >= vpr; o >>= 1) {
+        a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
+        a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < vpr) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        s_part[0][warp][lane * 8 + j] = a0[j];
+        s_part[1][warp][lane * 8 + j] = a1[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kGThreads) {
+      const int which = i / C, c = i % C;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGThreads / 32; w++) s += s_part[which][w][c];
+      atomicAdd(red_out + which * C + c, (double)s);
+    }
+  }
+}
+
+int pool_variant() {
+  const char* e = getenv("ADNI_POOL_STREAM");
+  return e ? atoi(e) : 1;
+}
+bool pow2_le32(int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; }
+
 int check_pool(int C, int k, int stride, int pad) {
   ADNI_REQUIRE(k == 3 && stride == 2 && pad == 1, ADNI_ENOTSUP,
                "fused stem pooling supports MaxPool3d(3, 2, 1) only (k=%d s=%d p=%d)", k, stride, pad);
@@ -295,6 +578,17 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
   int rc = check_pool(C, k, stride, pad);
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  if (pool_variant()) {
+    const int th = (Ho + kSFh - 1) / kSFh, tw = (Wo + kSFw - 1) / kSFw;
+    const int dsplit = Do >= 16 ? 2 : 1;
+    dim3 grid((unsigned)((long long)N * th * tw * dsplit), (unsigned)((C / 8 + 7) / 8));
+    bn_relu_pool_fwd_stream_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift,
+                                                                        D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
+                                                                        reinterpret_cast<bf16*>(p), argmax);
+    count_launch();
+    ADNI_LAUNCH_CHECK("bn_relu_pool_fwd_stream_kernel");
+    return ADNI_OK;
+  }
   const int td = (Do + kFT - 1) / kFT, th = (Ho + kFT - 1) / kFT, tw = (Wo + kFT - 1) / kFT;
   dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kFCv - 1) / kFCv)));
   bn_relu_pool_fwd_kernel<<<grid, kThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift, N, D, H, W,
@@ -311,6 +605,14 @@ int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const
   int rc = check_pool(C, k, stride, pad);
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  if (pool_variant() && pow2_le32(C / 8)) {
+    pool_bn_bwd_cell_kernel<0><<<num_sms() * 3, kGThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(dp), argmax, reinterpret_cast<const bf16*>(y), bnp, nullptr, nullptr, 0.0, N, D, H,
+        W, C, Do, Ho, Wo, red, nullptr);
+    count_launch();
+    ADNI_LAUNCH_CHECK("pool_bn_bwd_cell_kernel<0>");
+    return ADNI_OK;
+  }
   const int td = (D + kBT - 1) / kBT, th = (H + kBT - 1) / kBT, tw = (W + kBT - 1) / kBT;
   dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kBCv - 1) / kBCv)));
   static bool attr0 = false;
@@ -335,6 +637,14 @@ int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const 
   int rc = check_pool(C, k, stride, pad);
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  if (pool_variant() && pow2_le32(C / 8)) {
+    pool_bn_bwd_cell_kernel<1><<<num_sms() * 3, kGThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const bf16*>(dp), argmax, reinterpret_cast<const bf16*>(y), bnp, gamma, red, 1.0 / count, N, D,
+        H, W, C, Do, Ho, Wo, nullptr, reinterpret_cast<bf16*>(dy));
+    count_launch();
+    ADNI_LAUNCH_CHECK("pool_bn_bwd_cell_kernel<1>");
+    return ADNI_OK;
+  }
   const int td = (D + kBT - 1) / kBT, th = (H + kBT - 1) / kBT, tw = (W + kBT - 1) / kBT;
   dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kBCv - 1) / kBCv)));
   static bool attr1 = false;
