@@ -255,6 +255,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     const int row = q * 32 + lane;
     const int rh = row / kHaloBoxW, rw = row % kHaloBoxW;
     const bool do_stats = p.stat_sum != nullptr;
+    // BatchNorm sums are carried per CTA in fp64 registers and flushed ONCE: same-address fp64 atomics retire at
+    // ~1 per 27 cycles in L2, so one atomic per (piece, channel) from 148 CTAs is a serial bottleneck of its own
+    // (stem: 65536 pieces x 27 cycles = the whole kernel time).
+    double cta_sum = 0.0, cta_sq = 0.0;
     int acc = 0;
     uint32_t accph = 0;
     for (int i = begin; i < end;) {
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       const bool valid = oh < p.H && ow < p.W;
       for (int d = s.dA; d < s.dB; d++) {
         const long long off = s.n * p.out_sn + d * p.out_sd + oh * p.out_sh + ow * p.out_sw;
-        mbar_wait_parked(&tfull[acc], accph);
+        mbar_wait_spin(&tfull[acc], accph);
         tc_fence_after();
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
@@ -329,20 +333,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
         }
         if (do_stats) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int col = et; col < BLOCK_N; col += 128) {
+          if (et < BLOCK_N) {  // BLOCK_N <= 128: thread et owns channel et
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int w4 = 0; w4 < 4; w4++) {
-              a += stat_smem[(w4 * 2 + 0) * BLOCK_N + col];
-              b += stat_smem[(w4 * 2 + 1) * BLOCK_N + col];
+              a += stat_smem[(w4 * 2 + 0) * BLOCK_N + et];
+              b += stat_smem[(w4 * 2 + 1) * BLOCK_N + et];
             }
-            atomicAdd(p.stat_sum + col, static_cast<double>(a));
-            atomicAdd(p.stat_sq + col, static_cast<double>(b));
+            cta_sum += static_cast<double>(a);
+            cta_sq += static_cast<double>(b);
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       i += s.dB - s.dA;
+    }
+    if (do_stats && et < BLOCK_N && begin < end) {
+      atomicAdd(p.stat_sum + et, cta_sum);
+      atomicAdd(p.stat_sq + et, cta_sq);
     }
   }
 

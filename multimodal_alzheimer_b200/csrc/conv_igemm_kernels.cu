@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
       const bool valid = rd < p.bd && od < p.Do && oh < p.Ho && ow < p.Wo;
       const long long off = c.n * p.out_sn + od * p.out_sd + oh * p.out_sh + ow * p.out_sw + c.n0;
 
-      mbar_wait_parked(&tfull[acc], accph);
+      mbar_wait_spin(&tfull[acc], accph);
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {

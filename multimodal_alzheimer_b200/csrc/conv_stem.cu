@@ -10,6 +10,8 @@
 // stays resident in shared memory for the life of the CTA.
 //   fprop : D[128 positions][64 cout]  = sum_{kd,kh} X8box(kd,kh)[128][8] * W[(kd,kh)][64][8]^T
 //   wgrad : D[(kd,kh,j)][64 cout]     += sum_pos X8box(kd,kh)[pos][j] * dY[pos][cout]   (A, B both MN-major)
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,6 +29,9 @@ constexpr int kTapsP = kK * kKP;  // 56 (kd, kh padded) taps
 struct StemParams {
   CUtensorMap x_maps[4];  // (pd, ph) parity views of X8: dims (8, W', H2, D2, N)
   CUtensorMap dy_map;     // wgrad only: (64, Wo, Ho, Do, N) box (64, bw, bh, bd, 1), 128-B swizzle
+  CUtensorMap x_plane;    // plane-resident fprop: (W'*8, H, D, N) view of X8, box (64, 38, 1, 1)
+  int D, H;               // input extents (plane-resident fprop)
+  int total;              // plane-resident fprop: N * tiles_h * tiles_w * Do plane pieces
   int ext_d[2], ext_h[2];
   const __nv_bfloat16* w2g;  // [56][64][8] bf16, zero padded
   int N, Do, Ho, Wo;
@@ -312,6 +317,248 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_kernel(const __gri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Plane-resident fprop (default).  The tap-box kernel above fetches 49 boxes (100 KB) of window pixels per
+// 128-position tile: 784 B out of L2 per output voxel, and TMA moves them as 16-byte rows - it runs at 1270
+// cycles per kd row against 240 cycles of MMA work.  Here the M tile is one output plane piece of 16 (oh) x 8 (ow)
+// positions and the CTA walks a column of pieces along od, keeping the X8 input planes 2*od-3 .. 2*od+3 resident in a
+// shared-memory ring: one TMA box (8 pixels x 38 rows, 4.75 KB) per input plane, two new planes per output piece
+// (74 B per output voxel).  With rows of 8 pixels = 128 B = one no-swizzle core matrix, the A operand of the taps
+// (kd, kh), (kd, kh+1) is a VIEW of plane kd: start = plane + kh * 128 B, LBO (next K core matrix = next input row)
+// = 128 B, SBO (next 8 positions = next oh = two input rows down, the conv stride) = 256 B.  The weights are
+// resident, so the MMA issuer only ever waits for two plane barriers per piece.
+constexpr int kPRows = 2 * 16 + 6;       // input rows feeding 16 output rows
+constexpr int kPlaneBytes = 5120;        // 38 rows x 128 B = 4864, padded
+constexpr int kPRing = 14;               // 7 planes in use + prefetch
+constexpr int kPBarOff = kWBytes + kPRing * kPlaneBytes;
+constexpr int kPStatOff = kPBarOff + 512;
+constexpr int kPSmem = kPStatOff + 4 * 2 * kCout * 4 + 1024;
+
+struct StemSeg {
+  int n, h0, w0, dA, dB, pf, pl;
+};
+__device__ __forceinline__ StemSeg stem_segment(const StemParams& p, int i, int end) {
+  StemSeg s;
+  int col = i / p.Do;
+  s.dA = i - col * p.Do;
+  s.dB = min(p.Do, s.dA + (end - i));
+  const int tw = col % p.tiles_w;
+  col /= p.tiles_w;
+  const int th = col % p.tiles_h;
+  s.n = col / p.tiles_h;
+  s.h0 = th * 16;
+  s.w0 = tw * 8;
+  s.pf = max(2 * s.dA - 3, 0);
+  s.pl = min(2 * (s.dB - 1) + 3, p.D - 1);
+  return s;
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_p = smem + kWBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPBarOff);
+  uint64_t* empty = full + kPRing;
+  uint64_t* tfull = empty + kPRing;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + kPStatOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int begin = static_cast<int>(static_cast<long long>(p.total) * blockIdx.x / gridDim.x);
+  const int end = static_cast<int>(static_cast<long long>(p.total) * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPRing; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kWBytes / 16; i += kStemThreads)
+    reinterpret_cast<uint4*>(smem_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2g) + i);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== plane producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.x_plane);
+      uint32_t seq = 0;
+      for (int i = begin; i < end;) {
+        const StemSeg s = stem_segment(p, i, end);
+        for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
+          const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
+          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
+          tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
+        }
+        i += s.dB - s.dA;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kCout, false, false);
+      // no-swizzle descriptors, split into 32-bit halves so that the per-MMA work is one 32-bit add per operand:
+      //   low word  = start address >> 4 | (LBO >> 4) << 16,   high word = SBO >> 4 | version bit
+      const uint32_t a_hi = (256u >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo0 = ((128u >> 4) << 16) + ((smem_u32(smem_p) & 0x3FFFFu) >> 4);
+      const uint32_t b_lo0 = (((kCout * 16u) >> 4) << 16) + ((smem_u32(smem_w) & 0x3FFFFu) >> 4);
+      int acc = 0;
+      uint32_t accph = 0;
+      uint32_t seq0 = 0, waited = 0, released = 0;
+      for (int i = begin; i < end;) {
+        const StemSeg s = stem_segment(p, i, end);
+        for (int od = s.dA; od < s.dB; od++) {
+          mbar_wait(&tempty[acc], accph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kCout);
+          uint32_t accum = 0;
+#pragma unroll 1
+          for (int kd = 0; kd < kK; kd++) {
+            const int pz = 2 * od - 3 + kd;
+            if (pz < 0 || pz >= p.D) continue;
+            const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
+            while (waited <= sq) {  // planes complete in load order; each is waited for once
+              mbar_wait(&full[waited % kPRing], (waited / kPRing) & 1u);
+              waited++;
+            }
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + (sq % kPRing) * (kPlaneBytes >> 4);
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(kd) * (kKP * kCout);  // 8 taps x 64 co x 16 B >> 4
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int i2 = 0; i2 < kKP / 2; i2++) {
+                const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + i2 * 16);           // + 2 rows
+                const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + i2 * (2 * kCout));  // + 2 taps
+                umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(i2));
+              }
+            }
+            __syncwarp();
+            accum = 1;
+          }
+          // input planes below 2*(od+1)-3 are not needed by any later piece of the column
+          const int last_free = (od == s.dB - 1) ? s.pl : min(2 * od - 2, s.pl);
+          if (elect_one_sync()) {
+            umma_commit(&tfull[acc]);
+            for (uint32_t r = released; static_cast<int>(r - seq0) + s.pf <= last_free; r++) umma_commit(&empty[r % kPRing]);
+          }
+          __syncwarp();
+          while (static_cast<int>(released - seq0) + s.pf <= last_free) released++;
+          if (++acc == 2) {
+            acc = 0;
+            accph ^= 1u;
+          }
+        }
+        seq0 += static_cast<uint32_t>(s.pl - s.pf + 1);
+        i += s.dB - s.dA;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    const int rh = row >> 3, rw = row & 7;
+    const bool do_stats = p.stat_sum != nullptr;
+    // per-CTA fp64 BatchNorm sums, flushed once (same-address fp64 atomics retire at ~1 / 27 cycles in L2: one
+    // atomic per piece and channel from every CTA was the bound of this kernel)
+    double cta_sum = 0.0, cta_sq = 0.0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int i = begin; i < end;) {
+      const StemSeg s = stem_segment(p, i, end);
+      const int oh = s.h0 + rh, ow = s.w0 + rw;
+      const bool valid = oh < p.Ho && ow < p.Wo;
+      for (int od = s.dA; od < s.dB; od++) {
+        const long long off = ((((long long)s.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * kCout;
+        mbar_wait(&tfull[acc], accph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < kCout / 32; chunk++) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kCout + chunk * 32),
+                        v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+          if (do_stats) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float x = valid ? f[j] : 0.f;
+              s1[j] = x;
+              s2[j] = x * x;
+            }
+            const float cs1 = warp_column_sums(s1, lane);
+            const float cs2 = warp_column_sums(s2, lane);
+            stat_smem[(ew * 2 + 0) * kCout + chunk * 32 + lane] = cs1;
+            stat_smem[(ew * 2 + 1) * kCout + chunk * 32 + lane] = cs2;
+          }
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+              uint4 o;
+              o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+              o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+              o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+              o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+              op[j4] = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          accph ^= 1u;
+        }
+        if (do_stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et < kCout) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; w4++) {
+              a += stat_smem[(w4 * 2 + 0) * kCout + et];
+              b += stat_smem[(w4 * 2 + 1) * kCout + et];
+            }
+            cta_sum += static_cast<double>(a);
+            cta_sq += static_cast<double>(b);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+      i += s.dB - s.dA;
+    }
+    if (do_stats && et < kCout && begin < end) {
+      atomicAdd(p.stat_sum + et, cta_sum);
+      atomicAdd(p.stat_sq + et, cta_sq);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // wgrad: every CTA accumulates D[4 M-tiles x 128 (tap,j) rows][64 cout] over its share of the position boxes
 // (64 positions per K-block) and adds the result to dw2 at the end.
@@ -454,6 +701,203 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_wgrad_kernel(const __gri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Plane-resident wgrad (default).  Same resident X8 planes as stem_fprop_plane_kernel; the dY piece (16 oh x 8 ow
+// positions x 64 channels, one swizzled TMA box) streams through a 4-stage ring.  For every input plane kd of a
+// piece:  D_kd[(kh, j)][cout] += sum_pos plane_kd[2*oh + kh][ow][j] * dY[pos][cout]
+//   A (no swizzle, MN-major): the 8 j of a pixel are the 16-byte MN run, the 8 ow of an input row the 8-position K
+//     group (128 B); next K group = next oh = two input rows down (LBO 256 B); next MN group = next kh = next input
+//     row (SBO 128 B).  M = 128 is issued, rows 64..127 (kh 8..15) read whatever follows and are never stored.
+//   B (128-byte swizzle, MN-major): dY rows, 8-position K groups 1024 B apart.
+// The 7 accumulators D_kd (64 columns each) live in TMEM for the whole CTA and are added to dw2 once at the end.
+constexpr int kWPStages = 4;
+constexpr int kWPDyBytes = 128 * 128;
+constexpr int kWPDyOff = kPRing * kPlaneBytes;  // 71680: 1024-aligned
+constexpr int kWPBarOff = kWPDyOff + kWPStages * kWPDyBytes;
+constexpr int kWPSmem = kWPBarOff + 512 + 1024;
+constexpr int kWPThreads = 224;
+
+__global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_p = smem;
+  uint8_t* smem_dy = smem + kWPDyOff;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWPBarOff);
+  uint64_t* empty = full + kPRing;
+  uint64_t* dfull = empty + kPRing;
+  uint64_t* dempty = dfull + kWPStages;
+  uint64_t* tfull = dempty + kWPStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int begin = static_cast<int>(static_cast<long long>(p.total) * blockIdx.x / gridDim.x);
+  const int end = static_cast<int>(static_cast<long long>(p.total) * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPRing; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kWPStages; i++) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 6) {
+    // ===================== plane producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.x_plane);
+      uint32_t seq = 0;
+      for (int i = begin; i < end;) {
+        const StemSeg s = stem_segment(p, i, end);
+        for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
+          const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
+          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
+          tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
+        }
+        i += s.dB - s.dA;
+      }
+    }
+  } else if (warp == 0) {
+    // ===================== dY producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.dy_map);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = begin; i < end;) {
+        const StemSeg s = stem_segment(p, i, end);
+        for (int od = s.dA; od < s.dB; od++) {
+          mbar_wait(&dempty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&dfull[st], kWPDyBytes);
+          tma_load_5d(smem_dy + st * kWPDyBytes, &p.dy_map, &dfull[st], 0, s.w0, s.h0, od, s.n);
+          if (++st == kWPStages) {
+            st = 0;
+            ph ^= 1u;
+          }
+        }
+        i += s.dB - s.dA;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kCout, true, true);
+    const uint32_t a_hi = (128u >> 4) | (1u << 14);                 // SBO = next kh row
+    const uint32_t a_lo0 = ((256u >> 4) << 16) + ((smem_u32(smem_p) & 0x3FFFFu) >> 4);  // LBO = next oh
+    const uint64_t b_desc0 = umma_smem_desc_sw128(0, 8192, 1024);
+    const uint32_t b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_desc0 & 0xFFFFFFFFull) + ((smem_u32(smem_dy) & 0x3FFFFu) >> 4);
+    int st = 0;
+    uint32_t ph = 0;
+    uint32_t seq0 = 0, waited = 0, released = 0, started = 0;
+    for (int i = begin; i < end;) {
+      const StemSeg s = stem_segment(p, i, end);
+      for (int od = s.dA; od < s.dB; od++) {
+        mbar_wait(&dfull[st], ph);
+        tc_fence_after();
+        const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(st) * (kWPDyBytes >> 4);
+#pragma unroll 1
+        for (int kd = 0; kd < kK; kd++) {
+          const int pz = 2 * od - 3 + kd;
+          if (pz < 0 || pz >= p.D) continue;
+          const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
+          while (waited <= sq) {
+            mbar_wait(&full[waited % kPRing], (waited / kPRing) & 1u);
+            waited++;
+          }
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (sq % kPRing) * (kPlaneBytes >> 4);
+          const uint32_t acc_on = (started >> kd) & 1u;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {  // 16 positions (two oh rows) per MMA
+              const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + ks * (512 >> 4));
+              const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + ks * (2048 >> 4));
+              umma_bf16(tmem_base + static_cast<uint32_t>(kd * kCout), adesc, bdesc, idesc, acc_on | static_cast<uint32_t>(ks));
+            }
+          }
+          __syncwarp();
+          started |= 1u << kd;
+        }
+        const int last_free = (od == s.dB - 1) ? s.pl : min(2 * od - 2, s.pl);
+        if (elect_one_sync()) {
+          umma_commit(&dempty[st]);
+          for (uint32_t r = released; static_cast<int>(r - seq0) + s.pf <= last_free; r++) umma_commit(&empty[r % kPRing]);
+        }
+        __syncwarp();
+        while (static_cast<int>(released - seq0) + s.pf <= last_free) released++;
+        if (++st == kWPStages) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+      seq0 += static_cast<uint32_t>(s.pl - s.pf + 1);
+      i += s.dB - s.dA;
+    }
+    if (elect_one_sync()) umma_commit(tfull);
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===================== epilogue (warps 2..5): D_kd -> red.add into dw2, once per CTA =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // rows 0..63 = (kh, j); rows 64..127 are the padding half of the M = 128 tile
+    // which kd accumulators received anything (a CTA range that never sees a valid input plane for kd leaves it unset)
+    uint32_t started = 0;
+    for (int i = begin; i < end;) {
+      const StemSeg s = stem_segment(p, i, end);
+      for (int od = s.dA; od < s.dB; od++)
+        for (int kd = 0; kd < kK; kd++) {
+          const int pz = 2 * od - 3 + kd;
+          if (pz >= 0 && pz < p.D) started |= 1u << kd;
+        }
+      i += s.dB - s.dA;
+    }
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int kh = row >> 3, j = row & 7;
+    const bool keep = row < 64 && kh < kK && j < kK;
+#pragma unroll 1
+    for (int kd = 0; kd < kK; kd++) {
+      if (!((started >> kd) & 1u)) continue;
+#pragma unroll 1
+      for (int chunk = 0; chunk < kCout / 32; chunk++) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(kd * kCout + chunk * 32), v);
+        tmem_ld_wait();
+        if (keep) {
+          float* dst = p.dw + (long long)(kd * 64 + row) * kCout + chunk * 32;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            float4 val;
+            val.x = __uint_as_float(v[j4 * 4 + 0]);
+            val.y = __uint_as_float(v[j4 * 4 + 1]);
+            val.z = __uint_as_float(v[j4 * 4 + 2]);
+            val.w = __uint_as_float(v[j4 * 4 + 3]);
+            atomicAdd(reinterpret_cast<float4*>(dst + j4 * 4), val);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct StemGeom {
   int N, D, H, W, Do, Ho, Wo;
@@ -551,6 +995,31 @@ int adni_stem_fprop(const adni_bf16* x8, int N, int D, int H, int W, const adni_
   p.out = reinterpret_cast<bf16*>(y);
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sqsum;
+  const char* env_planes = getenv("ADNI_STEM_PLANES");
+  if (!env_planes || atoi(env_planes) != 0) {
+    // a whole X8 row (Wo pixels x 8) is the innermost dimension: the 8 pixels of a piece are ONE 128-byte run for TMA
+    const uint64_t dims[4] = {(uint64_t)g.Wo * 8, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    const uint64_t strides[4] = {1, (uint64_t)g.Wo * 8, (uint64_t)H * g.Wo * 8, (uint64_t)D * H * g.Wo * 8};
+    const uint32_t box[4] = {64, (uint32_t)kPRows, 1, 1};
+    rc = make_tmap_bf16(&p.x_plane, x8, 4, dims, strides, box, false);
+    if (rc) return rc;
+    p.D = D;
+    p.H = H;
+    p.tiles_h = (g.Ho + 15) / 16;
+    p.tiles_w = (g.Wo + 7) / 8;
+    const long long total_pieces = (long long)N * p.tiles_h * p.tiles_w * g.Do;
+    ADNI_REQUIRE(total_pieces <= 0x7fffffffLL, ADNI_ENOTSUP, "stem_fprop: too many plane pieces");
+    p.total = (int)total_pieces;
+    static bool attr_p = false;
+    if (!attr_p) {
+      ADNI_CUDA_OK(cudaFuncSetAttribute(stem_fprop_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+      attr_p = true;
+    }
+    stem_fprop_plane_kernel<<<std::min(p.total, num_sms()), kStemThreads, kPSmem, ST(stream)>>>(p);
+    count_launch();
+    ADNI_LAUNCH_CHECK("stem_fprop_plane_kernel");
+    return ADNI_OK;
+  }
   static bool attr = false;
   if (!attr) {
     ADNI_CUDA_OK(cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
@@ -592,6 +1061,43 @@ int adni_stem_wgrad(const adni_bf16* x8, const adni_bf16* dy, int N, int D, int 
   p.tiles_w = (g.Wo + p.bw - 1) / p.bw;
   p.dw = workspace;
   ADNI_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(float) * 512 * kCout, ST(stream)));
+  const char* env_planes = getenv("ADNI_STEM_PLANES");
+  if (!env_planes || atoi(env_planes) != 0) {
+    {
+      const uint64_t dims[4] = {(uint64_t)g.Wo * 8, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+      const uint64_t strides[4] = {1, (uint64_t)g.Wo * 8, (uint64_t)H * g.Wo * 8, (uint64_t)D * H * g.Wo * 8};
+      const uint32_t box[4] = {64, (uint32_t)kPRows, 1, 1};
+      rc = make_tmap_bf16(&p.x_plane, x8, 4, dims, strides, box, false);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[5] = {64, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)N};
+      const uint64_t strides[5] = {1, 64, (uint64_t)g.Wo * 64, (uint64_t)g.Ho * g.Wo * 64,
+                                   (uint64_t)g.Do * g.Ho * g.Wo * 64};
+      const uint32_t box[5] = {64, 8, 16, 1, 1};
+      rc = make_tmap_bf16(&p.dy_map, dy, 5, dims, strides, box, true);
+      if (rc) return rc;
+    }
+    p.D = D;
+    p.H = H;
+    p.tiles_h = (g.Ho + 15) / 16;
+    p.tiles_w = (g.Wo + 7) / 8;
+    const long long total_pieces = (long long)N * p.tiles_h * p.tiles_w * g.Do;
+    ADNI_REQUIRE(total_pieces <= 0x7fffffffLL, ADNI_ENOTSUP, "stem_wgrad: too many plane pieces");
+    p.total = (int)total_pieces;
+    static bool attr_p = false;
+    if (!attr_p) {
+      ADNI_CUDA_OK(cudaFuncSetAttribute(stem_wgrad_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWPSmem));
+      attr_p = true;
+    }
+    stem_wgrad_plane_kernel<<<std::min(p.total, num_sms()), kWPThreads, kWPSmem, ST(stream)>>>(p);
+    count_launch();
+    ADNI_LAUNCH_CHECK("stem_wgrad_plane_kernel");
+    stem_wgrad_unpack_kernel<<<(kCout * 343 + 255) / 256, 256, 0, ST(stream)>>>(workspace, grad_ncdhw);
+    count_launch();
+    ADNI_LAUNCH_CHECK("stem_wgrad_unpack_kernel");
+    return ADNI_OK;
+  }
   static bool attr = false;
   if (!attr) {
     ADNI_CUDA_OK(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
