@@ -32,6 +32,7 @@ struct StemParams {
   CUtensorMap x_plane;    // plane-resident fprop: (W'*8, H, D, N) view of X8, box (64, 38, 1, 1)
   int D, H;               // input extents (plane-resident fprop)
   int total;              // plane-resident fprop: N * tiles_h * tiles_w * Do plane pieces
+  int debug;              // diagnostics (ADNI_STEM_DEBUG bits): 1 no BN sums, 2 no stores, 4 no MMA issue
   int ext_d[2], ext_h[2];
   const __nv_bfloat16* w2g;  // [56][64][8] bf16, zero padded
   int N, Do, Ho, Wo;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
         const StemSeg s = stem_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
           const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
-          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_wait_spin(&empty[slot], par ^ 1u);
           mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
           tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
         }
@@ -411,6 +412,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    // Everything per piece is scalar ring arithmetic (no divisions, no parameter loads): the issuing thread's own
+    // instruction stream was the bound of this kernel (ncu: no stall reason dominant, ~60 instructions per kd).
     {
       constexpr uint32_t idesc = umma_idesc_bf16(128, kCout, false, false);
       // no-swizzle descriptors, split into 32-bit halves so that the per-MMA work is one 32-bit add per operand:
@@ -418,53 +421,71 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
       const uint32_t a_hi = (256u >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo0 = ((128u >> 4) << 16) + ((smem_u32(smem_p) & 0x3FFFFu) >> 4);
       const uint32_t b_lo0 = (((kCout * 16u) >> 4) << 16) + ((smem_u32(smem_w) & 0x3FFFFu) >> 4);
+      const int D = p.D;
+      const bool issue = !(p.debug & 4);
       int acc = 0;
       uint32_t accph = 0;
-      uint32_t seq0 = 0, waited = 0, released = 0;
+      // ring cursors (slot, parity) of the next plane to wait for / to hand back, and the running plane count
+      int w_slot = 0, r_slot = 0;
+      uint32_t w_par = 0;
+      int n_waited = 0, n_released = 0, seq0 = 0;
       for (int i = begin; i < end;) {
         const StemSeg s = stem_segment(p, i, end);
-        for (int od = s.dA; od < s.dB; od++) {
-          mbar_wait(&tempty[acc], accph ^ 1u);
+        int rel0 = 2 * s.dA - 3 - s.pf;                   // plane 2*od-3 relative to the first loaded plane (<= 0)
+        int sl0 = (seq0 + rel0 + 4 * kPRing) % kPRing;   // its ring slot (virtual for planes above the volume)
+        for (int od = s.dA; od < s.dB; od++, rel0 += 2) {
+          const int kd_lo = max(0, 3 - 2 * od), kd_hi = min(kK - 1, D + 2 - 2 * od);
+          mbar_wait_spin(&tempty[acc], accph ^ 1u);
+          const int need = seq0 + rel0 + kd_hi;  // last plane of this piece, as a running count
+          while (n_waited <= need) {
+            mbar_wait_spin(&full[w_slot], w_par);
+            n_waited++;
+            if (++w_slot == kPRing) {
+              w_slot = 0;
+              w_par ^= 1u;
+            }
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kCout);
-          uint32_t accum = 0;
-#pragma unroll 1
-          for (int kd = 0; kd < kK; kd++) {
-            const int pz = 2 * od - 3 + kd;
-            if (pz < 0 || pz >= p.D) continue;
-            const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
-            while (waited <= sq) {  // planes complete in load order; each is waited for once
-              mbar_wait(&full[waited % kPRing], (waited / kPRing) & 1u);
-              waited++;
-            }
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + (sq % kPRing) * (kPlaneBytes >> 4);
-            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(kd) * (kKP * kCout);  // 8 taps x 64 co x 16 B >> 4
-            if (elect_one_sync()) {
+          // input planes below 2*(od+1)-3 are not needed by any later piece of the column
+          const int last_free = seq0 + ((od == s.dB - 1) ? s.pl - s.pf : min(rel0 + 1, s.pl - s.pf));
+          if (elect_one_sync()) {
+            if (issue) {
 #pragma unroll
-              for (int i2 = 0; i2 < kKP / 2; i2++) {
-                const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + i2 * 16);           // + 2 rows
-                const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + i2 * (2 * kCout));  // + 2 taps
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(i2));
+              for (int kd = 0; kd < kK; kd++) {
+                if (kd < kd_lo || kd > kd_hi) continue;
+                int slot = sl0 + kd;
+                if (slot >= kPRing) slot -= kPRing;
+                const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(slot) * (kPlaneBytes >> 4);
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(kd) * (kKP * kCout);  // 8 taps x 64 co x 16 B >> 4
+#pragma unroll
+                for (int i2 = 0; i2 < kKP / 2; i2++) {
+                  const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + i2 * 16);           // + 2 rows
+                  const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + i2 * (2 * kCout));  // + 2 taps
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, (kd == kd_lo && i2 == 0) ? 0u : 1u);
+                }
               }
             }
-            __syncwarp();
-            accum = 1;
-          }
-          // input planes below 2*(od+1)-3 are not needed by any later piece of the column
-          const int last_free = (od == s.dB - 1) ? s.pl : min(2 * od - 2, s.pl);
-          if (elect_one_sync()) {
             umma_commit(&tfull[acc]);
-            for (uint32_t r = released; static_cast<int>(r - seq0) + s.pf <= last_free; r++) umma_commit(&empty[r % kPRing]);
+            int rs = r_slot;
+            for (int r = n_released; r <= last_free; r++) {
+              umma_commit(&empty[rs]);
+              if (++rs == kPRing) rs = 0;
+            }
           }
           __syncwarp();
-          while (static_cast<int>(released - seq0) + s.pf <= last_free) released++;
+          while (n_released <= last_free) {
+            n_released++;
+            if (++r_slot == kPRing) r_slot = 0;
+          }
+          sl0 += 2;
+          if (sl0 >= kPRing) sl0 -= kPRing;
           if (++acc == 2) {
             acc = 0;
             accph ^= 1u;
           }
         }
-        seq0 += static_cast<uint32_t>(s.pl - s.pf + 1);
+        seq0 += s.pl - s.pf + 1;
         i += s.dB - s.dA;
       }
     }
@@ -473,10 +494,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
     const int q = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
     const int row = q * 32 + lane;
     const int rh = row >> 3, rw = row & 7;
-    const bool do_stats = p.stat_sum != nullptr;
-    // per-CTA fp64 BatchNorm sums, flushed once (same-address fp64 atomics retire at ~1 / 27 cycles in L2: one
-    // atomic per piece and channel from every CTA was the bound of this kernel)
-    double cta_sum = 0.0, cta_sq = 0.0;
+    const bool do_stats = p.stat_sum != nullptr && !(p.debug & 1);
+    const bool do_store = !(p.debug & 2);
+    // BatchNorm sums: every thread owns one tile row and keeps fp32 partial sums of its 64 channels in registers
+    // for the whole CTA (one row per piece, a few hundred pieces): 2 FMA-class instructions per element, and ONE
+    // cross-lane transpose-reduce + fp64 atomic per channel at the very end.  (Reducing per piece cost two
+    // 62-instruction shuffle trees, two named barriers and, before that, 128 same-address atomics per piece.)
+    float cs1[kCout], cs2[kCout];
+#pragma unroll
+    for (int j = 0; j < kCout; j++) cs1[j] = cs2[j] = 0.f;
     int acc = 0;
     uint32_t accph = 0;
     for (int i = begin; i < end;) {
@@ -485,9 +511,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
       const bool valid = oh < p.Ho && ow < p.Wo;
       for (int od = s.dA; od < s.dB; od++) {
         const long long off = ((((long long)s.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * kCout;
-        mbar_wait(&tfull[acc], accph);
+        mbar_wait_spin(&tfull[acc], accph);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int chunk = 0; chunk < kCout / 32; chunk++) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kCout + chunk * 32),
@@ -496,20 +522,14 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-          if (do_stats) {
-            float s1[32], s2[32];
+          if (do_stats && valid) {
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              const float x = valid ? f[j] : 0.f;
-              s1[j] = x;
-              s2[j] = x * x;
+              cs1[chunk * 32 + j] += f[j];
+              cs2[chunk * 32 + j] = fmaf(f[j], f[j], cs2[chunk * 32 + j]);
             }
-            const float cs1 = warp_column_sums(s1, lane);
-            const float cs2 = warp_column_sums(s2, lane);
-            stat_smem[(ew * 2 + 0) * kCout + chunk * 32 + lane] = cs1;
-            stat_smem[(ew * 2 + 1) * kCout + chunk * 32 + lane] = cs2;
           }
-          if (valid) {
+          if (valid && do_store) {
             uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
@@ -529,26 +549,34 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
           acc = 0;
           accph ^= 1u;
         }
-        if (do_stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et < kCout) {
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int w4 = 0; w4 < 4; w4++) {
-              a += stat_smem[(w4 * 2 + 0) * kCout + et];
-              b += stat_smem[(w4 * 2 + 1) * kCout + et];
-            }
-            cta_sum += static_cast<double>(a);
-            cta_sq += static_cast<double>(b);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
       }
       i += s.dB - s.dA;
     }
-    if (do_stats && et < kCout && begin < end) {
-      atomicAdd(p.stat_sum + et, cta_sum);
-      atomicAdd(p.stat_sq + et, cta_sq);
+    if (do_stats) {
+#pragma unroll
+      for (int chunk = 0; chunk < kCout / 32; chunk++) {
+        float t1[32], t2[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          t1[j] = cs1[chunk * 32 + j];
+          t2[j] = cs2[chunk * 32 + j];
+        }
+        const float c1 = warp_column_sums(t1, lane);
+        const float c2 = warp_column_sums(t2, lane);
+        stat_smem[(ew * 2 + 0) * kCout + chunk * 32 + lane] = c1;
+        stat_smem[(ew * 2 + 1) * kCout + chunk * 32 + lane] = c2;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < kCout && begin < end) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; w4++) {
+          a += static_cast<double>(stat_smem[(w4 * 2 + 0) * kCout + et]);
+          b += static_cast<double>(stat_smem[(w4 * 2 + 1) * kCout + et]);
+        }
+        atomicAdd(p.stat_sum + et, a);
+        atomicAdd(p.stat_sq + et, b);
+      }
     }
   }
   tc_fence_before();
@@ -764,7 +792,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
         const StemSeg s = stem_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
           const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
-          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_wait_spin(&empty[slot], par ^ 1u);
           mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
           tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
         }
@@ -780,7 +808,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
       for (int i = begin; i < end;) {
         const StemSeg s = stem_segment(p, i, end);
         for (int od = s.dA; od < s.dB; od++) {
-          mbar_wait(&dempty[st], ph ^ 1u);
+          mbar_wait_spin(&dempty[st], ph ^ 1u);
           mbar_arrive_expect_tx(&dfull[st], kWPDyBytes);
           tma_load_5d(smem_dy + st * kWPDyBytes, &p.dy_map, &dfull[st], 0, s.w0, s.h0, od, s.n);
           if (++st == kWPStages) {
@@ -799,28 +827,41 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
     const uint64_t b_desc0 = umma_smem_desc_sw128(0, 8192, 1024);
     const uint32_t b_hi = static_cast<uint32_t>(b_desc0 >> 32);
     const uint32_t b_lo0 = static_cast<uint32_t>(b_desc0 & 0xFFFFFFFFull) + ((smem_u32(smem_dy) & 0x3FFFFu) >> 4);
+    const int D = p.D;
     int st = 0;
     uint32_t ph = 0;
-    uint32_t seq0 = 0, waited = 0, released = 0, started = 0;
+    // ring cursors as in stem_fprop_plane_kernel
+    int w_slot = 0, r_slot = 0;
+    uint32_t w_par = 0;
+    int n_waited = 0, n_released = 0, seq0 = 0;
+    uint32_t started = 0;
     for (int i = begin; i < end;) {
       const StemSeg s = stem_segment(p, i, end);
-      for (int od = s.dA; od < s.dB; od++) {
-        mbar_wait(&dfull[st], ph);
+      int rel0 = 2 * s.dA - 3 - s.pf;
+      int sl0 = (seq0 + rel0 + 4 * kPRing) % kPRing;
+      for (int od = s.dA; od < s.dB; od++, rel0 += 2) {
+        const int kd_lo = max(0, 3 - 2 * od), kd_hi = min(kK - 1, D + 2 - 2 * od);
+        mbar_wait_spin(&dfull[st], ph);
+        const int need = seq0 + rel0 + kd_hi;
+        while (n_waited <= need) {
+          mbar_wait_spin(&full[w_slot], w_par);
+          n_waited++;
+          if (++w_slot == kPRing) {
+            w_slot = 0;
+            w_par ^= 1u;
+          }
+        }
         tc_fence_after();
         const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(st) * (kWPDyBytes >> 4);
-#pragma unroll 1
-        for (int kd = 0; kd < kK; kd++) {
-          const int pz = 2 * od - 3 + kd;
-          if (pz < 0 || pz >= p.D) continue;
-          const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
-          while (waited <= sq) {
-            mbar_wait(&full[waited % kPRing], (waited / kPRing) & 1u);
-            waited++;
-          }
-          tc_fence_after();
-          const uint32_t a_lo = a_lo0 + (sq % kPRing) * (kPlaneBytes >> 4);
-          const uint32_t acc_on = (started >> kd) & 1u;
-          if (elect_one_sync()) {
+        const int last_free = seq0 + ((od == s.dB - 1) ? s.pl - s.pf : min(rel0 + 1, s.pl - s.pf));
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kd = 0; kd < kK; kd++) {
+            if (kd < kd_lo || kd > kd_hi) continue;
+            int slot = sl0 + kd;
+            if (slot >= kPRing) slot -= kPRing;
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(slot) * (kPlaneBytes >> 4);
+            const uint32_t acc_on = (started >> kd) & 1u;
 #pragma unroll
             for (int ks = 0; ks < 8; ks++) {  // 16 positions (two oh rows) per MMA
               const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + ks * (512 >> 4));
@@ -828,22 +869,29 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
               umma_bf16(tmem_base + static_cast<uint32_t>(kd * kCout), adesc, bdesc, idesc, acc_on | static_cast<uint32_t>(ks));
             }
           }
-          __syncwarp();
-          started |= 1u << kd;
-        }
-        const int last_free = (od == s.dB - 1) ? s.pl : min(2 * od - 2, s.pl);
-        if (elect_one_sync()) {
           umma_commit(&dempty[st]);
-          for (uint32_t r = released; static_cast<int>(r - seq0) + s.pf <= last_free; r++) umma_commit(&empty[r % kPRing]);
+          int rs = r_slot;
+          for (int r = n_released; r <= last_free; r++) {
+            umma_commit(&empty[rs]);
+            if (++rs == kPRing) rs = 0;
+          }
         }
         __syncwarp();
-        while (static_cast<int>(released - seq0) + s.pf <= last_free) released++;
+#pragma unroll
+        for (int kd = 0; kd < kK; kd++)
+          if (kd >= kd_lo && kd <= kd_hi) started |= 1u << kd;
+        while (n_released <= last_free) {
+          n_released++;
+          if (++r_slot == kPRing) r_slot = 0;
+        }
+        sl0 += 2;
+        if (sl0 >= kPRing) sl0 -= kPRing;
         if (++st == kWPStages) {
           st = 0;
           ph ^= 1u;
         }
       }
-      seq0 += static_cast<uint32_t>(s.pl - s.pf + 1);
+      seq0 += s.pl - s.pf + 1;
       i += s.dB - s.dA;
     }
     if (elect_one_sync()) umma_commit(tfull);
@@ -863,7 +911,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
         }
       i += s.dB - s.dA;
     }
-    mbar_wait(tfull, 0);
+    mbar_wait_spin(tfull, 0);
     tc_fence_after();
     const int kh = row >> 3, j = row & 7;
     const bool keep = row < 64 && kh < kK && j < kK;
@@ -1010,6 +1058,10 @@ int adni_stem_fprop(const adni_bf16* x8, int N, int D, int H, int W, const adni_
     const long long total_pieces = (long long)N * p.tiles_h * p.tiles_w * g.Do;
     ADNI_REQUIRE(total_pieces <= 0x7fffffffLL, ADNI_ENOTSUP, "stem_fprop: too many plane pieces");
     p.total = (int)total_pieces;
+    {
+      const char* dbg = getenv("ADNI_STEM_DEBUG");
+      p.debug = dbg ? atoi(dbg) : 0;
+    }
     static bool attr_p = false;
     if (!attr_p) {
       ADNI_CUDA_OK(cudaFuncSetAttribute(stem_fprop_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
