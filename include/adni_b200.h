@@ -61,6 +61,12 @@ typedef struct {
 /* out spatial extent for one axis */
 int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil);
 
+/* Planner query (measurement only): which engine a geometry is routed to for pass 0 = fprop, 1 = dgrad, 2 = wgrad
+ * (engine_kind 0 = direct CUDA-core, 1 = tcgen05 tap-per-box implicit GEMM, 2 = tcgen05 halo-resident) and the
+ * fraction of the (tile, tap) MMA blocks that are actually issued - taps whose shifted box lies entirely in the
+ * zero padding are skipped, so executed FLOPs = algorithmic FLOPs x executed_fraction. */
+int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind, double* executed_fraction);
+
 /* y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_oti) (+bias).  If stat_sum/stat_sqsum are non-null,
  * per-channel sum(y) and sum(y*y) (fp64, from the fp32 accumulators) are ADDED into them: the
  * BatchNorm3d batch statistics fused into the conv epilogue (MedicalNet bn1/bn2/bn3). */
@@ -98,6 +104,15 @@ int adni_stem_wgrad(const adni_bf16* x8, const adni_bf16* dy, int N, int D, int 
  * w_ncdhw: [Cout][Cin][taps] fp32.  Either output may be null. */
 int adni_weights_to_kernel_layout(const float* w_ncdhw, int Cout, int Cin, int taps, adni_bf16* w_oti,
                                   adni_bf16* w_ito, void* stream);
+/* All conv weights of an encoder in one launch (same result as adni_weights_to_kernel_layout per tensor, taps <= 27).
+ * `jobs` is a DEVICE array of n_jobs records laid out as
+ *   struct { const float* src; adni_bf16* oti; adni_bf16* ito; int cout, cin, taps, tile_begin, tiles_ci; }
+ * (adni_weights_multi_job_bytes() bytes each); tensor j owns blocks [tile_begin, tile_begin + ceil(cout/16)*tiles_ci),
+ * tiles_ci = ceil(cin/16); total_tiles is the grid size.  Replaces the per-module weight conversion the reference
+ * leaves to cuDNN's internal filter transforms (MedicalNet Conv3d layers, anat_cnn.py:95). */
+int adni_weights_multi_job_bytes(void);
+int adni_weights_to_kernel_layout_multi(const void* jobs, int n_jobs, int total_tiles, void* stream);
+
 /* dw_oti [Cout][taps][Cin] fp32 -> grad_ncdhw [Cout][Cin][taps] fp32 (accumulate=1 adds into grad). */
 int adni_wgrad_to_param_layout(const float* dw_oti, int Cout, int Cin, int taps, float* grad_ncdhw, int accumulate,
                                void* stream);
@@ -127,12 +142,22 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
                        double* red, void* stream);
 
 /* Backward, pass 2: dy = gamma*invstd*( g - red_g/count - xhat*red_gx/count ) (bf16);
- * dres (nullable) = g (the gradient flowing into the residual input); dgamma = red_gx, dbeta = red_g
- * are written (fp32) when non-null.  `count` is the GLOBAL element count per channel (sync-BN). */
+ * dres (nullable) = g (the gradient flowing into the residual input); dgamma = red_gx * param_grad_scale, dbeta =
+ * red_g * param_grad_scale are written (fp32) when non-null.  `count` is the GLOBAL element count per channel
+ * (sync-BN); with all-reduced sums pass param_grad_scale = 1 / world_size so that the SUM of the ranks' parameter
+ * gradients (the data-parallel gradient all-reduce) is the full-batch gradient. */
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
                       const float* invstd, const float* gamma, const float* scale, const float* shift,
                       const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
-                      float* dgamma, float* dbeta, void* stream);
+                      float* dgamma, float* dbeta, double param_grad_scale, void* stream);
+
+/* Training-mode BatchNorm forward in ONE launch (adni_bn_finalize + adni_bn_apply): scale / shift are derived from the
+ * fp64 batch sums inside the apply kernel; bnp (fp32 [4][C]: mean, invstd, scale, shift) is written for the backward
+ * pass and the running statistics are updated (torch semantics), both by one block. */
+int adni_bn_train_apply(const adni_bf16* y, const double* stat_sum, const double* stat_sqsum, double count,
+                        const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                        float* running_var, float* bnp, const adni_bf16* residual, adni_bf16* out, long long rows, int C,
+                        int relu, void* stream);
 
 /* dgamma[c] = red[C+c], dbeta[c] = red[c] (fp64 -> fp32): BatchNorm parameter gradients from the LOCAL backward
  * sums (under data parallelism the gradient all-reduce adds the ranks' contributions). */

@@ -35,6 +35,7 @@ _SZ = ctypes.c_size_t
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     "adni_conv3d_out_extent": [_I, _I, _I, _I, _I],
+    "adni_conv3d_plan_info": [ctypes.POINTER(ConvGeom), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
     "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P],
     "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
     "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
@@ -45,10 +46,13 @@ _SIGNATURES = {
     "adni_stem_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "adni_weights_to_kernel_layout": [_P, _I, _I, _I, _P, _P, _P],
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
+    "adni_weights_multi_job_bytes": [],
+    "adni_weights_to_kernel_layout_multi": [_P, _I, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "adni_bn_apply": [_P, _P, _P, _P, _P, _LL, _I, _I, _P, _P, _P],
     "adni_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P],
-    "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _P],
+    "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _D, _P],
+    "adni_bn_train_apply": [_P, _P, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _LL, _I, _I, _P],
     "adni_channel_stats": [_P, _LL, _I, _P, _P, _P],
     "adni_maxpool3d_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "adni_maxpool3d_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -59,6 +59,29 @@ def _with_forward_group(backward):
     return wrapped
 
 
+# BatchNorm.num_batches_tracked counters: inside `defer_bn_counters()` (an encoder's forward) the +1 of every layer is
+# collected and applied by one multi-tensor add at exit instead of one tiny kernel per BatchNorm layer.
+_DEFERRED_COUNTERS = [None]
+
+
+class defer_bn_counters:
+    def __enter__(self):
+        self.prev, _DEFERRED_COUNTERS[0] = _DEFERRED_COUNTERS[0], []
+
+    def __exit__(self, *exc):
+        pending, _DEFERRED_COUNTERS[0] = _DEFERRED_COUNTERS[0], self.prev
+        if pending:
+            torch._foreach_add_(pending, 1)
+
+
+def _count_batch(bn):
+    if bn.module is not None and bn.module.num_batches_tracked is not None:
+        if _DEFERRED_COUNTERS[0] is not None:
+            _DEFERRED_COUNTERS[0].append(bn.module.num_batches_tracked)
+        else:
+            bn.module.num_batches_tracked += 1
+
+
 class BNState:
     """Non-tensor BatchNorm configuration handed to the Functions (running buffers are updated in place)."""
 
@@ -81,16 +104,14 @@ def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
             stats = K.channel_stats(y.view(-1, C))
         _allreduce_(stats)
         count = rows * _world()
-        bnp = K.bn_finalize(stats, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
-        scale, shift = bnp[2], bnp[3]
-        if bn.module is not None and bn.module.num_batches_tracked is not None:
-            bn.module.num_batches_tracked += 1
-    else:
-        scale, shift = K.bn_eval_params(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
-        bnp = None
-        count = rows
+        _count_batch(bn)
+        # finalize (scale / shift / running statistics) and apply in one launch
+        out, bnp = K.bn_train_apply(y, stats, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                                    residual=residual, relu=relu)
+        return out, bnp, count
+    scale, shift = K.bn_eval_params(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
     out = K.bn_apply(y, scale, shift, residual=residual, relu=relu)
-    return out, bnp, count
+    return out, None, rows
 
 
 def _bn_backward(dout, out, y, bnp, gamma, count, relu, want_dres, want_pg):
@@ -101,11 +122,12 @@ def _bn_backward(dout, out, y, bnp, gamma, count, relu, want_dres, want_pg):
     if not relu or out is not None:
         scale = shift = None
     red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale, shift)
-    # dgamma / dbeta are the LOCAL sums: the gradient all-reduce that follows the backward pass makes them global
-    # (taking them from the all-reduced statistics would count every rank's contribution world_size times).
-    dgamma, dbeta = K.bn_param_grads(red) if want_pg else (None, None)
     _allreduce_(red)
-    dy, dres, _, _ = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, False, scale, shift)
+    # dgamma / dbeta are written by the apply kernel from the all-reduced sums scaled by 1 / world_size: the gradient
+    # all-reduce that follows the backward pass SUMS the ranks' parameter gradients, which restores the global sums
+    # (handing every rank the full sums would count them world_size times).
+    dy, dres, dgamma, dbeta = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_pg,
+                                             scale, shift, param_grad_scale=1.0 / _world())
     return dy, dres, dgamma, dbeta
 
 
@@ -115,7 +137,7 @@ class ConvCfg:
 
 
 def _conv_fwd(x, w, cfg, bias=None, stats=True, need_ito=True):
-    oti, ito = K.weights_to_kernel_layout(w, want_ito=need_ito)
+    oti, ito = K.kernel_layout(w, want_ito=need_ito)
     y, st = K.conv3d_fprop(x, oti, bias, cfg.k, cfg.stride, cfg.pad, cfg.dil, stats=stats)
     return y, st, ito
 
@@ -162,8 +184,7 @@ class StemFn(torch.autograd.Function):
             _allreduce_(st)
             count = (y.numel() // C) * _world()
             bnp = K.bn_finalize(st, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
-            if bn.module is not None and bn.module.num_batches_tracked is not None:
-                bn.module.num_batches_tracked += 1
+            _count_batch(bn)
             p, am = K.bn_relu_maxpool_fwd(y, bnp, *pool)
             a_shape = tuple(y.shape)
         else:

@@ -498,6 +498,53 @@ extern "C" {
 
 int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil) { return out_extent(in, k, stride, pad, dil); }
 
+int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind, double* executed_fraction) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(engine_kind && executed_fraction && pass >= 0 && pass <= 2, ADNI_EINVAL, "conv3d_plan_info: bad arguments");
+  *executed_fraction = 1.0;
+  if (!tc_supported(*g)) {
+    *engine_kind = 0;
+    return ADNI_OK;
+  }
+  *engine_kind = 1;
+  if (pass == 2) return ADNI_OK;  // wgrad: split-K over position boxes, reported as issued
+  if (halo_supported(*g)) {
+    *engine_kind = 2;
+    *executed_fraction = (3.0 * g->D - 2.0) / (3.0 * g->D);  // the kd = 0 / 2 taps of the first / last plane
+    return ADNI_OK;
+  }
+  if (pass == 1 && g->stride != 1) return ADNI_OK;  // strided dgrad: per parity class, reported as issued
+  const int Do = out_extent(g->D, g->k, g->stride, g->pad, g->dil), Ho = out_extent(g->H, g->k, g->stride, g->pad, g->dil),
+            Wo = out_extent(g->W, g->k, g->stride, g->pad, g->dil);
+  std::vector<AxisTap> at;
+  std::vector<int> ext_d, ext_h, ext_w;
+  int od = Do, oh = Ho, ow = Wo;
+  if (pass == 0) {
+    at = fwd_axis_taps(g->k, g->stride, g->pad, g->dil);
+    for (int p = 0; p < g->stride; p++) {
+      ext_d.push_back((g->D - p + g->stride - 1) / g->stride);
+      ext_h.push_back((g->H - p + g->stride - 1) / g->stride);
+      ext_w.push_back((g->W - p + g->stride - 1) / g->stride);
+    }
+  } else {  // stride-1 dgrad: the taps slide over dy, the output is dx
+    for (int kk = 0; kk < g->k; kk++) at.push_back({0, g->pad - kk * g->dil});
+    ext_d = {Do};
+    ext_h = {Ho};
+    ext_w = {Wo};
+    od = g->D;
+    oh = g->H;
+    ow = g->W;
+  }
+  const Box b = plan_box(od, oh, ow, 128, false, at, at, at, ext_d, ext_h, ext_w);
+  const double done = double(axis_score(b.bd, od, at, ext_d)) * double(axis_score(b.bh, oh, at, ext_h)) *
+                      double(axis_score(b.bw, ow, at, ext_w));
+  const double all = double((od + b.bd - 1) / b.bd) * double((oh + b.bh - 1) / b.bh) * double((ow + b.bw - 1) / b.bw) *
+                     double(g->k) * g->k * g->k;
+  *executed_fraction = done / all;
+  return ADNI_OK;
+}
+
 int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* w_oti, const float* bias,
                       adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* stream) {
   int rc = check_geom(g);

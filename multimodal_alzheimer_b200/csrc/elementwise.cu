@@ -62,25 +62,41 @@ __device__ __forceinline__ Vec8 loadf8(const float* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+struct BnChannel {
+  float mean, invstd, scale, shift;
+  double var;
+};
+// One channel's BatchNorm parameters from the fp64 sums; bn_finalize_kernel and the fused bn_train_apply_kernel
+// evaluate exactly this expression, so every block of the fused kernel derives bit-identical scale / shift.
+__device__ __forceinline__ BnChannel bn_channel(const double* ssum, const double* ssq, double count, const float* gamma,
+                                                const float* beta, float eps, int c) {
+  BnChannel o;
+  const double m = ssum[c] / count;
+  double var = ssq[c] / count - m * m;
+  if (var < 0) var = 0;
+  o.var = var;
+  o.invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  o.mean = (float)m;
+  o.scale = g * o.invstd;
+  o.shift = b - (float)m * o.scale;
+  return o;
+}
+
 __global__ void bn_finalize_kernel(const double* ssum, const double* ssq, double count, int C, const float* gamma,
                                    const float* beta, float eps, float momentum, float* rmean, float* rvar,
                                    float* mean, float* invstd, float* scale, float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = ssum[c] / count;
-  double var = ssq[c] / count - m * m;
-  if (var < 0) var = 0;
-  const float istd = (float)(1.0 / sqrt(var + (double)eps));
-  const float g = gamma ? gamma[c] : 1.f;
-  const float b = beta ? beta[c] : 0.f;
-  const float sc = g * istd;
-  if (mean) mean[c] = (float)m;
-  if (invstd) invstd[c] = istd;
-  if (scale) scale[c] = sc;
-  if (shift) shift[c] = b - (float)m * sc;
-  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+  const BnChannel ch = bn_channel(ssum, ssq, count, gamma, beta, eps, c);
+  if (mean) mean[c] = ch.mean;
+  if (invstd) invstd[c] = ch.invstd;
+  if (scale) scale[c] = ch.scale;
+  if (shift) shift[c] = ch.shift;
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * ch.mean;
   if (rvar) {
-    const double unb = count > 1 ? var * count / (count - 1) : var;
+    const double unb = count > 1 ? ch.var * count / (count - 1) : ch.var;
     rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
   }
 }
@@ -136,6 +152,72 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat1
         sc = loadf8(scale + c0);
         sh = loadf8(shift + c0);
       }
+#pragma unroll
+      for (int j = 0; j < 8; j++) a.v[j] = fmaf(a.v[j], sc.v[j], sh.v[j]);
+      if (res) {
+        const Vec8 r = unpack_vec8(rr[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.v[j] += r.v[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a.v[j] = fmaxf(a.v[j], 0.f);
+      }
+      store8(out + i * 8, a);
+    }
+  }
+}
+
+// Training-mode BatchNorm forward in one launch: every thread derives scale / shift of ITS 8 channels from the fp64
+// batch sums (blockDim % vpr == 0, so they never change), block 0 additionally publishes mean / invstd / scale /
+// shift for the backward pass and updates the running statistics.  Saves the separate bn_finalize launch and its
+// dependency bubble per BatchNorm layer (21 per encoder and step).
+__global__ void __launch_bounds__(kEwThreads)
+    bn_train_apply_kernel(const __nv_bfloat16* __restrict__ y, const double* __restrict__ ssum,
+                          const double* __restrict__ ssq, double count, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
+                          float* __restrict__ rvar, float* __restrict__ bnp, const __nv_bfloat16* __restrict__ res,
+                          __nv_bfloat16* __restrict__ out, long long nvec, int vpr, int C, int relu) {
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const BnChannel ch = bn_channel(ssum, ssq, count, gamma, beta, eps, c);
+      bnp[c] = ch.mean;
+      bnp[C + c] = ch.invstd;
+      bnp[2 * C + c] = ch.scale;
+      bnp[3 * C + c] = ch.shift;
+      if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * ch.mean;
+      if (rvar) {
+        const double unb = count > 1 ? ch.var * count / (count - 1) : ch.var;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+      }
+    }
+  }
+  Vec8 sc, sh;
+  {
+    const int c0 = (int)(threadIdx.x % vpr) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const BnChannel ch = bn_channel(ssum, ssq, count, gamma, beta, eps, c0 + j);
+      sc.v[j] = ch.scale;
+      sh.v[j] = ch.shift;
+    }
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kEwUnroll) {
+    uint4 ry[kEwUnroll], rr[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        ry[u] = __ldg(reinterpret_cast<const uint4*>(y + i * 8));
+        if (res) rr[u] = __ldg(reinterpret_cast<const uint4*>(res + i * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; u++) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) break;
+      Vec8 a = unpack_vec8(ry[u]);
 #pragma unroll
       for (int j = 0; j < 8; j++) a.v[j] = fmaf(a.v[j], sc.v[j], sh.v[j]);
       if (res) {
@@ -270,7 +352,14 @@ __global__ void __launch_bounds__(kEwThreads)
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const double* __restrict__ red, double inv_count, long long nvec, int vpr, int C, int relu,
-                        __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres) {
+                        __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, double pg_scale) {
+  if (blockIdx.x == 0 && (dgamma || dbeta)) {  // dgamma = sum g*xhat, dbeta = sum g (x pg_scale, see the C-ABI comment)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)(red[c] * pg_scale);
+      if (dgamma) dgamma[c] = (float)(red[C + c] * pg_scale);
+    }
+  }
   extern __shared__ float coef[];  // [5][C]: A, B, K, scale, shift (only used when the channel vector is not fixed)
   // dy = A*g + B*y + K with A = gamma*invstd, B = -A*invstd*mean(g*xhat), K = -A*mean(g) - B*mu
   auto coefs = [&](int c, float& a, float& b, float& k) {
@@ -678,6 +767,58 @@ int launch_transpose(const float* in, TOut* out, int batch, int R, int Cc, bool 
   return ADNI_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-tensor weight conversion: every conv weight of an encoder in ONE launch.
+// fp32 parameter [Cout][Cin][taps]  ->  bf16 OTI [Cout][taps][Cin] (fprop B operand) and ITO [Cin][taps][Cout] (dgrad).
+// A ResNet-18 encoder has 19 tensor-core convs: 38 + 38 transpose launches per step otherwise, a fixed cost that
+// does not shrink with the per-GPU batch (11 % of the 8-GPU step).
+struct WeightJob {
+  const float* src;
+  __nv_bfloat16* oti;
+  __nv_bfloat16* ito;
+  int cout, cin, taps;
+  int tile_begin;  // first block of this tensor
+  int tiles_ci;    // 16-channel tiles along Cin
+};
+constexpr int kWTile = 16;
+constexpr int kWMaxTaps = 27;
+
+__global__ void __launch_bounds__(256) weights_multi_kernel(const WeightJob* __restrict__ jobs, int n_jobs) {
+  __shared__ float tile[kWTile][kWTile + 1][kWMaxTaps];  // +1: the ITO pass reads with the co index fastest
+  int j = 0;
+  while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].tile_begin) j++;
+  const WeightJob job = jobs[j];
+  const int t = blockIdx.x - job.tile_begin;
+  const int co0 = (t / job.tiles_ci) * kWTile, ci0 = (t % job.tiles_ci) * kWTile;
+  const int taps = job.taps;
+  // thread (a, b) of the 16 x 16 tile walks the taps: no divisions anywhere (the index arithmetic of a generic
+  // element-per-thread mapping cost more than the memory traffic)
+  const int a = threadIdx.x >> 4, b = threadIdx.x & 15;
+  {
+    const int co = a, ci = b;  // a thread reads the `taps` contiguous floats of one (co, ci)
+    if (co0 + co < job.cout && ci0 + ci < job.cin) {
+      const float* src = job.src + ((long long)(co0 + co) * job.cin + ci0 + ci) * taps;
+      for (int tp = 0; tp < taps; tp++) tile[co][ci][tp] = __ldg(src + tp);
+    }
+  }
+  __syncthreads();
+  if (job.oti) {
+    const int co = a, ci = b;  // 16 lanes write 16 consecutive Cin (32 bytes)
+    if (co0 + co < job.cout && ci0 + ci < job.cin) {
+      __nv_bfloat16* dst = job.oti + (long long)(co0 + co) * taps * job.cin + ci0 + ci;
+      for (int tp = 0; tp < taps; tp++) dst[(long long)tp * job.cin] = __float2bfloat16_rn(tile[co][ci][tp]);
+    }
+  }
+  if (job.ito) {
+    const int ci = a, co = b;  // 16 lanes write 16 consecutive Cout
+    if (co0 + co < job.cout && ci0 + ci < job.cin) {
+      __nv_bfloat16* dst = job.ito + (long long)(ci0 + ci) * taps * job.cout + co0 + co;
+      for (int tp = 0; tp < taps; tp++) dst[(long long)tp * job.cout] = __float2bfloat16_rn(tile[co][ci][tp]);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace adni
 
@@ -781,7 +922,7 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
                       const float* invstd, const float* gamma, const float* scale, const float* shift,
                       const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
-                      float* dgamma, float* dbeta, void* stream) {
+                      float* dgamma, float* dbeta, double param_grad_scale, void* stream) {
   ADNI_REQUIRE(dout && y && mean && invstd && red && dy && rows > 0 && count > 0, ADNI_EINVAL,
                "bn_bwd_apply: bad arguments");
   ADNI_REQUIRE(!relu || out || (scale && shift), ADNI_EINVAL,
@@ -792,14 +933,32 @@ int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf
   ADNI_REQUIRE(C <= 2048, ADNI_ENOTSUP, "bn_bwd_apply: C=%d > 2048", C);
   bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 5 * C * sizeof(float), ST(stream)>>>(
       CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, scale, shift, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy),
-      BF(dres));
+      BF(dres), dgamma, dbeta, param_grad_scale);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_bwd_apply_kernel");
-  if (dgamma || dbeta) {
-    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(red, C, dgamma, dbeta);
-    count_launch();
-    ADNI_LAUNCH_CHECK("bn_param_grads_kernel");
+  return ADNI_OK;
+}
+
+int adni_bn_train_apply(const adni_bf16* y, const double* stat_sum, const double* stat_sqsum, double count,
+                        const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                        float* running_var, float* bnp, const adni_bf16* residual, adni_bf16* out, long long rows, int C,
+                        int relu, void* stream) {
+  ADNI_REQUIRE(y && stat_sum && stat_sqsum && bnp && out && rows > 0 && count > 0, ADNI_EINVAL,
+               "bn_train_apply: bad arguments");
+  ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_train_apply: C=%d must be a multiple of 8", C);
+  const int vpr = C / 8;
+  if (kEwThreads % vpr != 0) {  // a thread's channels change from vector to vector: finalize first, then apply
+    int rc = adni_bn_finalize(stat_sum, stat_sqsum, count, C, gamma, beta, eps, momentum, running_mean, running_var, bnp,
+                              bnp + C, bnp + 2 * C, bnp + 3 * C, stream);
+    if (rc) return rc;
+    return adni_bn_apply(y, bnp + 2 * C, bnp + 3 * C, residual, out, rows, C, relu, nullptr, nullptr, stream);
   }
+  const long long nvec = rows * vpr;
+  bn_train_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(
+      CBF(y), stat_sum, stat_sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, bnp, CBF(residual),
+      BF(out), nvec, vpr, C, relu);
+  count_launch();
+  ADNI_LAUNCH_CHECK("bn_train_apply_kernel");
   return ADNI_OK;
 }
 
@@ -895,6 +1054,18 @@ int adni_weights_to_kernel_layout(const float* w_ncdhw, int Cout, int Cin, int t
   // ITO: [Cout][Cin*taps] -> [Cin*taps][Cout]
   if (rc == ADNI_OK && w_ito) rc = launch_transpose<bf16>(w_ncdhw, BF(w_ito), 1, Cout, Cin * taps, false, ST(stream));
   return rc;
+}
+
+int adni_weights_multi_job_bytes(void) { return (int)sizeof(WeightJob); }
+
+/* jobs: device array of n_jobs records {src, oti, ito, cout, cin, taps, tile_begin, tiles_ci} (see
+ * adni_weights_multi_job_bytes and multimodal_alzheimer_b200/kernels.py: WeightArena); total_tiles = sum of tiles. */
+int adni_weights_to_kernel_layout_multi(const void* jobs, int n_jobs, int total_tiles, void* stream) {
+  ADNI_REQUIRE(jobs && n_jobs > 0 && total_tiles > 0, ADNI_EINVAL, "weights_to_kernel_layout_multi: bad arguments");
+  weights_multi_kernel<<<total_tiles, 256, 0, ST(stream)>>>(static_cast<const WeightJob*>(jobs), n_jobs);
+  count_launch();
+  ADNI_LAUNCH_CHECK("weights_multi_kernel");
+  return ADNI_OK;
 }
 
 int adni_wgrad_to_param_layout(const float* dw_oti, int Cout, int Cin, int taps, float* grad_ncdhw, int accumulate,

@@ -29,11 +29,12 @@ class _Profile:
         torch.cuda.synchronize()
         out = {}
         shapes = {}
-        for tag, flops, e0, e1, shape in self.records:
+        for tag, flops, e0, e1, shape, frac in self.records:
             ms = e0.elapsed_time(e1)
             for dd, key in ((out, tag), (shapes, f"{tag} {shape}")):
-                d = dd.setdefault(key, {"flops": 0, "ms": 0.0, "n": 0})
+                d = dd.setdefault(key, {"flops": 0, "executed_flops": 0, "ms": 0.0, "n": 0})
                 d["flops"] += flops
+                d["executed_flops"] += flops * frac
                 d["ms"] += ms
                 d["n"] += 1
         self.shapes = shapes
@@ -47,23 +48,39 @@ class _Profile:
         e.record()
         return e
 
-    def end(self, e0, tag, flops, shape=""):
+    def end(self, e0, tag, flops, shape="", executed_fraction=1.0):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.records.append((tag, flops, e0, e1, shape))
+        self.records.append((tag, flops, e0, e1, shape, executed_fraction))
 
 
 PROFILE = _Profile()
 
 
-def _engine_tag(Cin, Cout, k, stride, engine, wgrad=False):
-    tc = engine == ENGINE_TCGEN05 or (engine == ENGINE_AUTO and Cin % 64 == 0 and Cout % 64 == 0 and
-                                      stride in (1, 2) and k ** 3 <= 64)
-    if not tc:
-        return "direct"
-    return "tc_wgrad" if wgrad else "tc_kmajor"
+_PLAN_CACHE = {}
+
+
+def _engine_tag(g, pass_, engine):
+    """(kernel-family tag, executed fraction of the algorithmic FLOPs) for bench.py's per-kernel roofline: asks the
+    library's own planner (adni_conv3d_plan_info) which engine the geometry is routed to."""
+    if not PROFILE.on:
+        return "", 1.0
+    key = (g.N, g.D, g.H, g.W, g.Cin, g.Cout, g.k, g.stride, g.pad, g.dil, pass_, engine)
+    hit = _PLAN_CACHE.get(key)
+    if hit is None:
+        import ctypes
+        kind, frac = ctypes.c_int(0), ctypes.c_double(1.0)
+        call("adni_conv3d_plan_info", g, pass_, ctypes.byref(kind), ctypes.byref(frac))
+        if engine == ENGINE_DIRECT or kind.value == 0:
+            hit = ("direct", 1.0)
+        elif pass_ == 2:
+            hit = ("tc_wgrad", 1.0)
+        else:
+            hit = ("tc_halo" if kind.value == 2 else "tc_kmajor", float(frac.value))
+        _PLAN_CACHE[key] = hit
+    return hit
 
 
 def _chk(t, dtype, name):
@@ -86,6 +103,105 @@ def weights_to_kernel_layout(w, want_ito=True):
     return oti, ito
 
 
+class _ZeroArena:
+    """fp64 accumulators (BatchNorm sums, loss partials) handed out as slices of a few pre-zeroed chunks: one fill
+    launch per 512 KB instead of one per [2, C] buffer (about 170 tiny fills per training step otherwise).  A slice is
+    never handed out twice; chunks are per (device, stream) because the fill is ordered on the allocating stream, and a
+    chunk zeroed outside CUDA-graph capture is never used inside one (its fill would not be part of the graph)."""
+
+    CHUNK = 65536
+
+    def __init__(self):
+        self.chunks = {}
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= d
+        n_al = (n + 15) & ~15  # 128-byte granules
+        capturing = torch.cuda.is_current_stream_capturing()
+        key = (device.index, stream_ptr().value)
+        rec = self.chunks.get(key)
+        if rec is None or rec[2] != capturing or rec[1] + n_al > rec[0].numel():
+            rec = [torch.zeros(max(self.CHUNK, n_al), dtype=torch.float64, device=device), 0, capturing]
+            self.chunks[key] = rec
+        v = rec[0][rec[1]:rec[1] + n].view(shape)
+        rec[1] += n_al
+        return v
+
+
+_ZEROS = _ZeroArena()
+
+
+def zeros_f64(shape, device):
+    return _ZEROS.take(tuple(shape), device)
+
+
+class WeightArena:
+    """Kernel-layout (bf16 OTI + ITO) copies of a fixed set of conv weights, refreshed by ONE launch
+    (adni_weights_to_kernel_layout_multi) instead of two transposes per conv.  The job table lives on the device and
+    is rebuilt only if a parameter is re-allocated; `lookup(w)` serves the copies while the parameter's version
+    counter is the one they were converted from, so a stale copy can never be used after an optimizer step."""
+
+    def __init__(self):
+        self.key = None
+        self.jobs = None
+        self.total_tiles = 0
+        self.copies = {}     # data_ptr -> (oti, ito)
+        self.versions = {}   # data_ptr -> parameter version the copies were made from
+
+    def refresh(self, weights):
+        import struct
+        ws = [w for w in weights if w.dim() == 5 and w[0, 0].numel() <= 27]
+        if not ws:
+            return
+        key = tuple((w.data_ptr(), tuple(w.shape)) for w in ws)
+        if key != self.key:
+            rec, tile_begin = [], 0
+            self.copies = {}
+            for w in ws:
+                cout, cin, taps = w.shape[0], w.shape[1], w[0, 0].numel()
+                oti = torch.empty((cout, taps, cin), dtype=BF16, device=w.device)
+                ito = torch.empty((cin, taps, cout), dtype=BF16, device=w.device)
+                self.copies[w.data_ptr()] = (oti, ito)
+                tiles_ci = (cin + 15) // 16
+                rec.append(struct.pack("<QQQiiiii", w.data_ptr(), oti.data_ptr(), ito.data_ptr(), cout, cin, taps,
+                                       tile_begin, tiles_ci))
+                tile_begin += ((cout + 15) // 16) * tiles_ci
+            size = int(_lib.load().adni_weights_multi_job_bytes())
+            blob = b"".join(r.ljust(size, b"\0") for r in rec)
+            self.jobs = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(ws[0].device)
+            self.total_tiles = tile_begin
+            self.key = key
+        call("adni_weights_to_kernel_layout_multi", ptr(self.jobs), len(ws), self.total_tiles, stream_ptr())
+        self.versions = {w.data_ptr(): w._version for w in ws}
+
+    def lookup(self, w):
+        hit = self.copies.get(w.data_ptr())
+        if hit is not None and self.versions.get(w.data_ptr()) == w._version:
+            return hit
+        return None
+
+
+import weakref
+
+_ARENAS = weakref.WeakSet()  # arenas of the live encoders (consulted by kernel_layout); owned by their modules
+
+
+def kernel_layout(w, want_ito=True):
+    """(OTI, ITO) of a conv weight: the arena copy if an enclosing encoder refreshed one for this version of the
+    parameter, else a per-tensor conversion."""
+    for arena in _ARENAS:
+        hit = arena.lookup(w)
+        if hit is not None:
+            return hit
+    return weights_to_kernel_layout(w, want_ito=want_ito)
+
+
+def register_arena(arena):
+    _ARENAS.add(arena)
+
+
 def wgrad_to_param_layout(dw_oti, shape, out=None):
     """fp32 [Cout, taps, Cin] -> fp32 parameter-shaped gradient [Cout, Cin, kd, kh, kw]."""
     cout, cin = shape[0], shape[1]
@@ -105,12 +221,13 @@ def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE
     g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
     Do, Ho, Wo = (out_extent(v, k, stride, pad, dil) for v in (D, H, W))
     y = torch.empty((N, Do, Ho, Wo, Cout), dtype=BF16, device=x.device)
-    st = torch.zeros((2, Cout), dtype=torch.float64, device=x.device) if stats else None
+    st = zeros_f64((2, Cout), x.device) if stats else None
     ev = PROFILE.begin()
     call("adni_conv3d_fprop", g, ptr(x), ptr(w_oti), ptr(bias), ptr(y), ptr(st[0]) if stats else None,
          ptr(st[1]) if stats else None, engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3,
-                f"fprop N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
+    tag, frac = _engine_tag(g, 0, engine)
+    PROFILE.end(ev, tag, 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3,
+                f"fprop N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
     return y, st
 
 
@@ -125,8 +242,9 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
         _chk(addend, BF16, "addend")
     ev = PROFILE.begin()
     call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine), 2 * dy.numel() * Cin * k ** 3,
-                f"dgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
+    tag, frac = _engine_tag(g, 1, engine)
+    PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
+                f"dgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
     return dx
 
 
@@ -149,8 +267,9 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
         db = s[0].to(torch.float32)
     ev = PROFILE.begin()
     call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, engine, stream_ptr())
-    PROFILE.end(ev, _engine_tag(Cin, Cout, k, stride, engine, wgrad=True), 2 * dy.numel() * Cin * k ** 3,
-                f"wgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}")
+    tag, frac = _engine_tag(g, 2, engine)
+    PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
+                f"wgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
     return dw, db
 
 
@@ -176,7 +295,7 @@ def stem_fprop(x8, in_shape, w, stats=True):
     call("adni_stem_weights", ptr(_chk(w.detach(), torch.float32, "weight")), ptr(w2g), stream_ptr())
     Do, Ho, Wo = ((v - 1) // 2 + 1 for v in (D, H, W))
     y = torch.empty((N, Do, Ho, Wo, 64), dtype=BF16, device=x8.device)
-    st = torch.zeros((2, 64), dtype=torch.float64, device=x8.device) if stats else None
+    st = zeros_f64((2, 64), x8.device) if stats else None
     ev = PROFILE.begin()
     call("adni_stem_fprop", ptr(x8), N, D, H, W, ptr(w2g), ptr(y), ptr(st[0]) if stats else None,
          ptr(st[1]) if stats else None, stream_ptr())
@@ -215,6 +334,20 @@ def bn_apply(y, scale, shift, residual=None, relu=True):
     call("adni_bn_apply", ptr(y), ptr(scale), ptr(shift), ptr(residual), ptr(out), rows, C, int(relu), None, None,
          stream_ptr())
     return out
+
+
+def bn_train_apply(y, stats, count, gamma, beta, eps, momentum, running_mean, running_var, residual=None, relu=True):
+    """Training-mode BatchNorm forward in one launch. Returns (out, bnp) with bnp = fp32 [4, C] (mean, invstd, scale,
+    shift); running statistics are updated in place."""
+    _chk(y, BF16, "y")
+    C = y.shape[-1]
+    rows = y.numel() // C
+    out = torch.empty_like(y)
+    bnp = torch.empty((4, C), dtype=torch.float32, device=y.device)
+    call("adni_bn_train_apply", ptr(y), ptr(stats[0]), ptr(stats[1]), float(count), ptr(gamma), ptr(beta), float(eps),
+         float(momentum), ptr(running_mean), ptr(running_var), ptr(bnp), ptr(residual), ptr(out), rows, C, int(relu),
+         stream_ptr())
+    return out, bnp
 
 
 def bn_param_grads(red):
@@ -259,7 +392,7 @@ def channel_stats(x2d):
     _chk(x2d, BF16, "x")
     C = x2d.shape[-1]
     rows = x2d.numel() // C
-    st = torch.zeros((2, C), dtype=torch.float64, device=x2d.device)
+    st = zeros_f64((2, C), x2d.device)
     call("adni_channel_stats", ptr(x2d), rows, C, ptr(st[0]), ptr(st[1]), stream_ptr())
     return st
 
@@ -268,14 +401,14 @@ def bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale=None, shift=None):
     """relu mask: from `out`, or (out None, no residual in the forward) recomputed from y*scale+shift."""
     C = y.shape[-1]
     rows = y.numel() // C
-    red = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+    red = zeros_f64((2, C), y.device)
     call("adni_bn_bwd_reduce", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(scale),
          ptr(shift), rows, C, int(relu), ptr(red), stream_ptr())
     return red
 
 
 def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_param_grads=True, scale=None,
-                 shift=None):
+                 shift=None, param_grad_scale=1.0):
     C = y.shape[-1]
     rows = y.numel() // C
     dy = torch.empty_like(y)
@@ -283,7 +416,8 @@ def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres,
     pg = torch.empty((2, C), dtype=torch.float32, device=y.device) if want_param_grads else None
     call("adni_bn_bwd_apply", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
          ptr(scale), ptr(shift), ptr(red), float(count), rows, C, int(relu), ptr(dy), ptr(dres),
-         ptr(pg[0]) if want_param_grads else None, ptr(pg[1]) if want_param_grads else None, stream_ptr())
+         ptr(pg[0]) if want_param_grads else None, ptr(pg[1]) if want_param_grads else None, float(param_grad_scale),
+         stream_ptr())
     if want_param_grads:
         return dy, dres, pg[0], pg[1]
     return dy, dres, None, None
@@ -325,7 +459,7 @@ def bn_relu_maxpool_fwd(y, bnp, k, stride, pad):
 
 def maxpool_bn_bwd_reduce(dp, argmax, y, bnp, k, stride, pad):
     N, D, H, W, C = y.shape
-    red = torch.zeros((2, C), dtype=torch.float64, device=y.device)
+    red = zeros_f64((2, C), y.device)
     call("adni_maxpool_bn_bwd_reduce", ptr(dp), ptr(argmax), ptr(y), ptr(bnp), N, D, H, W, C, k, stride, pad, ptr(red),
          stream_ptr())
     return red
@@ -389,7 +523,7 @@ def linear_bwd(x, W, y, dy, relu, need_dx=True, need_dw=True, has_bias=True):
 
 def rows_stats_f32(x):
     B, C = x.shape
-    st = torch.zeros((2, C), dtype=torch.float64, device=x.device)
+    st = zeros_f64((2, C), x.device)
     call("adni_rows_stats_f32", ptr(x), _ld(x), B, C, ptr(st), stream_ptr())
     return st
 
@@ -403,7 +537,7 @@ def bn1d_apply(x, scale, shift, relu):
 
 def bn1d_bwd_reduce(dy, y, x, mean, invstd, relu):
     B, C = x.shape
-    red = torch.zeros((2, C), dtype=torch.float64, device=x.device)
+    red = zeros_f64((2, C), x.device)
     call("adni_bn1d_bwd_reduce", ptr(dy), _ld(dy), ptr(y), _ld(y), ptr(x), _ld(x), ptr(mean), ptr(invstd), B, C,
          int(relu), ptr(red), stream_ptr())
     return red

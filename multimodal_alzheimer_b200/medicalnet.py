@@ -10,6 +10,7 @@ residual block runs as one autograd Function (multimodal_alzheimer_b200/autograd
 import torch.nn as tnn
 
 from . import autograd as A
+from . import kernels as K
 from . import nn as bnn
 
 
@@ -109,9 +110,18 @@ class ResNet(tnn.Module):
         return A.StemFn.apply(bnn.as_volume(x), self.conv1.weight, self.bn1.weight, self.bn1.bias, self.bn1.state(),
                               self.conv1.cfg, (mp.kernel_size, mp.stride, mp.padding))
 
+    def _refresh_kernel_weights(self):
+        """bf16 kernel-layout copies of every tensor-core conv weight of the encoder, in one launch."""
+        if getattr(self, "_arena", None) is None:
+            self._arena = K.WeightArena()
+            K.register_arena(self._arena)
+        self._arena.refresh([m.weight for m in self.modules() if isinstance(m, bnn.Conv3d) and m is not self.conv1])
+
     def features(self, x):
-        x = self.stem(x)
-        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        self._refresh_kernel_weights()
+        with A.defer_bn_counters():
+            x = self.stem(x)
+            return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):
         return self.conv_seg(self.features(x))
