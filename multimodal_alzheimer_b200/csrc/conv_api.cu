@@ -16,8 +16,9 @@ namespace adni {
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
-int halo_plan_smem(HaloParams* p, int block_n);
-int launch_igemm_halo(const HaloParams& p, int block_n, int smem_bytes, cudaStream_t stream);
+int halo_pitch();
+int halo_rows();
+int launch_igemm_halo(const HaloParams& p, int channels, cudaStream_t stream);
 
 int direct_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti,
                       const float* bias, __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
@@ -154,17 +155,12 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
   const int C = g.Cin;
   HaloParams p;
   memset(&p, 0, sizeof(p));
-  p.pitch = env_int("ADNI_HALO_PITCH", 10);
-  p.debug = env_int("ADNI_HALO_DEBUG", 0);
-  p.kb = C / 64;
-  if (p.pitch < 10 || p.pitch > 16) return ADNI_ENOTSUP;
-  const int smem_bytes = halo_plan_smem(&p, C);
-  if (smem_bytes == 0) return ADNI_ENOTSUP;
+  p.mirror = mirror ? 1 : 0;
   {
     const uint64_t dims[5] = {uint64_t(C), uint64_t(g.W), uint64_t(g.H), uint64_t(g.D), uint64_t(g.N)};
     const uint64_t strides[5] = {1, uint64_t(C), uint64_t(g.W) * C, uint64_t(g.H) * g.W * C,
                                  uint64_t(g.D) * g.H * g.W * C};
-    const uint32_t box[5] = {64, uint32_t(p.pitch), 18, 1, 1};
+    const uint32_t box[5] = {64, uint32_t(halo_pitch()), uint32_t(halo_rows()), 1, 1};
     int rc = make_tmap_bf16(&p.a_map, a, 5, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -175,12 +171,6 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
     int rc = make_tmap_bf16(&p.b_map, w, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  for (int od = 0; od < 3; od++)
-    for (int oh = 0; oh < 3; oh++)
-      for (int ow = 0; ow < 3; ow++) {
-        const int t = mirror ? ((2 - od) * 3 + (2 - oh)) * 3 + (2 - ow) : (od * 3 + oh) * 3 + ow;
-        p.kofs[(od * 3 + oh) * 3 + ow] = t * C;
-      }
   p.N = g.N;
   p.D = g.D;
   p.H = g.H;
@@ -199,7 +189,7 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
   p.bias = bias;
   p.stat_sum = ssum;
   p.stat_sq = ssq;
-  return launch_igemm_halo(p, C, smem_bytes, stream);
+  return launch_igemm_halo(p, C, stream);
 }
 
 int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,

@@ -6,24 +6,26 @@
 // With only 64 / 128 output channels to amortise it over, that A-operand stream (measured ~5.2 TB/s out of L2 on
 // every layer) is the bound: layer1 runs at 0.33 PFLOP/s, 16 % tensor-pipe active.  Here the CTA owns a COLUMN
 // of output plane pieces (8 w x 16 h positions, walking along d) and keeps the zero-padded input planes
-// d-1, d, d+1 ((8+2) x (16+2) positions x 64 channels each, one TMA box per plane, hardware zero fill at the
-// borders) in a shared-memory ring.  Every tap's A operand is a shifted VIEW of a resident plane: the UMMA
-// shared-memory descriptor starts at row (kh*pitch + kw) of the plane and strides `pitch` rows between the
-// 16 eight-row groups of the M = 128 tile, so the 128-byte swizzle phase (address bits 7..9) stays the one
-// TMA wrote.  L2 -> SM traffic for activations drops from 27x to ~1.4x the tensor; only the weight tiles
-// (shared by all CTAs) are streamed per tap.
+// ((8+2) x (16+2) positions x 64 channels each, one TMA box per plane, hardware zero fill at the borders) in a
+// shared-memory ring.  Every tap's A operand is a shifted VIEW of a resident plane: the UMMA shared-memory
+// descriptor starts at row (kh*10 + kw) of the plane and strides 10 rows between the 16 eight-row groups of the
+// M = 128 tile, so the 128-byte swizzle phase (address bits 7..9) stays the one TMA wrote.  L2 -> SM traffic for
+// activations drops from 27x to ~1.4x the tensor; only the weight tiles (shared by all CTAs) are streamed.
 //
-// Issue-side bound.  tools/ubench/pipe_bench.cu: one pipeline stage costs the issuing thread ~190 cycles of
-// mbarrier wait / tcgen05.commit plus ~48 cycles per tcgen05.mma, and the tensor pipe only queues 1-2 MMAs ahead,
-// so with N = 64 / 128 (60 / 64-cycle MMAs) a single issuer leaves the pipe idle for most of that overhead.
-// Two remedies here: (1) TWO MMA-issuing warps take alternate weight stages and accumulate into their own TMEM
-// accumulators (summed in the epilogue in a fixed order, so results stay deterministic) - one warp's barrier
-// overhead overlaps the other's MMAs; (2) a weight stage carries `tps` taps (3 for N = 64: one kh row, 12 MMAs).
+// What bounds it after that, and the three answers (measured with the diagnostics described in DESIGN.md):
+//  (1) the issuing thread: one pipeline stage costs ~190 cycles of mbarrier wait / tcgen05.commit plus ~48 cycles
+//      per tcgen05.mma, and the tensor pipe only queues 1-2 MMAs ahead (tools/ubench/pipe_bench.cu).  TWO MMA
+//      warps take alternate weight stages and accumulate into their own TMEM accumulators (summed in the epilogue in
+//      a fixed order: deterministic); a weight stage carries TPS taps (3 for N = 64: one kh row);
+//  (2) the weight stream itself (24 KB per 12 MMAs = 33 B/clk/SM of the same lines for all 148 CTAs): with G = 2 a
+//      weight stage is applied to TWO consecutive output pieces of the column (planes d-1 .. d+2 resident);
+//  (3) instruction overhead: everything is a template constant or scalar ring arithmetic - no divisions, no
+//      parameter-table lookups inside the loops.
 //
-// Warp roles (256 threads, 1 CTA / SM): warp 0 = weight-tile TMA producer, warps 1 and 7 = MMA issuers (warp 1 owns
+// Warp roles (256 threads, 1 CTA / SM): warp 0 = weight-stage TMA producer, warps 1 and 7 = MMA issuers (warp 1 owns
 // TMEM), warps 2-5 = epilogue (TMEM -> bias / residual-gradient add / BatchNorm sums -> bf16 stores), warp 6 =
-// halo-plane TMA producer.  Two accumulator buffers per issuer overlap the epilogue of piece i with the MMAs of
-// piece i+1 (4 x BLOCK_N TMEM columns in total).
+// halo-plane TMA producer.  Accumulators: [issuer 2][buffer 2][piece G] x BLOCK_N columns = all 512 TMEM columns;
+// the two buffers overlap the epilogue of group i with the MMAs of group i+1.
 #include "conv_igemm.cuh"
 
 namespace adni {
@@ -35,7 +37,26 @@ namespace {
 constexpr int kHaloThreads = 256;
 constexpr int kHaloBoxH = 16, kHaloBoxW = 8;
 constexpr int kHaloRows = kHaloBoxH + 2;
-constexpr int kMaxRing = 4, kMaxBStages = 16;
+constexpr int kHaloPitch = kHaloBoxW + 2;                                         // positions per halo row
+constexpr int kHaloPlaneKbBytes = (kHaloPitch * kHaloRows * 128 + 1023) & ~1023;  // one 64-channel plane: 23552
+
+template <int BLOCK_N, int KB, int TPS, int G>
+struct HaloCfg {
+  static constexpr int B_TILE = BLOCK_N * 128;      // one tap x 64 channels of weights
+  static constexpr int STAGE_BYTES = TPS * B_TILE;  // one weight stage
+  static constexpr int PLANE_BYTES = KB * kHaloPlaneKbBytes;
+  static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 4;
+  static constexpr int AVAIL = 232448 - 1024 - 512 - STAT_BYTES;
+  static constexpr int RING = (G + 2) + (G == 2 ? 2 : (KB == 1 ? 1 : 0));  // planes in use + prefetch
+  static constexpr int NBST_FIT = (AVAIL - RING * PLANE_BYTES) / STAGE_BYTES;
+  static constexpr int NBST = NBST_FIT > 8 ? 8 : NBST_FIT;
+  static constexpr int BAR_OFF = RING * PLANE_BYTES + NBST * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + STAT_BYTES + 1024;
+  static constexpr int TMEM_COLS = 4 * G * BLOCK_N;
+  static_assert(NBST >= 3, "weight pipeline too shallow");
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(2 * (RING + NBST) + 4 <= 60, "barrier block too small");
+};
 
 struct HaloSeg {
   int n, h0, w0;  // sample and origin of the plane piece
@@ -59,22 +80,21 @@ __device__ __forceinline__ HaloSeg halo_segment(const HaloParams& p, int i, int 
   return s;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KB, int TPS, int G>
 __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
-  constexpr int B_TILE = BLOCK_N * 128;  // one tap x 64 channels of weights
-  constexpr int TMEM_COLS = 4 * BLOCK_N;
-  const int stage_bytes = p.tps * B_TILE;
+  using Cfg = HaloCfg<BLOCK_N, KB, TPS, G>;
+  constexpr int RING = Cfg::RING, NBST = Cfg::NBST;
+  constexpr int B_TILE = Cfg::B_TILE, STAGE_BYTES = Cfg::STAGE_BYTES, PLANE_BYTES = Cfg::PLANE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int plane_bytes = p.kb * p.plane_kb_bytes;
   uint8_t* smem_p = smem;
-  uint8_t* smem_b = smem + p.ring * plane_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * stage_bytes);
+  uint8_t* smem_b = smem + RING * PLANE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* full_p = bars;
-  uint64_t* empty_p = bars + kMaxRing;
-  uint64_t* full_b = bars + 2 * kMaxRing;
-  uint64_t* empty_b = full_b + kMaxBStages;
-  uint64_t* tfull = empty_b + kMaxBStages;
+  uint64_t* empty_p = full_p + RING;
+  uint64_t* full_b = empty_p + RING;
+  uint64_t* empty_b = full_b + NBST;
+  uint64_t* tfull = empty_b + NBST;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
@@ -83,15 +103,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
   const int lane = threadIdx.x & 31;
   const int begin = static_cast<int>(static_cast<long long>(p.total) * blockIdx.x / gridDim.x);
   const int end = static_cast<int>(static_cast<long long>(p.total) * (blockIdx.x + 1) / gridDim.x);
-  const int ring = p.ring, nbst = p.b_stages;
-  // diagnostics (ADNI_HALO_DEBUG bits): 1 no MMA issue, 2 no weight TMA, 4 no plane TMA, 8 no epilogue stores
+  const int D = p.D;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxRing; i++) {
+    for (int i = 0; i < RING; i++) {
       mbar_init(&full_p[i], 1);
-      mbar_init(&empty_p[i], 2);
+      mbar_init(&empty_p[i], 2);  // both MMA issuers release a plane
     }
-    for (int i = 0; i < kMaxBStages; i++) {
+    for (int i = 0; i < NBST; i++) {
       mbar_init(&full_b[i], 1);
       mbar_init(&empty_b[i], 1);
     }
@@ -102,7 +121,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -114,53 +133,56 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     // ===================== halo-plane producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&p.a_map);
-      const uint32_t tx = static_cast<uint32_t>(p.kb * p.pitch * kHaloRows) * 128u;
-      uint32_t seq = 0;
+      constexpr uint32_t tx = static_cast<uint32_t>(KB * kHaloPitch * kHaloRows) * 128u;
+      int slot = 0;
+      uint32_t par = 0;
       for (int i = begin; i < end;) {
         const HaloSeg s = halo_segment(p, i, end);
-        for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
-          const uint32_t slot = seq % ring, par = (seq / ring) & 1u;
+        for (int pz = s.pf; pz <= s.pl; pz++) {
           mbar_wait_spin(&empty_p[slot], par ^ 1u);
-          if (p.debug & 4) {
-            mbar_arrive(&full_p[slot]);
-            continue;
-          }
           mbar_arrive_expect_tx(&full_p[slot], tx);
-          for (int kb = 0; kb < p.kb; kb++)
-            tma_load_5d(smem_p + slot * plane_bytes + kb * p.plane_kb_bytes, &p.a_map, &full_p[slot], kb * 64,
-                        s.w0 - 1, s.h0 - 1, pz, s.n);
+#pragma unroll
+          for (int kb = 0; kb < KB; kb++)
+            tma_load_5d(smem_p + slot * PLANE_BYTES + kb * kHaloPlaneKbBytes, &p.a_map, &full_p[slot], kb * 64, s.w0 - 1,
+                        s.h0 - 1, pz, s.n);
+          if (++slot == RING) {
+            slot = 0;
+            par ^= 1u;
+          }
         }
         i += s.dB - s.dA;
       }
     }
   } else if (warp == 0) {
-    // ===================== weight-tile producer =====================
+    // ===================== weight-stage producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&p.b_map);
+      constexpr int C = KB * 64;
+      const int mirror = p.mirror;
       int st = 0;
       uint32_t ph = 0;
       for (int i = begin; i < end;) {
         const HaloSeg s = halo_segment(p, i, end);
-        for (int d = s.dA; d < s.dB; d++) {
+        for (int d = s.dA; d < s.dB; d += G) {
+          const int g = min(G, s.dB - d);
+#pragma unroll 1
           for (int kd = 0; kd < 3; kd++) {
-            const int pz = d + kd - 1;
-            if (pz < 0 || pz >= p.D) continue;
-            for (int kh = 0; kh < 3; kh++) {
-              for (int kw0 = 0; kw0 < 3; kw0 += p.tps) {
-                for (int kb = 0; kb < p.kb; kb++) {
-                  mbar_wait_spin(&empty_b[st], ph ^ 1u);
-                  if (p.debug & 2) {
-                    mbar_arrive(&full_b[st]);
-                  } else {
-                    mbar_arrive_expect_tx(&full_b[st], static_cast<uint32_t>(stage_bytes));
-                    for (int tp = 0; tp < p.tps; tp++)
-                      tma_load_2d(smem_b + st * stage_bytes + tp * B_TILE, &p.b_map, &full_b[st],
-                                  p.kofs[kd * 9 + kh * 3 + kw0 + tp] + kb * 64, 0);
-                  }
-                  if (++st == nbst) {
-                    st = 0;
-                    ph ^= 1u;
-                  }
+            if (d + kd + g - 2 < 0 || d + kd - 1 > D - 1) continue;  // no piece of the group has this input plane
+#pragma unroll 1
+            for (int t9 = 0; t9 < 9; t9 += TPS) {
+#pragma unroll
+              for (int kb = 0; kb < KB; kb++) {
+                mbar_wait_spin(&empty_b[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_b[st], STAGE_BYTES);
+#pragma unroll
+                for (int tp = 0; tp < TPS; tp++) {
+                  const int idx = kd * 9 + t9 + tp;  // halo offset (od, oh, ow) -> weight tap (mirrored for dgrad)
+                  tma_load_2d(smem_b + st * STAGE_BYTES + tp * B_TILE, &p.b_map, &full_b[st],
+                              (mirror ? 26 - idx : idx) * C + kb * 64, 0);
+                }
+                if (++st == NBST) {
+                  st = 0;
+                  ph ^= 1u;
                 }
               }
             }
@@ -173,184 +195,268 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) =====================
     const uint32_t mw = warp == 1 ? 0u : 1u;  // this warp issues the weight stages whose running index has parity mw
     constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, false, false);
-    const uint64_t a_hi = umma_smem_desc_sw128(0, 16, static_cast<uint32_t>(p.pitch) * 128u) & 0xFFFFFFFF00000000ull;
-    const uint64_t b_hi = umma_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFF00000000ull;
-    const uint32_t smem_p_u32 = smem_u32(smem_p), smem_b_u32 = smem_u32(smem_b);
+    // descriptors as 32-bit halves: low word = start address >> 4 (LBO unused for swizzled K-major),
+    // high word = SBO >> 4 | version | SWIZZLE_128B
+    const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, kHaloPitch * 128u) >> 32);
+    const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024) >> 32);
+    const uint32_t lo_c = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024) & 0xFFFFFFFFull);
+    const uint32_t a_lo0 = lo_c + ((smem_u32(smem_p) & 0x3FFFFu) >> 4);
+    const uint32_t b_lo0 = lo_c + ((smem_u32(smem_b) & 0x3FFFFu) >> 4);
     int st = 0;
     uint32_t ph = 0;
-    int acc = 0;
-    uint32_t accph = 0;
-    uint32_t seq0 = 0, waited = 0, gs = 0;
+    int buf = 0;
+    uint32_t bufph = 0;
+    uint32_t gs = 0;
+    int w_slot = 0, r_slot = 0;  // ring cursors of the next plane to wait for / to hand back
+    uint32_t w_par = 0;
+    int n_waited = 0, n_released = 0, seq0 = 0;
     for (int i = begin; i < end;) {
       const HaloSeg s = halo_segment(p, i, end);
-      for (int d = s.dA; d < s.dB; d++) {
-        mbar_wait_spin(&tempty[acc], accph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (mw * 2u + static_cast<uint32_t>(acc)) * BLOCK_N;
-        uint32_t accum = 0;
-        for (int kd = 0; kd < 3; kd++) {
-          const int pz = d + kd - 1;
-          if (pz < 0 || pz >= p.D) continue;
-          const uint32_t sq = seq0 + static_cast<uint32_t>(pz - s.pf);
-          const uint32_t slot = sq % ring;
-          while (waited <= sq) {  // planes become visible in load order; each is waited for exactly once
-            mbar_wait_spin(&full_p[waited % ring], (waited / ring) & 1u);
-            waited++;
+      const int rel0 = s.dA - 1 - s.pf;           // plane dA-1 relative to the first loaded plane (-1 or 0)
+      int sl0 = (seq0 + rel0 + 2 * RING) % RING;  // ring slot of plane d-1 (virtual for the plane above the volume)
+      for (int d = s.dA; d < s.dB; d += G) {
+        const int g = min(G, s.dB - d);
+        mbar_wait_spin(&tempty[buf], bufph ^ 1u);
+        const int need = seq0 + min(d + g, D - 1) - s.pf;  // last plane of the group, as a running count
+        while (n_waited <= need) {
+          mbar_wait_spin(&full_p[w_slot], w_par);
+          n_waited++;
+          if (++w_slot == RING) {
+            w_slot = 0;
+            w_par ^= 1u;
           }
-          const uint32_t plane_addr = smem_p_u32 + slot * plane_bytes;
-          for (int kh = 0; kh < 3; kh++) {
-            for (int kw0 = 0; kw0 < 3; kw0 += p.tps) {
-              for (int kb = 0; kb < p.kb; kb++, gs++) {
-                if ((gs & 1u) == mw) {
-                  mbar_wait_spin(&full_b[st], ph);
-                  tc_fence_after();
-                  const uint32_t a_lo =
-                      ((plane_addr + kb * p.plane_kb_bytes + static_cast<uint32_t>(kh * p.pitch + kw0) * 128u) & 0x3FFFFu) >> 4;
-                  const uint32_t b_lo = ((smem_b_u32 + st * stage_bytes) & 0x3FFFFu) >> 4;
-                  if (elect_one_sync()) {
-                    if (!(p.debug & 1)) {
-                      for (int tp = 0; tp < p.tps; tp++) {
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (mw * 2u + static_cast<uint32_t>(buf)) * (G * BLOCK_N);
+        uint32_t started = 0;  // bit q: this issuer's accumulator of piece q has been written in this group
+#pragma unroll 1
+        for (int kd = 0; kd < 3; kd++) {
+          if (d + kd + g - 2 < 0 || d + kd - 1 > D - 1) continue;
+          // descriptor base and validity of the input plane of every piece for this kd
+          uint32_t a_plane[G];
+          bool q_ok[G];
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                          umma_bf16(d_tmem, a_hi | (a_lo + tp * 8 + k * 2), b_hi | (b_lo + tp * (B_TILE >> 4) + k * 2), idesc,
-                                    accum | static_cast<uint32_t>(tp | k));
-                      }
+          for (int q = 0; q < G; q++) {
+            const int z = d + q + kd - 1;
+            q_ok[q] = q < g && z >= 0 && z < D;
+            int sl = sl0 + q + kd;
+            if (sl >= RING) sl -= RING;
+            a_plane[q] = a_lo0 + static_cast<uint32_t>(sl) * (PLANE_BYTES >> 4);
+          }
+#pragma unroll 1
+          for (int t9 = 0; t9 < 9; t9 += TPS) {
+            const int kh = t9 / 3, kw0 = t9 - kh * 3;
+            const uint32_t row_off = static_cast<uint32_t>(kh * kHaloPitch + kw0) * (128u >> 4);
+#pragma unroll
+            for (int kb = 0; kb < KB; kb++, gs++) {
+              if ((gs & 1u) == mw) {
+                mbar_wait_spin(&full_b[st], ph);
+                tc_fence_after();
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(st) * (STAGE_BYTES >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                  for (int q = 0; q < G; q++) {
+                    if (!q_ok[q]) continue;
+                    const uint32_t a_lo = a_plane[q] + kb * (kHaloPlaneKbBytes >> 4) + row_off;
+                    const uint32_t first = (started >> q) & 1u;
+#pragma unroll
+                    for (int tp = 0; tp < TPS; tp++) {
+#pragma unroll
+                      for (int k = 0; k < 4; k++)
+                        umma_bf16(d_tmem + q * BLOCK_N, (static_cast<uint64_t>(a_hi) << 32) | (a_lo + tp * 8 + k * 2),
+                                  (static_cast<uint64_t>(b_hi) << 32) | (b_lo + tp * (B_TILE >> 4) + k * 2), idesc,
+                                  first | static_cast<uint32_t>(tp | k));
                     }
-                    umma_commit(&empty_b[st]);  // frees the weight stage once these MMAs have read it
                   }
-                  __syncwarp();
-                  accum = 1;
+                  umma_commit(&empty_b[st]);  // frees the weight stage once these MMAs have read it
                 }
-                if (++st == nbst) {
-                  st = 0;
-                  ph ^= 1u;
-                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < G; q++)
+                  if (q_ok[q]) started |= 1u << q;
+              }
+              if (++st == NBST) {
+                st = 0;
+                ph ^= 1u;
               }
             }
           }
         }
+        // planes no later group of this column needs go back to the producer once these MMAs retire
+        const int last_free = seq0 + ((d + g >= s.dB) ? s.pl - s.pf : (d + g - 2 - s.pf));
         if (elect_one_sync()) {
-          umma_commit(&tfull[acc]);
-          // planes no later piece of this column needs go back to the producer once these MMAs retire
-          if (d - 1 >= s.pf) umma_commit(&empty_p[(seq0 + static_cast<uint32_t>(d - 1 - s.pf)) % ring]);
-          if (d == s.dB - 1) {
-            umma_commit(&empty_p[(seq0 + static_cast<uint32_t>(d - s.pf)) % ring]);
-            if (d + 1 <= s.pl) umma_commit(&empty_p[(seq0 + static_cast<uint32_t>(d + 1 - s.pf)) % ring]);
+          umma_commit(&tfull[buf]);
+          int rs = r_slot;
+          for (int r = n_released; r <= last_free; r++) {
+            umma_commit(&empty_p[rs]);
+            if (++rs == RING) rs = 0;
           }
         }
         __syncwarp();
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1u;
+        while (n_released <= last_free) {
+          n_released++;
+          if (++r_slot == RING) r_slot = 0;
+        }
+        sl0 += g;
+        if (sl0 >= RING) sl0 -= RING;
+        if (++buf == 2) {
+          buf = 0;
+          bufph ^= 1u;
         }
       }
-      seq0 += static_cast<uint32_t>(s.pl - s.pf + 1);
+      seq0 += s.pl - s.pf + 1;
       i += s.dB - s.dA;
     }
   } else {
     // ===================== Epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q4 = warp & 3;  // TMEM lane quadrant this warp may access
     const int ew = warp - 2;
     const int et = threadIdx.x - 64;  // 0..127
-    const int row = q * 32 + lane;
+    const int row = q4 * 32 + lane;
     const int rh = row / kHaloBoxW, rw = row % kHaloBoxW;
     const bool do_stats = p.stat_sum != nullptr;
-    // BatchNorm sums are carried per CTA in fp64 registers and flushed ONCE: same-address fp64 atomics retire at
-    // ~1 per 27 cycles in L2, so one atomic per (piece, channel) from 148 CTAs is a serial bottleneck of its own
-    // (stem: 65536 pieces x 27 cycles = the whole kernel time).
+    // BatchNorm sums.  BLOCK_N = 64: every thread owns one tile row and keeps fp32 partial sums of its 64 channels in
+    // registers for the whole CTA; one transpose-reduce and one fp64 atomic per channel at the end.  BLOCK_N = 128:
+    // per-piece transpose-reduce into per-CTA fp64 sums (the register file does not hold 256 accumulators).
+    constexpr bool REG_STATS = BLOCK_N == 64;
+    constexpr int NREG = REG_STATS ? BLOCK_N : 1;
+    float rs1[NREG], rs2[NREG];
+#pragma unroll
+    for (int j = 0; j < NREG; j++) rs1[j] = rs2[j] = 0.f;
     double cta_sum = 0.0, cta_sq = 0.0;
-    int acc = 0;
-    uint32_t accph = 0;
+    int buf = 0;
+    uint32_t bufph = 0;
     for (int i = begin; i < end;) {
       const HaloSeg s = halo_segment(p, i, end);
       const int oh = s.h0 + rh, ow = s.w0 + rw;
       const bool valid = oh < p.H && ow < p.W;
-      for (int d = s.dA; d < s.dB; d++) {
-        const long long off = s.n * p.out_sn + d * p.out_sd + oh * p.out_sh + ow * p.out_sw;
-        mbar_wait_spin(&tfull[acc], accph);
+      for (int d = s.dA; d < s.dB; d += G) {
+        const int g = min(G, s.dB - d);
+        mbar_wait_spin(&tfull[buf], bufph);
         tc_fence_after();
 #pragma unroll 1
-        for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
-          uint32_t v[32], v2[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(acc * BLOCK_N + chunk * 32);
-          tmem_ld_32x32(taddr, v);                 // issuer 0's partial sums
-          tmem_ld_32x32(taddr + 2 * BLOCK_N, v2);  // issuer 1's
-          tmem_ld_wait();
-          float f[32];
+        for (int q = 0; q < g; q++) {
+          const long long off = s.n * p.out_sn + (d + q) * p.out_sd + oh * p.out_sh + ow * p.out_sw;
 #pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          if (p.bias != nullptr) {
+          for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
+            uint32_t v[32], v2[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) +
+                                   static_cast<uint32_t>((buf * G + q) * BLOCK_N + chunk * 32);
+            tmem_ld_32x32(taddr, v);                     // issuer 0's partial sums
+            tmem_ld_32x32(taddr + 2 * G * BLOCK_N, v2);  // issuer 1's
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) f[j] += __ldg(p.bias + chunk * 32 + j);
-          }
-          if (do_stats) {
-            float s1[32], s2[32];
+            for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const float x = valid ? f[j] : 0.f;
-              s1[j] = x;
-              s2[j] = x * x;
+              for (int j = 0; j < 32; j++) f[j] += __ldg(p.bias + chunk * 32 + j);
             }
-            const float cs1 = warp_column_sums(s1, lane);
-            const float cs2 = warp_column_sums(s2, lane);
-            stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
-            stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
-          }
-          if (valid && !(p.debug & 8)) {
-            if (p.addend != nullptr) {
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
+            if (do_stats) {
+              if constexpr (REG_STATS) {
+                if (valid) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; j4++) {
-                const uint4 a = __ldg(ap + j4);
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                  f[j4 * 8 + e * 2 + 0] += bf16_lo(aw[e]);
-                  f[j4 * 8 + e * 2 + 1] += bf16_hi(aw[e]);
+                  for (int j = 0; j < 32; j++) {
+                    rs1[chunk * 32 + j] += f[j];
+                    rs2[chunk * 32 + j] = fmaf(f[j], f[j], rs2[chunk * 32 + j]);
+                  }
                 }
+              } else {
+                float s1[32], s2[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                  const float x = valid ? f[j] : 0.f;
+                  s1[j] = x;
+                  s2[j] = x * x;
+                }
+                const float cs1 = warp_column_sums(s1, lane);
+                const float cs2 = warp_column_sums(s2, lane);
+                stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
+                stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
               }
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
+            if (valid) {
+              if (p.addend != nullptr) {
+                const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; j4++) {
-              uint4 o;
-              o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-              o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-              o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-              o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
-              op[j4] = o;
+                for (int j4 = 0; j4 < 4; j4++) {
+                  const uint4 a = __ldg(ap + j4);
+                  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                  for (int e = 0; e < 4; e++) {
+                    f[j4 * 8 + e * 2 + 0] += bf16_lo(aw[e]);
+                    f[j4 * 8 + e * 2 + 1] += bf16_hi(aw[e]);
+                  }
+                }
+              }
+              uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; j4++) {
+                uint4 o;
+                o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+                o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+                o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+                o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+                op[j4] = o;
+              }
             }
           }
+          if (do_stats && !REG_STATS) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < BLOCK_N) {  // BLOCK_N <= 128: thread et owns channel et
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int w4 = 0; w4 < 4; w4++) {
+                a += stat_smem[(w4 * 2 + 0) * BLOCK_N + et];
+                b += stat_smem[(w4 * 2 + 1) * BLOCK_N + et];
+              }
+              cta_sum += static_cast<double>(a);
+              cta_sq += static_cast<double>(b);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
         }
-        // accumulator drained -> hand the TMEM buffer back to the MMA warp
+        // accumulators drained -> hand the TMEM buffer back to the MMA warps
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1u;
-        }
-        if (do_stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et < BLOCK_N) {  // BLOCK_N <= 128: thread et owns channel et
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int w4 = 0; w4 < 4; w4++) {
-              a += stat_smem[(w4 * 2 + 0) * BLOCK_N + et];
-              b += stat_smem[(w4 * 2 + 1) * BLOCK_N + et];
-            }
-            cta_sum += static_cast<double>(a);
-            cta_sq += static_cast<double>(b);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (++buf == 2) {
+          buf = 0;
+          bufph ^= 1u;
         }
       }
       i += s.dB - s.dA;
     }
-    if (do_stats && et < BLOCK_N && begin < end) {
-      atomicAdd(p.stat_sum + et, cta_sum);
-      atomicAdd(p.stat_sq + et, cta_sq);
+    if (do_stats && begin < end) {
+      if constexpr (REG_STATS) {
+#pragma unroll
+        for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
+          float t1[32], t2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            t1[j] = rs1[chunk * 32 + j];
+            t2[j] = rs2[chunk * 32 + j];
+          }
+          const float c1 = warp_column_sums(t1, lane);
+          const float c2 = warp_column_sums(t2, lane);
+          stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = c1;
+          stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = c2;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < BLOCK_N) {
+#pragma unroll
+          for (int w4 = 0; w4 < 4; w4++) {
+            cta_sum += static_cast<double>(stat_smem[(w4 * 2 + 0) * BLOCK_N + et]);
+            cta_sq += static_cast<double>(stat_smem[(w4 * 2 + 1) * BLOCK_N + et]);
+          }
+        }
+      }
+      // flushed ONCE per CTA: same-address fp64 atomics retire at ~1 per 27 cycles in L2, one per (piece, channel)
+      // from 148 CTAs is a serial bottleneck of its own
+      if (et < BLOCK_N) {
+        atomicAdd(p.stat_sum + et, cta_sum);
+        atomicAdd(p.stat_sq + et, cta_sq);
+      }
     }
   }
 
@@ -358,20 +464,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N>
-int launch_halo_t(const HaloParams& p, int smem_bytes, cudaStream_t stream) {
-  auto kern = igemm_halo_kernel<BLOCK_N>;
-  static int attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
-    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
+template <int BLOCK_N, int KB, int TPS, int G>
+int launch_halo_t(const HaloParams& p, cudaStream_t stream) {
+  using Cfg = HaloCfg<BLOCK_N, KB, TPS, G>;
+  auto kern = igemm_halo_kernel<BLOCK_N, KB, TPS, G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
   }
   const int grid = p.total < num_sms() ? p.total : num_sms();
-  kern<<<grid, kHaloThreads, smem_bytes, stream>>>(p);
+  kern<<<grid, kHaloThreads, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   ADNI_LAUNCH_CHECK("igemm_halo_kernel");
   return ADNI_OK;
@@ -379,33 +486,18 @@ int launch_halo_t(const HaloParams& p, int smem_bytes, cudaStream_t stream) {
 
 }  // namespace
 
-// Fills ring / b_stages / plane_kb_bytes for the given (block_n, kb, pitch); returns the dynamic shared-memory size
-// or 0 when the configuration does not fit one SM.
-int halo_plan_smem(HaloParams* p, int block_n) {
-  const int stat_bytes = 4 * 2 * block_n * 4;
-  const int avail = 232448 - 1024 - 512 - stat_bytes;
-  p->plane_kb_bytes = (p->pitch * kHaloRows * 128 + 1023) & ~1023;
-  const int plane_bytes = p->kb * p->plane_kb_bytes;
-  p->tps = block_n == 64 ? 3 : 1;  // taps per weight stage (one kh row for N = 64)
-  const int b_stage = p->tps * block_n * 128;
-  for (int ring = kMaxRing; ring >= 3; ring--) {
-    const int left = avail - ring * plane_bytes;
-    if (left < 4 * b_stage) continue;
-    p->ring = ring;
-    p->b_stages = left / b_stage < 12 ? left / b_stage : 12;
-    return ring * plane_bytes + p->b_stages * b_stage + 512 + stat_bytes + 1024;
-  }
-  return 0;
-}
+int halo_pitch() { return kHaloPitch; }
+int halo_rows() { return kHaloRows; }
 
-int launch_igemm_halo(const HaloParams& p, int block_n, int smem_bytes, cudaStream_t stream) {
-  switch (block_n) {
+// channels = Cin = Cout (64 or 128)
+int launch_igemm_halo(const HaloParams& p, int channels, cudaStream_t stream) {
+  switch (channels) {
     case 64:
-      return launch_halo_t<64>(p, smem_bytes, stream);
+      return launch_halo_t<64, 1, 3, 2>(p, stream);
     case 128:
-      return launch_halo_t<128>(p, smem_bytes, stream);
+      return launch_halo_t<128, 2, 1, 1>(p, stream);
     default:
-      set_error("igemm_halo: unsupported BLOCK_N %d", block_n);
+      set_error("igemm_halo: unsupported channel count %d", channels);
       return ADNI_ENOTSUP;
   }
 }

@@ -59,26 +59,16 @@ struct WgradParams {
   float* dw;    // [Cout][K_total] fp32, accumulated with red.add
 };
 
-// Halo-resident fprop / dgrad for 3x3x3, stride 1, dilation 1, pad 1 convs with Cin in {64, 128} and
-// Cout == Cin (ResNet layer1 / layer2): the M tile is one output plane piece of 8 (w) x 16 (h) positions; the
-// CTA walks a column of such pieces along d and keeps the (pitch x 18)-position input planes d-1, d, d+1 in a
-// shared-memory ring, so every input element is fetched from L2 ~1.4x instead of 27x.  The A operand of
-// every tap is a shifted VIEW of the resident plane (UMMA descriptor start = plane + (kh*pitch + kw) rows,
-// SBO = pitch rows).
+// Halo-resident fprop / dgrad for 3x3x3, stride 1, dilation 1, pad 1 convs with Cin == Cout in {64, 128}
+// (ResNet layer1 / layer2), see conv_halo.cu: the M tile is one output plane piece of 8 (w) x 16 (h) positions; the
+// CTA walks a column of such pieces along d and keeps the (10 x 18)-position input planes in a shared-memory ring.
 struct HaloParams {
-  CUtensorMap a_map;  // 5-D (C, W, H, D, N) view, box (64, pitch, 18, 1, 1), 128-B swizzle
-  CUtensorMap b_map;  // 2-D (K_total, N_total) weight matrix, box (64, BLOCK_N)
-  int kofs[27];       // weight column of the tap that reads halo offset (od, oh, ow): index (od*3 + oh)*3 + ow
+  CUtensorMap a_map;  // 5-D (C, W, H, D, N) view, box (64, 10, 18, 1, 1), 128-B swizzle
+  CUtensorMap b_map;  // 2-D (K_total, N_total) weight matrix, box (64, C)
+  int mirror;         // 0: halo offset (od, oh, ow) reads weight tap (od*3+oh)*3+ow (fprop); 1: tap 26 - that (dgrad)
   int N, D, H, W;     // output extents == input extents
   int tiles_h, tiles_w;
-  int total;           // N * tiles_h * tiles_w * D plane pieces, split evenly (and contiguously) over the CTAs
-  int pitch;           // positions per halo row in shared memory (>= 10)
-  int kb;              // Cin / 64
-  int ring;            // resident halo planes (3 or 4)
-  int b_stages;        // weight-stage pipeline depth
-  int tps;             // filter taps (consecutive kw) per weight stage: 1 or 3
-  int plane_kb_bytes;  // bytes of one 64-channel halo plane (1024-aligned)
-  int debug;           // diagnostics / tuning bits, see conv_halo.cu
+  int total;  // N * tiles_h * tiles_w * D plane pieces, split evenly (and contiguously) over the CTAs
   long long out_sn, out_sd, out_sh, out_sw;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
