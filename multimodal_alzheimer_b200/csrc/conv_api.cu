@@ -16,6 +16,7 @@ namespace adni {
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
+int wgrad2_box_rows(int mt_cfg);
 int halo_pitch();
 int halo_rows();
 int launch_igemm_halo(const HaloParams& p, int channels, cudaStream_t stream);
@@ -384,7 +385,14 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     ext_h.push_back((g.H - p + g.stride - 1) / g.stride);
     ext_w.push_back((g.W - p + g.stride - 1) / g.stride);
   }
-  const Box b = plan_box(Do, Ho, Wo, 32, true, at, at, at, ext_d, ext_h, ext_w);
+  // one CTA owns all 512 TMEM columns: mt_cfg accumulators of 128 Cout rows x (512/mt_cfg) K_total columns
+  int mt_cfg = g.Cout >= 256 ? 2 : 1;  // measured best on B200 (tools/wgrad_probe.py)
+  if (const char* e = getenv("ADNI_WGRAD_MT")) {  // tuning / diagnostics override
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) mt_cfg = v;
+  }
+  const int box_rows = wgrad2_box_rows(mt_cfg);
+  const Box b = plan_box(Do, Ho, Wo, box_rows, true, at, at, at, ext_d, ext_h, ext_w);
 
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -420,12 +428,6 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.ntaps = taps;
   p.cin_blocks = g.Cin / 64;
   p.n_groups = taps * p.cin_blocks;
-  // one CTA owns all 512 TMEM columns: mt_cfg accumulators of 128 Cout rows x (512/mt_cfg) K_total columns
-  int mt_cfg = g.Cout >= 256 ? 2 : 1;  // measured best on B200 (tools/wgrad_probe.py)
-  if (const char* e = getenv("ADNI_WGRAD_MT")) {  // tuning / diagnostics override
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) mt_cfg = v;
-  }
   const int groups = 8 / mt_cfg;
   p.N = g.N;
   p.Do = Do;
@@ -442,7 +444,7 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.n_tiles = (p.n_groups + groups - 1) / groups;
   const int base_items = p.m_tiles * p.n_tiles;
   int splits = (4 * num_sms() + base_items - 1) / base_items;
-  splits = std::min(splits, std::max(1, p.pos_boxes / 32));
+  splits = std::min(splits, std::max(1, p.pos_boxes * box_rows / 1024));
   splits = std::max(splits, 1);
   p.boxes_per_split = (p.pos_boxes + splits - 1) / splits;
   p.splits = (p.pos_boxes + p.boxes_per_split - 1) / p.boxes_per_split;

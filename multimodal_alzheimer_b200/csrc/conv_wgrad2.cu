@@ -16,8 +16,10 @@ extern void count_launch();
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kBoxRows = 32;
-constexpr int kBoxBytes = kBoxRows * 128;  // 4096
+// positions per TMA box = K of one pipeline stage.  MT = 2 (Cout >= 256, 8 boxes per stage) takes 64-position boxes:
+// 8 MMAs per stage instead of 4 halves the barrier / commit overhead per MMA; the 10-box stages of MT = 1 / 4 keep 32
+// (a 64-position stage would be 80 KB: only two stages deep).
+constexpr int wgrad2_box_rows_c(int mt) { return mt == 2 ? 64 : 32; }
 
 __device__ __forceinline__ bool box_hits(const int* ext, int d, int h, int w, int bd, int bh, int bw) {
   return d + bd > 0 && d < ext[0] && h + bh > 0 && h < ext[1] && w + bw > 0 && w < ext[2];
@@ -25,13 +27,15 @@ __device__ __forceinline__ bool box_hits(const int* ext, int d, int h, int w, in
 
 template <int MT>
 struct W2Cfg {
+  static constexpr int ROWS = wgrad2_box_rows_c(MT);
+  static constexpr int BOX_BYTES = ROWS * 128;
   static constexpr int BLOCK_N = 512 / MT;
   static constexpr int NG = BLOCK_N / 64;                       // 64-column groups per tile
   static constexpr int NSUB = BLOCK_N > 256 ? 256 : BLOCK_N;    // N of one tcgen05.mma
   static constexpr int N_SUBS = BLOCK_N / NSUB;
   static constexpr int A_BOXES = 2 * MT;
   static constexpr int STAGE_BOXES = A_BOXES + NG;
-  static constexpr int STAGE_BYTES = STAGE_BOXES * kBoxBytes;
+  static constexpr int STAGE_BYTES = STAGE_BOXES * BOX_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
@@ -106,6 +110,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
   using Cfg = W2Cfg<MT>;
   constexpr int NG = Cfg::NG;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int kBoxRows = Cfg::ROWS;
+  constexpr int kBoxBytes = Cfg::BOX_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -321,6 +327,7 @@ int launch_t(const WgradParams& p, cudaStream_t stream) {
 
 // mt_cfg: accumulator rows per CTA / 128 (1, 2 or 4)
 int wgrad2_groups_per_tile(int mt_cfg) { return 8 / mt_cfg; }
+int wgrad2_box_rows(int mt_cfg) { return wgrad2_box_rows_c(mt_cfg); }
 
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream) {
   switch (mt_cfg) {
