@@ -276,6 +276,17 @@ int adni_cast_f32_to_bf16(const float* x, adni_bf16* y, long long n, void* strea
 int adni_cast_f64_to_bf16(const double* x, adni_bf16* y, long long n, void* stream);
 int adni_cast_bf16_to_f32(const adni_bf16* x, float* y, long long n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one-shot all-reduce (sum) of a small fp64 vector over NVLink peer memory - the synchronised-BatchNorm
+ * statistic sums and the loss normaliser of the data-parallel step (the reference is single-GPU).
+ * `peers` is a DEVICE array of `world` pointers (uint64), entry r = this process's mapping of rank r's symmetric
+ * buffer of adni_peer_buffer_bytes(world, max_n) bytes, zero-initialised before the first call; `call_counter` is a
+ * device uint64, zero-initialised, private to this (rank, buffer).  Every rank must issue the same sequence of calls
+ * on a buffer.  In place; all ranks obtain bit-identical sums (fixed rank order). */
+size_t adni_peer_buffer_bytes(int world, int max_n);
+int adni_peer_allreduce_f64(double* data, int n, const void* peers, void* call_counter, int rank, int world, int max_n,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

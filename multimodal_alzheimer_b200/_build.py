@@ -23,6 +23,7 @@ SOURCES = [
     "elementwise.cu",
     "head_loss.cu",
     "normalize.cu",
+    "peer_reduce.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

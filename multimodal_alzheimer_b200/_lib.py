@@ -46,6 +46,8 @@ _SIGNATURES = {
     "adni_stem_wgrad": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
     "adni_weights_to_kernel_layout": [_P, _I, _I, _I, _P, _P, _P],
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
+    "adni_peer_buffer_bytes": [_I, _I],
+    "adni_peer_allreduce_f64": [_P, _I, _P, _P, _I, _I, _I, _P],
     "adni_weights_multi_job_bytes": [],
     "adni_weights_to_kernel_layout_multi": [_P, _I, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
@@ -91,6 +93,7 @@ _RESTYPES = {
     "adni_launch_count": ctypes.c_longlong,
     "adni_stem_x8_elems": ctypes.c_longlong,
     "adni_quantile_workspace_bytes": ctypes.c_size_t,
+    "adni_peer_buffer_bytes": ctypes.c_size_t,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())

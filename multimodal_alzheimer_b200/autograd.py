@@ -46,7 +46,14 @@ class dp_group:
 
 
 def _allreduce_(t):
+    """Sum over the data-parallel ranks: the one-shot NVLink kernel for the small fp64 statistic vectors
+    (data_parallel.PeerReducer), NCCL otherwise."""
     if _world() > 1:
+        if t.is_cuda:
+            from . import data_parallel as dp
+            red = dp.peer_reducer(_GROUP[0], t.device)
+            if red is not None and red.usable(t):
+                return red.all_reduce_(t)
         dist.all_reduce(t, group=_GROUP[0])
     return t
 

@@ -324,6 +324,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
 #pragma unroll
     for (int j = 0; j < NREG; j++) rs1[j] = rs2[j] = 0.f;
     double cta_sum = 0.0, cta_sq = 0.0;
+    // fp32 register partials are folded into the fp64 per-CTA sums every kFlushGroups groups: a thread never chains
+    // more than 2 * kFlushGroups fp32 additions per channel, which keeps sum(x) accurate when it nearly cancels
+    constexpr int kFlushGroups = 8;
+    int since_flush = 0;
+    auto flush_reg_stats = [&]() {
+#pragma unroll
+      for (int chunk = 0; chunk < (REG_STATS ? BLOCK_N / 32 : 0); chunk++) {
+        float t1[32], t2[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          t1[j] = rs1[chunk * 32 + j];
+          t2[j] = rs2[chunk * 32 + j];
+          rs1[chunk * 32 + j] = 0.f;
+          rs2[chunk * 32 + j] = 0.f;
+        }
+        const float c1 = warp_column_sums(t1, lane);
+        const float c2 = warp_column_sums(t2, lane);
+        stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = c1;
+        stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = c2;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < BLOCK_N) {
+#pragma unroll
+        for (int w4 = 0; w4 < 4; w4++) {
+          cta_sum += static_cast<double>(stat_smem[(w4 * 2 + 0) * BLOCK_N + et]);
+          cta_sq += static_cast<double>(stat_smem[(w4 * 2 + 1) * BLOCK_N + et]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      since_flush = 0;
+    };
     int buf = 0;
     uint32_t bufph = 0;
     for (int i = begin; i < end;) {
@@ -332,6 +363,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       const bool valid = oh < p.H && ow < p.W;
       for (int d = s.dA; d < s.dB; d += G) {
         const int g = min(G, s.dB - d);
+        if (REG_STATS && do_stats && ++since_flush > kFlushGroups) flush_reg_stats();
         mbar_wait_spin(&tfull[buf], bufph);
         tc_fence_after();
 #pragma unroll 1
@@ -428,29 +460,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       i += s.dB - s.dA;
     }
     if (do_stats && begin < end) {
-      if constexpr (REG_STATS) {
-#pragma unroll
-        for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
-          float t1[32], t2[32];
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            t1[j] = rs1[chunk * 32 + j];
-            t2[j] = rs2[chunk * 32 + j];
-          }
-          const float c1 = warp_column_sums(t1, lane);
-          const float c2 = warp_column_sums(t2, lane);
-          stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = c1;
-          stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = c2;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et < BLOCK_N) {
-#pragma unroll
-          for (int w4 = 0; w4 < 4; w4++) {
-            cta_sum += static_cast<double>(stat_smem[(w4 * 2 + 0) * BLOCK_N + et]);
-            cta_sq += static_cast<double>(stat_smem[(w4 * 2 + 1) * BLOCK_N + et]);
-          }
-        }
-      }
+      if constexpr (REG_STATS) flush_reg_stats();
       // flushed ONCE per CTA: same-address fp64 atomics retire at ~1 per 27 cycles in L2, one per (piece, channel)
       // from 148 CTAs is a serial bottleneck of its own
       if (et < BLOCK_N) {

@@ -503,6 +503,38 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
     float cs1[kCout], cs2[kCout];
 #pragma unroll
     for (int j = 0; j < kCout; j++) cs1[j] = cs2[j] = 0.f;
+    // the fp32 partials are folded into per-CTA fp64 sums every kFlushPieces pieces (bounded fp32 chains: sum(x) stays
+    // accurate when it nearly cancels)
+    double cta_sum = 0.0, cta_sq = 0.0;
+    constexpr int kFlushPieces = 16;
+    int since_flush = 0;
+    auto flush_reg_stats = [&]() {
+#pragma unroll
+      for (int chunk = 0; chunk < kCout / 32; chunk++) {
+        float t1[32], t2[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          t1[j] = cs1[chunk * 32 + j];
+          t2[j] = cs2[chunk * 32 + j];
+          cs1[chunk * 32 + j] = 0.f;
+          cs2[chunk * 32 + j] = 0.f;
+        }
+        const float c1 = warp_column_sums(t1, lane);
+        const float c2 = warp_column_sums(t2, lane);
+        stat_smem[(ew * 2 + 0) * kCout + chunk * 32 + lane] = c1;
+        stat_smem[(ew * 2 + 1) * kCout + chunk * 32 + lane] = c2;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < kCout) {
+#pragma unroll
+        for (int w4 = 0; w4 < 4; w4++) {
+          cta_sum += static_cast<double>(stat_smem[(w4 * 2 + 0) * kCout + et]);
+          cta_sq += static_cast<double>(stat_smem[(w4 * 2 + 1) * kCout + et]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      since_flush = 0;
+    };
     int acc = 0;
     uint32_t accph = 0;
     for (int i = begin; i < end;) {
@@ -511,6 +543,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
       const bool valid = oh < p.Ho && ow < p.Wo;
       for (int od = s.dA; od < s.dB; od++) {
         const long long off = ((((long long)s.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * kCout;
+        if (do_stats && ++since_flush > kFlushPieces) flush_reg_stats();
         mbar_wait_spin(&tfull[acc], accph);
         tc_fence_after();
 #pragma unroll
@@ -553,29 +586,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
       i += s.dB - s.dA;
     }
     if (do_stats) {
-#pragma unroll
-      for (int chunk = 0; chunk < kCout / 32; chunk++) {
-        float t1[32], t2[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          t1[j] = cs1[chunk * 32 + j];
-          t2[j] = cs2[chunk * 32 + j];
-        }
-        const float c1 = warp_column_sums(t1, lane);
-        const float c2 = warp_column_sums(t2, lane);
-        stat_smem[(ew * 2 + 0) * kCout + chunk * 32 + lane] = c1;
-        stat_smem[(ew * 2 + 1) * kCout + chunk * 32 + lane] = c2;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      flush_reg_stats();
       if (et < kCout && begin < end) {
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int w4 = 0; w4 < 4; w4++) {
-          a += static_cast<double>(stat_smem[(w4 * 2 + 0) * kCout + et]);
-          b += static_cast<double>(stat_smem[(w4 * 2 + 1) * kCout + et]);
-        }
-        atomicAdd(p.stat_sum + et, a);
-        atomicAdd(p.stat_sq + et, b);
+        atomicAdd(p.stat_sum + et, cta_sum);
+        atomicAdd(p.stat_sq + et, cta_sq);
       }
     }
   }

@@ -8,3 +8,9 @@ echo "dp2 exit $?"; tail -n 1 gpurun_out/bench_dp2.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print({k:d[k] for k in ('value','ms_per_step','launch_mode','gpu_launches')}, d['e2e']['value'] if d['e2e'] else None)"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/shapes_dp2.json'))['__entry_points__']
+for k,v in sorted(d.items(), key=lambda kv:-kv[1]['ms_per_step'])[:30]:
+    if 'peer' in k or 'bn_' in k or 'conv3d' in k: print(f"  {k:36s} {v['calls_per_step']:5.0f} calls {v['ms_per_step']:7.3f} ms")
+PY
