@@ -22,6 +22,9 @@ TC_SHAPES = [
     (1, 12, 14, 12, 128, 128, 3, 1, 1, 1),  # ragged extents (91x109x91 input family)
     (1, 11, 13, 9, 64, 64, 3, 2, 1, 1),     # odd extents with stride 2
     (3, 8, 8, 8, 192, 64, 3, 1, 1, 1),      # Cin not a power of two
+    (20, 33, 16, 8, 64, 64, 3, 1, 1, 1),    # halo engine: long columns, odd depth (unpaired last piece), many CTAs
+    (9, 21, 16, 16, 128, 128, 3, 1, 1, 1),  # halo engine, two K blocks, several pieces per CTA
+    (1, 5, 40, 20, 64, 64, 3, 1, 1, 1),     # halo engine: three H tiles (ragged), more CTAs than planes per column
 ]
 
 

@@ -291,3 +291,84 @@ def test_fused_stem_tail_matches_unfused_kernels(cuda_dev, shape):
     xh = ((y.float().view(-1, C) - bnp[0]) * bnp[1]).double()
     assert_close(red[0], g.sum(0), 1e-5, "fused reduce vs fp32 reference (sum g)")
     assert_close(red[1], (g * xh).sum(0), 1e-5, "fused reduce vs fp32 reference (sum g*xhat)")
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (3, 8, 8, 8, 512), (1, 3, 5, 7, 24)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bn_train_apply_equals_finalize_plus_apply(cuda_dev, shape, with_res):
+    """The fused training-mode BatchNorm forward is BIT-identical to bn_finalize + bn_apply (same expression per
+    channel), including bnp and the running statistics; C = 24 exercises the non-fixed-channel fallback."""
+    from multimodal_alzheimer_b200 import kernels as K
+    C = shape[-1]
+    y = _rand_act(shape, cuda_dev) * 3 + 1
+    res = _rand_act(shape, cuda_dev, 1) if with_res else None
+    rows = y.numel() // C
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    beta = torch.randn(C, device=cuda_dev)
+    st = K.channel_stats(y.view(-1, C))
+    rm0, rv0 = torch.zeros(C, device=cuda_dev), torch.ones(C, device=cuda_dev)
+    rm1, rv1 = rm0.clone(), rv0.clone()
+    bnp_ref = K.bn_finalize(st, rows, gamma, beta, 1e-5, 0.1, rm0, rv0)
+    out_ref = K.bn_apply(y, bnp_ref[2], bnp_ref[3], residual=res, relu=True)
+    out, bnp = K.bn_train_apply(y, st, rows, gamma, beta, 1e-5, 0.1, rm1, rv1, residual=res, relu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_ref)
+    assert torch.equal(bnp, bnp_ref)
+    assert torch.equal(rm1, rm0) and torch.equal(rv1, rv0)
+
+
+def test_bn_param_grad_scale(cuda_dev):
+    """param_grad_scale = 1/world: the ranks' parameter gradients SUM to the global sums (data-parallel step)."""
+    from multimodal_alzheimer_b200 import kernels as K
+    shape, C = (2, 4, 4, 8, 64), 64
+    y, dout = _rand_act(shape, cuda_dev), _rand_act(shape, cuda_dev, 2)
+    rows = y.numel() // C
+    gamma = torch.rand(C, device=cuda_dev) + 0.5
+    mean, invstd, scale, shift = K.bn_finalize(K.channel_stats(y.view(-1, C)), rows, gamma, None, 1e-5, 0.1, None, None)
+    red = K.bn_bwd_reduce(dout, None, y, mean, invstd, False)
+    _, _, dg1, db1 = K.bn_bwd_apply(dout, None, y, mean, invstd, gamma, red, rows, False, False)
+    _, _, dg4, db4 = K.bn_bwd_apply(dout, None, y, mean, invstd, gamma, red, rows, False, False, param_grad_scale=0.25)
+    torch.cuda.synchronize()
+    assert torch.equal(dg1, red[1].float()) and torch.equal(db1, red[0].float())
+    assert_close(dg4 * 4, dg1, 1e-7, "dgamma / 4")
+    assert_close(db4 * 4, db1, 1e-7, "dbeta / 4")
+
+
+def test_weight_arena_matches_per_tensor_conversion(cuda_dev):
+    """One-launch multi-tensor weight conversion == the per-tensor transposes (bit-exact), ragged channel counts
+    included; a stale copy is never served after the parameter changed."""
+    from multimodal_alzheimer_b200 import kernels as K
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 64, 3), (128, 64, 3), (128, 64, 1), (40, 24, 3), (512, 256, 3), (72, 200, 1)]
+    ws = [torch.nn.Parameter(torch.randn((co, ci, k, k, k), generator=g).to(cuda_dev)) for co, ci, k in shapes]
+    arena = K.WeightArena()
+    arena.refresh(ws)
+    torch.cuda.synchronize()
+    for w in ws:
+        oti, ito = arena.lookup(w)
+        oti_ref, ito_ref = K.weights_to_kernel_layout(w)
+        assert torch.equal(oti, oti_ref), tuple(w.shape)
+        assert torch.equal(ito, ito_ref), tuple(w.shape)
+    with torch.no_grad():
+        ws[0].add_(1.0)  # an optimizer step bumps the version counter
+    assert arena.lookup(ws[0]) is None and arena.lookup(ws[1]) is not None
+    arena.refresh(ws)
+    assert torch.equal(arena.lookup(ws[0])[0], K.weights_to_kernel_layout(ws[0])[0])
+
+
+def test_conv_plan_info(cuda_dev):
+    """Planner query used by bench.py: engine routing and executed-tap fraction (all-padding taps are skipped)."""
+    import ctypes
+    from multimodal_alzheimer_b200._lib import call, geom
+
+    def info(N, D, C, dil, pass_):
+        kind, frac = ctypes.c_int(-1), ctypes.c_double(-1.0)
+        call("adni_conv3d_plan_info", geom(N, D, D, D, C, C, 3, 1, dil, dil), pass_, ctypes.byref(kind), ctypes.byref(frac))
+        return kind.value, frac.value
+
+    assert info(2, 32, 64, 1, 0)[0] == 2 and info(2, 16, 128, 1, 1)[0] == 2          # halo-resident engine
+    k4, f4 = info(2, 16, 512, 4, 0)
+    assert k4 == 1 and 0.5 < f4 < 0.9                                                  # dilation 4: ~31 % of the taps skipped
+    assert info(2, 16, 256, 2, 1)[0] == 1 and 0.7 < info(2, 16, 256, 2, 1)[1] <= 1.0
+    assert info(2, 16, 512, 4, 2) == (1, 1.0)
+    assert info(2, 8, 8, 1, 0)[0] == 0                                                 # small channels: direct engine
