@@ -80,9 +80,12 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
 
 /* dw_oti[Cout][taps][Cin] (fp32) += sum over positions of dy^T * im2col(x).  The caller zeroes dw
  * (the split-K partial sums are accumulated with red.global.add). dbias[Cout] (fp32, may be null) +=
- * sum(dy). */
+ * sum(dy).  `scratch` (nullable): adni_conv3d_wgrad_scratch_floats(g) ZEROED floats; when given and non-empty the
+ * geometry (64 -> 64, 3x3x3, stride 1: ResNet layer1) runs on the halo-plane wgrad engine, which accumulates in
+ * [tap][Cin][Cout] order in the scratch and then OVERWRITES dw_oti. */
+long long adni_conv3d_wgrad_scratch_floats(const adni_conv3d_geom* g);
 int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* dy, float* dw_oti,
-                      float* dbias, int engine, void* stream);
+                      float* dbias, float* scratch, int engine, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core path of the 1-channel stem  conv1 = Conv3d(1, 64, k=7, stride=2, pad=3, bias=False)  (MedicalNet

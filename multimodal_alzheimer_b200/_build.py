@@ -16,6 +16,7 @@ SOURCES = [
     "conv_igemm_kernels.cu",
     "conv_halo.cu",
     "conv_wgrad2.cu",
+    "conv_wgrad_halo.cu",
     "conv_api.cu",
     "conv_direct.cu",
     "conv_stem.cu",

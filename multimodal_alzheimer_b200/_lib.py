@@ -38,7 +38,8 @@ _SIGNATURES = {
     "adni_conv3d_plan_info": [ctypes.POINTER(ConvGeom), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
     "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P],
     "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
-    "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
+    "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _I, _P],
+    "adni_conv3d_wgrad_scratch_floats": [ctypes.POINTER(ConvGeom)],
     "adni_stem_x8_elems": [_I, _I, _I, _I],
     "adni_stem_expand": [_P, _I, _I, _I, _I, _P, _P],
     "adni_stem_weights": [_P, _P, _P],
@@ -94,6 +95,7 @@ _RESTYPES = {
     "adni_stem_x8_elems": ctypes.c_longlong,
     "adni_quantile_workspace_bytes": ctypes.c_size_t,
     "adni_peer_buffer_bytes": ctypes.c_size_t,
+    "adni_conv3d_wgrad_scratch_floats": ctypes.c_longlong,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())

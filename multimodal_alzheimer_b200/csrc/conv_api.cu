@@ -17,6 +17,9 @@ int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
 int wgrad2_box_rows(int mt_cfg);
+bool wgrad_halo_supported(const adni_conv3d_geom& g);
+int launch_wgrad_halo(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tic, float* dw_oti,
+                      cudaStream_t stream);
 int halo_pitch();
 int halo_rows();
 int launch_igemm_halo(const HaloParams& p, int channels, cudaStream_t stream);
@@ -570,8 +573,13 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
   return direct_conv_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
 }
 
+long long adni_conv3d_wgrad_scratch_floats(const adni_conv3d_geom* g) {
+  if (g == nullptr || check_geom(g) != ADNI_OK) return 0;
+  return (tc_supported(*g) && wgrad_halo_supported(*g)) ? 27LL * 64 * 64 : 0;
+}
+
 int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* dy, float* dw_oti, float* dbias,
-                      int engine, void* stream) {
+                      float* scratch, int engine, void* stream) {
   int rc = check_geom(g);
   if (rc) return rc;
   ADNI_REQUIRE(x && dy && dw_oti, ADNI_EINVAL, "conv3d_wgrad: null pointer");
@@ -582,6 +590,8 @@ int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
   auto dys = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (eng == ADNI_ENGINE_TCGEN05) {
     ADNI_REQUIRE(dbias == nullptr, ADNI_ENOTSUP, "conv3d_wgrad: tcgen05 engine has no bias gradient (use channel_stats)");
+    if (scratch != nullptr && wgrad_halo_supported(*g))
+      return launch_wgrad_halo(*g, xs, dys, scratch, dw_oti, static_cast<cudaStream_t>(stream));
     return tc_wgrad(*g, xs, dys, dw_oti, static_cast<cudaStream_t>(stream));
   }
   return direct_conv_wgrad(*g, xs, dys, dw_oti, dbias, static_cast<cudaStream_t>(stream));

@@ -248,6 +248,17 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
     return dx
 
 
+_SCRATCH_CACHE = {}
+
+
+def _wgrad_scratch_floats(g):
+    key = (g.Cin, g.Cout, g.k, g.stride, g.pad, g.dil)
+    n = _SCRATCH_CACHE.get(key)
+    if n is None:
+        n = _SCRATCH_CACHE[key] = int(_lib.load().adni_conv3d_wgrad_scratch_floats(g))
+    return n
+
+
 def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUTO):
     _chk(x, BF16, "x")
     _chk(dy, BF16, "dy")
@@ -260,13 +271,18 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
         if engine == ENGINE_DIRECT or (Cin % 64 != 0 or Cout % 64 != 0):
             db = torch.zeros((Cout,), dtype=torch.float32, device=x.device)
             ev = PROFILE.begin()
-            call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), ptr(db), ENGINE_DIRECT, stream_ptr())
+            call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), ptr(db), None, ENGINE_DIRECT, stream_ptr())
             PROFILE.end(ev, "direct", 2 * dy.numel() * Cin * k ** 3)
             return dw, db
         s = channel_stats(dy.view(-1, Cout))
         db = s[0].to(torch.float32)
+    scratch = None
+    if engine != ENGINE_DIRECT:
+        n_scratch = _wgrad_scratch_floats(g)
+        if n_scratch:  # halo-plane engine (layer1): accumulates in a small scratch, then overwrites dw
+            scratch = torch.zeros(n_scratch, dtype=torch.float32, device=x.device)
     ev = PROFILE.begin()
-    call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, engine, stream_ptr())
+    call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, ptr(scratch), engine, stream_ptr())
     tag, frac = _engine_tag(g, 2, engine)
     PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
                 f"wgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
