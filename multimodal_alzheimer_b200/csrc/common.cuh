@@ -129,7 +129,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Tight polling variant.  Measured better for the producer / MMA-issuer threads of the igemm and halo conv kernels
 // (short stages, double-buffered accumulators: fprop+dgrad 27.4 -> 26.3 ms per step) and worse for wgrad2 / stem.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -138,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
       if (t0 == 0) {
         t0 = t;
       } else if (t - t0 > 4000000000ull) {  // 4 s: the pipeline is dead
-        printf("adni_b200: mbarrier timeout (spin) block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+        printf("adni_b200: mbarrier timeout (spin) kernel-tag %d block %d thread %d parity %u\n", tag, blockIdx.x, threadIdx.x, parity);
         __trap();
       }
     }

@@ -16,7 +16,8 @@
 //  (1) the issuing thread: one pipeline stage costs ~190 cycles of mbarrier wait / tcgen05.commit plus ~48 cycles
 //      per tcgen05.mma, and the tensor pipe only queues 1-2 MMAs ahead (tools/ubench/pipe_bench.cu).  TWO MMA
 //      warps take alternate weight stages and accumulate into their own TMEM accumulators (summed in the epilogue in
-//      a fixed order: deterministic); a weight stage carries TPS taps (3 for N = 64: one kh row);
+//      a fixed order: deterministic) - the ring depth is EVEN so that every ring slot has one owner; a weight stage
+//      carries TPS taps (3 for N = 64: one kh row);
 //  (2) the weight stream itself (24 KB per 12 MMAs = 33 B/clk/SM of the same lines for all 148 CTAs): with G = 2 a
 //      weight stage is applied to TWO consecutive output pieces of the column (planes d-1 .. d+2 resident);
 //  (3) instruction overhead: everything is a template constant or scalar ring arithmetic - no divisions, no
@@ -47,13 +48,17 @@ struct HaloCfg {
   static constexpr int PLANE_BYTES = KB * kHaloPlaneKbBytes;
   static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 4;
   static constexpr int AVAIL = 232448 - 1024 - 512 - STAT_BYTES;
-  static constexpr int RING = (G + 2) + (G == 2 ? 2 : (KB == 1 ? 1 : 0));  // planes in use + prefetch
+  static constexpr int RING = (G + 2) + (KB == 1 ? 1 : 0);  // planes in use + one prefetch slot where it fits
   static constexpr int NBST_FIT = (AVAIL - RING * PLANE_BYTES) / STAGE_BYTES;
-  static constexpr int NBST = NBST_FIT > 8 ? 8 : NBST_FIT;
+  // EVEN ring depth: stage i is issued by MMA warp (i & 1), so every ring slot has ONE owner.  With an odd depth the
+  // uses of a slot alternate between the two issuers; an issuer waiting only for its own uses is then two barrier
+  // phases further on its next visit, which a parity wait cannot tell from zero: it could run ahead onto a stage
+  // whose TMA load is still in flight and corrupt the empty barrier's arrival count (a rare hang, found the hard way).
+  static constexpr int NBST = (NBST_FIT > 8 ? 8 : NBST_FIT) & ~1;
   static constexpr int BAR_OFF = RING * PLANE_BYTES + NBST * STAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 512 + STAT_BYTES + 1024;
   static constexpr int TMEM_COLS = 4 * G * BLOCK_N;
-  static_assert(NBST >= 3, "weight pipeline too shallow");
+  static_assert(NBST >= 4 && (NBST & 1) == 0, "weight pipeline: need an even depth >= 4");
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   static_assert(2 * (RING + NBST) + 4 <= 60, "barrier block too small");
 };
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       for (int i = begin; i < end;) {
         const HaloSeg s = halo_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++) {
-          mbar_wait_spin(&empty_p[slot], par ^ 1u);
+          mbar_wait_spin(&empty_p[slot], par ^ 1u, 1142);
           mbar_arrive_expect_tx(&full_p[slot], tx);
 #pragma unroll
           for (int kb = 0; kb < KB; kb++)
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
             for (int t9 = 0; t9 < 9; t9 += TPS) {
 #pragma unroll
               for (int kb = 0; kb < KB; kb++) {
-                mbar_wait_spin(&empty_b[st], ph ^ 1u);
+                mbar_wait_spin(&empty_b[st], ph ^ 1u, 1175);
                 mbar_arrive_expect_tx(&full_b[st], STAGE_BYTES);
 #pragma unroll
                 for (int tp = 0; tp < TPS; tp++) {
@@ -206,7 +211,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     uint32_t ph = 0;
     int buf = 0;
     uint32_t bufph = 0;
-    uint32_t gs = 0;
     int w_slot = 0, r_slot = 0;  // ring cursors of the next plane to wait for / to hand back
     uint32_t w_par = 0;
     int n_waited = 0, n_released = 0, seq0 = 0;
@@ -216,22 +220,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       int sl0 = (seq0 + rel0 + 2 * RING) % RING;  // ring slot of plane d-1 (virtual for the plane above the volume)
       for (int d = s.dA; d < s.dB; d += G) {
         const int g = min(G, s.dB - d);
-        mbar_wait_spin(&tempty[buf], bufph ^ 1u);
-        const int need = seq0 + min(d + g, D - 1) - s.pf;  // last plane of the group, as a running count
-        while (n_waited <= need) {
-          mbar_wait_spin(&full_p[w_slot], w_par);
-          n_waited++;
-          if (++w_slot == RING) {
-            w_slot = 0;
-            w_par ^= 1u;
-          }
-        }
+        mbar_wait_spin(&tempty[buf], bufph ^ 1u, 1219);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (mw * 2u + static_cast<uint32_t>(buf)) * (G * BLOCK_N);
         uint32_t started = 0;  // bit q: this issuer's accumulator of piece q has been written in this group
 #pragma unroll 1
         for (int kd = 0; kd < 3; kd++) {
           if (d + kd + g - 2 < 0 || d + kd - 1 > D - 1) continue;
+          // planes are waited for when their kd comes up (the last one is only needed by the final third of the
+          // group, so its load overlaps the first two thirds); both issuers observe every plane, in load order
+          const int need = seq0 + min(d + g + kd - 2, D - 1) - s.pf;
+          while (n_waited <= need) {
+            mbar_wait_spin(&full_p[w_slot], w_par, 1222);
+            n_waited++;
+            if (++w_slot == RING) {
+              w_slot = 0;
+              w_par ^= 1u;
+            }
+          }
+          tc_fence_after();
           // descriptor base and validity of the input plane of every piece for this kd
           uint32_t a_plane[G];
           bool q_ok[G];
@@ -248,9 +255,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
             const int kh = t9 / 3, kw0 = t9 - kh * 3;
             const uint32_t row_off = static_cast<uint32_t>(kh * kHaloPitch + kw0) * (128u >> 4);
 #pragma unroll
-            for (int kb = 0; kb < KB; kb++, gs++) {
-              if ((gs & 1u) == mw) {
-                mbar_wait_spin(&full_b[st], ph);
+            for (int kb = 0; kb < KB; kb++) {
+              if ((static_cast<uint32_t>(st) & 1u) == mw) {  // ring slot st belongs to issuer (st & 1), see HaloCfg::NBST
+                mbar_wait_spin(&full_b[st], ph, 1253);
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(st) * (STAGE_BYTES >> 4);
                 if (elect_one_sync()) {
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
       for (int d = s.dA; d < s.dB; d += G) {
         const int g = min(G, s.dB - d);
         if (REG_STATS && do_stats && ++since_flush > kFlushGroups) flush_reg_stats();
-        mbar_wait_spin(&tfull[buf], bufph);
+        mbar_wait_spin(&tfull[buf], bufph, 1367);
         tc_fence_after();
 #pragma unroll 1
         for (int q = 0; q < g; q++) {

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
         const CUtensorMap* amap = &p.a_maps[tap.map];
         for (int kb = 0; kb < p.kc_blocks; kb++) {
           if (lane == 0) {
-            mbar_wait_spin(&empty[st], ph ^ 1);
+            mbar_wait_spin(&empty[st], ph ^ 1, 2136);
             if (p.debug == 2)
               mbar_arrive(&full[st]);
             else
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
       const int nkb = __popcll(tap_mask(c)) * p.kc_blocks;
       // The whole warp walks the loop with warp-uniform state (so ptxas keeps stage / descriptor arithmetic on the
       // uniform datapath instead of ELECT + R2UR per operand); one elected lane issues the tcgen05 instructions.
-      mbar_wait_spin(&tempty[acc], accph ^ 1);
+      mbar_wait_spin(&tempty[acc], accph ^ 1, 2168);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
       for (int i = 0; i < nkb; i++) {
-        mbar_wait_spin(&full[st], ph);
+        mbar_wait_spin(&full[st], ph, 2172);
         tc_fence_after();
         const uint32_t a_lo = desc_lo0 + ((smem_u32(smem_a + st * Cfg::A_BYTES) & 0x3FFFFu) >> 4);
         const uint32_t b_lo = desc_lo0 + ((smem_u32(smem_b + st * Cfg::B_BYTES) & 0x3FFFFu) >> 4);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
       const bool valid = rd < p.bd && od < p.Do && oh < p.Ho && ow < p.Wo;
       const long long off = c.n * p.out_sn + od * p.out_sd + oh * p.out_sh + ow * p.out_sw + c.n0;
 
-      mbar_wait_spin(&tfull[acc], accph);
+      mbar_wait_spin(&tfull[acc], accph, 2217);
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {

@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
         const StemSeg s = stem_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
           const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
-          mbar_wait_spin(&empty[slot], par ^ 1u);
+          mbar_wait_spin(&empty[slot], par ^ 1u, 3406);
           mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
           tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
         }
@@ -435,10 +435,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
         int sl0 = (seq0 + rel0 + 4 * kPRing) % kPRing;   // its ring slot (virtual for planes above the volume)
         for (int od = s.dA; od < s.dB; od++, rel0 += 2) {
           const int kd_lo = max(0, 3 - 2 * od), kd_hi = min(kK - 1, D + 2 - 2 * od);
-          mbar_wait_spin(&tempty[acc], accph ^ 1u);
+          mbar_wait_spin(&tempty[acc], accph ^ 1u, 3438);
           const int need = seq0 + rel0 + kd_hi;  // last plane of this piece, as a running count
           while (n_waited <= need) {
-            mbar_wait_spin(&full[w_slot], w_par);
+            mbar_wait_spin(&full[w_slot], w_par, 3441);
             n_waited++;
             if (++w_slot == kPRing) {
               w_slot = 0;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const
       for (int od = s.dA; od < s.dB; od++) {
         const long long off = ((((long long)s.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * kCout;
         if (do_stats && ++since_flush > kFlushPieces) flush_reg_stats();
-        mbar_wait_spin(&tfull[acc], accph);
+        mbar_wait_spin(&tfull[acc], accph, 3547);
         tc_fence_after();
 #pragma unroll
         for (int chunk = 0; chunk < kCout / 32; chunk++) {
@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
         const StemSeg s = stem_segment(p, i, end);
         for (int pz = s.pf; pz <= s.pl; pz++, seq++) {
           const uint32_t slot = seq % kPRing, par = (seq / kPRing) & 1u;
-          mbar_wait_spin(&empty[slot], par ^ 1u);
+          mbar_wait_spin(&empty[slot], par ^ 1u, 3809);
           mbar_arrive_expect_tx(&full[slot], 8u * kPRows * 16u);
           tma_load_4d(smem_p + slot * kPlaneBytes, &p.x_plane, &full[slot], s.w0 * 8, 2 * s.h0 - 3, pz, s.n);
         }
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
       for (int i = begin; i < end;) {
         const StemSeg s = stem_segment(p, i, end);
         for (int od = s.dA; od < s.dB; od++) {
-          mbar_wait_spin(&dempty[st], ph ^ 1u);
+          mbar_wait_spin(&dempty[st], ph ^ 1u, 3825);
           mbar_arrive_expect_tx(&dfull[st], kWPDyBytes);
           tma_load_5d(smem_dy + st * kWPDyBytes, &p.dy_map, &dfull[st], 0, s.w0, s.h0, od, s.n);
           if (++st == kWPStages) {
@@ -855,10 +855,10 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
       int sl0 = (seq0 + rel0 + 4 * kPRing) % kPRing;
       for (int od = s.dA; od < s.dB; od++, rel0 += 2) {
         const int kd_lo = max(0, 3 - 2 * od), kd_hi = min(kK - 1, D + 2 - 2 * od);
-        mbar_wait_spin(&dfull[st], ph);
+        mbar_wait_spin(&dfull[st], ph, 3858);
         const int need = seq0 + rel0 + kd_hi;
         while (n_waited <= need) {
-          mbar_wait_spin(&full[w_slot], w_par);
+          mbar_wait_spin(&full[w_slot], w_par, 3861);
           n_waited++;
           if (++w_slot == kPRing) {
             w_slot = 0;
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const _
         }
       i += s.dB - s.dA;
     }
-    mbar_wait_spin(tfull, 0);
+    mbar_wait_spin(tfull, 0, 3928);
     tc_fence_after();
     const int kh = row >> 3, j = row & 7;
     const bool keep = row < 64 && kh < kK && j < kK;

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) wgrad_halo_kernel(const __grid_
       const int z = u.d + kd - 1;
       if (z < 0 || z >= D) continue;
       if (lane == 0) {
-        mbar_wait_spin(&empty[st], ph ^ 1u);
+        mbar_wait_spin(&empty[st], ph ^ 1u, 5105);
         mbar_arrive_expect_tx(&full[st], kWHPitch * kWHRows * 128 + kWHDyBytes);
       }
       __syncwarp();
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) wgrad_halo_kernel(const __grid_
       const WHUnit u = wh_decode(p, piece);
       const int z = u.d + kd - 1;
       if (z < 0 || z >= D) continue;
-      mbar_wait_spin(&full[st], ph);
+      mbar_wait_spin(&full[st], ph, 5130);
       tc_fence_after();
       const uint32_t a_base = smem_lo + static_cast<uint32_t>(st) * (kWHStageBytes >> 4);
       const uint32_t b_base = a_base + (kWHPlaneBytes >> 4);

@@ -47,14 +47,19 @@ __device__ __forceinline__ unsigned int* hist_of(void* ws, int scan) {
   return reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + (size_t)scan * kScanWsBytes + kStateBytes);
 }
 
+// Histogram pass of the radix select.  PASS 0 (11 leading bits, every non-zero masked voxel counts): shared-memory
+// histogram per block.  PASS 1 / 2 (only voxels inside the bucket chosen so far count - typically < 1 %): no shared
+// histogram to clear and flush (that fixed cost made these passes 3x slower than pass 0); the few matches go to the
+// global histogram directly, one atomic per distinct bin and warp (__match_any), so a constant image does not
+// serialise on one address.  Loads are 16-byte (4 voxels + 4 mask bytes per thread and iteration).
 template <int PASS>
 __global__ void __launch_bounds__(kHistThreads) q_hist_kernel(const float* __restrict__ x,
                                                              const uint8_t* __restrict__ mask, long long nvox,
                                                              void* ws) {
-  constexpr int NH = PASS == 0 ? 1 : 4;
-  __shared__ unsigned int h[NH * kBins];
+  __shared__ unsigned int h[PASS == 0 ? kBins : 1];
   const int scan = blockIdx.y;
-  for (int i = threadIdx.x; i < NH * kBins; i += kHistThreads) h[i] = 0;
+  if (PASS == 0)
+    for (int i = threadIdx.x; i < kBins; i += kHistThreads) h[i] = 0;
   unsigned int pre[4] = {0, 0, 0, 0};
   if (PASS > 0) {
     const ScanState* st = state_of(ws, scan);
@@ -62,30 +67,49 @@ __global__ void __launch_bounds__(kHistThreads) q_hist_kernel(const float* __res
     for (int j = 0; j < 4; j++) pre[j] = st->prefix[j];
   }
   __syncthreads();
+  unsigned int* gh = hist_of(ws, scan);
   const float* xs = x + (long long)scan * nvox;
   const uint8_t* ms = mask + (long long)scan * nvox;
-  for (long long i = (long long)blockIdx.x * kHistThreads + threadIdx.x; i < nvox;
-       i += (long long)gridDim.x * kHistThreads) {
-    const float v = ms[i] ? xs[i] : 0.f;
-    if (v != 0.f) {
-      const unsigned int key = f2key(v);
-      if (PASS == 0) {
-        atomicAdd(&h[key >> 21], 1u);
-      } else if (PASS == 1) {
+  auto count = [&](float xv, uint8_t mv) {
+    const float v = mv ? xv : 0.f;
+    if (v == 0.f) return;
+    const unsigned int key = f2key(v);
+    if (PASS == 0) {
+      atomicAdd(&h[key >> 21], 1u);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if ((key >> 21) == (pre[j] >> 21)) atomicAdd(&h[j * kBins + ((key >> 10) & 2047u)], 1u);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if ((key >> 10) == (pre[j] >> 10)) atomicAdd(&h[j * kBins + (key & 1023u)], 1u);
+      for (int j = 0; j < 4; j++) {
+        const bool hit = PASS == 1 ? (key >> 21) == (pre[j] >> 21) : (key >> 10) == (pre[j] >> 10);
+        if (hit) {
+          const unsigned int bin = PASS == 1 ? ((key >> 10) & 2047u) : (key & 1023u);
+          const unsigned int act = __activemask();
+          const unsigned int grp = __match_any_sync(act, bin);
+          if ((threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&gh[j * kBins + bin], (unsigned int)__popc(grp));
+        }
       }
     }
+  };
+  const long long stride = (long long)gridDim.x * kHistThreads;
+  const long long tid = (long long)blockIdx.x * kHistThreads + threadIdx.x;
+  if ((nvox & 3) == 0 && (reinterpret_cast<uintptr_t>(xs) & 15) == 0 && (reinterpret_cast<uintptr_t>(ms) & 3) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    const uchar4* m4 = reinterpret_cast<const uchar4*>(ms);
+    for (long long i = tid; i < (nvox >> 2); i += stride) {
+      const float4 xv = __ldg(x4 + i);
+      const uchar4 mv = __ldg(m4 + i);
+      count(xv.x, mv.x);
+      count(xv.y, mv.y);
+      count(xv.z, mv.z);
+      count(xv.w, mv.w);
+    }
+  } else {
+    for (long long i = tid; i < nvox; i += stride) count(xs[i], ms[i]);
   }
-  __syncthreads();
-  unsigned int* gh = hist_of(ws, scan);
-  for (int i = threadIdx.x; i < NH * kBins; i += kHistThreads)
-    if (h[i]) atomicAdd(&gh[i], h[i]);
+  if (PASS == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins; i += kHistThreads)
+      if (h[i]) atomicAdd(&gh[i], h[i]);
+  }
 }
 
 // one block of 4 warps per scan; warp j resolves rank j
@@ -171,15 +195,44 @@ __global__ void __launch_bounds__(256) q_apply_kernel(const float* __restrict__ 
   const double qmax = st->qv[0], qmin = st->qv[1];
   const double range = qmax - qmin;
   const long long base = (long long)scan * nvox;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvox;
-       i += (long long)gridDim.x * blockDim.x) {
-    double v = ((double)x[base + i] - qmin) / range;
+  auto norm = [&](float xv, uint8_t mv) -> float {  // the reference's fp64 sequence, rounded to fp32 once
+    double v = ((double)xv - qmin) / range;
     if (v > 1.0) v = 1.0;
     if (v < 0.0) v = 0.0;
-    v *= mask[base + i] ? 1.0 : 0.0;
-    const float f = (float)v;
-    if (of) of[base + i] = f;
-    if (ob) ob[base + i] = __float2bfloat16_rn(f);
+    v *= mv ? 1.0 : 0.0;
+    return (float)v;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = (nvox & 3) == 0 && (reinterpret_cast<uintptr_t>(x + base) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(mask + base) & 3) == 0 &&
+                   (!of || (reinterpret_cast<uintptr_t>(of + base) & 15) == 0) &&
+                   (!ob || (reinterpret_cast<uintptr_t>(ob + base) & 7) == 0);
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    const uchar4* m4 = reinterpret_cast<const uchar4*>(mask + base);
+    for (long long i = tid; i < (nvox >> 2); i += stride) {
+      const float4 xv = __ldg(x4 + i);
+      const uchar4 mv = __ldg(m4 + i);
+      float4 f;
+      f.x = norm(xv.x, mv.x);
+      f.y = norm(xv.y, mv.y);
+      f.z = norm(xv.z, mv.z);
+      f.w = norm(xv.w, mv.w);
+      if (of) reinterpret_cast<float4*>(of + base)[i] = f;
+      if (ob) {
+        uint2 o;
+        o.x = pack_bf16x2(f.x, f.y);
+        o.y = pack_bf16x2(f.z, f.w);
+        reinterpret_cast<uint2*>(ob + base)[i] = o;
+      }
+    }
+  } else {
+    for (long long i = tid; i < nvox; i += stride) {
+      const float f = norm(x[base + i], mask[base + i]);
+      if (of) of[base + i] = f;
+      if (ob) ob[base + i] = __float2bfloat16_rn(f);
+    }
   }
 }
 
