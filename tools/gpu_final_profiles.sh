@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 echo "ncu launch list exit $?"; wc -l gpurun_out/launches.csv
 CMD2="python tools/profile_kernels.py 32"
 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"igemm_kmajor|wgrad2|stem_fprop|stem_wgrad" -s 14 -c 14 -o gpurun_out/prof_conv $CMD2 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"igemm_kmajor|igemm_halo|wgrad2_kernel|wgrad_halo_kernel|stem_fprop_plane|stem_wgrad_plane" -s 14 -c 14 -o gpurun_out/prof_conv $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > gpurun_out/prof_conv_raw.csv 2>/dev/null
 SZ=$(stat -c %s gpurun_out/prof_conv.ncu-rep); if [ "$SZ" -gt 40000000 ]; then rm gpurun_out/prof_conv.ncu-rep; echo "rep too large ($SZ), kept csv only"; fi

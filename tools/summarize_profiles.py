@@ -41,12 +41,16 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
     out.append(f"| {a[1] / tot * 100:.2f}% | {a[1] / 1e3:.2f} | {a[0]} | {a[2] / 1e9:.3f} | {a[3] / 1e9:.3f} | `{k[:90]}` |")
 open(f"profiles/{tag}_launch_summary.md", "w").write("\n".join(out) + "\n")
 ig = [a for k, a in agg.items() if "igemm_kmajor" in k]
+hl = [a for k, a in agg.items() if "igemm_halo" in k]
 n = sum(a[0] for a in ig)
 traffic = {"kernel": "igemm_kmajor_kernel", "launches_per_step": n,
            "dram_bytes_per_launch": (sum(a[2] + a[3] for a in ig) / n) if n else None,
            "share_of_step_kernel_time": sum(a[1] for a in ig) / tot,
+           "halo_kernel": {"launches_per_step": sum(a[0] for a in hl),
+                           "dram_bytes_per_launch": (sum(a[2] + a[3] for a in hl) / max(1, sum(a[0] for a in hl))),
+                           "share_of_step_kernel_time": sum(a[1] for a in hl) / tot},
            "source": f"profiles/{tag}_launch_summary.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the "
-                     "76 fprop+dgrad launches of one step, global batch 32)"}
+                     "igemm_kmajor fprop+dgrad launches of one step, global batch 32)"}
 json.dump(traffic, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 print("\n".join(out[:24]))
 print(traffic)
