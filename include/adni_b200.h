@@ -280,6 +280,44 @@ int adni_cast_f64_to_bf16(const double* x, adni_bf16* y, long long n, void* stre
 int adni_cast_bf16_to_f32(const adni_bf16* x, float* y, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Volume-level fusion operators (early fusion and feature-map fusion models).
+ * ------------------------------------------------------------------------------------------- */
+/* Multi-modality module input: x [N][C][vox] fp32 (x_is_f64 = 0) or fp64 NCDHW -> out bf16 NDHWC [N][vox][C], C in
+ * {2, 3, 4}  (pkg/models/fusion_models/early_fusion.py:84-88: torch.stack((x_pet, x_mri), dim=1).to(float32)). */
+int adni_volumes_to_ndhwc_bf16(const void* x, int x_is_f64, int N, int C, long long vox, adni_bf16* out, void* stream);
+/* Voxel-wise maximum of two feature maps, out = a >= b ? a : b, and its gradient routing da = (a >= b) dout,
+ * db = (a < b) dout (either may be null): torch.max over the stacked pair returns the FIRST maximal index, so ties -
+ * two post-ReLU zeros - go to `a`, the PET branch (anat_pet_featuremapfusion.py:121-123).  n % 8 == 0. */
+int adni_maxout_fwd(const adni_bf16* a, const adni_bf16* b, adni_bf16* out, long long n, void* stream);
+int adni_maxout_bwd(const adni_bf16* dout, const adni_bf16* a, const adni_bf16* b, adni_bf16* da, adni_bf16* db,
+                    long long n, void* stream);
+/* Channel concatenation of two NDHWC feature maps (torch.cat(dim=1) of the reference's NCDHW tensors,
+ * anat_pet_featuremapfusion.py:118-119): out[row] = [a[row] | b[row]], and the split of its gradient (da / db may be
+ * null).  Ca, Cb multiples of 8. */
+int adni_concat_channels(const adni_bf16* a, int Ca, const adni_bf16* b, int Cb, long long rows, adni_bf16* out,
+                         void* stream);
+int adni_split_channels(const adni_bf16* dout, int Ca, int Cb, long long rows, adni_bf16* da, adni_bf16* db,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step: torch.optim.Adam (amsgrad=False) with L2 weight decay and one learning rate per tensor - what
+ * every configure_optimizers of the path builds (pkg/models/mri_models/anat_cnn.py:111-136: one param group per
+ * encoder tensor at lr_pretrained, the head at lr, weight_decay = l2_reg; fusion_models/anat_pet_fusion.py:94-127;
+ * fusion_models/all_modalities_fusion.py:98-137).  SURVEY.md 8(f) N1.
+ * The seven tables are HOST arrays of n_tensors entries: fp32 DEVICE pointers params / grads / exp_avg / exp_avg_sq
+ * (numel[i] elements each), steps[i] = DEVICE fp32 scalar holding the number of updates tensor i has received
+ * (torch keeps state['step'] the same way; read as t-1, used as t, incremented in stream order after the update),
+ * lr[i], weight_decay[i].  Per element, in torch's operation order:
+ *   g' = g + wd p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps).
+ * Tensors travel by value in the kernel parameters, adni_adam_max_tensors_per_launch() per launch (graph-capturable:
+ * no host-side state, no device-side table).  Entries with numel 0 are skipped. */
+int adni_adam_max_tensors_per_launch(void);
+int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                         void* const* exp_avg_sq, void* const* steps, const long long* numel, const float* lr,
+                         const float* weight_decay, double beta1, double beta2, double eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU: one-shot all-reduce (sum) of a small fp64 vector over NVLink peer memory - the synchronised-BatchNorm
  * statistic sums and the loss normaliser of the data-parallel step (the reference is single-GPU).
  * `peers` is a DEVICE array of `world` pointers (uint64), entry r = this process's mapping of rank r's symmetric

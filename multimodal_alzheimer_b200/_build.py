@@ -24,6 +24,8 @@ SOURCES = [
     "elementwise.cu",
     "head_loss.cu",
     "normalize.cu",
+    "optimizer.cu",
+    "fusion_ops.cu",
     "peer_reduce.cu",
 ]
 NVCC_FLAGS = [

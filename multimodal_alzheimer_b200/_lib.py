@@ -49,6 +49,13 @@ _SIGNATURES = {
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
     "adni_peer_buffer_bytes": [_I, _I],
     "adni_peer_allreduce_f64": [_P, _I, _P, _P, _I, _I, _I, _P],
+    "adni_volumes_to_ndhwc_bf16": [_P, _I, _I, _I, _LL, _P, _P],
+    "adni_maxout_fwd": [_P, _P, _P, _LL, _P],
+    "adni_maxout_bwd": [_P, _P, _P, _P, _P, _LL, _P],
+    "adni_concat_channels": [_P, _I, _P, _I, _LL, _P, _P],
+    "adni_split_channels": [_P, _I, _I, _LL, _P, _P, _P],
+    "adni_adam_max_tensors_per_launch": [],
+    "adni_adam_step_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _P],
     "adni_weights_multi_job_bytes": [],
     "adni_weights_to_kernel_layout_multi": [_P, _I, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],

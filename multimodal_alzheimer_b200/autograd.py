@@ -156,19 +156,52 @@ def _conv_wgrad(x, dy, cfg, wshape, want_dbias=False):
 
 # --------------------------------------------------------------------------------------------- input cast
 class InputToVolume(torch.autograd.Function):
-    """(B,1,D,H,W) fp32/fp64 NCDHW module input -> bf16 NDHWC (same memory order because C == 1)."""
+    """(B,C,D,H,W) fp32/fp64 NCDHW module input -> bf16 NDHWC.  C == 1 (every encoder of the path) has the same memory
+    order and is a plain cast; C in {2,3,4} is the early-fusion stack of modalities (early_fusion.py:84-88)."""
 
     @staticmethod
     def forward(ctx, x):
-        if x.dim() != 5 or x.shape[1] != 1:
-            raise NotImplementedError("encoder inputs must be (B, 1, D, H, W); multi-channel input volumes are "
-                                      "outside the supported path")
-        N, _, D, H, W = x.shape
-        return K.cast_to_bf16(x.contiguous()).view(N, D, H, W, 1)
+        if x.dim() != 5:
+            raise NotImplementedError("volume inputs must be (B, C, D, H, W)")
+        N, C, D, H, W = x.shape
+        if C == 1:
+            return K.cast_to_bf16(x.contiguous()).view(N, D, H, W, 1)
+        return K.volumes_to_ndhwc(x)
 
     @staticmethod
     def backward(ctx, g):
         return None
+
+
+class MaxOutFn(torch.autograd.Function):
+    """torch.max(torch.stack((a, b), dim=0), dim=0)[0] on two feature maps (anat_pet_featuremapfusion.py:121-123);
+    ties route the gradient to `a` like torch's first-index rule."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return K.maxout_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da, db = K.maxout_bwd(g.contiguous(), a, b, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return da, db
+
+
+class ConcatChannelsFn(torch.autograd.Function):
+    """torch.cat((a, b), dim=1) of the reference's NCDHW feature maps = concatenation of the NDHWC channel axis
+    (anat_pet_featuremapfusion.py:118-119)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.widths = (a.shape[-1], b.shape[-1])
+        return K.concat_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        da, db = K.split_channels(g.contiguous(), *ctx.widths, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return da, db
 
 
 # --------------------------------------------------------------------------------------------- stem

@@ -59,6 +59,15 @@ class _Profile:
 PROFILE = _Profile()
 
 
+def call_hbm(tag, nbytes, name, *args):
+    """`call` for an HBM-bound kernel: when bench.py's profiling pass is on, the launch is bracketed by CUDA events and
+    recorded under `tag` with its ALGORITHMIC bytes (the tensors the operation must read and
+    write once, at their storage width) in the record's work field."""
+    ev = PROFILE.begin()
+    call(name, *args)
+    PROFILE.end(ev, tag, nbytes)
+
+
 _PLAN_CACHE = {}
 
 
@@ -109,21 +118,20 @@ class _ZeroArena:
     never handed out twice; chunks are per (device, stream) because the fill is ordered on the allocating stream, and a
     chunk zeroed outside CUDA-graph capture is never used inside one (its fill would not be part of the graph)."""
 
-    CHUNK = 65536
-
-    def __init__(self):
+    def __init__(self, dtype=torch.float64, chunk=65536):
         self.chunks = {}
+        self.dtype, self.CHUNK = dtype, chunk
 
     def take(self, shape, device):
         n = 1
         for d in shape:
             n *= d
-        n_al = (n + 15) & ~15  # 128-byte granules
+        n_al = (n + 31) & ~31  # 128-byte granules (fp32) or more
         capturing = torch.cuda.is_current_stream_capturing()
         key = (device.index, stream_ptr().value)
         rec = self.chunks.get(key)
         if rec is None or rec[2] != capturing or rec[1] + n_al > rec[0].numel():
-            rec = [torch.zeros(max(self.CHUNK, n_al), dtype=torch.float64, device=device), 0, capturing]
+            rec = [torch.zeros(max(self.CHUNK, n_al), dtype=self.dtype, device=device), 0, capturing]
             self.chunks[key] = rec
         v = rec[0][rec[1]:rec[1] + n].view(shape)
         rec[1] += n_al
@@ -135,6 +143,15 @@ _ZEROS = _ZeroArena()
 
 def zeros_f64(shape, device):
     return _ZEROS.take(tuple(shape), device)
+
+
+# fp32 split-K wgrad accumulators: one ResNet-18 encoder needs 33 M floats per backward pass in 21 buffers; a 144 MB
+# chunk turns their 21 fill launches into one (the fills are a fixed per-step cost that does not shrink with the batch)
+_ZEROS_F32 = _ZeroArena(torch.float32, 36 << 20)
+
+
+def zeros_f32(shape, device):
+    return _ZEROS_F32.take(tuple(shape), device)
 
 
 class WeightArena:
@@ -173,7 +190,8 @@ class WeightArena:
             self.jobs = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(ws[0].device)
             self.total_tiles = tile_begin
             self.key = key
-        call("adni_weights_to_kernel_layout_multi", ptr(self.jobs), len(ws), self.total_tiles, stream_ptr())
+        call_hbm("hbm_weight_layouts", 8 * sum(w.numel() for w in ws), "adni_weights_to_kernel_layout_multi",
+                 ptr(self.jobs), len(ws), self.total_tiles, stream_ptr())
         self.versions = {w.data_ptr(): w._version for w in ws}
 
     def lookup(self, w):
@@ -265,7 +283,7 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
     N, D, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
-    dw = torch.zeros((Cout, k * k * k, Cin), dtype=torch.float32, device=x.device)
+    dw = zeros_f32((Cout, k * k * k, Cin), x.device)
     db = None
     if want_dbias:
         if engine == ENGINE_DIRECT or (Cin % 64 != 0 or Cout % 64 != 0):
@@ -280,7 +298,7 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
     if engine != ENGINE_DIRECT:
         n_scratch = _wgrad_scratch_floats(g)
         if n_scratch:  # halo-plane engine (layer1): accumulates in a small scratch, then overwrites dw
-            scratch = torch.zeros(n_scratch, dtype=torch.float32, device=x.device)
+            scratch = zeros_f32((n_scratch,), x.device)
     ev = PROFILE.begin()
     call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), None, ptr(scratch), engine, stream_ptr())
     tag, frac = _engine_tag(g, 2, engine)
@@ -300,7 +318,8 @@ def stem_expand(x):
     N, D, H, W = x.shape[:4]
     Wo = (W - 1) // 2 + 1
     x8 = torch.empty((N, D, H, Wo, 8), dtype=BF16, device=x.device)
-    call("adni_stem_expand", ptr(x), N, D, H, W, ptr(x8), stream_ptr())
+    call_hbm("hbm_stem_expand", 2 * x.numel() + 2 * x8.numel(), "adni_stem_expand", ptr(x), N, D, H, W, ptr(x8),
+             stream_ptr())
     return x8
 
 
@@ -360,9 +379,9 @@ def bn_train_apply(y, stats, count, gamma, beta, eps, momentum, running_mean, ru
     rows = y.numel() // C
     out = torch.empty_like(y)
     bnp = torch.empty((4, C), dtype=torch.float32, device=y.device)
-    call("adni_bn_train_apply", ptr(y), ptr(stats[0]), ptr(stats[1]), float(count), ptr(gamma), ptr(beta), float(eps),
-         float(momentum), ptr(running_mean), ptr(running_var), ptr(bnp), ptr(residual), ptr(out), rows, C, int(relu),
-         stream_ptr())
+    call_hbm("hbm_bn_fwd", 2 * y.numel() * (3 if residual is not None else 2), "adni_bn_train_apply", ptr(y),
+             ptr(stats[0]), ptr(stats[1]), float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
+             ptr(running_mean), ptr(running_var), ptr(bnp), ptr(residual), ptr(out), rows, C, int(relu), stream_ptr())
     return out, bnp
 
 
@@ -418,8 +437,9 @@ def bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale=None, shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
     red = zeros_f64((2, C), y.device)
-    call("adni_bn_bwd_reduce", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(scale),
-         ptr(shift), rows, C, int(relu), ptr(red), stream_ptr())
+    call_hbm("hbm_bn_bwd_reduce", 2 * y.numel() * (3 if (relu and out is not None) else 2), "adni_bn_bwd_reduce",
+             ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), rows, C,
+             int(relu), ptr(red), stream_ptr())
     return red
 
 
@@ -430,10 +450,11 @@ def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres,
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     pg = torch.empty((2, C), dtype=torch.float32, device=y.device) if want_param_grads else None
-    call("adni_bn_bwd_apply", ptr(dout), ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
-         ptr(scale), ptr(shift), ptr(red), float(count), rows, C, int(relu), ptr(dy), ptr(dres),
-         ptr(pg[0]) if want_param_grads else None, ptr(pg[1]) if want_param_grads else None, float(param_grad_scale),
-         stream_ptr())
+    n_tensors = 3 + (1 if (relu and out is not None) else 0) + (1 if want_dres else 0)  # dout, y, dy (+out) (+dres)
+    call_hbm("hbm_bn_bwd_apply", 2 * y.numel() * n_tensors, "adni_bn_bwd_apply", ptr(dout),
+             ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale), ptr(shift), ptr(red),
+             float(count), rows, C, int(relu), ptr(dy), ptr(dres), ptr(pg[0]) if want_param_grads else None,
+             ptr(pg[1]) if want_param_grads else None, float(param_grad_scale), stream_ptr())
     if want_param_grads:
         return dy, dres, pg[0], pg[1]
     return dy, dres, None, None
@@ -468,24 +489,24 @@ def bn_relu_maxpool_fwd(y, bnp, k, stride, pad):
     Do, Ho, Wo = ((v + 2 * pad - k) // stride + 1 for v in (D, H, W))
     p = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=y.device)
     am = torch.empty((N, Do, Ho, Wo, C), dtype=torch.uint8, device=y.device)
-    call("adni_bn_relu_maxpool_fwd", ptr(y), ptr(bnp[2]), ptr(bnp[3]), N, D, H, W, C, k, stride, pad, ptr(p), ptr(am),
-         stream_ptr())
+    call_hbm("hbm_pool_fwd", 2 * y.numel() + 3 * p.numel(), "adni_bn_relu_maxpool_fwd", ptr(y), ptr(bnp[2]),
+             ptr(bnp[3]), N, D, H, W, C, k, stride, pad, ptr(p), ptr(am), stream_ptr())
     return p, am
 
 
 def maxpool_bn_bwd_reduce(dp, argmax, y, bnp, k, stride, pad):
     N, D, H, W, C = y.shape
     red = zeros_f64((2, C), y.device)
-    call("adni_maxpool_bn_bwd_reduce", ptr(dp), ptr(argmax), ptr(y), ptr(bnp), N, D, H, W, C, k, stride, pad, ptr(red),
-         stream_ptr())
+    call_hbm("hbm_pool_bwd_reduce", 2 * y.numel() + 3 * dp.numel(), "adni_maxpool_bn_bwd_reduce", ptr(dp),
+             ptr(argmax), ptr(y), ptr(bnp), N, D, H, W, C, k, stride, pad, ptr(red), stream_ptr())
     return red
 
 
 def maxpool_bn_bwd_apply(dp, argmax, y, bnp, gamma, red, count, k, stride, pad):
     N, D, H, W, C = y.shape
     dy = torch.empty_like(y)
-    call("adni_maxpool_bn_bwd_apply", ptr(dp), ptr(argmax), ptr(y), ptr(bnp), ptr(gamma), ptr(red), float(count), N, D,
-         H, W, C, k, stride, pad, ptr(dy), stream_ptr())
+    call_hbm("hbm_pool_bwd_apply", 4 * y.numel() + 3 * dp.numel(), "adni_maxpool_bn_bwd_apply", ptr(dp), ptr(argmax),
+             ptr(y), ptr(bnp), ptr(gamma), ptr(red), float(count), N, D, H, W, C, k, stride, pad, ptr(dy), stream_ptr())
     return dy
 
 
@@ -494,7 +515,7 @@ def gap_fwd(x):
     N, C = x.shape[0], x.shape[-1]
     P = x.numel() // (N * C)
     feat = torch.empty((N, C), dtype=torch.float32, device=x.device)
-    call("adni_gap_fwd", ptr(x), N, P, C, ptr(feat), stream_ptr())
+    call_hbm("hbm_gap", 2 * x.numel() + 4 * feat.numel(), "adni_gap_fwd", ptr(x), N, P, C, ptr(feat), stream_ptr())
     return feat
 
 
@@ -505,7 +526,7 @@ def gap_bwd(dfeat, shape):
         P *= v
     dfeat = _chk(dfeat, torch.float32, "dfeat")
     dx = torch.empty(shape, dtype=BF16, device=dfeat.device)
-    call("adni_gap_bwd", ptr(dfeat), N, P, C, ptr(dx), stream_ptr())
+    call_hbm("hbm_gap", 2 * dx.numel() + 4 * dfeat.numel(), "adni_gap_bwd", ptr(dfeat), N, P, C, ptr(dx), stream_ptr())
     return dx
 
 
@@ -604,8 +625,9 @@ def quantile_minmax_normalize(x, mask, q, out_dtype=torch.float32, want_info=Fal
     ob = torch.empty(x.shape, dtype=BF16, device=x.device) if out_dtype == BF16 else None
     info = torch.empty((S, 8), dtype=torch.int64, device=x.device) if want_info else None
     qv = torch.empty((S, 2), dtype=torch.float64, device=x.device) if want_info else None
-    call("adni_quantile_minmax_normalize", ptr(x), ptr(mask), S, nvox, float(q), ptr(of), ptr(ob), ptr(info), ptr(qv),
-         ptr(ws), ws_bytes, stream_ptr())
+    # select pass N*(4+1) + apply pass N*(4+1+o); the extra radix passes count against the kernel
+    call_hbm("hbm_quantile_normalize", x.numel() * (10 + (4 if of is not None else 2)), "adni_quantile_minmax_normalize",
+             ptr(x), ptr(mask), S, nvox, float(q), ptr(of), ptr(ob), ptr(info), ptr(qv), ptr(ws), ws_bytes, stream_ptr())
     out = of if of is not None else ob
     if want_info:
         return out, info, qv
@@ -616,7 +638,8 @@ def standardize(x, mean, std, mask=None, out_dtype=torch.float32):
     _chk(x, torch.float32, "x")
     of = torch.empty_like(x) if out_dtype == torch.float32 else None
     ob = torch.empty(x.shape, dtype=BF16, device=x.device) if out_dtype == BF16 else None
-    call("adni_standardize", ptr(x), ptr(mask), x.numel(), float(mean), float(std), ptr(of), ptr(ob), stream_ptr())
+    call_hbm("hbm_standardize", x.numel() * (4 + (1 if mask is not None else 0) + (4 if of is not None else 2)),
+             "adni_standardize", ptr(x), ptr(mask), x.numel(), float(mean), float(std), ptr(of), ptr(ob), stream_ptr())
     return of if of is not None else ob
 
 
@@ -647,6 +670,59 @@ def cast_to_bf16(x):
     else:
         raise ValueError(f"cast_to_bf16: unsupported dtype {x.dtype}")
     return y
+
+
+def volumes_to_ndhwc(x):
+    """(B, C, D, H, W) fp32/fp64 NCDHW module input with C in {2, 3, 4} modalities -> bf16 NDHWC (B, D, H, W, C)."""
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"volumes_to_ndhwc: unsupported dtype {x.dtype}")
+    x = x.contiguous()
+    N, C, D, H, W = x.shape
+    out = torch.empty((N, D, H, W, C), dtype=BF16, device=x.device)
+    call_hbm("hbm_input_cast", x.numel() * (x.element_size() + 2), "adni_volumes_to_ndhwc_bf16", ptr(x),
+             int(x.dtype == torch.float64), N, C, D * H * W, ptr(out), stream_ptr())
+    return out
+
+
+def maxout_fwd(a, b):
+    _chk(a, BF16, "a")
+    _chk(b, BF16, "b")
+    if a.shape != b.shape:
+        raise ValueError(f"maxout: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    out = torch.empty_like(a)
+    call_hbm("hbm_maxout", 6 * a.numel(), "adni_maxout_fwd", ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr())
+    return out
+
+
+def maxout_bwd(dout, a, b, want_a=True, want_b=True):
+    _chk(dout, BF16, "dout")
+    da = torch.empty_like(a) if want_a else None
+    db = torch.empty_like(b) if want_b else None
+    call_hbm("hbm_maxout", 2 * a.numel() * (3 + int(want_a) + int(want_b)), "adni_maxout_bwd", ptr(dout), ptr(a), ptr(b),
+             ptr(da), ptr(db), a.numel(), stream_ptr())
+    return da, db
+
+
+def concat_channels(a, b):
+    _chk(a, BF16, "a")
+    _chk(b, BF16, "b")
+    if a.shape[:-1] != b.shape[:-1]:
+        raise ValueError(f"concat_channels: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    out = torch.empty(tuple(a.shape[:-1]) + (Ca + Cb,), dtype=BF16, device=a.device)
+    call_hbm("hbm_concat", 4 * out.numel(), "adni_concat_channels", ptr(a), Ca, ptr(b), Cb, a.numel() // Ca, ptr(out),
+             stream_ptr())
+    return out
+
+
+def split_channels(dout, Ca, Cb, want_a=True, want_b=True):
+    _chk(dout, BF16, "dout")
+    lead = tuple(dout.shape[:-1])
+    da = torch.empty(lead + (Ca,), dtype=BF16, device=dout.device) if want_a else None
+    db = torch.empty(lead + (Cb,), dtype=BF16, device=dout.device) if want_b else None
+    call_hbm("hbm_concat", 4 * dout.numel(), "adni_split_channels", ptr(dout), Ca, Cb, dout.numel() // (Ca + Cb), ptr(da),
+             ptr(db), stream_ptr())
+    return da, db
 
 
 def cast_to_f32(x):

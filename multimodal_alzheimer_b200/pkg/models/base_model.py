@@ -121,8 +121,10 @@ def volume_input(x):
 
 def adam_or_plateau(hparams, parameters_optim, **adam_kwargs):
     """Adam (+ optional ReduceLROnPlateau on val_loss_epoch), as every configure_optimizers of the path ends
-    (anat_cnn.py:127-136)."""
-    optimizer = torch.optim.Adam(parameters_optim, **adam_kwargs)
+    (anat_cnn.py:127-136).  The optimizer is a torch.optim.Adam subclass (same groups, state names, state_dict)
+    whose step() is the multi-tensor CUDA kernel of csrc/optimizer.cu."""
+    from ...optim import Adam
+    optimizer = Adam(parameters_optim, **adam_kwargs)
     if hparams.get("reduce_factor_lr_schedule"):
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=hparams["reduce_factor_lr_schedule"])
         return {"optimizer": optimizer, "lr_scheduler": scheduler, "monitor": "val_loss_epoch"}

@@ -298,3 +298,113 @@ class All_Modalities_Fusion(LightningStandIn):
         loss = self.criterion(y_hat, y)
         self.log(mode + "_loss", loss)
         return {"loss": loss, "outputs": y_hat, "labels": y}
+
+
+def _small_backbone(hparams, n_in):
+    """The conv stack shared by pet_cnn.py:18-28, early_fusion.py:34-44 and anat_pet_featuremapfusion.py:40-64."""
+    modules = nn.ModuleList()
+    for n_out, filter_size in zip(hparams["conv_out"], hparams["filter_size"]):
+        modules.append(nn.Conv3d(n_in, n_out, filter_size, padding="same"))
+        if "batchnorm" in hparams and hparams["batchnorm"]:
+            modules.append(nn.BatchNorm3d(n_out))
+        modules.append(nn.ReLU())
+        modules.append(nn.MaxPool3d(2))
+        if "dropout_conv_p" in hparams:
+            modules.append(nn.Dropout(p=hparams["dropout_conv_p"]))
+        n_in = n_out
+    return modules, n_in
+
+
+class PET_MRI_EF(LightningStandIn):
+    """pkg/models/fusion_models/early_fusion.py:19-110."""
+
+    def __init__(self, hparams, gpu_id=None):
+        super().__init__()
+        self.save_hyperparameters(hparams)
+        modules, n_in = _small_backbone(hparams, 2)                     # :31-44 two input channels
+        modules.append(nn.AdaptiveAvgPool3d(1))
+        modules.append(nn.Flatten())
+        if "linear_out" in hparams and hparams["linear_out"]:           # :51-58
+            n_out = hparams["linear_out"]
+            if "dropout_dense_p" in hparams:
+                modules.append(nn.Dropout(p=hparams["dropout_dense_p"]))
+            modules.append(nn.Linear(n_in, n_out))
+            modules.append(nn.ReLU())
+        modules.append(nn.Linear(n_out, hparams["n_classes"]))
+        self.model = nn.Sequential(*modules)
+        self.criterion = nn.CrossEntropyLoss(weight=hparams["loss_class_weights"])   # :66-67
+
+    def forward(self, x):
+        return self.model(x)
+
+    def general_step(self, batch, batch_idx, mode):
+        x = torch.stack((batch["pet1451"], batch["mri"]), dim=1).to(dtype=torch.float32)   # :84-88
+        y = batch["label"]
+        y_hat = self.forward(x).to(dtype=torch.double)
+        loss = self.criterion(y_hat, y)
+        if mode != "pred":
+            self.log(mode + "_loss", loss)
+        return {"loss": loss, "outputs": y_hat, "labels": y}
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.model.parameters(), lr=self.hparams["lr"])        # :104-105
+
+
+class PET_MRI_FMF(LightningStandIn):
+    """pkg/models/fusion_models/anat_pet_featuremapfusion.py:20-172."""
+
+    def __init__(self, hparams, gpu_id=None):
+        super().__init__()
+        self.save_hyperparameters(hparams)
+        assert hparams["fusion_mode"] == "concatenate" or hparams["fusion_mode"] == "maxout"   # :31-32
+        self.fusion_mode = hparams["fusion_mode"]
+        modules_pet, n_in = _small_backbone(hparams, 1)
+        modules_mri, _ = _small_backbone(hparams, 1)
+        self.backbone_pet = nn.Sequential(*modules_pet)
+        self.backbone_mri = nn.Sequential(*modules_mri)
+        n_in_fusion = 2 * n_in if self.fusion_mode == "concatenate" else n_in             # :70-73
+        modules_fused = nn.ModuleList()
+        for _ in range(hparams["n_layers_fusion"]):                                       # :75-81
+            modules_fused.append(nn.Conv3d(n_in_fusion, hparams["n_out_fusion"], hparams["filter_size_fusion"],
+                                           padding="same"))
+            if "batchnorm_fusion" in hparams and hparams["batchnorm_fusion"]:
+                modules_fused.append(nn.BatchNorm3d(hparams["n_out_fusion"]))
+            modules_fused.append(nn.ReLU())
+            modules_fused.append(nn.MaxPool3d(2))
+            n_in_fusion = n_in_fusion * 2
+        modules_fused.append(nn.AdaptiveAvgPool3d(1))
+        modules_fused.append(nn.Flatten())
+        if "dropout_dense_p" in hparams:
+            modules_fused.append(nn.Dropout(p=hparams["dropout_dense_p"]))
+        modules_fused.append(nn.Linear(hparams["n_out_fusion"], 64))
+        modules_fused.append(nn.ReLU())
+        modules_fused.append(nn.Linear(64, hparams["n_classes"]))
+        self.fuse_model = nn.Sequential(*modules_fused)
+        self.criterion = nn.CrossEntropyLoss(weight=hparams["loss_class_weights"])
+
+    def forward(self, x_pet, x_mri):
+        out_pet = self.backbone_pet(x_pet)
+        out_mri = self.backbone_mri(x_mri)
+        if self.fusion_mode == "concatenate":
+            out_fused = torch.cat((out_pet, out_mri), dim=1)                               # :118-119
+        else:
+            out_fused = torch.stack((out_pet, out_mri), dim=0)                             # :121-123
+            out_fused, _ = torch.max(out_fused, dim=0)
+        return self.fuse_model(out_fused)
+
+    def general_step(self, batch, batch_idx, mode):
+        x_pet = batch["pet1451"].unsqueeze(1).to(dtype=torch.float32)
+        x_mri = batch["mri"].unsqueeze(1).to(dtype=torch.float32)
+        y = batch["label"]
+        y_hat = self.forward(x_pet=x_pet, x_mri=x_mri).to(dtype=torch.double)
+        loss = self.criterion(y_hat, y)
+        if mode != "pred":
+            self.log(mode + "_loss", loss)
+        return {"loss": loss, "outputs": y_hat, "labels": y}
+
+    def configure_optimizers(self):
+        params = []
+        for module in (self.backbone_mri, self.backbone_pet, self.fuse_model):             # :149-161
+            for _, p in module.named_parameters():
+                params.append({"params": p, "lr": self.hparams["lr"]})
+        return torch.optim.Adam(params, weight_decay=self.hparams["l2_reg"])

@@ -19,6 +19,15 @@ def hp_pet(n_classes=3, batchnorm=False, conv_out=(8, 16, 32, 64), filter_size=(
                 reduce_factor_lr_schedule=None)
 
 
+def hp_fmf(n_classes=3, fusion_mode="maxout", batchnorm=True, batchnorm_fusion=True, filter_size_fusion=3, n_out_fusion=64,
+           conv_out=(8, 16, 32, 64), filter_size=(5, 5, 3, 3)):
+    # train_anat_pet_featuremapfusion.py:60-117 (the HPO search space)
+    return dict(n_classes=n_classes, conv_out=list(conv_out), filter_size=list(filter_size), batchnorm=batchnorm,
+                fusion_mode=fusion_mode, n_layers_fusion=1, filter_size_fusion=filter_size_fusion,
+                n_out_fusion=n_out_fusion, batchnorm_fusion=batchnorm_fusion, loss_class_weights=CW3[:n_classes].clone(),
+                lr=1e-3, l2_reg=1e-4, reduce_factor_lr_schedule=None)
+
+
 def hp_fusion(n_classes=3, fl_gamma=1, simple_dim_red=False):
     return dict(n_classes=n_classes, fl_gamma=fl_gamma, loss_class_weights=CW3[:n_classes].clone(), lr=1e-3,
                 lr_pretrained=1e-4, l2_reg=0.0, reduce_factor_lr_schedule=None, simple_dim_red=simple_dim_red,
@@ -27,7 +36,9 @@ def hp_fusion(n_classes=3, fl_gamma=1, simple_dim_red=False):
 
 def build_pair(kind, seed=15, **kw):
     """Returns (oracle_model_cpu, product_model) with identical weights. kind in
-    {'anat','pet_resnet','small_pet','anat_pet','anat_pet_2resnet','mri_tab','pet_tab','all'}."""
+    {'anat','pet_resnet','small_pet','anat_pet','anat_pet_2resnet','mri_tab','pet_tab','all','early_fusion','fmf'}."""
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import anat_pet_featuremapfusion as P_fmf
+    from multimodal_alzheimer_b200.pkg.models.fusion_models import early_fusion as P_ef
     import oracle.models as O
     from multimodal_alzheimer_b200.pkg.models.fusion_models import all_modalities_fusion as P_all
     from multimodal_alzheimer_b200.pkg.models.fusion_models import anat_pet_fusion as P_ap
@@ -98,6 +109,14 @@ def build_pair(kind, seed=15, **kw):
             return mri_tab(o)
         if kind == "pet_tab":
             return pet_tab(o)
+        if kind == "early_fusion":
+            hp = hp_pet(nc, kw.get("pet_batchnorm", False), kw.get("conv_out", (8, 16, 32, 64)),
+                        kw.get("filter_size", (5, 5, 3, 3)))
+            return (O.PET_MRI_EF if o else P_ef.PET_MRI_EF)(hp)
+        if kind == "fmf":
+            hp = hp_fmf(nc, kw.get("fusion_mode", "maxout"), kw.get("pet_batchnorm", True), kw.get("batchnorm_fusion", True),
+                        kw.get("filter_size_fusion", 3), kw.get("n_out_fusion", 64))
+            return (O.PET_MRI_FMF if o else P_fmf.PET_MRI_FMF)(hp)
         if kind == "all":
             hp = hp_fusion(nc, kw.get("fl_gamma", 1))
             cls = O.All_Modalities_Fusion if o else P_all.All_Modalities_Fusion
@@ -178,8 +197,10 @@ def autocast_step(model, batch, dev):
             yh = model(b["pet1451"].unsqueeze(1).float(), b["tabular"])
         elif name == "All_Modalities_Fusion":
             yh = model(b["pet1451"].unsqueeze(1).float(), b["mri"].unsqueeze(1).float(), b["tabular"])
-        elif name == "Anat_PET_CNN":
+        elif name in ("Anat_PET_CNN", "PET_MRI_FMF"):
             yh = model(b["pet1451"].unsqueeze(1).float(), b["mri"].unsqueeze(1).float())
+        elif name == "PET_MRI_EF":
+            yh = model(torch.stack((b["pet1451"], b["mri"]), dim=1).float())
         elif name in ("Small_PET_CNN", "PET_CNN_ResNet"):
             yh = model(b["pet1451"].unsqueeze(1).float())
         else:

@@ -26,6 +26,14 @@ TC_SHAPES = [
     (9, 21, 16, 16, 128, 128, 3, 1, 1, 1),  # halo engine, two K blocks, several pieces per CTA
     (1, 5, 40, 20, 64, 64, 3, 1, 1, 1),     # halo engine: three H tiles (ragged), more CTAs than planes per column
 ]
+# feature maps smaller than one tile: the fusion conv of PET_MRI_FMF (anat_pet_featuremapfusion.py:75-81) sees 8^3 maps
+# for 128^3 inputs, 5x6x5 for the MNI 91x109x91 grid and 2^3 for the 32^3 test volumes
+TINY_SHAPES = [
+    (4, 2, 2, 2, 64, 64, 3, 1, 1, 1),
+    (2, 5, 6, 5, 128, 128, 3, 1, 1, 1),
+    (2, 1, 3, 2, 128, 64, 3, 1, 1, 1),
+    (3, 4, 4, 4, 64, 64, 3, 1, 1, 1),
+]
 
 
 def _mk(shape, dev, seed=0):
@@ -85,6 +93,14 @@ def test_tc_wgrad(cuda_dev, shape):
     g = K.wgrad_to_param_layout(dw, tuple(w.shape))
     torch.cuda.synchronize()
     assert_close(g, w_ref.grad, 2e-4, f"wgrad {shape}")
+
+
+@pytest.mark.parametrize("shape", TINY_SHAPES)
+def test_tc_tiny_feature_maps(cuda_dev, shape):
+    """fprop + dgrad + wgrad on feature maps smaller than one tile, through the planner's own engine choice."""
+    test_tc_fprop(cuda_dev, shape)
+    test_tc_dgrad(cuda_dev, shape)
+    test_tc_wgrad(cuda_dev, shape)
 
 
 DIRECT_SHAPES = [

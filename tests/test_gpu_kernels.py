@@ -372,3 +372,122 @@ def test_conv_plan_info(cuda_dev):
     assert info(2, 16, 256, 2, 1)[0] == 1 and 0.7 < info(2, 16, 256, 2, 1)[1] <= 1.0
     assert info(2, 16, 512, 4, 2) == (1, 1.0)
     assert info(2, 8, 8, 1, 0)[0] == 0                                                 # small channels: direct engine
+
+
+def test_adam_multi_tensor_matches_torch_adam(cuda_dev):
+    """csrc/optimizer.cu against torch.optim.Adam on the CPU (what every configure_optimizers of the reference builds:
+    one group per tensor, two learning rates, weight_decay = l2_reg; anat_cnn.py:111-128).  150 tensors = 3 launches,
+    ragged sizes (numel % 4 != 0, > one 8192-element chunk), a tensor that skips a step (grad None), a misaligned
+    parameter view.  fp32 arithmetic in torch's operation order: <= 2e-6 relative after 4 steps."""
+    from multimodal_alzheimer_b200.optim import Adam
+    g = torch.Generator().manual_seed(11)
+    sizes = [(64, 64, 27), (8192 * 2 + 5,), (3,), (1,), (513, 7), (64,), (128, 64, 3, 3, 3)] + [(17 + i,) for i in range(142)]
+    base = torch.randn(40, generator=g)
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in sizes] + [torch.nn.Parameter(base[1:38].clone())]
+    dev_base = base.to(cuda_dev)
+    our_p = [torch.nn.Parameter(p.detach().to(cuda_dev)) for p in ref_p[:-1]] + [torch.nn.Parameter(dev_base[1:38])]
+    assert our_p[-1].data_ptr() % 16 != 0
+
+    def groups(ps):
+        return [{"params": p, "lr": 1e-2 if i % 3 else 1e-3} for i, p in enumerate(ps)]
+
+    ref = torch.optim.Adam(groups(ref_p), weight_decay=1e-2)
+    our = Adam(groups(our_p), weight_decay=1e-2)
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(ref_p, our_p)):
+            if i == 4 and step == 1:
+                a.grad, b.grad = None, None          # this tensor's step counter must lag by one afterwards
+                continue
+            gr = torch.randn(a.shape, generator=g) * (10.0 ** (i % 5 - 2))
+            a.grad, b.grad = gr.clone(), gr.to(cuda_dev)
+        ref.step()
+        our.step()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(ref_p, our_p)):
+        assert_close(b.detach().cpu(), a.detach(), 2e-6, f"param {i} {tuple(a.shape)}")
+        assert_close(our.state[b]["exp_avg"].cpu(), ref.state[a]["exp_avg"], 2e-6, f"exp_avg {i}")
+        assert_close(our.state[b]["exp_avg_sq"].cpu(), ref.state[a]["exp_avg_sq"], 2e-6, f"exp_avg_sq {i}")
+        assert float(our.state[b]["step"]) == float(ref.state[a]["step"]) == (3.0 if i == 4 else 4.0)
+    # the state dict interchanges with torch.optim.Adam: load ours into a stock optimizer and vice versa
+    stock = torch.optim.Adam(groups(our_p), weight_decay=1e-2)
+    stock.load_state_dict(our.state_dict())
+    again = Adam(groups(our_p), weight_decay=1e-2)
+    again.load_state_dict(ref.state_dict())
+    for b in our_p:
+        b.grad = torch.ones_like(b)
+    before = [b.detach().clone() for b in our_p]
+    again.step()
+    assert float(again.state[our_p[0]]["step"]) == 5.0
+    assert all(not torch.equal(x, b.detach()) for x, b in zip(before, our_p))
+
+
+def test_adam_under_cuda_graph(cuda_dev):
+    """The table rides in the kernel parameters, the step counters live on the device: replaying a captured step
+    advances the bias correction exactly like eager steps."""
+    from multimodal_alzheimer_b200.optim import Adam
+    g = torch.Generator().manual_seed(3)
+    init = [torch.randn(s, generator=g) for s in [(1000,), (64, 9)]]
+    grads = [torch.randn(t.shape, generator=g) for t in init]
+    graph_p = [torch.nn.Parameter(t.to(cuda_dev)) for t in init]
+    dev_grads = [t.to(cuda_dev) for t in grads]
+    graphed = Adam(graph_p, lr=1e-2)
+    for p, gr in zip(graph_p, dev_grads):
+        p.grad = gr.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        graphed.step()                               # allocates the state outside the capture
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg, stream=s):
+            graphed.step()
+        for _ in range(3):
+            cg.replay()
+    torch.cuda.synchronize()
+    # capture does not execute: the graphed optimizer ran 1 eager step + 3 replays = 4 updates
+    assert float(graphed.state[graph_p[0]]["step"]) == 4.0
+    eager4_p = [torch.nn.Parameter(t.to(cuda_dev)) for t in init]
+    e4 = Adam(eager4_p, lr=1e-2)
+    for p, gr in zip(eager4_p, dev_grads):
+        p.grad = gr.clone()
+    for _ in range(4):
+        e4.step()
+    torch.cuda.synchronize()
+    for a, b in zip(eager4_p, graph_p):
+        assert torch.equal(a.detach(), b.detach())
+
+
+def test_fusion_ops_bit_exact(cuda_dev):
+    """csrc/fusion_ops.cu against torch on the same bf16 values: multi-channel input cast (early_fusion.py:84-88),
+    maxout with torch.max's first-index tie rule and its gradient routing (anat_pet_featuremapfusion.py:121-123),
+    channel concatenation and the split of its gradient (:118-119).  Pure data movement / comparisons: bit-exact."""
+    from multimodal_alzheimer_b200 import kernels as K
+    g = torch.Generator().manual_seed(21)
+    for dtype in (torch.float32, torch.float64):
+        for C in (2, 3, 4):
+            x = torch.randn((3, C, 5, 6, 7), generator=g, dtype=dtype)
+            got = K.volumes_to_ndhwc(x.to(cuda_dev))
+            ref = x.float().permute(0, 2, 3, 4, 1).contiguous().to(BF)
+            assert torch.equal(got.cpu(), ref), (dtype, C)
+    with pytest.raises(NotImplementedError):
+        K.volumes_to_ndhwc(torch.zeros((1, 5, 2, 2, 2), device=cuda_dev))
+    shape = (2, 3, 5, 4, 16)
+    a = torch.randn(shape, generator=g).clamp_min(0).to(BF)          # post-ReLU maps: many exact ties at zero
+    b = torch.randn(shape, generator=g).clamp_min(0).to(BF)
+    b[0, 0] = a[0, 0]                                                # and ties at non-zero values
+    dout = torch.randn(shape, generator=g).to(BF)
+    af, bf_ = a.float().requires_grad_(), b.float().requires_grad_()
+    ref, _ = torch.max(torch.stack((af, bf_), dim=0), dim=0)
+    ref.backward(dout.float())
+    ad, bd = a.to(cuda_dev), b.to(cuda_dev)
+    out = K.maxout_fwd(ad, bd)
+    da, db = K.maxout_bwd(dout.to(cuda_dev), ad, bd)
+    assert torch.equal(out.cpu().float(), ref.detach())
+    assert torch.equal(da.cpu().float(), af.grad) and torch.equal(db.cpu().float(), bf_.grad)
+    only_b = K.maxout_bwd(dout.to(cuda_dev), ad, bd, want_a=False)
+    assert only_b[0] is None and torch.equal(only_b[1], db)
+    c = torch.randn(shape[:-1] + (24,), generator=g).to(BF)
+    cat = K.concat_channels(ad, c.to(cuda_dev))
+    assert torch.equal(cat.cpu(), torch.cat((a, c), dim=-1))
+    sa, sc = K.split_channels(cat, 16, 24)
+    assert torch.equal(sa.cpu(), a) and torch.equal(sc.cpu(), c)
+    with pytest.raises(NotImplementedError):
+        K.concat_channels(ad[..., :4].contiguous(), ad)

@@ -5,7 +5,12 @@ Tolerances (bf16 operands / fp32 accumulation vs the fp32 CPU oracle; SURVEY.md 
 loss abs <= 2e-2, BatchNorm running statistics rel-L2 <= 3e-2, parameter gradients rel-L2 <= 3e-2 — each OR within 2x
 of the error that PyTorch's own bf16-autocast execution of the oracle makes on the same inputs (tiny batches make
 the last BatchNorm's backward cancel catastrophically in bf16 — for torch exactly as for these kernels — so the
-autocast run is the honest noise floor; the bracket is measured, not assumed)."""
+autocast run is the honest noise floor; the bracket is measured, not assumed).  Where the bracket itself is off by
+more than 5 % on some tensor (ILL = 5e-2: batch 3 through BatchNorm1d amplifies the 1e-2 feature rounding error to
+10-40 % and flips ReLU masks, for torch's bf16 run as much as for these kernels, and the error of the head propagates
+to every gradient upstream) the backward pass is not reproducible in bf16 at all; two independent noise realisations
+are being compared, and the rule becomes: every gradient within 2x of the bracket's WORST tensor error, cosine >= 0.9.
+The well-conditioned twin of that case (same model, batch 6) is held to the per-tensor rule."""
 import pytest
 import torch
 
@@ -13,6 +18,9 @@ from tests._models import autocast_step, build_pair, oracle_step, product_step, 
 from tests._util import rel_l2
 
 pytestmark = pytest.mark.gpu
+
+
+ILL = 5e-2  # bracket error above which a gradient counts as ill-conditioned in bf16 (see the module docstring)
 
 
 def _cos(a, b):
@@ -46,8 +54,10 @@ def _compare(oracle, product, out_o, out_p, check_grads=True, bracket=None, out_
     worst.sort(reverse=True)
     report = "\n".join(f"  cos={c:.5f} rel={e:.3e} autocast_rel={ea:.3e} {n}" for _, c, e, ea, n in worst[:8])
     if check_grads:
+        floor = max((ea for _, _, _, ea, _ in worst), default=0.0)
         for _, c, e, ea, n in worst:
-            assert e <= max(3e-2, 2 * ea), "gradient mismatch:\n" + report
+            ok = e <= max(3e-2, 2 * ea) or (floor > ILL and e <= 2 * floor and c >= 0.9)
+            assert ok, f"gradient mismatch (worst bracket error of the step {floor:.3e}):\n" + report
     bo = dict(oracle.named_buffers())
     ba = dict(bracket.named_buffers()) if bracket is not None else {}
     for name, b in product.named_buffers():
@@ -64,6 +74,7 @@ CASES = [
     # kind, kwargs, batch, volume shape, modalities
     ("anat", dict(depth=10), 2, (64, 64, 64), ("mri",)),                                   # config 1 (reduced size)
     ("anat", dict(depth=18, bn_begin=True, bn_dense=True, linear_out=(32,), fl_gamma=2), 3, (48, 56, 48), ("mri",)),
+    ("anat", dict(depth=18, bn_begin=True, bn_dense=True, linear_out=(32,), fl_gamma=2), 6, (40, 40, 40), ("mri",)),
     ("anat", dict(depth=50, fl_gamma=1), 2, (40, 48, 40), ("mri",)),                       # Bottleneck path
     ("pet_resnet", dict(depth=10, n_classes=2), 2, (48, 48, 48), ("pet1451",)),
     ("small_pet", dict(), 2, (32, 32, 32), ("pet1451",)),
@@ -73,6 +84,13 @@ CASES = [
     ("mri_tab", dict(depth=10), 2, (48, 48, 48), ("mri", "tabular")),
     ("pet_tab", dict(simple_dim_red=True), 2, (32, 32, 32), ("pet1451", "tabular")),
     ("all", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451", "tabular")),               # config 4
+    # early fusion (2-channel input) and feature-map fusion (maxout / concatenate)
+    ("early_fusion", dict(), 2, (32, 32, 32), ("mri", "pet1451")),
+    ("early_fusion", dict(pet_batchnorm=True, n_classes=2), 4, (32, 40, 32), ("mri", "pet1451")),
+    ("fmf", dict(fusion_mode="maxout"), 4, (64, 64, 64), ("mri", "pet1451")),
+    ("fmf", dict(fusion_mode="concatenate", batchnorm_fusion=False, pet_batchnorm=False, n_out_fusion=128), 2,
+     (48, 64, 48), ("mri", "pet1451")),
+    ("fmf", dict(fusion_mode="maxout", filter_size_fusion=5, n_classes=2), 3, (32, 32, 32), ("mri", "pet1451")),
 ]
 
 

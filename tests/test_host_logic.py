@@ -7,7 +7,8 @@ import torch
 from tests._models import build_pair, hp_anat, hp_fusion, hp_pet
 
 
-ALL_KINDS = ["anat", "pet_resnet", "small_pet", "anat_pet", "anat_pet_2resnet", "mri_tab", "pet_tab", "all"]
+ALL_KINDS = ["anat", "pet_resnet", "small_pet", "anat_pet", "anat_pet_2resnet", "mri_tab", "pet_tab", "all",
+             "early_fusion", "fmf"]
 
 
 @pytest.mark.parametrize("kind", ALL_KINDS)
@@ -138,3 +139,28 @@ def test_loss_modules_follow_reference_selection():
     hp = hp_pet()
     hp["fl_gamma"] = 5
     assert isinstance(Small_PET_CNN(hp).criterion, CrossEntropyLoss)     # pet_cnn.py:47-48 ignores fl_gamma
+
+
+def test_feature_map_fusion_construction_rules():
+    """anat_pet_featuremapfusion.py:31-32 (fusion_mode assert), :70-79 (fusion stack widths), :149-161 (one Adam group
+    per tensor at hparams['lr'] with weight_decay = l2_reg); early_fusion.py:31-33 (two input channels)."""
+    from tests._models import hp_fmf
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.anat_pet_featuremapfusion import PET_MRI_FMF
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.early_fusion import PET_MRI_EF
+    with pytest.raises(AssertionError):
+        PET_MRI_FMF(hp_fmf(fusion_mode="sum"))
+    m = PET_MRI_FMF(hp_fmf(fusion_mode="concatenate", n_out_fusion=128))
+    assert m.fuse_model[0].in_channels == 128 and m.fuse_model[0].out_channels == 128
+    assert PET_MRI_FMF(hp_fmf(fusion_mode="maxout")).fuse_model[0].in_channels == 64
+    opt = m.configure_optimizers()
+    assert len(opt.param_groups) == len(list(m.parameters())) and {g["lr"] for g in opt.param_groups} == {1e-3}
+    assert all(g["weight_decay"] == 1e-4 for g in opt.param_groups)
+    with pytest.raises(NotImplementedError):          # 'same' with an even kernel pads asymmetrically: not implemented
+        PET_MRI_FMF(hp_fmf(filter_size_fusion=4))
+    hp = hp_fmf()
+    hp["n_layers_fusion"] = 2                         # inconsistent in the reference as well (fails at its first forward)
+    with pytest.raises(ValueError):
+        PET_MRI_FMF(hp)
+    ef = PET_MRI_EF(hp_pet())
+    assert ef.model[0].in_channels == 2 and tuple(ef.model[0].weight.shape) == (8, 2, 5, 5, 5)
+    assert len(ef.configure_optimizers().param_groups) == 1
