@@ -231,6 +231,16 @@ def test_standardize_and_moments(cuda_dev):
     out = K.standardize(x, 0.5145, 0.5383)
     ref = pet_standardize_oracle(x.cpu().double(), 0.5145, 0.5383).float()
     assert torch.equal(out.cpu(), ref)
+    # vector path + scalar tail + misaligned views, masked (dataloader.py:252-260) and bf16 outputs: all bit-exact
+    flat = torch.randn(4 * 1000 + 7, generator=torch.Generator().manual_seed(9)).to(cuda_dev) * 300 + 400
+    mflat = (torch.rand(flat.numel(), generator=torch.Generator().manual_seed(10)) < 0.4).to(torch.uint8).to(cuda_dev)
+    for off in (0, 1, 4):
+        xs, ms = flat[off:], mflat[off:]            # off = 1: misaligned views take the scalar path
+        refm = (((xs.cpu().double() - 426.9336) / 1018.7830) * ms.cpu().double()).float()
+        got = K.standardize(xs, 426.9336, 1018.7830, mask=ms)
+        assert torch.equal(got.cpu(), refm), off
+        gotb = K.standardize(xs, 426.9336, 1018.7830, mask=ms, out_dtype=BF)
+        assert torch.equal(gotb.cpu(), refm.to(BF)), off
     m = K.scan_moments(x)
     mean, std, per_scan = split_moments_oracle([x[s].cpu().double() for s in range(2)])
     assert_close(m.cpu(), per_scan, 1e-12, "scan moments")
