@@ -298,6 +298,14 @@ int adni_concat_channels(const adni_bf16* a, int Ca, const adni_bf16* b, int Cb,
                          void* stream);
 int adni_split_channels(const adni_bf16* dout, int Ca, int Cb, long long rows, adni_bf16* da, adni_bf16* db,
                         void* stream);
+/* nn.Conv3d(padding='same') with an EVEN kernel (filter_size_fusion = 4, train_anat_pet_featuremapfusion.py:70) pads
+ * total = dil*(k-1) voxels per axis as lo = total/2, hi = total - lo.  The conv entry points take the symmetric part
+ * (pad = lo); these two supply the extra high-side voxels: out [N][D+ed][H+eh][W+ew][C] = x with a zero border, and
+ * the inverse for the input gradient (out [N][D][H][W][C] = leading box of x_padded). */
+int adni_pad_volume_high(const adni_bf16* x, int N, int D, int H, int W, int C, int ed, int eh, int ew, adni_bf16* out,
+                         void* stream);
+int adni_crop_volume_high(const adni_bf16* x_padded, int N, int D, int H, int W, int C, int ed, int eh, int ew,
+                          adni_bf16* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step: torch.optim.Adam (amsgrad=False) with L2 weight decay and one learning rate per tensor - what

@@ -173,6 +173,20 @@ class InputToVolume(torch.autograd.Function):
         return None
 
 
+class PadHighFn(torch.autograd.Function):
+    """Extra high-side zero voxels of padding='same' with an even kernel (torch pads lo = total//2, hi = total - lo);
+    the gradient is the leading box of the padded gradient."""
+
+    @staticmethod
+    def forward(ctx, x, extra):
+        ctx.extra = extra
+        return K.pad_volume_high(x, extra)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.crop_volume_high(g.contiguous(), ctx.extra), None
+
+
 class MaxOutFn(torch.autograd.Function):
     """torch.max(torch.stack((a, b), dim=0), dim=0)[0] on two feature maps (anat_pet_featuremapfusion.py:121-123);
     ties route the gradient to `a` like torch's first-index rule."""

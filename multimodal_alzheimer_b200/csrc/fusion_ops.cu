@@ -109,11 +109,58 @@ __global__ void __launch_bounds__(kThreads) concat_kernel(uint4* __restrict__ a,
   }
 }
 
+// Zero padding on the HIGH side of D, H, W (torch's padding='same' with an even kernel pads total = dil*(k-1) as
+// lo = total/2, hi = total - lo; the conv engines take the symmetric part, this kernel supplies the extra voxel):
+// big = [N][D+ed][H+eh][W+ew][C], small = [N][D][H][W][C].  CROP = false: big <- small with a zero border (forward);
+// CROP = true: small <- leading box of big (gradient).  VEC = channels per thread access (8 = 16 bytes, or 1).
+template <bool CROP, int VEC>
+__global__ void __launch_bounds__(kThreads) pad_high_kernel(const __nv_bfloat16* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst, int N, int D, int H, int W,
+                                                            int C, int ed, int eh, int ew) {
+  const int cv = C / VEC;
+  const int Dd = CROP ? D : D + ed, Hd = CROP ? H : H + eh, Wd = CROP ? W : W + ew;   // destination extents
+  const int Ds = CROP ? D + ed : D, Hs = CROP ? H + eh : H, Ws = CROP ? W + ew : W;   // source extents
+  const long long total = (long long)N * Dd * Hd * Wd * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int c = (int)(r % cv);
+    r /= cv;
+    const int w = (int)(r % Wd);
+    r /= Wd;
+    const int h = (int)(r % Hd);
+    r /= Hd;
+    const int d = (int)(r % Dd);
+    const int n = (int)(r / Dd);
+    const bool inside = d < Ds && h < Hs && w < Ws;  // always true for CROP
+    const long long so = ((((long long)n * Ds + d) * Hs + h) * Ws + w) * cv + c;
+    if (VEC == 8) {
+      const uint4 v = inside ? __ldg(reinterpret_cast<const uint4*>(src) + so) : make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(dst)[i] = v;
+    } else {
+      dst[i] = inside ? src[so] : __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace adni
 
 using namespace adni;
 #define ST(s) static_cast<cudaStream_t>(s)
+
+template <bool CROP>
+static int launch_pad_high(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int D, int H, int W, int C, int ed, int eh,
+                           int ew, cudaStream_t st) {
+  const long long elems = (long long)N * (CROP ? D : D + ed) * (CROP ? H : H + eh) * (CROP ? W : W + ew) * C;
+  if (C % 8 == 0) {
+    pad_high_kernel<CROP, 8><<<grid_for(elems / 8, kThreads * 2), kThreads, 0, st>>>(src, dst, N, D, H, W, C, ed, eh, ew);
+  } else {
+    pad_high_kernel<CROP, 1><<<grid_for(elems, kThreads * 4), kThreads, 0, st>>>(src, dst, N, D, H, W, C, ed, eh, ew);
+  }
+  count_launch();
+  ADNI_LAUNCH_CHECK("pad_high_kernel");
+  return ADNI_OK;
+}
 
 template <typename T>
 static int launch_to_ndhwc(const T* x, int N, int C, long long vox, __nv_bfloat16* out, cudaStream_t st) {
@@ -138,6 +185,22 @@ int adni_volumes_to_ndhwc_bf16(const void* x, int x_is_f64, int N, int C, long l
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   return x_is_f64 ? launch_to_ndhwc(static_cast<const double*>(x), N, C, vox, o, ST(stream))
                   : launch_to_ndhwc(static_cast<const float*>(x), N, C, vox, o, ST(stream));
+}
+
+int adni_pad_volume_high(const adni_bf16* x, int N, int D, int H, int W, int C, int ed, int eh, int ew, adni_bf16* out,
+                         void* stream) {
+  ADNI_REQUIRE(x && out && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && ed >= 0 && eh >= 0 && ew >= 0, ADNI_EINVAL,
+               "pad_volume_high: bad arguments");
+  return launch_pad_high<false>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), N, D, H,
+                                W, C, ed, eh, ew, ST(stream));
+}
+
+int adni_crop_volume_high(const adni_bf16* x_padded, int N, int D, int H, int W, int C, int ed, int eh, int ew,
+                          adni_bf16* out, void* stream) {
+  ADNI_REQUIRE(x_padded && out && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && ed >= 0 && eh >= 0 && ew >= 0, ADNI_EINVAL,
+               "crop_volume_high: bad arguments");
+  return launch_pad_high<true>(reinterpret_cast<const __nv_bfloat16*>(x_padded), reinterpret_cast<__nv_bfloat16*>(out), N,
+                               D, H, W, C, ed, eh, ew, ST(stream));
 }
 
 int adni_maxout_fwd(const adni_bf16* a, const adni_bf16* b, adni_bf16* out, long long n, void* stream) {

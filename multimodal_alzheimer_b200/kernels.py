@@ -725,6 +725,27 @@ def split_channels(dout, Ca, Cb, want_a=True, want_b=True):
     return da, db
 
 
+def pad_volume_high(x, extra):
+    """bf16 NDHWC volume with `extra` zero voxels appended on the high side of D, H and W."""
+    _chk(x, BF16, "x")
+    N, D, H, W, C = x.shape
+    out = torch.empty((N, D + extra, H + extra, W + extra, C), dtype=BF16, device=x.device)
+    call_hbm("hbm_pad", 2 * (x.numel() + out.numel()), "adni_pad_volume_high", ptr(x), N, D, H, W, C, extra, extra, extra,
+             ptr(out), stream_ptr())
+    return out
+
+
+def crop_volume_high(xp, extra):
+    """Inverse of pad_volume_high: the leading (D, H, W) box of a padded volume (gradient of the padding)."""
+    _chk(xp, BF16, "x_padded")
+    N, Dp, Hp, Wp, C = xp.shape
+    D, H, W = Dp - extra, Hp - extra, Wp - extra
+    out = torch.empty((N, D, H, W, C), dtype=BF16, device=xp.device)
+    call_hbm("hbm_pad", 4 * out.numel(), "adni_crop_volume_high", ptr(xp), N, D, H, W, C, extra, extra, extra, ptr(out),
+             stream_ptr())
+    return out
+
+
 def cast_to_f32(x):
     _chk(x, BF16, "x")
     y = torch.empty(x.shape, dtype=torch.float32, device=x.device)

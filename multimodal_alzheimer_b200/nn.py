@@ -27,7 +27,8 @@ def as_volume(x):
 
 class Conv3d(tnn.Module):
     """torch.nn.Conv3d(in, out, k, stride, padding, dilation, bias) with isotropic geometry.
-    padding may be an int or 'same' (odd kernels), as in pkg/models/pet_models/pet_cnn.py:21."""
+    padding may be an int or 'same' (pkg/models/pet_models/pet_cnn.py:21); an even kernel with 'same'
+    (filter_size_fusion = 4, train_anat_pet_featuremapfusion.py:70) pads like torch: lo = total // 2, hi = total - lo."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
         super().__init__()
@@ -41,12 +42,13 @@ class Conv3d(tnn.Module):
 
         k, stride, dilation = _iso(kernel_size, "kernel_size"), _iso(stride, "stride"), _iso(dilation, "dilation")
         padding = _iso(padding, "padding")
+        self.pad_high_extra = 0
         if padding == "same":
             if stride != 1:
                 raise ValueError("padding='same' is not supported for strided convolutions")
-            if k % 2 == 0:
-                raise NotImplementedError("padding='same' with an even kernel needs asymmetric padding")
-            padding = dilation * (k - 1) // 2
+            total = dilation * (k - 1)            # torch: lo = total // 2, hi = total - lo (the odd voxel goes high)
+            padding = total // 2
+            self.pad_high_extra = total - 2 * padding
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding, self.dilation = (k,) * 3, (stride,) * 3, (padding,) * 3, (dilation,) * 3
         self.cfg = A.ConvCfg(k, stride, padding, dilation)
@@ -62,7 +64,10 @@ class Conv3d(tnn.Module):
             tnn.init.uniform_(self.bias, -bound, bound)
 
     def forward_with_stats(self, x, want_stats=True):
-        return A.Conv3dFn.apply(as_volume(x), self.weight, self.bias, self.cfg, want_stats)
+        x = as_volume(x)
+        if self.pad_high_extra:  # even kernel with padding='same': one more zero voxel on the high side of each axis
+            x = A.PadHighFn.apply(x, self.pad_high_extra)
+        return A.Conv3dFn.apply(x, self.weight, self.bias, self.cfg, want_stats)
 
     def forward(self, x):
         return self.forward_with_stats(x, False)[0]

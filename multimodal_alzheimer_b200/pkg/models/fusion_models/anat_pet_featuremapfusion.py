@@ -5,7 +5,7 @@ concatenation or voxel-wise maximum, a fusion conv stack and an MLP head
 As in the reference: `n_in_fusion` doubles per fusion layer while every fusion conv emits `n_out_fusion` channels
 (:73-79), so only `n_layers_fusion == 1` (the only value the HPO script offers, train_anat_pet_featuremapfusion.py:69)
 yields a consistent stack; more layers fail at run time in the reference too and are rejected here at construction.
-`filter_size_fusion == 4` ('same' with an even kernel pads asymmetrically) is not implemented: NotImplementedError."""
+`filter_size_fusion == 4` ('same' with an even kernel) pads like torch: one voxel low, two high (nn.Conv3d here)."""
 import torch
 
 from .... import autograd as A

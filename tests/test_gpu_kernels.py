@@ -501,3 +501,36 @@ def test_fusion_ops_bit_exact(cuda_dev):
     assert torch.equal(sa.cpu(), a) and torch.equal(sc.cpu(), c)
     with pytest.raises(NotImplementedError):
         K.concat_channels(ad[..., :4].contiguous(), ad)
+
+
+@pytest.mark.parametrize("C", [64, 8, 2])
+def test_even_kernel_same_padding(cuda_dev, C):
+    """nn.Conv3d(C, Cout, 4, padding='same') (filter_size_fusion = 4): torch pads 1 low / 2 high.  The pad / crop kernels
+    are bit-exact data movement; the module matches torch's conv on the same bf16 operands (fwd, dgrad, wgrad)."""
+    from multimodal_alzheimer_b200 import kernels as K
+    from multimodal_alzheimer_b200 import nn as bnn
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn((2, 3, 5, 4, C), generator=g).to(BF)
+    xp = K.pad_volume_high(x.to(cuda_dev), 1)
+    ref = F.pad(x, (0, 0, 0, 1, 0, 1, 0, 1))
+    assert torch.equal(xp.cpu(), ref)
+    assert torch.equal(K.crop_volume_high(xp, 1).cpu(), x)
+    conv = bnn.Conv3d(C, 16, 4, padding="same").to(cuda_dev)
+    tconv = torch.nn.Conv3d(C, 16, 4, padding="same")
+    with torch.no_grad():
+        tconv.weight.copy_(conv.weight.detach().cpu().to(BF).float())
+        tconv.bias.copy_(conv.bias.detach().cpu())
+    xin = x.to(cuda_dev).requires_grad_(True)
+    y = conv(xin)
+    xr = to_ncdhw_f32(x).requires_grad_(True)
+    yr = tconv(xr)
+    assert tuple(y.shape) == (2, 3, 5, 4, 16)
+    assert_close(to_ncdhw_f32(y.detach().cpu()), yr.detach(), 6e-3, "even-kernel fprop")
+    dy = torch.randn(yr.shape, generator=g)
+    dy_b = to_ndhwc_bf16(dy)
+    yr.backward(to_ncdhw_f32(dy_b))
+    y.backward(dy_b.to(cuda_dev))
+    torch.cuda.synchronize()
+    assert_close(to_ncdhw_f32(xin.grad.cpu()), xr.grad, 6e-3, "even-kernel dgrad")
+    assert_close(conv.weight.grad.cpu(), tconv.weight.grad, 2e-3, "even-kernel wgrad")
+    assert_close(conv.bias.grad.cpu(), tconv.bias.grad, 2e-3, "even-kernel dbias")

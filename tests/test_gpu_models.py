@@ -91,6 +91,7 @@ CASES = [
     ("fmf", dict(fusion_mode="concatenate", batchnorm_fusion=False, pet_batchnorm=False, n_out_fusion=128), 2,
      (48, 64, 48), ("mri", "pet1451")),
     ("fmf", dict(fusion_mode="maxout", filter_size_fusion=5, n_classes=2), 3, (32, 32, 32), ("mri", "pet1451")),
+    ("fmf", dict(fusion_mode="concatenate", filter_size_fusion=4), 4, (48, 48, 64), ("mri", "pet1451")),   # even kernel
 ]
 
 

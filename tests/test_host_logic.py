@@ -112,10 +112,13 @@ def test_conv_same_padding_and_geometry():
     from multimodal_alzheimer_b200 import nn as bnn
     c = bnn.Conv3d(1, 8, 5, padding="same")
     assert (c.cfg.k, c.cfg.stride, c.cfg.pad, c.cfg.dil) == (5, 1, 2, 1) and c.bias is not None
-    with pytest.raises(NotImplementedError):
-        bnn.Conv3d(1, 8, 4, padding="same")
+    e = bnn.Conv3d(1, 8, 4, padding="same")     # even kernel: torch pads total 3 as (1, 2); the odd voxel goes high
+    assert (e.cfg.pad, e.pad_high_extra) == (1, 1) and c.pad_high_extra == 0
+    assert bnn.Conv3d(8, 8, 4, padding="same", dilation=2).cfg.pad == 3 and bnn.Conv3d(8, 8, 4, padding=1).pad_high_extra == 0
     with pytest.raises(ValueError):
         bnn.Conv3d(1, 8, (3, 5, 3))
+    with pytest.raises(ValueError):
+        bnn.Conv3d(1, 8, 3, stride=2, padding="same")
 
 
 def test_checkpoint_round_trip(tmp_path):
@@ -155,8 +158,9 @@ def test_feature_map_fusion_construction_rules():
     opt = m.configure_optimizers()
     assert len(opt.param_groups) == len(list(m.parameters())) and {g["lr"] for g in opt.param_groups} == {1e-3}
     assert all(g["weight_decay"] == 1e-4 for g in opt.param_groups)
-    with pytest.raises(NotImplementedError):          # 'same' with an even kernel pads asymmetrically: not implemented
-        PET_MRI_FMF(hp_fmf(filter_size_fusion=4))
+    even = PET_MRI_FMF(hp_fmf(filter_size_fusion=4)).fuse_model[0]   # 'same' with an even kernel: torch pads (1, 2)
+    assert even.cfg.pad == 1 and even.pad_high_extra == 1 and tuple(even.weight.shape) == (64, 64, 4, 4, 4)
+    assert PET_MRI_FMF(hp_fmf(filter_size_fusion=5)).fuse_model[0].pad_high_extra == 0
     hp = hp_fmf()
     hp["n_layers_fusion"] = 2                         # inconsistent in the reference as well (fails at its first forward)
     with pytest.raises(ValueError):
