@@ -322,7 +322,9 @@ __device__ __forceinline__ PlaneMax plane_reduce(const PlaneRaw& pr, uint32_t ok
   m.idx = 0;
 #pragma unroll
   for (int t = 0; t < 9; t++) {
-    if (!((okmask >> t) & 1u)) continue;
+    // branch-free: a tap outside the plane (zero vector, border threads only) is computed and then ignored through the
+    // predicate of the compare - a per-tap branch cost ~20 reconvergence instructions per tap on every thread
+    const bool ok = (okmask >> t) & 1u;
     float f[8];
     unpack8(pr.r[t], f);
 #pragma unroll
@@ -331,7 +333,7 @@ __device__ __forceinline__ PlaneMax plane_reduce(const PlaneRaw& pr, uint32_t ok
     unpack8(pack8(f), r);  // compare what bn_apply would have stored: the bf16-rounded activation
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      if (r[j] > m.v[j]) {  // first maximum in (kh, kw) order wins
+      if (ok && r[j] > m.v[j]) {  // first maximum in (kh, kw) order wins
         m.v[j] = r[j];
         m.idx = (m.idx & ~(0xFu << (4 * j))) | (static_cast<uint32_t>(t) << (4 * j));
       }
@@ -523,13 +525,14 @@ __global__ void __launch_bounds__(kGThreads, 3)
         const int ad = w >> 2, ah = (w >> 1) & 1, aw = w & 1;
         if (ad > ed || ah > eh || aw > ew) continue;  // compile-time: an even coordinate only sees window c
         const uint32_t slot = static_cast<uint32_t>((pool_tap(ed, ad) * 3 + pool_tap(eh, ah)) * 3 + pool_tap(ew, aw));
-        const uint32_t eq_lo = __vcmpeq4(wm[w].x, slot * 0x01010101u), eq_hi = __vcmpeq4(wm[w].y, slot * 0x01010101u);
+        // a zero byte of x = the arg-max slot of that channel is this voxel's tap (no SIMD byte compare: its
+        // emulation cost more than the eight tests it feeds)
+        const uint32_t x_lo = wm[w].x ^ (slot * 0x01010101u), x_hi = wm[w].y ^ (slot * 0x01010101u);
         float f[8];
         unpack8(wd[w], f);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const uint32_t m = (j < 4 ? eq_lo : eq_hi) & (0xFFu << ((j & 3) * 8));
-          g[j] += m ? f[j] : 0.f;
+          if (((j < 4 ? x_lo : x_hi) & (0xFFu << ((j & 3) * 8))) == 0u) g[j] += f[j];
         }
       }
       float yv[8];
