@@ -14,7 +14,8 @@ The well-conditioned twin of that case (same model, batch 6) is held to the per-
 import pytest
 import torch
 
-from tests._models import autocast_step, build_pair, oracle_step, product_step, synthetic_batch
+from tests._models import (CASE_IDS, CASES, autocast_step, build_pair, compare_with_golden, golden_record, oracle_step,
+                           product_step, synthetic_batch)
 from tests._util import rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -70,33 +71,8 @@ def _compare(oracle, product, out_o, out_p, check_grads=True, bracket=None, out_
     return report
 
 
-CASES = [
-    # kind, kwargs, batch, volume shape, modalities
-    ("anat", dict(depth=10), 2, (64, 64, 64), ("mri",)),                                   # config 1 (reduced size)
-    ("anat", dict(depth=18, bn_begin=True, bn_dense=True, linear_out=(32,), fl_gamma=2), 3, (48, 56, 48), ("mri",)),
-    ("anat", dict(depth=18, bn_begin=True, bn_dense=True, linear_out=(32,), fl_gamma=2), 6, (40, 40, 40), ("mri",)),
-    ("anat", dict(depth=50, fl_gamma=1), 2, (40, 48, 40), ("mri",)),                       # Bottleneck path
-    ("pet_resnet", dict(depth=10, n_classes=2), 2, (48, 48, 48), ("pet1451",)),
-    ("small_pet", dict(), 2, (32, 32, 32), ("pet1451",)),
-    ("small_pet", dict(pet_batchnorm=True, n_classes=2), 3, (32, 40, 32), ("pet1451",)),
-    ("anat_pet", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451")),                     # faithful config 3
-    ("anat_pet_2resnet", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451")),             # north-star config 3
-    ("mri_tab", dict(depth=10), 2, (48, 48, 48), ("mri", "tabular")),
-    ("pet_tab", dict(simple_dim_red=True), 2, (32, 32, 32), ("pet1451", "tabular")),
-    ("all", dict(depth=10), 2, (48, 48, 48), ("mri", "pet1451", "tabular")),               # config 4
-    # early fusion (2-channel input) and feature-map fusion (maxout / concatenate)
-    ("early_fusion", dict(), 2, (32, 32, 32), ("mri", "pet1451")),
-    ("early_fusion", dict(pet_batchnorm=True, n_classes=2), 4, (32, 40, 32), ("mri", "pet1451")),
-    ("fmf", dict(fusion_mode="maxout"), 4, (64, 64, 64), ("mri", "pet1451")),
-    ("fmf", dict(fusion_mode="concatenate", batchnorm_fusion=False, pet_batchnorm=False, n_out_fusion=128), 2,
-     (48, 64, 48), ("mri", "pet1451")),
-    ("fmf", dict(fusion_mode="maxout", filter_size_fusion=5, n_classes=2), 3, (32, 32, 32), ("mri", "pet1451")),
-    ("fmf", dict(fusion_mode="concatenate", filter_size_fusion=4), 4, (48, 48, 64), ("mri", "pet1451")),   # even kernel
-]
-
-
-@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
-def test_training_step_parity(cuda_dev, case):
+@pytest.mark.parametrize("case_id,case", list(zip(CASE_IDS, CASES)), ids=CASE_IDS)
+def test_training_step_parity(cuda_dev, case_id, case):
     kind, kw, B, shape, mods = case
     oracle, product = build_pair(kind, **kw)
     batch = synthetic_batch(B, shape, kw.get("n_classes", 3), modalities=mods)
@@ -105,6 +81,14 @@ def test_training_step_parity(cuda_dev, case):
     out_p = product_step(product, batch, cuda_dev)
     report = _compare(oracle, product, out_o, out_p, bracket=bracket, out_a=out_a)
     print(report)
+    rec = golden_record(case_id)
+    if rec is not None:
+        # the same logits / loss against the record of the reference's OWN classes (tools/make_golden_models.py),
+        # under the tolerances _compare just applied against the oracle
+        la = rel_l2(out_a["outputs"].detach().cpu(), out_o["outputs"].detach())
+        lossa = abs(float(out_a["loss"].detach()) - float(out_o["loss"].detach()))
+        e, d = compare_with_golden(rec, out_o, out_p, max(2e-2, 2 * la), max(2e-2, 2 * lossa))
+        print(f"vs reference record: logits rel-L2 {e:.3e} (oracle on this CPU vs record {d:.1e})")
 
 
 def test_config1_full_size(cuda_dev):

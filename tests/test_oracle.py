@@ -90,3 +90,56 @@ def test_medicalnet_restatement_matches_reference_facts():
     assert abs(sum(p.numel() for p in m18.parameters()) / 1e6 - 33.16) < 0.01
     with pytest.raises(ValueError):
         generate_model(42)
+
+
+def _golden_models():
+    with open(os.path.join(GOLD, "models.json")) as f:
+        return json.load(f)
+
+
+def _golden_model_cases():
+    return _golden_models()["cases"]
+
+
+@pytest.fixture
+def recorded_threads():
+    """The intra-op thread count tools/make_golden_models.py ran with (CPU conv kernels split sums by thread)."""
+    before = torch.get_num_threads()
+    torch.set_num_threads(_golden_models()["num_threads"])
+    yield
+    torch.set_num_threads(before)
+
+
+@pytest.mark.parametrize("case_id", sorted(_golden_model_cases().keys()))
+def test_oracle_models_reproduce_reference_classes(case_id, recorded_threads):
+    """oracle/models.py vs tests/golden/models.json = one training step of the reference's OWN LightningModules
+    (pkg/models/**, imported unmodified by tools/reference_harness.py; stage-N models built through their
+    load_from_checkpoint / truncation / freezing code) on the seeded inputs and weights of tests/_models.py::CASES.
+    Same fp32 CPU arithmetic on both sides: bit-identical when generated.  Asserted: logits rel-L2 <= 1e-5, loss
+    <= 1e-6, running statistics <= 1e-5, every gradient's fingerprint (norm and two unit-vector projections) within
+    1e-4 of its norm + 20x the re-association noise the generator measured on the REFERENCE for that tensor by
+    re-running it with 1 and 3 threads (conv biases in front of a BatchNorm have an exactly-zero gradient whose
+    computed value is nothing but that noise).  state_dict keys/shapes, the set of parameters that receive a
+    gradient and the requires_grad flags must be identical."""
+    from tests._models import build_oracle, fingerprint, oracle_step, synthetic_batch
+    rec = _golden_model_cases()[case_id]
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in rec["kw"].items()}
+    oracle = build_oracle(rec["kind"], **kw)
+    assert {k: list(v.shape) for k, v in oracle.state_dict().items()} == rec["state_dict"]
+    assert list(oracle.state_dict().keys()) == list(rec["state_dict"].keys())
+    assert {n: bool(p.requires_grad) for n, p in oracle.named_parameters()} == rec["requires_grad"]
+    batch = synthetic_batch(rec["batch"], rec["shape"], kw.get("n_classes", 3), modalities=tuple(rec["modalities"]))
+    out = oracle_step(oracle, batch)
+    ref_logits = torch.tensor(rec["outputs"], dtype=torch.float64)
+    assert out["outputs"].dtype == torch.float64 and out["outputs"].shape == ref_logits.shape
+    assert float((out["outputs"].detach() - ref_logits).norm() / ref_logits.norm().clamp_min(1e-300)) <= 1e-5
+    assert abs(float(out["loss"].detach()) - rec["loss"]) <= 1e-6
+    got = dict(oracle.named_parameters())
+    assert {n for n, p in got.items() if p.grad is not None} == set(rec["grads"])
+    for n, fp in rec["grads"].items():
+        f = fingerprint(n, got[n].grad)
+        assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-4 * fp[0] + 20 * rec["grad_noise"][n], (n, f, fp)
+    bufs = dict(oracle.named_buffers())
+    for n, fp in rec["running"].items():
+        f = fingerprint(n, bufs[n])
+        assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-5 * max(fp[0], 1e-30), (n, f, fp)
