@@ -85,5 +85,31 @@ def build(force=False, verbose=False):
     return LIB
 
 
+STAGE_SRC = os.path.join(CSRC, "stage", "nifti_stage.cpp")
+STAGE_LIB = os.path.join(CSRC, "libadni_stage.so")
+STAGE_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wall", "-Wl,--exclude-libs,ALL"]
+
+
+def stage_needs_build():
+    if not os.path.exists(STAGE_LIB):
+        return True
+    t = os.path.getmtime(STAGE_LIB)
+    deps = [STAGE_SRC, os.path.join(os.path.dirname(HERE), "include", "adni_staging.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_stage(force=False):
+    """g++ build of the host-side input staging library (NIfTI decode; zlib, no CUDA) -> csrc/libadni_stage.so."""
+    if not force and not stage_needs_build():
+        return STAGE_LIB
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx] + STAGE_FLAGS + [STAGE_SRC, "-o", STAGE_LIB, "-lz"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("staging library build failed:\n" + r.stdout)
+    return STAGE_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_stage(force="--force" in sys.argv))
