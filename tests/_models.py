@@ -61,6 +61,20 @@ CASES = [
 ]
 CASE_IDS = [f"{c[0]}-{i}" for i, c in enumerate(CASES)]
 
+# Short training runs (training_step -> backward -> configure_optimizers().step(), a fresh synthetic batch per step):
+# the reference's own classes and optimizer in tests/golden/models.json["trajectories"], the oracle on the CPU, the
+# product on the GPU.  kind, kwargs, batch, volume shape, modalities, steps
+TRAJECTORIES = {
+    "traj-anat": ("anat", dict(depth=10, bn_begin=True, linear_out=(16,)), 4, (32, 32, 32), ("mri",), 4),
+    "traj-anat_pet": ("anat_pet", dict(depth=10, fl_gamma=1), 4, (32, 32, 32), ("mri", "pet1451"), 4),
+    "traj-small_pet": ("small_pet", dict(pet_batchnorm=True), 4, (32, 32, 32), ("pet1451",), 4),
+}
+
+
+def trajectory_batches(traj_id):
+    kind, kw, B, shape, mods, steps = TRAJECTORIES[traj_id]
+    return [synthetic_batch(B, shape, kw.get("n_classes", 3), seed=15 + k, modalities=mods) for k in range(steps)]
+
 
 def golden_record(case_id):
     """The record tools/make_golden_models.py wrote for this case from the reference's own classes, or None (the

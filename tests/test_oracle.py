@@ -143,3 +143,34 @@ def test_oracle_models_reproduce_reference_classes(case_id, recorded_threads):
     for n, fp in rec["running"].items():
         f = fingerprint(n, bufs[n])
         assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-5 * max(fp[0], 1e-30), (n, f, fp)
+
+
+@pytest.mark.parametrize("traj_id", sorted(_golden_models()["trajectories"].keys()))
+def test_oracle_training_trajectory_matches_reference(traj_id, recorded_threads):
+    """Four optimisation steps (reference `training_step` -> backward -> the Adam instance its own
+    `configure_optimizers()` returned, a fresh synthetic batch per step; tools/make_golden_models.py) replayed with
+    the oracle and torch.optim.Adam over the recorded parameter groups: loss of every step <= 1e-5, logits rel-L2
+    <= 1e-4, parameters and running statistics after the last step within 1e-4 of their norm."""
+    from tests._models import build_oracle, fingerprint, trajectory_batches
+    rec = _golden_models()["trajectories"][traj_id]
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in rec["kw"].items()}
+    oracle = build_oracle(rec["kind"], **kw)
+    oracle.train()
+    params = dict(oracle.named_parameters())
+    opt = torch.optim.Adam([{"params": [params[n]], "lr": lr, "weight_decay": wd} for n, lr, wd in rec["optimizer"]],
+                           betas=tuple(rec["adam"]["betas"]), eps=rec["adam"]["eps"])
+    for k, batch in enumerate(trajectory_batches(traj_id)):
+        out = oracle.general_step(dict(batch), k, "train")
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        assert abs(float(out["loss"].detach()) - rec["losses"][k]) <= 1e-5, (k, float(out["loss"]), rec["losses"][k])
+        want = torch.tensor(rec["logits"][k], dtype=torch.float64)
+        assert float((out["outputs"].detach() - want).norm() / want.norm().clamp_min(1e-300)) <= 1e-4, k
+    for n, fp in rec["final_params"].items():
+        f = fingerprint(n, params[n])
+        assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-4 * max(fp[0], 1e-30), (n, f, fp)
+    bufs = dict(oracle.named_buffers())
+    for n, fp in rec["final_running"].items():
+        f = fingerprint(n, bufs[n])
+        assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-4 * max(fp[0], 1e-30), (n, f, fp)

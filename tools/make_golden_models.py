@@ -191,13 +191,38 @@ def main():
                    shape=list(shape), modalities=list(mods), reference_class=type(ref).__module__ + "." + type(ref).__name__)
         check_oracle(case_id, rec, oracle, batch)
         cases[case_id] = rec
+    trajectories = {}
+    for traj_id, (kind, kw, B, shape, mods, steps) in M.TRAJECTORIES.items():
+        torch.set_num_threads(THREADS)
+        oracle = M.build_oracle(kind, **kw)
+        ref = build_reference(R, kind, kw, oracle)
+        ref.train()
+        opt = ref.configure_optimizers()
+        opt = opt["optimizer"] if isinstance(opt, dict) else opt
+        groups = optimizer_groups(ref, opt)
+        losses, logits = [], []
+        for k, batch in enumerate(M.trajectory_batches(traj_id)):
+            out = ref.training_step(dict(batch), k)                      # base_model.py:60-66
+            opt.zero_grad()
+            out["loss"].backward()
+            opt.step()
+            losses.append(float(out["loss"].detach()))
+            logits.append(out["outputs"].detach().tolist())
+        trajectories[traj_id] = {
+            "kind": kind, "kw": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, "batch": B,
+            "shape": list(shape), "modalities": list(mods), "steps": steps, "losses": losses, "logits": logits,
+            "optimizer": groups, "adam": {"betas": list(opt.defaults["betas"]), "eps": opt.defaults["eps"]},
+            "final_params": {n: fingerprint(n, p) for n, p in ref.named_parameters()},
+            "final_running": {n: fingerprint(n, b) for n, b in ref.named_buffers()
+                              if n.endswith("running_mean") or n.endswith("running_var")}}
+        print(f"{traj_id:22s} losses {[round(x, 5) for x in losses]}")
     if "tabular" in "".join(sum((list(c[4]) for _, c in todo), [])):
         assert H.ENSEMBLE_SEEN and all(e == 4 for e in H.ENSEMBLE_SEEN)
     with open(OUT, "w") as f:
         json.dump({"source": "reference pkg/models/** imported unmodified via tools/reference_harness.py; MedicalNet "
                              "ResNet = oracle/medicalnet.py (third-party clone, absent from the reference tree)",
                    "torch": torch.__version__, "num_threads": THREADS, "noise_threads": list(NOISE_THREADS),
-                   "cases": cases}, f)
+                   "cases": cases, "trajectories": trajectories}, f)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(cases), "cases")
 
 
