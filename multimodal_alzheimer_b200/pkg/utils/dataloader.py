@@ -131,6 +131,14 @@ class MultiModalDataset(Dataset):
                 raise ValueError('If you use the argument "normalize_mri" only "per_scan_norm" or "all_scan_norm" '
                                  'are allowed as keys!')
         self.quantile = quantile
+        self._cache, self._cache_bytes, self.cache_limit_bytes = {}, 0, 0
+
+    def enable_cache(self, gigabytes):
+        """Keep decoded volumes (fp32 / uint8, exactly what the decoder produced) in host memory up to `gigabytes`:
+        from the second epoch on a cached scan costs one memcpy into the pinned batch slot instead of a gzip inflate
+        (14.6 ms per 91x109x91 volume).  The reference re-reads and re-normalises every file every epoch."""
+        self.cache_limit_bytes = int(gigabytes * (1 << 30))
+        return self
 
     def __len__(self) -> int:
         return len(self.ds)
@@ -194,7 +202,22 @@ class MultiModalDataset(Dataset):
                 continue
             if any(c is None for c in col):
                 raise ValueError(f"batch mixes samples with and without '{name}' (the reference's collate_fn fails too)")
-            staging.stage_volumes(col, buffers[name][:n], threads=threads)
+            dst = buffers[name][:n]
+            todo = list(col)
+            for i, path in enumerate(col):          # cached scans: one memcpy, no inflate
+                hit = self._cache.get((name, path))
+                if hit is not None:
+                    dst[i].copy_(hit)
+                    todo[i] = None
+            if any(t is not None for t in todo):
+                staging.stage_volumes(todo, dst, threads=threads)
+                for i, path in enumerate(todo):
+                    if path is None:
+                        continue
+                    nbytes = dst[i].numel() * dst[i].element_size()
+                    if self._cache_bytes + nbytes <= self.cache_limit_bytes and (name, path) not in self._cache:
+                        self._cache[(name, path)] = dst[i].clone()
+                        self._cache_bytes += nbytes
             present.append(name)
         return present
 

@@ -187,6 +187,45 @@ def test_dataset_argument_errors(adni_csv):
         MultiModalDataset(adni_csv, modalities=["pet1451"], transform_pet=lambda x: x)
 
 
+def test_stage_batch_and_decoded_cache(adni_csv):
+    """MultiModalDataset.stage: batch buffers == per-sample reads; with the cache on, the second pass is served from
+    memory (identical bytes, no file access: the files are made unreadable in between)."""
+    from multimodal_alzheimer_b200.pkg.utils.dataloader import MultiModalDataset
+    ds = MultiModalDataset(adni_csv, modalities=["pet1451", "t1w"], normalize_mri={"per_scan_norm": "min_max"}, quantile=0.98)
+    n = min(5, len(ds))
+    idx = list(range(n))
+    mk = lambda: {"pet1451": torch.zeros((n,) + SHAPE), "mri": torch.zeros((n,) + SHAPE),   # noqa: E731
+                  "mri_mask": torch.zeros((n,) + SHAPE, dtype=torch.uint8)}
+    a = mk()
+    assert ds.stage(idx, a, threads=3) == ["pet1451", "mri", "mri_mask"]
+    for i in idx:
+        s = ds[i]
+        assert torch.equal(a["pet1451"][i], s["pet1451"]) and torch.equal(a["mri"][i], s["mri"])
+        assert torch.equal(a["mri_mask"][i], s["mri_mask"])
+    ds.enable_cache(0.5)
+    b = mk()
+    ds.stage(idx, b, threads=2)                     # fills the cache
+    files = {c: {ds.ds.iloc[i][c] for i in idx} for c in ("path_pet1451", "path_anat", "path_anat_mask")}
+    vox = int(np.prod(SHAPE))                       # a scan paired with two partners is cached once
+    assert len(ds._cache) == sum(len(v) for v in files.values())
+    assert ds._cache_bytes == vox * (4 * len(files["path_pet1451"]) + 4 * len(files["path_anat"]) + len(files["path_anat_mask"]))
+    moved = []
+    for pth in set().union(*files.values()):        # hide the files: a cache hit must not touch them
+        os.rename(pth, pth + ".hidden")
+        moved.append(pth)
+    try:
+        c = mk()
+        ds.stage(idx, c, threads=2)
+    finally:
+        for pth in moved:
+            os.rename(pth + ".hidden", pth)
+    for k in a:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k])
+    ds2 = MultiModalDataset(adni_csv, modalities=["t1w"], normalize_mri={"per_scan_norm": "min_max"}).enable_cache(1e-5)
+    ds2.stage([0, 1], {"mri": torch.zeros((2,) + SHAPE), "mri_mask": torch.zeros((2,) + SHAPE, dtype=torch.uint8)})
+    assert ds2._cache_bytes <= ds2.cache_limit_bytes      # budget respected (about one volume fits)
+
+
 def test_epoch_batches_cover_the_dataset_once_across_ranks():
     from multimodal_alzheimer_b200.pkg.utils.dataloader import StagedLoader, epoch_batches
     assert epoch_batches(10, 4) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
