@@ -143,15 +143,14 @@ bool tc_supported(const adni_conv3d_geom& g) {
 int pick_block_n(int n_total) { return n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64); }
 
 // CTA-pair engine (conv_igemm_2cta.cu): OFF unless ADNI_IGEMM_2CTA=1.  Needs the N = 256 tile and an even number of
-// M tiles (two boxes per cluster); decided before the weight tensor map is encoded because its box is (64, 128) there.
+// samples (two boxes per cluster); decided before the weight tensor map is encoded because its box is (64, 128) there.
 bool use_igemm_2cta(int block_n, int N, int Do, int Ho, int Wo, int bd, int bh, int bw) {
   static const bool enabled = [] {
     const char* e = getenv("ADNI_IGEMM_2CTA");
     return e && atoi(e) != 0;
   }();
   if (!enabled || block_n != 256 || num_sms() < 2) return false;
-  const long long m_tiles = 1ll * N * ((Do + bd - 1) / bd) * ((Ho + bh - 1) / bh) * ((Wo + bw - 1) / bw);
-  return m_tiles >= 2 && m_tiles % 2 == 0;
+  return N >= 2 && N % 2 == 0;  // a pair = the same spatial box of two consecutive samples (identical tap masks)
 }
 
 // ---------------------------------------------------------------------------------------------

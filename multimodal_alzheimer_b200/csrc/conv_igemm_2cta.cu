@@ -1,4 +1,5 @@
-// EXPERIMENTAL (opt-in: ADNI_IGEMM_2CTA=1; not on the default path, not yet validated on a B200):
+// EXPERIMENTAL (opt-in: ADNI_IGEMM_2CTA=1; not on the default path.  On a B200: outputs bit-identical to the 1-CTA
+// kernel, conv parity tests green, 0-3.4 % faster on layers 3-4 - profiles/r01_2cta_ab.json):
 // CTA-pair variant of igemm_kmajor_kernel for the N = 256 convs of layers 3-4 (reference call sites
 // pkg/models/mri_models/anat_cnn.py:18-31,95 -> MedicalNet layer3/layer4 3x3x3 dilated convs, cuDNN there).
 //
@@ -16,8 +17,8 @@
 //           BOTH CTAs with tcgen05.commit...multicast::cluster; rank 1: only owns the TMEM allocation of its SM.
 //   warps 2-5  epilogue of the CTA's own 128 rows (own TMEM lanes), identical to the 1-CTA kernel; hands the
 //           accumulator back by arriving on the leader's tempty barrier (8 arrivals: 4 warps x 2 CTAs).
-// The two M tiles of a pair walk the UNION of their tap masks (a tap that is all padding for one of them loads a
-// zero-filled box), so that both producers push the same sequence of stages.
+// The two M tiles of a pair are the same spatial box of two consecutive samples: identical tap masks, so both
+// producers push the same sequence of stages without executing taps that are all padding for one of them.
 #include "conv_igemm.cuh"
 
 namespace adni {
@@ -153,8 +154,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int m_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w;  // even (checked on the host)
-  const int total_pairs = (m_tiles / 2) * p.n_tiles;
+  const int sp_tiles = p.tiles_d * p.tiles_h * p.tiles_w;  // spatial tiles of one sample
+  const int total_pairs = (p.N / 2) * sp_tiles * p.n_tiles;  // N is even (checked on the host)
   const int pair0 = static_cast<int>(cluster_id_x());
   const int pair_step = static_cast<int>(n_clusters_x());
 
@@ -197,13 +198,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
     const unsigned long long lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
     return lo | (hi << 32);
   };
-  // pair index -> channel tile (fastest, like the 1-CTA tile order) and the two M tiles
+  // pair index -> channel tile (fastest, like the 1-CTA tile order) and the two M tiles: the SAME spatial box of two
+  // consecutive samples, so that both have the same tap mask (pairing neighbouring boxes of one sample made the pair
+  // execute the union of two different masks: +13 % MMAs on layer4's dilation-4 convs, measured slower than 1 CTA)
   auto decode_pair = [&](int pair, int& n0, Tile2& t0, Tile2& t1) {
     const int nt = pair % p.n_tiles;
     const int mp = pair / p.n_tiles;
+    const int sp = mp % sp_tiles;
+    const int np = mp / sp_tiles;
     n0 = nt * k2BlockN;
-    t0 = decode_mtile(p, 2 * mp);
-    t1 = decode_mtile(p, 2 * mp + 1);
+    t0 = decode_mtile(p, (2 * np) * sp_tiles + sp);
+    t1 = decode_mtile(p, (2 * np + 1) * sp_tiles + sp);
   };
 
   if (warp == 0) {
@@ -407,10 +412,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 
 }  // namespace
 
-// Whether the CTA-pair engine can take this plan: N tile of 256, an even number of M tiles, >= 2 SMs.
+// Whether the CTA-pair engine can take this plan: N tile of 256, an even number of samples, >= 2 SMs.
 bool igemm_2cta_supported(const IgemmParams& p, int block_n) {
-  const long long m_tiles = 1ll * p.N * p.tiles_d * p.tiles_h * p.tiles_w;
-  return block_n == k2BlockN && m_tiles >= 2 && (m_tiles % 2) == 0 && num_sms() >= 2;
+  return block_n == k2BlockN && p.N >= 2 && (p.N % 2) == 0 && num_sms() >= 2;
 }
 
 // `p.b_map` must have been encoded with a (64, 128) box: each CTA of a pair loads half of the 256 weight rows.
@@ -421,8 +425,7 @@ int launch_igemm_2cta(const IgemmParams& p, cudaStream_t stream) {
     ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w;
-  const int total_pairs = (m_tiles / 2) * p.n_tiles;
+  const int total_pairs = (p.N / 2) * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
   const int max_clusters = num_sms() / 2;
   const int clusters = total_pairs < max_clusters ? total_pairs : max_clusters;
   kern<<<2 * clusters, k2Threads, Cfg2::SMEM_BYTES, stream>>>(p);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 validation of the experimental CTA-pair conv engine (csrc/conv_igemm_2cta.cu, opt-in):
+# Validation + A/B of the opt-in CTA-pair conv engine (csrc/conv_igemm_2cta.cu); first results: profiles/r01_2cta_ab.json
 #   gpurun --timeout 900 -- 'bash tools/gpu_2cta.sh'
 # 1. conv parity tests with the engine forced on for every N = 256 tile (fprop Cout 256/512, dgrad Cin 256/512);
 # 2. if green: the bench with and without it (same box, back to back).
