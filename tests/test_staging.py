@@ -89,6 +89,21 @@ def test_reader_matches_get_fdata_restatement(tmp_path, case):
     assert torch.equal(out[:ref.numel()].reshape(ref.shape), ref.float()) and bool((out[ref.numel():] == -7).all())
 
 
+def test_reader_random_shapes_and_ranks(tmp_path):
+    """2-D ... 5-D images, extents of 1, extents around the 16-wide transposition tile: C-order of get_fdata()."""
+    S = _staging()
+    rng = np.random.default_rng(11)
+    shapes = [(5, 4), (1, 7, 3), (17, 1, 2), (16, 3, 3), (33, 2, 5), (4, 3, 2, 6), (3, 2, 2, 2, 3), (91, 10, 9)]
+    for i, shape in enumerate(shapes):
+        a = rng.integers(-30000, 30000, shape, dtype=np.int16)
+        p = str(tmp_path / f"r{i}.nii.gz")
+        N.write_nifti(p, a, scl_slope=1.5, scl_inter=-2.0, big_endian=bool(i % 2))
+        ref = torch.tensor(N.read_fdata(p))
+        assert S.read_info(p).shape == shape
+        assert torch.equal(S.read_volume(p, torch.float64), ref), shape
+        assert torch.equal(S.read_volume(p, torch.float32), ref.float()), shape
+
+
 def test_reader_errors(tmp_path):
     S = _staging()
     with pytest.raises(FileNotFoundError):
