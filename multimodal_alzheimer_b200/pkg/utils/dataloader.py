@@ -286,7 +286,8 @@ class StagedLoader:
         return epoch_batches(len(self.ds), self.bs, self.shuffle, self.drop_last, self.generator, self.rank, self.world)
 
     def __len__(self):
-        return len(self._batches())
+        n = len(range(self.rank, len(self.ds), self.world))      # no permutation drawn: len() must not advance the RNG
+        return n // self.bs if self.drop_last else (n + self.bs - 1) // self.bs
 
     def _decode(self, idx, slot, box):
         try:
