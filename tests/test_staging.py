@@ -295,3 +295,26 @@ def test_staged_loader_batches_match_reference_samples(cuda_dev, adni_csv, name)
         for key in ("mri", "pet1451"):
             assert lb[key].dtype == torch.bfloat16
             assert rel_l2(lb[key].float().cpu(), first[key].cpu()) <= 4e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modality,mods", [("mri", ["t1w"]), ("pet1451", ["pet1451"])])
+def test_split_statistics_match_reference_formula(cuda_dev, adni_csv, modality, mods):
+    """NormalizeDataset.compute_std_mean (staged decode + adni_scan_moments) vs the reference's loop
+    (standardization.py:41-53) evaluated in fp64 on the CPU over the same files: 1e-12 relative."""
+    from multimodal_alzheimer_b200.pkg.utils.dataloader import MultiModalDataset
+    from multimodal_alzheimer_b200.pkg.utils.standardization import NormalizeDataset
+    ds = MultiModalDataset(adni_csv, modalities=mods, normalize_mri=None, normalize_pet=None)
+    mean, std = NormalizeDataset.compute_std_mean(ds, modality=modality, device=cuda_dev, batch_size=4, threads=3)
+    col = "path_anat" if modality == "mri" else "path_pet1451"
+    mean_x, mean_x2 = 0.0, 0.0
+    for i in range(len(ds)):
+        x = torch.tensor(N.read_fdata(ds.ds.iloc[i][col]))
+        mean_x += x.mean()
+        mean_x2 += (x ** 2).mean()
+    ref_mean = mean_x / len(ds)
+    ref_std = torch.sqrt(mean_x2 / len(ds) - ref_mean ** 2)
+    assert abs(float(mean) - float(ref_mean)) <= 1e-12 * abs(float(ref_mean)), (float(mean), float(ref_mean))
+    assert abs(float(std) - float(ref_std)) <= 1e-10 * abs(float(ref_std)), (float(std), float(ref_std))
+    with pytest.raises(NotImplementedError):
+        NormalizeDataset.compute_std_mean(ds, dim=0, modality=modality, device=cuda_dev)
