@@ -209,3 +209,46 @@ def test_module_surface_matches_reference_classes(case_id):
     # classifier is an sklearn estimator) and outside this path - its activation is an input here
     assert groups == [g for g in rec["optimizer"] if g[0] != "?"]
     assert {n: bool(p.requires_grad) for n, p in product.named_parameters()} == rec["requires_grad_after_configure"]
+
+
+def test_three_stage_construction_from_checkpoint_paths(tmp_path):
+    """The reference builds stage 2 and 3 from `.ckpt` paths only (anat_pet_fusion.py:13-23,
+    all_modalities_fusion.py:13-27: `Cls.load_from_checkpoint(path, path_pet=..., path_anat=...)`).  The same chain
+    here - stage-1 checkpoints -> stage-2 models from paths -> their checkpoints -> All_Modalities_Fusion(hparams)
+    with nothing but paths - must yield the state_dict (keys in order, shapes, values) of the module-passing
+    construction used elsewhere in the tests, whose keys are pinned to the reference's own classes."""
+    import json
+    import os
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.all_modalities_fusion import All_Modalities_Fusion
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.anat_pet_fusion import Anat_PET_CNN
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.pet_tabular_fusion import PET_TABULAR_CNN
+    from multimodal_alzheimer_b200.pkg.models.fusion_models.tabular_mri_fusion import Tabular_MRT_Model
+    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_cnn import Small_PET_CNN
+    p = {k: str(tmp_path / f"{k}.ckpt") for k in ("mri", "pet", "anat_pet", "anat_tab", "pet_tab")}
+    torch.manual_seed(3)
+    Anat_CNN(hp_anat(10)).save_checkpoint(p["mri"])
+    Small_PET_CNN(hp_pet()).save_checkpoint(p["pet"])
+    hp2 = hp_fusion()
+    ap = Anat_PET_CNN(dict(hp2, path_pet=p["pet"], path_mri=p["mri"]))
+    ap.save_checkpoint(p["anat_pet"])
+    at = Tabular_MRT_Model(dict(hp2, path_mri=p["mri"]))
+    at.save_checkpoint(p["anat_tab"])
+    pt = PET_TABULAR_CNN(dict(hp2, path_pet=p["pet"]))
+    pt.save_checkpoint(p["pet_tab"])
+    hp3 = dict(hp_fusion(), path_anat_pet=p["anat_pet"], path_anat_tab=p["anat_tab"], path_pet_tab=p["pet_tab"],
+               path_pet=p["pet"], path_anat=p["mri"])
+    m = All_Modalities_Fusion(hp3)
+    # stage-2 weights arrived through two checkpoint hops
+    for sub, src in ((m.model_anat_pet, ap), (m.model_anat_tab, at), (m.model_pet_tab, pt)):
+        a, b = sub.state_dict(), src.state_dict()
+        assert [k for k in a] == [k for k in b if k in a]
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    # ... and the stage-1 encoder inside stage 3 still carries the stage-1 checkpoint's weights
+    enc = torch.load(p["mri"], weights_only=False)["state_dict"]
+    got = m.model_anat_pet.model_mri.state_dict()
+    assert all(torch.equal(got[k], enc[k]) for k in got)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "models.json")) as f:
+        ref_keys = list(json.load(f)["cases"]["all-11"]["state_dict"].keys())
+    assert list(m.state_dict().keys()) == ref_keys          # == the reference's All_Modalities_Fusion.state_dict()
+    assert len(m.model_anat_pet.model_fuse) == 1             # all_modalities_fusion.py:29-31 applied after loading
