@@ -186,6 +186,23 @@ def test_dataset_index_matches_reference(adni_csv, name):
             assert torch.equal(s["pet1451"], torch.tensor(N.read_fdata(row["path_pet1451"])).float())
 
 
+def test_pairing_matches_reference_on_other_cohorts(tmp_path):
+    """Modality pairing (dataloader.py:100-158, 346-434) on two more synthetic cohorts vs the reference's own class."""
+    from multimodal_alzheimer_b200.pkg.utils.dataloader import MultiModalDataset
+    g = _golden()
+    base = lambda p: None if p is None else os.path.basename(p)  # noqa: E731
+    for seed, rec in g["extra_cohorts"].items():
+        csv = make_synthetic_adni(str(tmp_path / f"c{seed}"), seed=int(seed), subjects=rec["subjects"])
+        for name, want in rec["index"].items():
+            cfg = g["configs"][name]
+            ds = MultiModalDataset(csv, binary_classification=cfg["binary"], modalities=cfg["modalities"],
+                                   normalize_pet=g["pet_norm"], normalize_mri=cfg["normalize_mri"], quantile=cfg["quantile"])
+            got = [[r["ID"], r["label"], base(r["path_pet1451"]), base(r["path_anat"]), base(r["path_anat_mask"]), r["AGE"]]
+                   for _, r in ds.ds.iterrows()]
+            assert got == want, (seed, name)
+            assert len(want) > 0
+
+
 def test_dataset_argument_errors(adni_csv):
     from multimodal_alzheimer_b200.pkg.utils.dataloader import MultiModalDataset
     with pytest.raises(AssertionError):

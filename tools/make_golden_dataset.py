@@ -87,8 +87,21 @@ def main():
             rec["samples"].append(item)
         records[name] = rec
         print(f"{name:24s} len {len(ds):3d}  sample keys {rec['samples'][0]['keys'] if rec['samples'] else None}")
+    # pairing only, on two more synthetic cohorts (more subjects, other session dates): index rows per configuration
+    extra = {}
+    for seed, subjects in ((3, 12), (2024, 9)):
+        root_s = tempfile.mkdtemp()
+        csv_s = make_synthetic_adni(root_s, seed=seed, subjects=subjects)
+        extra[str(seed)] = {"subjects": subjects, "index": {}}
+        for name in ("pet_mri", "mri_tab_binary", "pet_tab", "all"):
+            mods, binary, nmri, q, _ = CONFIGS[name]
+            ds = RD.MultiModalDataset(csv_s, binary_classification=binary, modalities=mods, normalize_pet=PET_NORM,
+                                      normalize_mri=nmri, quantile=q)
+            extra[str(seed)]["index"][name] = [[r["ID"], r["label"], base(r["path_pet1451"]), base(r["path_anat"]),
+                                                base(r["path_anat_mask"]), r["AGE"]] for _, r in ds.ds.iterrows()]
+            print(f"seed {seed:5d} {name:16s} len {len(ds)}")
     with open(OUT, "w") as f:
-        json.dump({"source": "reference pkg/utils/dataloader.py MultiModalDataset, imported unmodified via "
+        json.dump({"extra_cohorts": extra, "source": "reference pkg/utils/dataloader.py MultiModalDataset, imported unmodified via "
                              "tools/reference_harness.py; nib.load().get_fdata() served by oracle/nifti.py",
                    "dataset": "tests/_dataset.py::make_synthetic_adni(seed=15)", "pet_norm": PET_NORM,
                    "configs": records}, f)
