@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 METRIC = "MRI+PET volumes/sec train (ResNet-18 3D, 128^3)"
 UNIT = "volumes/s"
 PET_MEAN, PET_STD = 0.5145, 0.5383  # pkg/models/pet_models/train_pet_cnn.py:77-78
+PORT_PINNING = ("oracle port; its model classes reproduce one training step of the reference's own LightningModules bit "
+                "for bit (tests/golden/models.json, tools/make_golden_models.py) - the reference itself needs "
+                "pytorch_lightning / MedicalNet / nibabel and cannot run on this box")
 
 
 def parse_args():
@@ -163,7 +166,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus, args.global_batch or (32 if args.workload == "pet_mri_fusion_r18" else 16)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "pinning": PORT_PINNING},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -468,7 +472,8 @@ def run_b200(args):
             best = dt if best is None else min(best, dt)
         cpu = {"value": cvols / best, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.cpu_sample_pairs} (MRI,PET) sample(s) of the same workload ({cvols} volumes {vol}^3): "
-                         f"fp64 torch.quantile normalisation + fp32 fwd + fp64 loss + bwd + Adam, best of 2 after 1 warm-up"}
+                         f"fp64 torch.quantile normalisation + fp32 fwd + fp64 loss + bwd + Adam, best of 2 after 1 warm-up",
+               "pinning": PORT_PINNING}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
