@@ -252,7 +252,7 @@ def run_b200(args):
     params = [p for p in model.parameters() if p.requires_grad]
     from multimodal_alzheimer_b200.optim import Adam  # csrc/optimizer.cu: multi-tensor Adam, 2 launches per 64 tensors
     opt = Adam(params, lr=1e-4, weight_decay=1e-4)
-    buckets = dp.GradientBuckets(params)
+    buckets = dp.make_gradient_buckets(params)      # ADNI_OVERLAP_GRADS=1: all-reduce overlapped with backward (opt-in)
 
     data = synth_inputs(n_local, vol, dev, 15 + rank, want_pet=fusion)
     vols_per_step = global_batch * (2 if fusion else 1)

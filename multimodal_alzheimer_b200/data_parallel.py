@@ -127,3 +127,83 @@ class GradientBuckets:
             work.wait()
             for g, synced in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
                 g.copy_(synced)
+
+
+class OverlappedGradientBuckets(GradientBuckets):
+    """EXPERIMENTAL (opt-in, ADNI_OVERLAP_GRADS=1 in bench.py; not yet measured on GPUs): the same buckets, but a
+    bucket's all-reduce starts as soon as the backward pass has produced its last gradient
+    (`register_post_accumulate_grad_hook`), so that the 265 MB of gradient traffic of the two-encoder model overlaps
+    the remaining dgrad / wgrad kernels instead of following them.  `all_reduce()` after `backward()` then only
+    launches what is still pending (parameters without a gradient), waits and copies back.
+
+    Stream safety: a hook runs on the stream its gradient was produced on (the two encoder branches use two streams);
+    every hook records an event, and the stream that launches a bucket first waits for the events of all of the
+    bucket's gradients.  Collective order: buckets complete in the autograd engine's (deterministic, rank-independent)
+    execution order.  One backward pass per optimizer step (no gradient accumulation across backward calls)."""
+
+    def __init__(self, params, bucket_mb=64):
+        super().__init__(params, bucket_mb)
+        self._bucket_of = {}
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._bucket_of[id(p)] = bi
+        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._reset()
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if self._active else []
+
+    def _reset(self):
+        self._seen = [0] * len(self.buckets)
+        self._events = [[] for _ in self.buckets]
+        self._launched = [None] * len(self.buckets)
+
+    def _launch(self, bi):
+        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
+        if not grads:
+            self._launched[bi] = False
+            return
+        if grads[0].is_cuda:
+            cur = torch.cuda.current_stream(grads[0].device)
+            for ev in self._events[bi]:
+                cur.wait_event(ev)
+        flat = torch._utils._flatten_dense_tensors(grads)
+        self._launched[bi] = (dist.all_reduce(flat, async_op=True), flat, grads)
+
+    def _on_grad(self, p):
+        bi = self._bucket_of[id(p)]
+        if self._launched[bi] is not None:
+            raise RuntimeError("OverlappedGradientBuckets: a second backward pass before all_reduce() "
+                               "(gradient accumulation is not supported)")
+        if p.grad is not None and p.grad.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.grad.device))
+            self._events[bi].append(ev)
+        self._seen[bi] += 1
+        if self._seen[bi] == len(self.buckets[bi]):
+            self._launch(bi)
+
+    def all_reduce(self):
+        if not self._active:
+            return
+        for bi in range(len(self.buckets)):
+            if self._launched[bi] is None:
+                self._launch(bi)            # parameters of this bucket that took no part in the backward pass
+        for item in self._launched:
+            if not item:
+                continue
+            work, flat, grads = item
+            work.wait()
+            for g, synced in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(synced)
+        self._reset()
+
+    def remove_hooks(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+def make_gradient_buckets(params, bucket_mb=64):
+    """GradientBuckets, or the overlapped variant when ADNI_OVERLAP_GRADS=1."""
+    if os.environ.get("ADNI_OVERLAP_GRADS", "0") == "1":
+        return OverlappedGradientBuckets(params, bucket_mb)
+    return GradientBuckets(params, bucket_mb)

@@ -54,6 +54,52 @@ def test_gradient_buckets_sum_across_ranks():
         assert out[rank] == [tot * 1.0, tot * 2.0, None, tot * 4.0, tot * 5.0]
 
 
+def _overlap_fn(rank, world):
+    """OverlappedGradientBuckets == GradientBuckets on a small MLP: hooks fire during backward, one parameter is
+    unused (its bucket is completed by all_reduce()), two steps in a row (state reset), double backward rejected."""
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(300, 200), torch.nn.ReLU(), torch.nn.Linear(200, 100), torch.nn.ReLU(),
+                              torch.nn.Linear(100, 3))
+    unused = torch.nn.Parameter(torch.zeros(7))
+    params = list(net.parameters()) + [unused]
+    ob = dp.OverlappedGradientBuckets(params, bucket_mb=0.05)
+    assert len(ob.buckets) >= 2
+    ok = True
+    for step in range(2):
+        g = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(5, 300, generator=g)
+        for p in params:
+            p.grad = None
+        net(x).square().sum().backward()
+        launched_early = sum(1 for it in ob._launched if it)         # before all_reduce(): complete buckets are in flight
+        local = [None if p.grad is None else p.grad.clone() for p in params]
+        # reference: what every rank's gradient sums to
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [None if t is None else t.tolist() for t in local])
+        ob.all_reduce()
+        for i, p in enumerate(params):
+            if local[i] is None:
+                ok = ok and p.grad is None
+                continue
+            want = sum(torch.tensor(gathered[r][i]) for r in range(world))
+            ok = ok and torch.allclose(p.grad, want, rtol=1e-6, atol=1e-7)
+        ok = ok and launched_early >= 1 and launched_early < len(ob.buckets)   # the bucket holding `unused` waits
+    net(torch.randn(2, 300)).sum().backward()
+    try:
+        net(torch.randn(2, 300)).sum().backward()
+        ok = False
+    except RuntimeError:
+        pass
+    ob.remove_hooks()
+    return bool(ok)
+
+
+def test_overlapped_gradient_buckets_equal_plain_buckets():
+    out = _run(_overlap_fn)
+    assert all(out[r] is True for r in range(2)), out
+
+
 def _syncbn_fn(rank, world):
     """The reductions the autograd Functions perform (sum x, sum x^2 | loss numerator, normaliser) reproduce the
     full-batch BatchNorm statistics and weighted-CE loss when every rank holds a shard."""
