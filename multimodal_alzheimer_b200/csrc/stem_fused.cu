@@ -436,6 +436,139 @@ __global__ void __launch_bounds__(kSFThreads, 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL packed-compare variant of the streaming forward (ADNI_POOL_STREAM=2; same results bit for bit, meant
+// to be validated by the existing tests with that setting before it becomes the default).  The forward kernel is
+// ALU-issue bound: after BN + ReLU + rounding the default path unpacks the rounded activation again and spends a
+// compare + two selects per (tap, channel).  Here the running maximum and its tap index stay in the packed bf16x2
+// domain - one HSET2 mask and two LOP3 selects per tap and channel PAIR; the winner's bits are stored as they are.
+struct PlaneMaxP {
+  uint32_t v[4];    // running maxima, two bf16 lanes per word (channels 2k, 2k + 1)
+  uint32_t idx[4];  // tap index kh*3 + kw of the winner in each 16-bit lane
+};
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+constexpr uint32_t kNegInf2 = 0xFF80FF80u;  // (-inf, -inf) in bf16
+
+__device__ __forceinline__ PlaneMaxP plane_reduce_packed(const PlaneRaw& pr, uint32_t okmask, const float (&sc)[8],
+                                                         const float (&sh)[8]) {
+  PlaneMaxP m;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    m.v[k] = kNegInf2;
+    m.idx[k] = 0;
+  }
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const uint32_t okm = ((okmask >> t) & 1u) ? 0xFFFFFFFFu : 0u;  // a tap outside the plane never wins
+    float f[8];
+    unpack8(pr.r[t], f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    const uint4 yb = pack8(f);  // what bn_apply would have stored: the bf16-rounded activation
+    const uint32_t w[4] = {yb.x, yb.y, yb.z, yb.w};
+    const uint32_t tt = static_cast<uint32_t>(t) * 0x00010001u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t g = gt2_mask(w[k], m.v[k]) & okm;  // strict '>': the first maximum in (kh, kw) order wins
+      m.v[k] = (w[k] & g) | (m.v[k] & ~g);
+      m.idx[k] = (tt & g) | (m.idx[k] & ~g);
+    }
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(kSFThreads, 3)
+    bn_relu_pool_fwd_stream_packed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho,
+                                          int Wo, int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
+                                          uint8_t* __restrict__ amax) {
+  const int vpr = C / 8;
+  __shared__ float s_sc[64], s_sh[64];
+  if (threadIdx.x < 64) {
+    const int c = min(blockIdx.y * 64 + (int)threadIdx.x, C - 1);
+    s_sc[threadIdx.x] = scale[c];
+    s_sh[threadIdx.x] = shift[c];
+  }
+  __syncthreads();
+  const int cv = blockIdx.y * 8 + (threadIdx.x & 7);
+  const int lw = (threadIdx.x >> 3) % kSFw, lh = threadIdx.x / (8 * kSFw);
+  int t = blockIdx.x;
+  const int ds = t % dsplit;
+  t /= dsplit;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  const int n = t / tiles_h;
+  const int oh = th * kSFh + lh, ow = tw * kSFw + lw;
+  if (oh >= Ho || ow >= Wo || cv >= vpr) return;
+  const int per = (Do + dsplit - 1) / dsplit;
+  const int od_begin = ds * per, od_end = min(Do, od_begin + per);
+  if (od_begin >= od_end) return;
+  const int coff = cv * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = s_sc[(threadIdx.x & 7) * 8 + j];
+    sh[j] = s_sh[(threadIdx.x & 7) * 8 + j];
+  }
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++) {
+      const int ih = oh * kS - kPad + kh, iw = ow * kS - kPad + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) okmask |= 1u << (kh * 3 + kw);
+    }
+  }
+  const long long row_stride = (long long)W * C;
+  const long long plane = (long long)H * row_stride;
+  const __nv_bfloat16* ys =
+      y + (long long)n * D * plane + ((long long)(oh * kS - kPad) * W + (ow * kS - kPad)) * C + coff;
+
+  PlaneRaw bufA, bufB;
+  PlaneMaxP carry;
+  bool have_carry = od_begin * kS - kPad >= 0;
+  if (have_carry) plane_load(bufB, ys + (long long)(od_begin * kS - kPad) * plane, row_stride, C, okmask);
+  plane_load(bufA, ys + (long long)(od_begin * kS) * plane, row_stride, C, okmask);
+  if (have_carry) carry = plane_reduce_packed(bufB, okmask, sc, sh);
+  for (int od = od_begin; od < od_end; od++) {
+    const bool has_odd = od * kS + 1 < D;
+    if (has_odd) plane_load(bufB, ys + (long long)(od * kS + 1) * plane, row_stride, C, okmask);
+    uint32_t best[4], bidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      best[k] = have_carry ? carry.v[k] : kNegInf2;
+      bidx[k] = have_carry ? carry.idx[k] : 0x00FF00FFu;
+    }
+    const PlaneMaxP mid = plane_reduce_packed(bufA, okmask, sc, sh);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t g = gt2_mask(mid.v[k], best[k]);  // planes in kd order, strict '>'
+      best[k] = (mid.v[k] & g) | (best[k] & ~g);
+      bidx[k] = ((mid.idx[k] + 9u * 0x00010001u) & g) | (bidx[k] & ~g);
+    }
+    if (od + 1 < od_end) plane_load(bufA, ys + (long long)((od + 1) * kS) * plane, row_stride, C, okmask);
+    have_carry = has_odd;
+    if (have_carry) {
+      carry = plane_reduce_packed(bufB, okmask, sc, sh);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t g = gt2_mask(carry.v[k], best[k]);
+        best[k] = (carry.v[k] & g) | (best[k] & ~g);
+        bidx[k] = ((carry.idx[k] + 18u * 0x00010001u) & g) | (bidx[k] & ~g);
+      }
+    }
+    const long long oi = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * vpr + cv;
+    *reinterpret_cast<uint4*>(p + oi * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    uint2 pk;  // bytes 0 and 2 of every index word: channels (0,1,2,3) and (4,5,6,7)
+    pk.x = __byte_perm(bidx[0], bidx[1], 0x6420);
+    pk.y = __byte_perm(bidx[2], bidx[3], 0x6420);
+    *reinterpret_cast<uint2*>(amax + oi * 8) = pk;
+  }
+}
+
 // Backward as a GATHER over 2x2x2 input cells.  Thread = the 8 voxels (2cd+ed, 2ch+eh, 2cw+ew), e in {0,1}, of one
 // cell x 8 channels.  Along every axis a voxel with an even coordinate is the centre tap of window c, an odd one the
 // last tap of window c and the first tap of window c+1, so the cell only ever receives gradient from the 2x2x2
@@ -614,6 +747,14 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
     const int th = (Ho + kSFh - 1) / kSFh, tw = (Wo + kSFw - 1) / kSFw;
     const int dsplit = Do >= 16 ? 2 : 1;
     dim3 grid((unsigned)((long long)N * th * tw * dsplit), (unsigned)((C / 8 + 7) / 8));
+    if (pool_variant() == 2) {  // experimental packed-compare variant, same results
+      bn_relu_pool_fwd_stream_packed_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(
+          reinterpret_cast<const bf16*>(y), scale, shift, D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
+          reinterpret_cast<bf16*>(p), argmax);
+      count_launch();
+      ADNI_LAUNCH_CHECK("bn_relu_pool_fwd_stream_packed_kernel");
+      return ADNI_OK;
+    }
     bn_relu_pool_fwd_stream_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift,
                                                                         D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
                                                                         reinterpret_cast<bf16*>(p), argmax);
