@@ -90,3 +90,50 @@ def test_adam_entry_point_validates_before_touching_a_gpu(lib):
         Adam([p], lr=-1.0)
     with pytest.raises(NotImplementedError):
         Adam([p], amsgrad=True)
+
+
+def _encoder_conv_geometries(depth, shape):
+    """(D, H, W, Cin, Cout, k, stride, pad, dil) of every Conv3d of the MedicalNet encoder for an input volume, from a
+    meta-device forward of the oracle's restatement."""
+    import torch
+    from oracle.medicalnet import generate_model
+    m = generate_model(depth).to("meta")
+    out = []
+
+    def hook(mod, inp, o):
+        x = inp[0]
+        out.append((x.shape[2], x.shape[3], x.shape[4], mod.in_channels, mod.out_channels, mod.kernel_size[0],
+                    mod.stride[0], mod.padding[0], mod.dilation[0]))
+
+    hooks = [mm.register_forward_hook(hook) for mm in m.modules() if isinstance(mm, torch.nn.Conv3d)]
+    with torch.no_grad():
+        m(torch.empty((1, 1) + tuple(shape), device="meta"))
+    for h in hooks:
+        h.remove()
+    return out
+
+
+@pytest.mark.parametrize("depth,shape,n_per_gpu", [
+    (10, (128, 128, 128), 2),     # BASELINE.json configs[0]
+    (18, (128, 128, 128), 16),    # configs[1]
+    (18, (128, 128, 128), 4),     # configs[2] at 8 GPUs (4 pairs per GPU)
+    (18, (91, 109, 91), 32),      # the reference's own grid (MNI 2 mm)
+    (50, (160, 192, 160), 8),     # configs[4]: the largest conv / wgrad path
+])
+def test_planner_routes_every_encoder_conv_to_a_tensor_core_engine(depth, shape, n_per_gpu):
+    """adni_conv3d_plan_info (a host-side query, no GPU needed) for every conv of the encoder at the BASELINE
+    configurations: fprop, dgrad and wgrad are all planned on a tcgen05 engine (kind 1 = tap-per-box, 2 =
+    halo-resident), never the CUDA-core fallback engine (0) and never ADNI_ENOTSUP; the executed fraction of the
+    (tile, tap) blocks is in (0, 1].  The 1-channel stem has its own entry points (adni_stem_*)."""
+    import ctypes
+    lib = _lib.load()
+    convs = [g for g in _encoder_conv_geometries(depth, shape) if g[3] > 1]
+    assert len(convs) == {10: 11, 18: 19, 50: 52}[depth]
+    for (D, H, W, Ci, Co, k, s, p, d) in convs:
+        for pass_ in (0, 1, 2):
+            g = _lib.ConvGeom(n_per_gpu, D, H, W, Ci, Co, k, s, p, d)
+            kind, frac = ctypes.c_int(-1), ctypes.c_double(-1.0)
+            rc = lib.adni_conv3d_plan_info(ctypes.byref(g), pass_, ctypes.byref(kind), ctypes.byref(frac))
+            assert rc == 0, ((D, H, W, Ci, Co, k, s, p, d), pass_, lib.adni_last_error_string())
+            assert kind.value in (1, 2), ((D, H, W, Ci, Co, k, s, p, d), pass_, kind.value)
+            assert 0.0 < frac.value <= 1.0
