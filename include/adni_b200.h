@@ -251,6 +251,17 @@ int adni_loss_bwd(const void* logits, int logits_f64, int ld, const int64_t* tar
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Test-epoch metrics (pkg/models/base_model.py:119-172 test_epoch_end, :212-236 bootstrap_metric; torchmetrics
+ * 0.10.2 MulticlassF1Score(average='macro' | 'none'), MulticlassMatthewsCorrCoef, confusion matrix).
+ * preds = argmax(logits[i][0..C)) (fp64 rows of stride ld), targets = labels[i].  For draw d the samples are
+ * idx[d][0..n) (the `torch.randint(0, n, (n,))` resample of bootstrap_metric; idx == NULL: the identity, i.e. the
+ * plain test-set metrics with draws == 1).  Outputs (each nullable): f1_macro[draws], f1_class[draws][C], mcc[draws]
+ * (fp32, torchmetrics' reductions), confmat[draws][C][C] (int64, [target][pred]).  2 <= C <= 8.
+ * ------------------------------------------------------------------------------------------- */
+int adni_bootstrap_metrics(const double* logits, int ld, const int64_t* labels, const int64_t* idx, int n, int C,
+                           int draws, float* f1_macro, float* f1_class, float* mcc, long long* confmat, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Input normalisation (pkg/utils/dataloader.py:213-215, 236-281; pkg/utils/standardization.py:34-55).
  * ------------------------------------------------------------------------------------------- */
 /* Per-scan quantile min-max (dataloader.py:239-249,261-270) for `nscans` volumes of `nvox` voxels:

@@ -24,6 +24,7 @@ SOURCES = [
     "stem_fused.cu",
     "elementwise.cu",
     "head_loss.cu",
+    "metrics.cu",
     "normalize.cu",
     "optimizer.cu",
     "fusion_ops.cu",

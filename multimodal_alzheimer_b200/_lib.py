@@ -56,6 +56,7 @@ _SIGNATURES = {
     "adni_split_channels": [_P, _I, _I, _LL, _P, _P, _P],
     "adni_pad_volume_high": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adni_crop_volume_high": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "adni_bootstrap_metrics": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "adni_adam_max_tensors_per_launch": [],
     "adni_adam_step_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _P],
     "adni_weights_multi_job_bytes": [],

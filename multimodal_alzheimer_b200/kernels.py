@@ -612,6 +612,29 @@ def loss_bwd(logits, target, coeff, denom, upstream=None):
     return dl
 
 
+# --------------------------------------------------------------------------------------------- test-epoch metrics
+def bootstrap_metrics(logits, labels, draws=None, want_confmat=False):
+    """logits (n, C) fp64, labels (n,) int64, draws (d, n) int64 resampling indices or None (the identity, d = 1).
+    Returns dict(f1 (d,), f1_class (d, C), mcc (d,)[, confmat (d, C, C) int64]) - one launch for all draws."""
+    _chk(logits, torch.float64, "logits")
+    _chk(labels, torch.int64, "labels")
+    n, C = logits.shape
+    d = 1 if draws is None else draws.shape[0]
+    if draws is not None:
+        _chk(draws, torch.int64, "draws")
+        assert draws.shape[1] == n
+    dev = logits.device
+    out = {"f1": torch.empty((d,), dtype=torch.float32, device=dev),
+           "f1_class": torch.empty((d, C), dtype=torch.float32, device=dev),
+           "mcc": torch.empty((d,), dtype=torch.float32, device=dev)}
+    cm = torch.empty((d, C, C), dtype=torch.int64, device=dev) if want_confmat else None
+    call("adni_bootstrap_metrics", ptr(logits), logits.stride(0), ptr(labels), ptr(draws), n, C, d, ptr(out["f1"]),
+         ptr(out["f1_class"]), ptr(out["mcc"]), ptr(cm), stream_ptr())
+    if cm is not None:
+        out["confmat"] = cm
+    return out
+
+
 # --------------------------------------------------------------------------------------------- normalisation
 def quantile_minmax_normalize(x, mask, q, out_dtype=torch.float32, want_info=False):
     """x fp32 [S, ...], mask uint8 same shape.  Returns normalised volumes (and (info, qvals) if asked)."""

@@ -2,8 +2,10 @@
 
 Keeps `__init__(hparams)`, `forward`, `general_step(batch, idx, mode) -> {'loss','outputs','labels'}`,
 `training_step/validation_step/test_step/predict_step`, `configure_optimizers`, `hparams`, `save`.
-The torchmetrics F1 bookkeeping and confusion-matrix plotting of the reference are logging, not path arithmetic
- and are not reproduced.  When pytorch_lightning is importable the class derives from
+The per-step torchmetrics bookkeeping and the confusion-matrix plotting of the reference are logging, not path
+arithmetic and are not reproduced; the numbers `test_epoch_end` reports (F1, MCC, their
+bootstrap intervals, the confusion matrix) come from `test_epoch_metrics` / `bootstrap_metric` below, computed by one
+kernel launch for all resamples.  When pytorch_lightning is importable the class derives from
 pl.LightningModule; otherwise from a small stand-in with the same few methods.
 """
 from abc import ABC, abstractmethod
@@ -107,6 +109,35 @@ class Base_Model(_LightningBase, ABC):
     @abstractmethod
     def configure_optimizers(self):
         pass
+
+    # ------------------------------------------------------------------ test-epoch metrics
+    def bootstrap_metric(self, metric, y_hat, y_labels, n_drawings=1000):
+        """base_model.py:212-236: mean and 1.96 x std of `metric` ('f1' = MulticlassF1Score macro, 'mcc' =
+        MulticlassMatthewsCorrCoef) over `n_drawings` resamples with replacement.  The draws are the reference's
+        (`torch.randint(0, n, (n,))` per drawing, CPU generator, same order); all of them are evaluated by ONE kernel
+        launch instead of 1000 torchmetrics update/compute/reset rounds."""
+        from ... import kernels as K
+        n = len(y_hat)
+        draws = torch.stack([torch.randint(0, n, (n,)) for _ in range(n_drawings)]).to(y_hat.device)
+        values = K.bootstrap_metrics(y_hat.contiguous(), y_labels.contiguous(), draws)[metric].cpu()
+        return torch.mean(values), 1.96 * torch.std(values)
+
+    def test_epoch_metrics(self, outputs):
+        """The numbers `test_epoch_end` logs (base_model.py:134-172): loss, macro / per-class F1 over the test set,
+        bootstrap mean and confidence interval of F1 and MCC, plus the confusion matrix the reference plots (as a
+        tensor: plotting is not part of this package)."""
+        from ... import kernels as K
+        avg_loss = torch.stack([x["loss"] for x in outputs]).mean()
+        y_hat = torch.cat([x["outputs"] for x in outputs]).detach().contiguous()
+        y_labels = torch.cat([x["labels"] for x in outputs]).contiguous()
+        whole = K.bootstrap_metrics(y_hat, y_labels, None, want_confmat=True)
+        log = {"test_loss_epoch": avg_loss, "test_f1_epoch": whole["f1"][0].cpu(), "step": float(getattr(self, "current_epoch", 0))}
+        for i in range(self.hparams["n_classes"]):
+            log[f"test_f1_epoch_class_{i}"] = whole["f1_class"][0, i].cpu()
+        log["test_f1_epoch_boot"], log["test_f1_epoch_ci"] = self.bootstrap_metric("f1", y_hat, y_labels)
+        log["test_mcc_epoch_boot"], log["test_mcc_epoch_ci"] = self.bootstrap_metric("mcc", y_hat, y_labels)
+        log["confusion_matrix"] = whole["confmat"][0].cpu()
+        return log
 
 
 def volume_input(x):

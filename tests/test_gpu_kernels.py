@@ -534,3 +534,56 @@ def test_even_kernel_same_padding(cuda_dev, C):
     assert_close(to_ncdhw_f32(xin.grad.cpu()), xr.grad, 6e-3, "even-kernel dgrad")
     assert_close(conv.weight.grad.cpu(), tconv.weight.grad, 2e-3, "even-kernel wgrad")
     assert_close(conv.bias.grad.cpu(), tconv.bias.grad, 2e-3, "even-kernel dbias")
+
+
+@pytest.mark.parametrize("C,n", [(2, 7), (3, 150), (3, 1000), (2, 333)])
+def test_bootstrap_metrics_match_oracle(cuda_dev, C, n):
+    """adni_bootstrap_metrics (all resamples in one launch) vs oracle/metrics.py (torchmetrics 0.10.2 reductions
+    restated, cross-checked against scikit-learn): confusion matrices exact, F1 (macro, per class) and MCC to 1e-6
+    (fp32 reductions in the same order), including resamples in which a class is missing."""
+    from multimodal_alzheimer_b200 import kernels as K
+    from oracle.metrics import confusion_matrix, f1_from_confmat, mcc_from_confmat
+    g = torch.Generator().manual_seed(15 + n)
+    logits = torch.randn((n, C), generator=g, dtype=torch.float64)
+    logits[::5, 0] = logits[::5, 1]                                   # ties: argmax takes the first maximum
+    labels = torch.randint(0, C, (n,), generator=g)
+    draws = torch.stack([torch.randint(0, n, (n,), generator=g) for _ in range(64)])
+    draws[1] = draws[1, 0]                                            # a resample that holds a single sample
+    got = K.bootstrap_metrics(logits.to(cuda_dev), labels.to(cuda_dev), draws.to(cuda_dev), want_confmat=True)
+    whole = K.bootstrap_metrics(logits.to(cuda_dev), labels.to(cuda_dev), None, want_confmat=True)
+    torch.cuda.synchronize()
+    for d in range(64):
+        cm = confusion_matrix(logits[draws[d]], labels[draws[d]], C)
+        assert torch.equal(got["confmat"][d].cpu(), cm), d
+        macro, per = f1_from_confmat(cm)
+        assert abs(float(got["f1"][d]) - float(macro)) <= 1e-6, (d, float(got["f1"][d]), float(macro))
+        assert torch.allclose(got["f1_class"][d].cpu(), per, atol=1e-6), d
+        assert abs(float(got["mcc"][d]) - float(mcc_from_confmat(cm))) <= 1e-6, d
+    cm = confusion_matrix(logits, labels, C)
+    assert torch.equal(whole["confmat"][0].cpu(), cm)
+    assert abs(float(whole["f1"][0]) - float(f1_from_confmat(cm)[0])) <= 1e-6
+
+
+def test_bootstrap_metric_method_follows_reference_draws(cuda_dev):
+    """Base_Model.bootstrap_metric / test_epoch_metrics: same `torch.randint` draws as base_model.py:212-236 for the
+    same global seed -> the oracle's mean and 1.96 x std."""
+    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_cnn import Small_PET_CNN
+    from oracle.metrics import bootstrap_metric
+    from tests._models import hp_pet
+    model = Small_PET_CNN(hp_pet(3, conv_out=(8,), filter_size=(3,)))
+    g = torch.Generator().manual_seed(3)
+    y_hat = torch.randn((90, 3), generator=g, dtype=torch.float64)
+    y = torch.randint(0, 3, (90,), generator=g)
+    for metric in ("f1", "mcc"):
+        torch.manual_seed(7)
+        mean_o, ci_o, _ = bootstrap_metric(metric, y_hat, y, 3, n_drawings=200)
+        torch.manual_seed(7)
+        mean_p, ci_p = model.bootstrap_metric(metric, y_hat.to(cuda_dev), y.to(cuda_dev), n_drawings=200)
+        assert abs(float(mean_p) - float(mean_o)) <= 1e-6 and abs(float(ci_p) - float(ci_o)) <= 1e-6, metric
+    outs = [{"loss": torch.tensor(0.5 + 0.1 * i, dtype=torch.float64, device=cuda_dev), "outputs": y_hat[30 * i:30 * i + 30].to(cuda_dev),
+             "labels": y[30 * i:30 * i + 30].to(cuda_dev)} for i in range(3)]
+    torch.manual_seed(1)
+    log = model.test_epoch_metrics(outs)
+    assert abs(float(log["test_loss_epoch"]) - 0.6) < 1e-12 and int(log["confusion_matrix"].sum()) == 90
+    assert {"test_f1_epoch", "test_f1_epoch_class_2", "test_f1_epoch_boot", "test_f1_epoch_ci", "test_mcc_epoch_boot",
+            "test_mcc_epoch_ci"} <= set(log)

@@ -174,3 +174,29 @@ def test_oracle_training_trajectory_matches_reference(traj_id, recorded_threads)
     for n, fp in rec["final_running"].items():
         f = fingerprint(n, bufs[n])
         assert max(abs(a - b) for a, b in zip(f, fp)) <= 1e-4 * max(fp[0], 1e-30), (n, f, fp)
+
+
+def test_metric_restatement_agrees_with_sklearn():
+    """oracle/metrics.py (torchmetrics 0.10.2 reductions restated; torchmetrics itself is absent: parity unpinned)
+    vs scikit-learn on random 2- and 3-class problems in which every class occurs: macro / per-class F1 and MCC
+    agree to fp32 rounding; a class absent from predictions AND targets is excluded from the macro mean
+    (torchmetrics) where sklearn would count it as 0."""
+    from sklearn.metrics import f1_score, matthews_corrcoef
+    from oracle.metrics import confusion_matrix, f1_from_confmat, mcc_from_confmat
+    g = torch.Generator().manual_seed(15)
+    for C in (2, 3):
+        for n in (12, 57, 300):
+            logits = torch.randn((n, C), generator=g, dtype=torch.float64)
+            labels = torch.randint(0, C, (n,), generator=g)
+            labels[:C] = torch.arange(C)
+            logits[torch.arange(C), torch.arange(C)] += 10            # every class predicted at least once
+            cm = confusion_matrix(logits, labels, C)
+            macro, per = f1_from_confmat(cm)
+            preds = logits.argmax(1).numpy()
+            assert abs(float(macro) - f1_score(labels.numpy(), preds, average="macro")) <= 1e-6
+            assert torch.allclose(per.double(), torch.tensor(f1_score(labels.numpy(), preds, average=None)), atol=1e-6)
+            assert abs(float(mcc_from_confmat(cm)) - matthews_corrcoef(labels.numpy(), preds)) <= 1e-6
+    cm = torch.tensor([[5, 1, 0], [2, 4, 0], [0, 0, 0]])
+    macro, per = f1_from_confmat(cm)
+    assert per[2] == 0 and abs(float(macro) - float(per[:2].mean())) < 1e-7
+    assert float(mcc_from_confmat(torch.tensor([[4, 0], [3, 0]]))) == 0.0   # zero denominator -> 0
