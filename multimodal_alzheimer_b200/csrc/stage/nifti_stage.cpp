@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -109,14 +110,14 @@ int parse_header(const unsigned char* h, const char* path, adni_nifti_info* info
     info->dim[i] = dim[i + 1];
     nvox *= dim[i + 1];
   }
+  if (nvox < 0 || nvox > (int64_t(1) << 40)) return fail(ADNI_STAGE_ENOTSUP, "%s: implausible voxel count", path);
   info->ndim = nd;
   info->nvox = nvox;
   info->datatype = rd<int16_t>(h + 70, swap);
   info->bitpix = rd<int16_t>(h + 72, swap);
   if (!bytes_of(info->datatype)) return fail(ADNI_STAGE_ENOTSUP, "%s: datatype code %d is not supported", path, info->datatype);
   const float vox = rd<float>(h + 108, swap);
-  info->vox_offset = static_cast<int64_t>(vox);
-  if (info->vox_offset < 352) info->vox_offset = 352;  // nibabel: single-file images start at >= 352
+  info->vox_offset = (vox >= 352.f && vox < 1e9f) ? static_cast<int64_t>(vox) : 352;  // single-file images start at >= 352
   const double slope = static_cast<double>(rd<float>(h + 112, swap));
   const double inter = static_cast<double>(rd<float>(h + 116, swap));
   info->swapped = swap ? 1 : 0;
@@ -224,7 +225,22 @@ int convert_any(const unsigned char* raw, const adni_nifti_info& in, OUT* dst, i
 }
 
 template <typename OUT>
+int read_volume_impl(const char* path, OUT* dst, int64_t capacity, adni_nifti_info* info_out, bool mask);
+
+// No exception may cross the C ABI (or escape a worker thread): allocation failures become an error code.
+template <typename OUT>
 int read_volume(const char* path, OUT* dst, int64_t capacity, adni_nifti_info* info_out, bool mask) {
+  try {
+    return read_volume_impl<OUT>(path, dst, capacity, info_out, mask);
+  } catch (const std::exception& e) {
+    return fail(ADNI_STAGE_EIO, "%s: %s", path ? path : "(null)", e.what());
+  } catch (...) {
+    return fail(ADNI_STAGE_EIO, "%s: unknown failure", path ? path : "(null)");
+  }
+}
+
+template <typename OUT>
+int read_volume_impl(const char* path, OUT* dst, int64_t capacity, adni_nifti_info* info_out, bool mask) {
   adni_nifti_info info;
   GzFile gz(path ? path : "");
   int rc = open_and_parse(path, gz, &info);
