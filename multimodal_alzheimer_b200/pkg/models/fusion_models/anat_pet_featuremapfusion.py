@@ -11,22 +11,13 @@ import torch
 from .... import autograd as A
 from .... import nn as bnn
 from ...loss_functions.focalloss import CrossEntropyLoss
+from .._stacks import stem_stack
 from ..base_model import Base_Model, adam_or_plateau, volume_input
 
 
 def _backbone(hparams):
-    modules = []
-    n_in = 1
-    for n_out, filter_size in zip(hparams["conv_out"], hparams["filter_size"]):
-        modules.append(bnn.Conv3d(n_in, n_out, filter_size, padding="same"))
-        if "batchnorm" in hparams and hparams["batchnorm"]:
-            modules.append(bnn.BatchNorm3d(n_out))
-        modules.append(bnn.ReLU())
-        modules.append(bnn.MaxPool3d(2))
-        if "dropout_conv_p" in hparams:
-            modules.append(bnn.Dropout(p=hparams["dropout_conv_p"]))
-        n_in = n_out
-    return bnn.Sequential(*modules), n_in
+    layers, width = stem_stack(hparams, in_channels=1)
+    return bnn.Sequential(*layers), width
 
 
 class PET_MRI_FMF(Base_Model):
