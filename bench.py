@@ -1,14 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the B200-native training hot path (contract: see README / DESIGN.md §measurement).
+"""Benchmark of the B200-native training hot path (contract: see README / DESIGN.md section 6).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+    python bench.py --workload mri_r50_160 ...               # the other BASELINE.json configurations
 
-Workload (BASELINE.json metric "MRI+PET volumes/sec train (ResNet-18 3D, 128^3)"; configs[2]): the PET-MRI
+Default workload (BASELINE.json metric "MRI+PET volumes/sec train (ResNet-18 3D, 128^3)"; configs[2]): the PET-MRI
 two-branch ResNet-18 fusion model, focal loss gamma=1, global batch 32 (MRI, PET) pairs of 1x128^3 volumes,
 random-init weights, synthetic data.  A step = per-scan quantile min-max normalisation of the MRI batch + PET
-standardisation + forward + fp64 focal loss + backward + gradient all-reduce + Adam step.  value = volumes
-(2 per pair) per second over all ranks, device-timed with CUDA events, max over ranks.
+standardisation + forward + fp64 loss + backward + gradient all-reduce + Adam step.  value = volumes per second over
+all ranks, device-timed with CUDA events, max over ranks.  Every rank count trains the SAME global batch (samples are
+generated per global index), so `parity.first_step_loss` / `parity.first_step_logits_checksum` must agree across N.
 """
 import argparse
 import json
@@ -20,139 +22,135 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "MRI+PET volumes/sec train (ResNet-18 3D, 128^3)"
 UNIT = "volumes/s"
-PET_MEAN, PET_STD = 0.5145, 0.5383  # pkg/models/pet_models/train_pet_cnn.py:77-78
 PORT_PINNING = ("oracle port; its model classes reproduce one training step of the reference's own LightningModules bit "
                 "for bit (tests/golden/models.json, tools/make_golden_models.py) - the reference itself needs "
                 "pytorch_lightning / MedicalNet / nibabel and cannot run on this box")
 
 
 def parse_args():
+    from multimodal_alzheimer_b200.workloads import WORKLOADS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pet_mri_fusion_r18", choices=["pet_mri_fusion_r18", "mri_r18"])
+    ap.add_argument("--workload", default="pet_mri_fusion_r18", choices=sorted(WORKLOADS))
     ap.add_argument("--global-batch", type=int, default=None)
-    ap.add_argument("--volume", type=int, default=128)
-    ap.add_argument("--depth", type=int, default=18)
+    ap.add_argument("--volume", type=int, nargs="+", default=None, help="override the volume: one edge or D H W")
+    ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=1)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1, help="samples per step of the CPU legs (bounded sample)")
     ap.add_argument("--shape-profile", default=None, help="write the per-conv-shape timing table to this JSON file")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of the CUDA graph")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------- shared config
-def hparams_for(workload, depth):
-    import torch
-    cw = torch.tensor([0.4651162790697675, 0.6712473572938689, 0.8636363636363636], dtype=torch.float64)
-    enc = dict(n_classes=3, resnet_depth=depth, batchnorm_begin=True, batchnorm_dense=True, linear_out=[],
-               fl_gamma=None, loss_class_weights=cw, lr=1e-3, lr_pretrained=1e-4, l2_reg=1e-4,
-               reduce_factor_lr_schedule=None, norm_percentile=0.98)
-    fus = dict(n_classes=3, fl_gamma=1, loss_class_weights=cw, lr=1e-3, lr_pretrained=1e-4, l2_reg=1e-4,
-               reduce_factor_lr_schedule=None)
-    return enc, fus
+def resolve(args, world):
+    """(workload record, depth, volume, global batch, scaling) after the command-line overrides."""
+    from multimodal_alzheimer_b200.workloads import WORKLOADS
+    w = WORKLOADS[args.workload]
+    depth = args.depth or w["depth"]
+    if args.volume is None:
+        volume = tuple(w["volume"])
+    else:
+        volume = tuple(args.volume * 3) if len(args.volume) == 1 else tuple(args.volume)
+    if args.global_batch:
+        gb, scaling = args.global_batch, "strong"
+    elif w["global_batch"] is not None:
+        gb, scaling = w["global_batch"], "strong"
+    else:
+        gb, scaling = w["per_gpu_batch"] * world, "weak"
+    return w, depth, volume, gb, scaling
 
 
-def conv_flops_per_volume(depth, vol):
-    """Algorithmic conv FLOPs of one training step per volume (fprop + wgrad + dgrad, no dgrad for the stem):
-    SURVEY.md §8d. Computed from the layer table so that any --volume / --depth is consistent."""
-    blocks = {10: [1, 1, 1, 1], 18: [2, 2, 2, 2], 34: [3, 4, 6, 3]}[depth]
-    s1 = (vol + 6 - 7) // 2 + 1  # stem output
-    fwd_stem = 2 * s1 ** 3 * 64 * 343
-    s = (s1 + 2 - 3) // 2 + 1  # after max-pool
-    total_fwd, inpl = 0, 64
-    for li, (planes, n) in enumerate(zip([64, 128, 256, 512], blocks)):
-        for b in range(n):
-            stride = 2 if (li == 1 and b == 0) else 1
-            so = (s - 1) // stride + 1
-            total_fwd += 2 * so ** 3 * planes * inpl * 27
-            total_fwd += 2 * so ** 3 * planes * planes * 27
-            if stride != 1 or inpl != planes:
-                total_fwd += 2 * so ** 3 * planes * inpl
-            inpl, s = planes, so
-    return 3 * total_fwd + 2 * fwd_stem
+def metric_name(args, w, depth, volume):
+    if args.workload == "pet_mri_fusion_r18" and depth == 18 and volume == (128, 128, 128):
+        return "MRI+PET volumes/sec train (ResNet-18 3D, 128^3)"      # BASELINE.json's metric
+    mods = "+".join({"mri": "MRI", "pet": "PET", "tab": "tabular"}[m] for m in w["modalities"])
+    return f"{mods} volumes/sec train ({args.workload}, ResNet-{depth} 3D, {'x'.join(map(str, volume))})"
 
 
-def synth_inputs(n_pairs, vol, device, seed, want_pet=True):
-    """Raw synthetic inputs: MRI 400|N(0,1)|+50U(0,1) with an ellipsoid brain mask (semi-axes 0.42)
-    and 0.5 % exact zeros inside it; PET max(0, N(0.5145, 0.5383)); labels randint(0,3)."""
-    import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    shape = (n_pairs, vol, vol, vol)
-    mri = 400 * torch.randn(shape, generator=g, device=device).abs() + 50 * torch.rand(shape, generator=g, device=device)
-    ax = (torch.arange(vol, device=device, dtype=torch.float32) - (vol - 1) / 2) / (0.42 * vol)
-    ell = (ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2) <= 1
-    mask = ell[None].expand(shape).contiguous()
-    zero = torch.rand(shape, generator=g, device=device) < 0.005
-    mri[zero & mask] = 0.0
-    out = {"mri_raw": mri.float().contiguous(), "mask": mask.to(torch.uint8).contiguous(),
-           "label": torch.randint(0, 3, (n_pairs,), generator=g, device=device)}
-    if want_pet:
-        pet = torch.randn(shape, generator=g, device=device) * PET_STD + PET_MEAN
-        out["pet_raw"] = pet.clamp_min(0).float().contiguous()
-    return out
+def workload_config(args, w, depth, volume, world, global_batch, step_global_batch=None):
+    cfg = {"workload": f"{w['title']}; per-scan quantile(0.98) MRI normalisation"
+                       + (" + PET standardisation" if "pet" in w["modalities"] else "") + ", fwd+bwd+allreduce+Adam",
+           "name": args.workload, "resnet_depth": depth, "global_batch": global_batch, "volume": list(volume),
+           "parallelism": f"dp{world}",
+           "l2": "inputs and activations of a step are far larger than the 126 MB L2 (>= 18 MB of raw input per sample)",
+           "baseline_config": w["config"]}
+    if step_global_batch is not None and step_global_batch != global_batch:
+        cfg["samples_per_timed_step"] = step_global_batch
+    return cfg
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def build_oracle(workload, depth):
-    import torch
-    import oracle.models as O
-    enc, fus = hparams_for(workload, depth)
-    torch.manual_seed(15)
-    if workload == "mri_r18":
-        return O.Anat_CNN(dict(enc))
+def oracle_namespace():
+    """The CPU oracle's classes in the shape workloads.build_model expects (bench.py's CPU legs only)."""
+    import types
 
-    class Trunk(torch.nn.Module):  # PET_CNN_ResNet encoder + Linear(512,64)+ReLU (two-ResNet fusion, SURVEY.md §0.3)
+    import torch
+
+    import oracle.models as O
+
+    class ResNet_PET_Trunk(torch.nn.Module):  # PET_CNN_ResNet encoder + Linear(512,64)+ReLU (two-ResNet fusion)
         def __init__(self, encm):
             super().__init__()
             self.encoder = encm
             self.encoder.model.conv_seg = self.encoder.model.conv_seg[:2]
-            self.reduce_dim_pet = torch.nn.Sequential(torch.nn.Linear(512, 64), torch.nn.ReLU())
+            self.relu = torch.nn.ReLU()
+            self.reduce_dim_pet = torch.nn.Sequential(torch.nn.Linear(512, 64), self.relu)
 
         def forward(self, x):
             o = self.encoder(x)
             return self.reduce_dim_pet(o.view(o.shape[0], -1))
 
-    return O.Anat_PET_CNN(dict(fus), model_mri=O.Anat_CNN(dict(enc)), pet_trunk=Trunk(O.PET_CNN_ResNet(dict(enc))))
+    return types.SimpleNamespace(Anat_CNN=O.Anat_CNN, PET_CNN_ResNet=O.PET_CNN_ResNet, Small_PET_CNN=O.Small_PET_CNN,
+                                 Anat_PET_CNN=O.Anat_PET_CNN, ResNet_PET_Trunk=ResNet_PET_Trunk,
+                                 Tabular_MRT_Model=O.Tabular_MRT_Model, PET_TABULAR_CNN=O.PET_TABULAR_CNN,
+                                 All_Modalities_Fusion=O.All_Modalities_Fusion, tab_key="tabular_features")
 
 
-def cpu_reference_step_fn(workload, depth, vol, n_pairs):
+def cpu_reference_step_fn(args, n_samples):
     """The reference's CPU path for the same step: dataloader.py normalisation (fp64 torch.quantile / Normalize),
-    fp32 torch.nn forward, fp64 loss, backward, Adam. Returns (callable, volumes per call, threads)."""
+    fp32 torch.nn forward, fp64 loss, backward, Adam with one group per tensor.  Runs on the first `n_samples` global
+    samples of the workload.  Returns (callable, volumes per call, threads)."""
     import torch
+
+    from multimodal_alzheimer_b200 import workloads as W
     from oracle.normalization import pet_standardize_oracle, quantile_minmax_oracle
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    model = build_oracle(workload, depth)
-    model.train()
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
-    data = synth_inputs(n_pairs, vol, torch.device("cpu"), 15, want_pet=(workload != "mri_r18"))
+    w, depth, volume, _, _ = resolve(args, 1)
+    ns = oracle_namespace()
+    model = W.build_model(ns, args.workload, depth=depth)
+    opt = torch.optim.Adam(W.per_tensor_groups(model), weight_decay=1e-4)
+    data = W.synth_batch(0, n_samples, volume, w["modalities"])
 
     def step():
-        mri = torch.stack([quantile_minmax_oracle(data["mri_raw"][i].double(), data["mask"][i].double(), 0.98)[0]
-                           for i in range(n_pairs)])
-        batch = {"mri": mri, "label": data["label"]}
-        if workload != "mri_r18":
-            batch["pet1451"] = pet_standardize_oracle(data["pet_raw"].double(), PET_MEAN, PET_STD)
+        batch = {"label": data["label"]}
+        if "mri_raw" in data:
+            batch["mri"] = torch.stack([quantile_minmax_oracle(data["mri_raw"][i].double(), data["mask"][i].double(),
+                                                               0.98)[0] for i in range(n_samples)])
+        if "pet_raw" in data:
+            batch["pet1451"] = pet_standardize_oracle(data["pet_raw"].double(), W.PET_MEAN, W.PET_STD)
+        if "tabular" in data:
+            batch[ns.tab_key] = data["tabular"]
         out = model.general_step(batch, 0, "train")
         opt.zero_grad(set_to_none=True)
         out["loss"].backward()
         opt.step()
         return float(out["loss"].detach())
 
-    vols = n_pairs * (1 if workload == "mri_r18" else 2)
-    return step, vols, threads
+    return step, n_samples * W.volumes_per_sample(args.workload), threads
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    step, vols, threads = cpu_reference_step_fn(args.workload, args.depth, args.volume, args.cpu_sample_pairs)
+    w, depth, volume, gb, scaling = resolve(args, args.gpus)
+    step, vols, threads = cpu_reference_step_fn(args, args.cpu_sample_pairs)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -160,27 +158,18 @@ def run_reference(args, rank):
         step()
     dt = time.perf_counter() - t0
     value = vols * args.steps / dt
-    sample = f"{args.cpu_sample_pairs} sample(s) of the workload per step ({vols} volumes of {args.volume}^3), fwd+loss+bwd+Adam"
+    sample = (f"each step = the first {args.cpu_sample_pairs} sample(s) of the workload's global batch ({vols} volumes of "
+              f"{'x'.join(map(str, volume))}): fp64 quantile normalisation + fp32 fwd + fp64 loss + bwd + per-tensor-group Adam")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus, args.global_batch or (32 if args.workload == "pet_mri_fusion_r18" else 16)),
+        "impl": "reference", "metric": metric_name(args, w, depth, volume), "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, w, depth, volume, args.gpus, gb, step_global_batch=args.cpu_sample_pairs),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "pinning": PORT_PINNING},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, world, global_batch):
-    name = ("PET-MRI two-branch ResNet-%d 3D fusion (feature concat -> MLP head), focal loss gamma=1" % args.depth
-            if args.workload == "pet_mri_fusion_r18" else
-            "ResNet-%d 3D MRI classifier, weighted CE" % args.depth)
-    return {"workload": name + ", per-scan quantile(0.98) MRI normalisation + PET standardisation, fwd+bwd+allreduce+Adam",
-            "global_batch": global_batch, "volume": [args.volume] * 3, "parallelism": f"dp{world}",
-            "l2": "inputs (>=18 MB per pair, 576 MB per step) and activations are larger than the 126 MB L2",
-            "baseline_config": "BASELINE.json configs[2]" if args.workload == "pet_mri_fusion_r18" else "configs[1]"}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -219,15 +208,13 @@ class ClockSampler(threading.Thread):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+
     from multimodal_alzheimer_b200 import _lib, data_parallel as dp
     from multimodal_alzheimer_b200 import kernels as K
-    from multimodal_alzheimer_b200.pkg.models.fusion_models.anat_pet_fusion import Anat_PET_CNN, ResNet_PET_Trunk
-    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
-    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_resnet_cnn import PET_CNN_ResNet
-    from multimodal_alzheimer_b200.pkg.utils import normalization as norm
+    from multimodal_alzheimer_b200 import workloads as W
 
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference)")
     _lib.load()
     rank, local_rank, world = dp.init_from_env()
     if world != args.gpus and world > 1:
@@ -235,47 +222,51 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # never the legacy default stream (CUDA-graph capture)
-    fusion = args.workload == "pet_mri_fusion_r18"
-    global_batch = args.global_batch or (32 if fusion else 16)
+    w, depth, volume, global_batch, scaling = resolve(args, world)
     lo, hi = dp.shard_bounds(global_batch, rank, world)
     n_local = hi - lo
-    vol = args.volume
+    vps = W.volumes_per_sample(args.workload)
+    vols_per_step = global_batch * vps
 
-    enc, fus = hparams_for(args.workload, args.depth)
-    torch.manual_seed(15)
-    if fusion:
-        model = Anat_PET_CNN(dict(fus), model_mri=Anat_CNN(dict(enc)),
-                             pet_trunk=ResNet_PET_Trunk(PET_CNN_ResNet(dict(enc))))
-    else:
-        model = Anat_CNN(dict(enc))
+    model = W.build_model(W.product_namespace(), args.workload, depth=depth)
     model.to(dev).train()
+    opt = model.configure_optimizers()          # the reference's per-tensor groups -> csrc/optimizer.cu
+    opt = opt["optimizer"] if isinstance(opt, dict) else opt
     params = [p for p in model.parameters() if p.requires_grad]
-    from multimodal_alzheimer_b200.optim import Adam  # csrc/optimizer.cu: multi-tensor Adam, 2 launches per 64 tensors
-    opt = Adam(params, lr=1e-4, weight_decay=1e-4)
-    buckets = dp.make_gradient_buckets(params)      # ADNI_OVERLAP_GRADS=1: all-reduce overlapped with backward (opt-in)
+    buckets = dp.make_gradient_buckets(params)
 
-    data = synth_inputs(n_local, vol, dev, 15 + rank, want_pet=fusion)
-    vols_per_step = global_batch * (2 if fusion else 1)
+    host_data = W.synth_batch(lo, n_local, volume, w["modalities"])   # this rank's shard of the fixed global batch
+    data = {k: v.to(dev) for k, v in host_data.items()}
+    probe = torch.linspace(-1.0, 1.0, 3 * global_batch, dtype=torch.float64, device=dev).view(global_batch, 3)[lo:hi]
 
     def step(d):
-        mri = norm.normalize_mri_per_scan_min_max(d["mri_raw"], d["mask"], 0.98, out_dtype=torch.bfloat16)
-        batch = {"mri": mri, "label": d["label"]}
-        if fusion:
-            batch["pet1451"] = norm.normalize_pet(d["pet_raw"], PET_MEAN, PET_STD, out_dtype=torch.bfloat16)
-        out = model.general_step(batch, 0, "train")
+        out = model.general_step(W.normalized_batch_gpu(d), 0, "train")
         out["loss"].backward()
         buckets.all_reduce()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return out["loss"]
+        return out["loss"], out["outputs"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def global_sum(t):
+        t = t.detach().clone()
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t)
+
+    # ---- first step: parity evidence (same weights, same global batch for every N) ------------------------------
+    loss, logits = step(data)
+    parity = {"first_step_loss": float(loss.detach()),
+              "first_step_logits_checksum": global_sum((logits.detach() * probe).sum()),
+              "first_step_logits_abs_sum": global_sum(logits.detach().abs().sum()),
+              "note": "weights seed 15, global samples 0..B-1 generated per index: identical for every --gpus N"}
+
     # ---- eager profiled pass: per-kernel CUDA events for the roofline, launch count, eager step time --------
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 1, 0)):
         step(data)
     barrier()
     prof_steps = max(1, min(args.steps, 3))
@@ -289,7 +280,7 @@ def run_b200(args):
     p0.record()
     host_t0 = time.perf_counter()
     for _ in range(prof_steps):
-        loss = step(data)
+        loss, _ = step(data)
     host_issue_ms = 1e3 * (time.perf_counter() - host_t0) / prof_steps  # CPU time to enqueue one eager step
     p1.record()
     barrier()
@@ -317,6 +308,7 @@ def run_b200(args):
     graphed = None
     if not args.no_graph:
         from multimodal_alzheimer_b200.graphed import GraphedStep
+        torch.cuda.empty_cache()
         graphed = GraphedStep(lambda: step(data), warmup=1)
         if not graphed.captured:
             if rank == 0:
@@ -333,7 +325,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = run_step()
+        loss, _ = run_step()
     e1.record()
     barrier()
     launches = launches_per_step * args.steps
@@ -348,13 +340,15 @@ def run_b200(args):
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H loss, every step ------------------
     e2e = None
     if not args.no_e2e:
-        host = {k: v.cpu().pin_memory() for k, v in data.items()}
+        host = {k: v.pin_memory() for k, v in host_data.items()}
         h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-        loss_host = torch.empty((), dtype=torch.float64).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
+        loss_host = [torch.empty((), dtype=torch.float64).pin_memory() for _ in range(2)]
+        loss_done = [torch.cuda.Event() for _ in range(2)]
+        losses_read = []
 
         def upload(i):
             with torch.cuda.stream(copy_stream):
@@ -364,25 +358,34 @@ def run_b200(args):
                 ready[i % 2].record(copy_stream)
 
         def e2e_run(n):
+            """Step i's inputs cross PCIe while step i-1 computes; the loss of step i-1 is read on the host while step
+            i runs (every step's loss reaches the host inside the timed region, one step behind the launches)."""
             for ev in free:
                 ev.record()
             upload(0)
             for i in range(n):
                 if i + 1 < n:
-                    upload(i + 1)  # next step's inputs cross PCIe while this step computes
+                    upload(i + 1)
                 torch.cuda.current_stream().wait_event(ready[i % 2])
                 if graphed:  # device-to-device hand-over into the graph's fixed input tensors, then one replay
                     for k, v in bufs[i % 2].items():
                         data[k].copy_(v, non_blocking=True)
-                    l = graphed.replay()
+                    free[i % 2].record()
+                    l, _ = graphed.replay()
                 else:
-                    l = step(bufs[i % 2])
-                free[i % 2].record()
-                loss_host.copy_(l.detach(), non_blocking=True)
-                torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+                    l, _ = step(bufs[i % 2])
+                    free[i % 2].record()
+                loss_host[i % 2].copy_(l.detach(), non_blocking=True)
+                loss_done[i % 2].record()
+                if i > 0:
+                    loss_done[(i - 1) % 2].synchronize()
+                    losses_read.append(float(loss_host[(i - 1) % 2]))
+            loss_done[(n - 1) % 2].synchronize()
+            losses_read.append(float(loss_host[(n - 1) % 2]))
 
         e2e_run(2)
         barrier()
+        losses_read.clear()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         e2e_run(args.steps)
@@ -393,21 +396,22 @@ def run_b200(args):
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": vols_per_step * args.steps / (float(ems) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d_bytes * world), "d2h_bytes_per_step": 8 * world,
-               "ms_per_step": float(ems) / args.steps,
+               "ms_per_step": float(ems) / args.steps, "losses_read_on_host": len(losses_read),
                "how": "pinned host raw volumes+masks -> cudaMemcpyAsync (double-buffered on a copy stream) -> "
-                      "general_step/backward/allreduce/Adam -> loss read back to host every step"}
+                      "general_step/backward/allreduce/Adam -> every step's loss copied to pinned host memory and read "
+                      "there while the next step runs"}
 
     if rank != 0:
         return
     peaks = load_peaks()
-    per_vol = conv_flops_per_volume(args.depth, vol)
-    step_flops = per_vol * vols_per_step / world  # per rank
+    step_flops = W.train_flops_per_sample(args.workload, depth, volume) * global_batch / world  # per rank
     empty = {"flops": 0, "executed_flops": 0, "ms": 0.0, "n": 0}
     tc = prof.get("tc_kmajor", empty)
     hl = prof.get("tc_halo", empty)
     wg = prof.get("tc_wgrad", empty)
     st = prof.get("tc_stem", empty)
     dr = prof.get("direct", empty)
+    sc = prof.get("tc_small", empty)
 
     def tf(d, key="flops"):
         return d.get(key, d["flops"]) / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else None
@@ -415,8 +419,8 @@ def run_b200(args):
     # Per-kernel numbers come from the eager pass: every conv launch is bracketed by CUDA events on its stream and
     # the host issues kernels ~2x slower than the GPU retires them, so each kernel runs alone at burst clocks ->
     # the burst figure of MEASURED_PEAKS.json is the denominator.  `achieved` counts ALGORITHMIC FLOPs (DESIGN.md
-    # section 4); taps whose shifted box lies entirely in the zero padding are skipped (31 % of layer4's dilation-4
-    # taps), so the rate the tensor pipe actually executes is `executed`, and that is the one bounded by the peak.
+    # section 4); taps / position boxes that lie entirely in the zero padding are skipped, so the rate the tensor pipe
+    # actually executes is `executed` (from the library's planner, adni_conv3d_plan_info), bounded by the peak.
     peak = peaks["bf16_tflops"]
 
     def fam(d):
@@ -425,21 +429,27 @@ def run_b200(args):
                 "frac_executed": (tf(d, "executed_flops") / peak) if tf(d) else None,
                 "launches_per_step": d["n"] / args.steps, "kernel_ms_per_step": d["ms"] / args.steps}
 
+    dominant = max((tc, hl, wg, st, sc, dr), key=lambda d: d["ms"])
+    dom_name = {id(tc): "igemm_kmajor_kernel (Conv3d fprop + dgrad, tcgen05/TMEM, TMA box loads)",
+                id(hl): "igemm_halo_kernel (layer1/layer2 3x3x3 convs, plane ring in smem)",
+                id(wg): "wgrad2_kernel (Conv3d wgrad, MN-major operands)",
+                id(st): "stem_fprop_plane / stem_wgrad_plane_kernel (tcgen05, 1-channel stem)",
+                id(sc): "small-channel conv kernels (Small_PET_CNN)",
+                id(dr): "direct_conv (CUDA cores)"}[id(dominant)]
     roofline = {
-        "bound": "tensor", "kernel": "igemm_kmajor_kernel (Conv3d fprop + dgrad, tcgen05/TMEM, TMA box loads)",
-        "achieved": tf(tc), "peak": peak, "unit": "TFLOP/s",
-        "frac": (tf(tc) / peak) if tf(tc) else None, "traffic": None,
-        "executed": tf(tc, "executed_flops"), "frac_executed": (tf(tc, "executed_flops") / peak) if tf(tc) else None,
+        "bound": "tensor", "kernel": dom_name,
+        "achieved": tf(dominant), "peak": peak, "unit": "TFLOP/s",
+        "frac": (tf(dominant) / peak) if tf(dominant) else None, "traffic": None,
+        "executed": tf(dominant, "executed_flops"),
+        "frac_executed": (tf(dominant, "executed_flops") / peak) if tf(dominant) else None,
         "peak_source": peaks["source"] + " (burst figure: every kernel is timed alone with CUDA events in the eager pass); "
                        "achieved = algorithmic FLOPs / time, executed = FLOPs actually issued (all-padding taps skipped)",
-        "launches_per_step": tc["n"] / args.steps, "kernel_ms_per_step": tc["ms"] / args.steps,
+        "launches_per_step": dominant["n"] / args.steps, "kernel_ms_per_step": dominant["ms"] / args.steps,
         "timed_in": "eager profiled pass of the same step (CUDA events around every conv launch)",
-        "algorithmic_flops_per_step": tc["flops"] / args.steps,
-        "other_kernels": {
-            "igemm_halo_kernel (layer1/layer2 3x3x3 convs, plane ring in smem)": fam(hl),
-            "wgrad2_kernel (Conv3d wgrad, MN-major operands)": fam(wg),
-            "stem_fprop_plane/stem_wgrad_plane_kernel (tcgen05, 1-channel stem)": fam(st),
-            "direct_conv (CUDA cores)": fam(dr),
+        "algorithmic_flops_per_step": dominant["flops"] / args.steps,
+        "kernels": {
+            "igemm_kmajor_kernel": fam(tc), "igemm_halo_kernel": fam(hl), "wgrad2_kernel": fam(wg),
+            "stem_plane_kernels": fam(st), "small_channel_conv": fam(sc), "direct_conv (CUDA cores)": fam(dr),
         },
         "whole_step_tensor_frac": step_flops / (ms_total / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
         "whole_step_peak": peaks["bf16_tflops_sustained"],
@@ -454,15 +464,11 @@ def run_b200(args):
                   "launches_per_step": d["n"] / args.steps, "kernel_ms_per_step": d["ms"] / args.steps}
         for tag, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if tag.startswith("hbm_")}
     roofline["hbm_peak_gbs"] = hbm_peak
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if fusion and vol == 128 and args.depth == 18 and world == 1 and os.path.exists(tpath):
-        with open(tpath) as f:  # DRAM bytes per launch of this kernel on this workload, from the committed ncu capture
-            tr = json.load(f)
-        roofline["traffic"] = tr.get("dram_bytes_per_launch")
-        roofline["traffic_source"] = tr.get("source")
+    roofline["traffic_note"] = ("dram bytes per launch are a profiler quantity (ncu --set full) and are not measured inside "
+                                "this run: see profiles/r02_traffic.json for the committed capture of this workload")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cstep, cvols, threads = cpu_reference_step_fn(args.workload, args.depth, vol, args.cpu_sample_pairs)
+        cstep, cvols, threads = cpu_reference_step_fn(args, args.cpu_sample_pairs)
         cstep()
         best = None
         for _ in range(2):
@@ -471,15 +477,18 @@ def run_b200(args):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         cpu = {"value": cvols / best, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_sample_pairs} (MRI,PET) sample(s) of the same workload ({cvols} volumes {vol}^3): "
-                         f"fp64 torch.quantile normalisation + fp32 fwd + fp64 loss + bwd + Adam, best of 2 after 1 warm-up",
+               "sample": f"the first {args.cpu_sample_pairs} sample(s) of the same global batch ({cvols} volumes "
+                         f"{'x'.join(map(str, volume))}): fp64 torch.quantile normalisation + fp32 fwd + fp64 loss + bwd + "
+                         f"Adam, best of 2 after 1 warm-up",
                "pinning": PORT_PINNING}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world, global_batch),
+        "metric": metric_name(args, w, depth, volume), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, w, depth, volume, world, global_batch),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "loss": loss_val, "launch_mode": "cuda_graph" if graphed else "eager",
+        "parity": parity, "loss": loss_val, "launch_mode": "cuda_graph" if graphed else "eager",
+        "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "eager": {"ms_per_step": eager_ms, "host_issue_ms_per_step": host_issue_ms,
                   "note": "same step launched kernel by kernel from Python with the two encoder branches serialised "
                           "(the pass the per-kernel roofline events come from)"},

@@ -175,6 +175,15 @@ int adni_bn_eval_params(const float* running_mean, const float* running_var, con
 int adni_relu_fwd(const adni_bf16* x, adni_bf16* y, long long n, void* stream);
 int adni_relu_bwd(const adni_bf16* dy, const adni_bf16* y, adni_bf16* dx, long long n, void* stream);
 
+/* Training-mode nn.Dropout(p) (pet_cnn.py:26-27,38-40; early_fusion.py:42-43; anat_pet_featuremapfusion.py:50-51):
+ * y[i] = keep(i) ? x[i] / (1 - p) : 0 with keep(i) a pure function of (seed, *offset_dev, i) through Philox4x32-10
+ * (uniform u in [0,1) from 24 bits, keep iff u >= p).  The mask is not stored: the backward pass calls the same
+ * function on dy with the same (seed, offset).  `offset_dev` is a DEVICE int64 (the host wrapper increments it after
+ * every forward), so a captured CUDA graph draws a new mask on every replay.  x, y: bf16 (is_f32 = 0, 16-byte
+ * aligned) or fp32 (is_f32 = 1) tensors of n elements in any layout (the operation is elementwise). */
+int adni_dropout(const void* x, void* y, long long n, int is_f32, double p, unsigned long long seed,
+                 const long long* offset_dev, void* stream);
+
 /* Per-channel fp64 sum / sum of squares of a bf16 rows x C tensor (added into sum/sqsum). */
 int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, double* sqsum, void* stream);
 
@@ -330,11 +339,15 @@ int adni_crop_volume_high(const adni_bf16* x_padded, int N, int D, int H, int W,
  *   g' = g + wd p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
  *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps).
  * Tensors travel by value in the kernel parameters, adni_adam_max_tensors_per_launch() per launch (graph-capturable:
- * no host-side state, no device-side table).  Entries with numel 0 are skipped. */
+ * no host-side state).  hyper_dev, if non-null, is a DEVICE fp32 table [2][n_tensors] (row 0 learning rates, row 1
+ * weight decays) that overrides lr[] / weight_decay[] and is read when the kernel RUNS: a captured CUDA graph then
+ * follows ReduceLROnPlateau (anat_cnn.py:131-135) through whatever the host last uploaded into the table.
+ * Entries with numel 0 are skipped. */
 int adni_adam_max_tensors_per_launch(void);
 int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                          void* const* exp_avg_sq, void* const* steps, const long long* numel, const float* lr,
-                         const float* weight_decay, double beta1, double beta2, double eps, void* stream);
+                         const float* weight_decay, const float* hyper_dev, double beta1, double beta2, double eps,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: one-shot all-reduce (sum) of a small fp64 vector over NVLink peer memory - the synchronised-BatchNorm

@@ -23,6 +23,7 @@ SOURCES = [
     "conv_stem.cu",
     "stem_fused.cu",
     "elementwise.cu",
+    "dropout.cu",
     "head_loss.cu",
     "metrics.cu",
     "normalize.cu",

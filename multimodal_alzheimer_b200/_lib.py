@@ -58,7 +58,7 @@ _SIGNATURES = {
     "adni_crop_volume_high": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adni_bootstrap_metrics": [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "adni_adam_max_tensors_per_launch": [],
-    "adni_adam_step_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _P],
+    "adni_adam_step_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _P],
     "adni_weights_multi_job_bytes": [],
     "adni_weights_to_kernel_layout_multi": [_P, _I, _I, _P],
     "adni_bn_finalize": [_P, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
@@ -84,6 +84,7 @@ _SIGNATURES = {
     "adni_loss_bwd": [_P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "adni_bn_param_grads": [_P, _I, _P, _P, _P],
     "adni_bn_eval_params": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
+    "adni_dropout": [_P, _P, _LL, _I, _D, ctypes.c_ulonglong, _P, _P],
     "adni_relu_fwd": [_P, _P, _LL, _P],
     "adni_relu_f32": [_P, _P, _P, _LL, _P],
     "adni_relu_bwd": [_P, _P, _P, _LL, _P],

@@ -451,6 +451,25 @@ class ReluF32Fn(torch.autograd.Function):
         return K.relu_f32(y, dy.contiguous())
 
 
+class DropoutFn(torch.autograd.Function):
+    """Training-mode nn.Dropout: the mask is regenerated in backward from (seed, the offset value of the forward)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, counter):
+        x = x.contiguous()
+        offset = counter.clone()        # this call's stream position, kept for the backward pass
+        counter += 1                    # next call (and the next CUDA-graph replay) draws a new mask
+        ctx.save_for_backward(offset)
+        ctx.cfg = (p, seed)
+        return K.dropout(x, p, seed, offset)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (offset,) = ctx.saved_tensors
+        p, seed = ctx.cfg
+        return K.dropout(dy.contiguous(), p, seed, offset), None, None, None
+
+
 class MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k, stride, pad):

@@ -15,7 +15,7 @@ namespace adni {
 extern void count_launch();
 namespace {
 
-constexpr int kAdamMaxTensors = 64;   // per launch: 64 x 56 B + 66 x 4 B = 3.8 KB of kernel parameters (limit 4 KB)
+constexpr int kAdamMaxTensors = 60;   // per launch: 60 x 58 B + 62 x 4 B + 16 B = 3.7 KB of kernel parameters (limit 4 KB)
 constexpr int kAdamThreads = 256;
 constexpr int kAdamChunk = kAdamThreads * 4 * 8;  // elements per block: 8 float4 per thread
 
@@ -30,6 +30,12 @@ struct AdamBatch {
   float wd[kAdamMaxTensors];
   int chunk_begin[kAdamMaxTensors + 1];  // first block of tensor i; [count] = total blocks
   int count;
+  // optional device-side hyper-parameter table fp32 [2][hyper_n] (row 0 lr, row 1 weight decay), entry hyper_index[i]
+  // for tensor i: read at run time, so a CUDA graph replays with the learning rate the host last uploaded
+  // (ReduceLROnPlateau, anat_cnn.py:131-135).  Null -> the by-value lr / wd above.
+  const float* hyper;
+  int hyper_n;
+  short hyper_index[kAdamMaxTensors];
 };
 
 struct AdamScalars {
@@ -65,14 +71,15 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const __grid_c
   const float* __restrict__ g = tb.g[i];
   float* __restrict__ m = tb.m[i];
   float* __restrict__ v = tb.v[i];
-  const float wd = tb.wd[i];
+  const float wd = tb.hyper ? __ldg(tb.hyper + tb.hyper_n + tb.hyper_index[i]) : tb.wd[i];
 
   __shared__ float sh[2];
   if (threadIdx.x == 0) {
     // the step counter is bumped by adam_bump_kernel AFTER every block of this launch has read it (stream order)
     const double t = (double)__ldg(tb.step[i]) + 1.0;
     const double bc1 = 1.0 - pow(s.beta1, t), bc2 = 1.0 - pow(s.beta2, t);
-    sh[0] = (float)((double)tb.lr[i] / bc1);
+    const float lr = tb.hyper ? __ldg(tb.hyper + tb.hyper_index[i]) : tb.lr[i];
+    sh[0] = (float)((double)lr / bc1);
     sh[1] = (float)sqrt(bc2);
   }
   __syncthreads();
@@ -125,10 +132,12 @@ int adni_adam_max_tensors_per_launch(void) { return kAdamMaxTensors; }
 
 int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                          void* const* exp_avg_sq, void* const* steps, const long long* numel, const float* lr,
-                         const float* weight_decay, double beta1, double beta2, double eps, void* stream) {
+                         const float* weight_decay, const float* hyper_dev, double beta1, double beta2, double eps,
+                         void* stream) {
   ADNI_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && steps && numel && lr &&
                                                      weight_decay)),
                ADNI_EINVAL, "adam_step_multi: null table");
+  ADNI_REQUIRE(hyper_dev == nullptr || n_tensors <= 32767, ADNI_ENOTSUP, "adam_step_multi: device hyper table holds <= 32767 tensors");
   ADNI_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, ADNI_EINVAL,
                "adam_step_multi: betas must lie in [0, 1) and eps must be >= 0 (torch.optim.Adam raises ValueError)");
   AdamScalars s;
@@ -157,6 +166,7 @@ int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* 
       tb.n[cnt] = numel[j];
       tb.lr[cnt] = lr[j];
       tb.wd[cnt] = weight_decay[j];
+      tb.hyper_index[cnt] = static_cast<short>(j);
       tb.chunk_begin[cnt] = blocks;
       blocks += (int)chunks;
       cnt++;
@@ -164,6 +174,8 @@ int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* 
     if (cnt == 0) continue;
     tb.chunk_begin[cnt] = blocks;
     tb.count = cnt;
+    tb.hyper = hyper_dev;
+    tb.hyper_n = n_tensors;
     adam_multi_kernel<<<blocks, kAdamThreads, 0, st>>>(tb, s);
     count_launch();
     ADNI_LAUNCH_CHECK("adam_multi_kernel");

@@ -108,9 +108,10 @@ int parse_header(const unsigned char* h, const char* path, adni_nifti_info* info
   for (int i = 0; i < nd; i++) {
     if (dim[i + 1] < 0) return fail(ADNI_STAGE_ENOTSUP, "%s: negative extent", path);
     info->dim[i] = dim[i + 1];
-    nvox *= dim[i + 1];
+    // checked product: seven int16 extents can reach 2^105, and a wrapped value could pass the bound below
+    if (__builtin_mul_overflow(nvox, static_cast<int64_t>(dim[i + 1]), &nvox) || nvox > (int64_t(1) << 40))
+      return fail(ADNI_STAGE_ENOTSUP, "%s: implausible voxel count", path);
   }
-  if (nvox < 0 || nvox > (int64_t(1) << 40)) return fail(ADNI_STAGE_ENOTSUP, "%s: implausible voxel count", path);
   info->ndim = nd;
   info->nvox = nvox;
   info->datatype = rd<int16_t>(h + 70, swap);
@@ -293,36 +294,54 @@ int adni_stage_volumes(const char* const* paths, int n, int kind, void* dst, int
   if (stride_bytes < expect_nvox * elem) return fail(ADNI_STAGE_EINVAL, "stage_volumes: stride smaller than one volume");
   if (threads < 1) threads = 1;
   if (threads > n) threads = n > 0 ? n : 1;
-  std::vector<int> codes(static_cast<size_t>(n), 0);
-  std::vector<std::string> errs(static_cast<size_t>(n));
-  std::atomic<int> next(0);
-  auto work = [&]() {
-    for (;;) {
-      const int i = next.fetch_add(1);
-      if (i >= n) break;
-      if (!paths[i]) continue;
-      adni_nifti_info info;
-      char* slot = static_cast<char*>(dst) + static_cast<int64_t>(i) * stride_bytes;
-      int rc = kind == 0 ? read_volume<float>(paths[i], reinterpret_cast<float*>(slot), expect_nvox, &info, false)
-                         : read_volume<uint8_t>(paths[i], reinterpret_cast<uint8_t*>(slot), expect_nvox, &info, true);
-      if (rc == 0 && info.nvox != expect_nvox)
-        rc = fail(ADNI_STAGE_EINVAL, "%s: %lld voxels, the batch expects %lld", paths[i], static_cast<long long>(info.nvox),
-                  static_cast<long long>(expect_nvox));
-      codes[static_cast<size_t>(i)] = rc;
-      if (rc) errs[static_cast<size_t>(i)] = g_err;  // g_err is thread-local: carry it to the caller's thread
-    }
-  };
+  // Nothing may cross the C ABI: allocation of the status vectors, thread creation (std::system_error) and the
+  // error-string copies are all inside the try block; threads that did start are always joined.
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; t++) pool.emplace_back(work);
-  work();
-  for (auto& th : pool) th.join();
   int first = 0;
-  for (int i = 0; i < n; i++) {
-    if (status) status[i] = codes[static_cast<size_t>(i)];
-    if (!first && codes[static_cast<size_t>(i)]) {
-      first = codes[static_cast<size_t>(i)];
-      g_err = errs[static_cast<size_t>(i)];
+  try {
+    std::vector<int> codes(static_cast<size_t>(n), 0);
+    std::vector<std::string> errs(static_cast<size_t>(n));
+    std::atomic<int> next(0);
+    auto work = [&]() {
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        if (!paths[i]) continue;
+        int rc;
+        try {
+          adni_nifti_info info;
+          char* slot = static_cast<char*>(dst) + static_cast<int64_t>(i) * stride_bytes;
+          rc = kind == 0 ? read_volume<float>(paths[i], reinterpret_cast<float*>(slot), expect_nvox, &info, false)
+                         : read_volume<uint8_t>(paths[i], reinterpret_cast<uint8_t*>(slot), expect_nvox, &info, true);
+          if (rc == 0 && info.nvox != expect_nvox)
+            rc = fail(ADNI_STAGE_EINVAL, "%s: %lld voxels, the batch expects %lld", paths[i],
+                      static_cast<long long>(info.nvox), static_cast<long long>(expect_nvox));
+          if (rc) errs[static_cast<size_t>(i)] = g_err;  // g_err is thread-local: carry it to the caller's thread
+        } catch (...) {
+          rc = ADNI_STAGE_EIO;  // (the string copy above may itself have thrown: keep the code, drop the text)
+        }
+        codes[static_cast<size_t>(i)] = rc;
+      }
+    };
+    try {
+      for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    } catch (...) {
+      // could not start every helper: the ones running plus this thread still drain the queue
     }
+    work();
+    for (auto& th : pool) th.join();
+    pool.clear();
+    for (int i = 0; i < n; i++) {
+      if (status) status[i] = codes[static_cast<size_t>(i)];
+      if (!first && codes[static_cast<size_t>(i)]) {
+        first = codes[static_cast<size_t>(i)];
+        if (!errs[static_cast<size_t>(i)].empty()) g_err = errs[static_cast<size_t>(i)];
+      }
+    }
+  } catch (...) {
+    for (auto& th : pool)
+      if (th.joinable()) th.join();
+    return fail(ADNI_STAGE_EIO, "stage_volumes: out of memory or thread failure");
   }
   return first;
 }

@@ -422,6 +422,20 @@ def relu_f32(x, dy=None):
     return out
 
 
+def dropout(x, p, seed, offset):
+    """y = x * keep / (1 - p); keep = Philox(seed, *offset, index) >= p.  x: bf16 or fp32, any shape (contiguous);
+    offset: one-element int64 DEVICE tensor.  The backward pass is the same call on the gradient."""
+    if x.dtype not in (BF16, torch.float32):
+        raise ValueError(f"dropout: unsupported dtype {x.dtype}")
+    if not x.is_contiguous():
+        raise ValueError("dropout: tensor must be contiguous")
+    _chk(offset, torch.int64, "offset")
+    y = torch.empty_like(x)
+    call_hbm("hbm_dropout", 2 * x.numel() * x.element_size(), "adni_dropout", ptr(x), ptr(y), x.numel(),
+             int(x.dtype == torch.float32), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(offset), stream_ptr())
+    return y
+
+
 def channel_stats(x2d):
     """bf16 [rows, C] -> fp64 [2, C] (sum, sum of squares)."""
     _chk(x2d, BF16, "x")

@@ -169,17 +169,37 @@ class Linear(tnn.Module):
 
 
 class Dropout(tnn.Module):
-    """nn.Dropout placeholder: identity in eval mode or for p == 0.  Training-mode dropout (p > 0) needs the
-    reference's RNG stream to be comparable and is not part of the parity configs."""
+    """nn.Dropout(p): identity in eval mode or for p == 0; in training mode a Philox keep-mask scaled by 1/(1-p)
+    (csrc/dropout.cu) that the backward pass regenerates instead of storing.  The random stream is this module's own
+    (seed drawn from torch's global generator at first use, i.e. it follows `torch.manual_seed` /
+    `pl.seed_everything`; a device-side call counter), not torch's CUDA generator: runs are reproducible under a seed,
+    but the masks differ from stock PyTorch's (SURVEY.md App. C.9 - dropout is outside the bit-parity configs)."""
 
-    def __init__(self, p=0.5):
+    def __init__(self, p=0.5, inplace=False):
         super().__init__()
+        if p < 0 or p > 1:
+            raise ValueError(f"dropout probability has to be between 0 and 1, but got {p}")
         self.p = p
+        self._seed = None
+        self._counter = None
 
     def forward(self, x):
-        if self.training and self.p > 0:
-            raise NotImplementedError("training-mode Dropout(p>0) is not implemented on the CUDA path")
-        return x
+        if not self.training or self.p == 0:
+            return x
+        if self.p == 1:
+            return x * 0
+        if self._seed is None:
+            self._seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if self._counter is None or self._counter.device != x.device:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("Dropout: run one eager training step before capturing a CUDA graph")
+            self._counter = torch.zeros(1, dtype=torch.int64, device=x.device)
+        if x.dtype not in (BF16, torch.float32):
+            x = as_volume(x) if x.dim() == 5 else x.to(torch.float32)
+        return A.DropoutFn.apply(x, self.p, self._seed, self._counter)
+
+    def extra_repr(self):
+        return f"p={self.p}"
 
 
 class Sequential(tnn.Sequential):

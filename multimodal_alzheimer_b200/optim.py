@@ -4,8 +4,11 @@
 Every `configure_optimizers` of the reference ends in `torch.optim.Adam(parameters_optim, weight_decay=l2_reg)` with
 ONE param group per tensor (pkg/models/mri_models/anat_cnn.py:111-128, fusion_models/anat_pet_fusion.py:94-118,
 fusion_models/all_modalities_fusion.py:98-128): 60-320 groups, which makes the stock per-tensor optimizer
-launch-bound.  Here the whole model is updated by ceil(n_tensors / 64) launches; learning rate
-and weight decay ride per tensor in the kernel parameters, so `ReduceLROnPlateau` keeps working on `param_groups`.
+launch-bound.  Here the whole model is updated by ceil(n_tensors / 60) launches.  Learning rate and
+weight decay are read by the kernel from a small DEVICE table that every `step()` refreshes from `param_groups` through a
+pinned host buffer (one asynchronous copy): eagerly `ReduceLROnPlateau` just works; under a captured CUDA graph the copy
+is a graph node that re-reads the pinned buffer on every replay, so after a scheduler step call
+`refresh_hyperparameters()` (host only) and the next replay trains with the new rates.
 
 No CPU path: stepping parameters that are not CUDA fp32 tensors raises (north_star: no CPU fallback).
 """
@@ -84,6 +87,9 @@ class Adam(torch.optim.Adam):
                     "g": VP(),
                     "lr": FL(),
                     "wd": FL(),
+                    "hyper_host": torch.empty((2, n), dtype=torch.float32).pin_memory(),
+                    "hyper_dev": torch.empty((2, n), dtype=torch.float32, device=items[0][0].device),
+                    "hyper_np": None,
                     "bytes": 28 * sum(p.numel() for p, _, _ in items),  # 16 B read + 12 B written per parameter
                     "states": states,  # keeps the moment tensors of the table alive
                 }
@@ -91,6 +97,9 @@ class Adam(torch.optim.Adam):
                     self._tables = {}
                 self._tables[tkey] = tab
             grads = []
+            if tab["hyper_np"] is None:
+                tab["hyper_np"] = tab["hyper_host"].numpy()     # shares the pinned memory
+            hyper = tab["hyper_np"]
             for i, (p, lr, wd) in enumerate(items):
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous():
@@ -99,7 +108,25 @@ class Adam(torch.optim.Adam):
                 tab["g"][i] = g.data_ptr()
                 tab["lr"][i] = lr
                 tab["wd"][i] = wd
+                hyper[0, i] = lr
+                hyper[1, i] = wd
+            tab["hyper_dev"].copy_(tab["hyper_host"], non_blocking=True)   # captured: re-read on every graph replay
             K.call_hbm("hbm_adam", tab["bytes"], "adni_adam_step_multi", n, tab["p"], tab["g"], tab["m"], tab["v"],
-                       tab["t"], tab["n"], tab["lr"], tab["wd"], beta1, beta2, eps, _lib.stream_ptr())
+                       tab["t"], tab["n"], tab["lr"], tab["wd"], _lib.ptr(tab["hyper_dev"]), beta1, beta2, eps,
+                       _lib.stream_ptr())
+            for p, _, _ in items:   # the kernel wrote through raw pointers: tell autograd / the weight arena
+                torch.autograd.graph.increment_version(p)
             del grads
         return loss
+
+    def refresh_hyperparameters(self):
+        """Host-only: rewrite the pinned lr / weight-decay tables from `param_groups` (after a scheduler step).  A
+        captured training graph picks the new values up on its next replay; eager `step()` does this itself."""
+        for tkey, tab in self._tables.items():
+            ptrs = {ptr_: i for i, ptr_ in enumerate(tkey[3])}
+            for group in self.param_groups:
+                for p in group["params"]:
+                    i = ptrs.get(p.data_ptr())
+                    if i is not None:
+                        tab["hyper_host"][0, i] = float(group["lr"])
+                        tab["hyper_host"][1, i] = float(group["weight_decay"])

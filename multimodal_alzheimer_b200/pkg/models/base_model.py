@@ -2,10 +2,10 @@
 
 Keeps `__init__(hparams)`, `forward`, `general_step(batch, idx, mode) -> {'loss','outputs','labels'}`,
 `training_step/validation_step/test_step/predict_step`, `configure_optimizers`, `hparams`, `save`.
-The per-step torchmetrics bookkeeping and the confusion-matrix plotting of the reference are logging, not path
-arithmetic and are not reproduced; the numbers `test_epoch_end` reports (F1, MCC, their
-bootstrap intervals, the confusion matrix) come from `test_epoch_metrics` / `bootstrap_metric` below, computed by one
-kernel launch for all resamples.  When pytorch_lightning is importable the class derives from
+`training_/validation_/test_epoch_end` log the reference's keys (`{train,val,test}_loss_epoch`, macro / per-class F1,
+`step`: `val_loss_epoch` is what its ReduceLROnPlateau, EarlyStopping and ModelCheckpoint monitor); instead of per-step
+torchmetrics objects the epoch's F1 / MCC / bootstrap intervals / confusion matrix come from one kernel launch over the
+concatenated step outputs.  Confusion-matrix PLOTS are logging, not path arithmetic.  When pytorch_lightning is importable the class derives from
 pl.LightningModule; otherwise from a small stand-in with the same few methods.
 """
 from abc import ABC, abstractmethod
@@ -109,6 +109,39 @@ class Base_Model(_LightningBase, ABC):
     @abstractmethod
     def configure_optimizers(self):
         pass
+
+    # ------------------------------------------------------------------ epoch-end hooks (base_model.py:91-172)
+    def _epoch_end(self, mode, step_outputs):
+        """`{mode}_loss_epoch` (the key ReduceLROnPlateau / EarlyStopping / ModelCheckpoint monitor,
+        anat_cnn.py:131-135, train_anat_cnn.py:206-211), macro and per-class F1 over the epoch, `step`.  The reference
+        accumulates torchmetrics states step by step; the same totals come from one confusion-matrix kernel launch over
+        the epoch's concatenated outputs.  The confusion-matrix image is logging, not path arithmetic: the matrix is
+        kept as `self.last_confusion_matrix[mode]`."""
+        from ... import kernels as K
+        avg_loss = torch.stack([x["loss"].detach() for x in step_outputs]).mean()
+        y_hat = torch.cat([x["outputs"] for x in step_outputs]).detach().to(torch.float64).contiguous()
+        y = torch.cat([x["labels"] for x in step_outputs]).contiguous()
+        whole = K.bootstrap_metrics(y_hat, y, None, want_confmat=True)
+        log = {f"{mode}_loss_epoch": avg_loss, f"{mode}_f1_epoch": whole["f1"][0],
+               "step": float(getattr(self, "current_epoch", 0))}
+        for i in range(self.hparams["n_classes"]):
+            log[f"{mode}_f1_epoch_class_{i}"] = whole["f1_class"][0, i]
+        self.log_dict(log)
+        if not hasattr(self, "last_confusion_matrix"):
+            self.last_confusion_matrix = {}
+        self.last_confusion_matrix[mode] = whole["confmat"][0].cpu()
+        return log
+
+    def training_epoch_end(self, training_step_outputs):
+        self._epoch_end("train", training_step_outputs)
+
+    def validation_epoch_end(self, validation_step_outputs):
+        self._epoch_end("val", validation_step_outputs)
+
+    def test_epoch_end(self, outputs):
+        log = self.test_epoch_metrics(outputs)
+        self.last_confusion_matrix = dict(getattr(self, "last_confusion_matrix", {}), test=log.pop("confusion_matrix"))
+        self.log_dict(log)
 
     # ------------------------------------------------------------------ test-epoch metrics (SURVEY.md 8(f) N4)
     def bootstrap_metric(self, metric, y_hat, y_labels, n_drawings=1000):

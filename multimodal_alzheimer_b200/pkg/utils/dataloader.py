@@ -248,10 +248,22 @@ class MultiModalDataset(Dataset):
         return out
 
 
+def per_rank_samples(n, world_size, drop_last=False):
+    """Samples every rank sees in one epoch: identical on all ranks, like torch's DistributedSampler (the tail is
+    dropped with drop_last, else the order wraps around to pad it)."""
+    return n // world_size if drop_last else (n + world_size - 1) // world_size
+
+
 def epoch_batches(n, batch_size, shuffle=False, drop_last=False, generator=None, rank=0, world_size=1):
     """Index lists of one epoch: a permutation when shuffling (every rank must pass an identically seeded generator),
-    strided over data-parallel ranks, cut into batches."""
+    strided over data-parallel ranks, cut into batches.  Every rank gets the SAME number of batches of the SAME sizes
+    (each step runs collectives - sync-BN sums, the loss normaliser, the gradient buckets - and the BatchNorm element
+    count is rows x world size): with world_size > 1 the order is padded by wrapping around (DistributedSampler's rule)
+    or, with drop_last, truncated to a multiple of the world size before it is strided."""
     order = torch.randperm(n, generator=generator).tolist() if shuffle else list(range(n))
+    if world_size > 1 and n > 0:
+        total = per_rank_samples(n, world_size, drop_last) * world_size
+        order = order[:total] if total <= n else order + [order[i % n] for i in range(total - n)]
     order = order[rank::world_size]
     out = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
     if drop_last and out and len(out[-1]) < batch_size:
@@ -286,7 +298,7 @@ class StagedLoader:
         return epoch_batches(len(self.ds), self.bs, self.shuffle, self.drop_last, self.generator, self.rank, self.world)
 
     def __len__(self):
-        n = len(range(self.rank, len(self.ds), self.world))      # no permutation drawn: len() must not advance the RNG
+        n = per_rank_samples(len(self.ds), self.world, self.drop_last)   # no permutation drawn: len() must not advance the RNG
         return n // self.bs if self.drop_last else (n + self.bs - 1) // self.bs
 
     def _decode(self, idx, slot, box):

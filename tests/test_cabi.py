@@ -74,10 +74,10 @@ def test_adam_entry_point_validates_before_touching_a_gpu(lib):
     """adni_adam_step_multi: empty table is a no-op, torch.optim.Adam's ValueError cases are ADNI_EINVAL, and the
     optimizer refuses CPU parameters (no CPU fallback)."""
     assert 16 <= lib.adni_adam_max_tensors_per_launch() <= 64
-    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8, None) == 0
-    assert lib.adni_adam_step_multi(1, None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8, None) == -1
-    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, 1.0, 0.999, 1e-8, None) == -1
-    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, 0.9, 0.999, -1.0, None) == -1
+    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8, None) == 0
+    assert lib.adni_adam_step_multi(1, None, None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8, None) == -1
+    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, None, 1.0, 0.999, 1e-8, None) == -1
+    assert lib.adni_adam_step_multi(0, None, None, None, None, None, None, None, None, None, 0.9, 0.999, -1.0, None) == -1
     from multimodal_alzheimer_b200.optim import Adam
     p = torch.nn.Parameter(torch.zeros(4))
     opt = Adam([{"params": p, "lr": 1e-3}], weight_decay=1e-4)

@@ -465,6 +465,47 @@ def test_adam_under_cuda_graph(cuda_dev):
         assert torch.equal(a.detach(), b.detach())
 
 
+def test_adam_graph_follows_lr_schedule_and_bumps_versions(cuda_dev):
+    """lr / weight decay are read from a device table refreshed through a pinned host buffer, so a captured
+    graph trains with the rate ReduceLROnPlateau last set (after `refresh_hyperparameters()`), and every step bumps the
+    parameters' version counters (the weight arena's staleness guard)."""
+    from multimodal_alzheimer_b200.optim import Adam
+    g = torch.Generator().manual_seed(5)
+    init = [torch.randn(s, generator=g) for s in [(700,), (33, 5)]]
+    grads = [torch.randn(t.shape, generator=g).to(cuda_dev) for t in init]
+
+    def make():
+        ps = [torch.nn.Parameter(t.to(cuda_dev)) for t in init]
+        for p, gr in zip(ps, grads):
+            p.grad = gr.clone()
+        return ps, Adam([{"params": ps[0], "lr": 1e-2}, {"params": ps[1], "lr": 1e-3}], weight_decay=1e-2)
+
+    gp, gopt = make()
+    ep, eopt = make()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        v0 = gp[0]._version
+        gopt.step()
+        assert gp[0]._version > v0
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg, stream=s):
+            gopt.step()
+        cg.replay()
+        for group in gopt.param_groups:          # what ReduceLROnPlateau(factor=0.1) does
+            group["lr"] *= 0.1
+        gopt.refresh_hyperparameters()
+        cg.replay()
+        cg.replay()
+    for k in range(4):
+        if k == 2:
+            for group in eopt.param_groups:
+                group["lr"] *= 0.1
+        eopt.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ep, gp):
+        assert torch.equal(a.detach(), b.detach())
+
+
 def test_fusion_ops_bit_exact(cuda_dev):
     """csrc/fusion_ops.cu against torch on the same bf16 values: multi-channel input cast (early_fusion.py:84-88),
     maxout with torch.max's first-index tie rule and its gradient routing (anat_pet_featuremapfusion.py:121-123),
@@ -587,3 +628,19 @@ def test_bootstrap_metric_method_follows_reference_draws(cuda_dev):
     assert abs(float(log["test_loss_epoch"]) - 0.6) < 1e-12 and int(log["confusion_matrix"].sum()) == 90
     assert {"test_f1_epoch", "test_f1_epoch_class_2", "test_f1_epoch_boot", "test_f1_epoch_ci", "test_mcc_epoch_boot",
             "test_mcc_epoch_ci"} <= set(log)
+    # epoch-end hooks (base_model.py:91-133): the keys ReduceLROnPlateau / EarlyStopping / ModelCheckpoint monitor
+    from oracle.metrics import confusion_matrix, f1_from_confmat
+    model.validation_epoch_end(outs)
+    model.training_epoch_end(outs)
+    cm = confusion_matrix(y_hat, y, 3)
+    macro, per = f1_from_confmat(cm)
+    for mode in ("val", "train"):
+        assert abs(float(model.logged[f"{mode}_loss_epoch"]) - 0.6) < 1e-12
+        assert abs(float(model.logged[f"{mode}_f1_epoch"]) - float(macro)) <= 1e-6
+        for i in range(3):
+            assert abs(float(model.logged[f"{mode}_f1_epoch_class_{i}"]) - float(per[i])) <= 1e-6
+        assert torch.equal(model.last_confusion_matrix[mode], cm)
+    torch.manual_seed(1)
+    model.test_epoch_end(outs)
+    assert abs(float(model.logged["test_f1_epoch"]) - float(macro)) <= 1e-6 and "test_mcc_epoch_ci" in model.logged
+    assert torch.equal(model.last_confusion_matrix["test"], cm)

@@ -200,3 +200,17 @@ def test_metric_restatement_agrees_with_sklearn():
     macro, per = f1_from_confmat(cm)
     assert per[2] == 0 and abs(float(macro) - float(per[:2].mean())) < 1e-7
     assert float(mcc_from_confmat(torch.tensor([[4, 0], [3, 0]]))) == 0.0   # zero denominator -> 0
+
+
+def test_dropout_oracle_philox_known_answers():
+    """Philox4x32-10 of oracle/dropout.py against the Random123 known-answer vectors (kat_vectors: philox4x32 10)."""
+    from oracle.dropout import keep_mask, philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in philox4x32_10(*ctr, *key)) == want
+    m = keep_mask(200000, 0.25, seed=99, offset=3)
+    assert abs(m.mean() - 0.75) < 4 * (0.25 * 0.75 / 200000) ** 0.5
+    assert not (keep_mask(4096, 0.25, 99, 3) == keep_mask(4096, 0.25, 99, 4)).all()

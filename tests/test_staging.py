@@ -127,6 +127,20 @@ def test_reader_errors(tmp_path):
         S.read_volume(m, torch.uint8)
     N.write_nifti(m, np.array([[[0, 1, 1]]], dtype=np.float32))
     assert S.read_volume(m, torch.uint8).flatten().tolist() == [0, 1, 1]
+    # a crafted header whose 7 extents multiply past 2^63 (32767^7 ~ 2^105) must be rejected, not wrapped into a
+    # small positive voxel count that passes the capacity check
+    import struct
+    raw = bytearray((tmp_path / "v.nii.gz").read_bytes())
+    import gzip
+    hdr = bytearray(gzip.decompress(bytes(raw)))
+    for dims in ([7] + [32767] * 7, [7, 32767, 32767, 32767, 32767, 2, 2, 2], [4, 16384, 16384, 16384, 8, 1, 1, 1]):
+        hdr[40:56] = struct.pack("<8h", *dims)
+        ov = tmp_path / "overflow.nii"
+        ov.write_bytes(bytes(hdr))
+        with pytest.raises(S.StagingError):
+            S.read_info(str(ov))
+        with pytest.raises((S.StagingError, ValueError)):
+            S.read_volume(str(ov), out=torch.empty(64))
 
 
 def test_parallel_batch_decode(tmp_path):
@@ -266,7 +280,15 @@ def test_epoch_batches_cover_the_dataset_once_across_ranks():
     for rank in range(3):
         g = torch.Generator().manual_seed(15)
         seen += [i for b in epoch_batches(11, 2, shuffle=True, generator=g, rank=rank, world_size=3) for i in b]
-    assert sorted(seen) == list(range(11))
+    assert sorted(set(seen)) == list(range(11)) and len(seen) == 12     # padded by wrapping, like DistributedSampler
+    # every rank must run the same number of steps with the same batch sizes: each step has collectives
+    for n, world, bs in ((119, 2, 10), (119, 2, 7), (10, 4, 3), (5, 8, 2), (64, 8, 4)):
+        for drop_last in (False, True):
+            shapes = [[len(b) for b in epoch_batches(n, bs, drop_last=drop_last, rank=r, world_size=world)]
+                      for r in range(world)]
+            assert all(s == shapes[0] for s in shapes), (n, world, bs, drop_last, shapes)
+            per = (n // world) if drop_last else -(-n // world)
+            assert len(shapes[0]) == (per // bs if drop_last else -(-per // bs))
     with pytest.raises(RuntimeError):                 # normalisation runs on the GPU: no CPU fallback
         StagedLoader(None, 2, device="cpu")
 
