@@ -487,7 +487,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, w, depth, volume, world, global_batch),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "parity": parity, "loss": loss_val, "launch_mode": "cuda_graph" if graphed else "eager",
+        "parity": parity, "loss": loss_val, "sync_bn_exchange": dp.exchange_status()["mode"],
+        "gradient_exchange": type(buckets).__name__, "launch_mode": "cuda_graph" if graphed else "eager",
         "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "eager": {"ms_per_step": eager_ms, "host_issue_ms_per_step": host_issue_ms,
                   "note": "same step launched kernel by kernel from Python with the two encoder branches serialised "

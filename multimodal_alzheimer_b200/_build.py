@@ -14,7 +14,6 @@ LIB = os.path.join(CSRC, "libadni_b200.so")
 SOURCES = [
     "runtime.cu",
     "conv_igemm_kernels.cu",
-    "conv_igemm_2cta.cu",
     "conv_halo.cu",
     "conv_wgrad2.cu",
     "conv_wgrad_halo.cu",

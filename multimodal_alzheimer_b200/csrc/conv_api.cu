@@ -14,9 +14,6 @@
 namespace adni {
 
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
-// conv_igemm_2cta.cu: experimental CTA-pair (cta_group::2) engine for N = 256 tiles, opt-in (ADNI_IGEMM_2CTA=1)
-int launch_igemm_2cta(const IgemmParams& p, cudaStream_t stream);
-int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
 int wgrad2_box_rows(int mt_cfg);
 bool wgrad_halo_supported(const adni_conv3d_geom& g);
@@ -142,17 +139,6 @@ bool tc_supported(const adni_conv3d_geom& g) {
 
 int pick_block_n(int n_total) { return n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64); }
 
-// CTA-pair engine (conv_igemm_2cta.cu): OFF unless ADNI_IGEMM_2CTA=1.  Needs the N = 256 tile and an even number of
-// samples (two boxes per cluster); decided before the weight tensor map is encoded because its box is (64, 128) there.
-bool use_igemm_2cta(int block_n, int N, int Do, int Ho, int Wo, int bd, int bh, int bw) {
-  static const bool enabled = [] {
-    const char* e = getenv("ADNI_IGEMM_2CTA");
-    return e && atoi(e) != 0;
-  }();
-  if (!enabled || block_n != 256 || num_sms() < 2) return false;
-  return N >= 2 && N % 2 == 0;  // a pair = the same spatial box of two consecutive samples (identical tap masks)
-}
-
 // ---------------------------------------------------------------------------------------------
 // Halo-resident engine (conv_halo.cu): 3x3x3 / stride 1 / dilation 1 / pad 1, Cin == Cout in {64, 128}.
 int env_int(const char* name, int dflt) {
@@ -239,11 +225,10 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   }
   const int taps = g.k * g.k * g.k;
   const int block_n = pick_block_n(g.Cout);
-  const bool two_cta = use_igemm_2cta(block_n, g.N, Do, Ho, Wo, b.bd, b.bh, b.bw);
   {
     const uint64_t dims[2] = {uint64_t(taps) * g.Cin, uint64_t(g.Cout)};
     const uint64_t strides[2] = {1, uint64_t(taps) * g.Cin};
-    const uint32_t box[2] = {64, uint32_t(two_cta ? 128 : block_n)};
+    const uint32_t box[2] = {64, uint32_t(block_n)};
     int rc = make_tmap_bf16(&p.b_map, w_oti, 2, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -285,7 +270,6 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     const char* dbg = getenv("ADNI_DEBUG_MODE");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  if (two_cta) return launch_igemm_2cta(p, stream);
   return launch_igemm(p, block_n, stream);
 }
 
@@ -345,11 +329,10 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
         p.a_ext[0][0] = Do;
         p.a_ext[0][1] = Ho;
         p.a_ext[0][2] = Wo;
-        const bool two_cta = use_igemm_2cta(block_n, g.N, ov.D, ov.H, ov.W, b.bd, b.bh, b.bw);
         {
           const uint64_t dims[2] = {uint64_t(taps) * g.Cout, uint64_t(g.Cin)};
           const uint64_t strides[2] = {1, uint64_t(taps) * g.Cout};
-          const uint32_t box[2] = {64, uint32_t(two_cta ? 128 : block_n)};
+          const uint32_t box[2] = {64, uint32_t(block_n)};
           rc = make_tmap_bf16(&p.b_map, w_ito, 2, dims, strides, box, true);
           if (rc) return rc;
         }
@@ -384,7 +367,7 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
         p.out_sw = ov.sw;
         p.out = const_cast<__nv_bfloat16*>(ov.base);
         p.addend = addend ? adds[cls].base : nullptr;
-        rc = two_cta ? launch_igemm_2cta(p, stream) : launch_igemm(p, block_n, stream);
+        rc = launch_igemm(p, block_n, stream);
         if (rc) return rc;
       }
   return ADNI_OK;

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM implicit-GEMM Conv3d kernels (fprop, dgrad, wgrad) fed by TMA box loads.
+// tcgen05 / TMEM implicit-GEMM Conv3d kernels (fprop, dgrad; wgrad lives in conv_wgrad2.cu) fed by TMA box loads.
 //
 // Replaces the cuDNN Conv3d forward/backward dispatched by MedicalNet's ResNet (SURVEY.md K1-K3;
 // reference call sites pkg/models/mri_models/anat_cnn.py:18-31,95).
@@ -308,301 +308,6 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 }
 
 // =================================================================================================
-// wgrad:  dW[Cout][K_total] += sum over positions  dY[pos][Cout]^T * X[pos + tap][Cin]
-// Both operands are stored channel-contiguous, i.e. MN-major for this GEMM: the same TMA boxes as above
-// (64 positions x 64 channels, 128-B swizzle) are consumed through MN-major UMMA descriptors
-// (LBO = distance between 64-channel groups, SBO = 1024 between 8-position groups).
-// =================================================================================================
-template <int GROUPS, int STAGES>
-struct WgradCfg {
-  static constexpr int BLOCK_N = GROUPS * 64;
-  static constexpr int BOX_BYTES = 64 * 128;
-  static constexpr int A_BYTES = 2 * BOX_BYTES;
-  static constexpr int B_BYTES = GROUPS * BOX_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
-};
-
-struct WItem {
-  int mt, nt, ks;
-};
-__device__ __forceinline__ WItem decode_item(const WgradParams& p, int item) {
-  WItem w;
-  w.nt = item % p.n_tiles;
-  const int r = item / p.n_tiles;
-  w.mt = r % p.m_tiles;
-  w.ks = r / p.m_tiles;
-  return w;
-}
-struct PosBox {
-  int n, d0, h0, w0;
-};
-__device__ __forceinline__ PosBox decode_box(const WgradParams& p, int b) {
-  PosBox c;
-  const int tw = b % p.tiles_w;
-  b /= p.tiles_w;
-  const int th = b % p.tiles_h;
-  b /= p.tiles_h;
-  const int td = b % p.tiles_d;
-  c.n = b / p.tiles_d;
-  c.d0 = td * p.bd;
-  c.h0 = th * p.bh;
-  c.w0 = tw * p.bw;
-  return c;
-}
-
-// Per-item constants: the (tensor map, box offset, channel slice) of each 64-column group of the output tile,
-// resolved once per item so that the per-K-block loops contain no divisions.
-template <int GROUPS>
-struct WItemCtx {
-  int map[GROUPS], dd[GROUPS], dh[GROUPS], dw[GROUPS], c0[GROUPS];
-  int ng;
-  int b_begin, b_end;
-  int mt, g0;
-};
-template <int GROUPS>
-__device__ __forceinline__ WItemCtx<GROUPS> make_item_ctx(const WgradParams& p, int item) {
-  WItemCtx<GROUPS> x;
-  const WItem it = decode_item(p, item);
-  x.mt = it.mt;
-  x.g0 = it.nt * GROUPS;
-  x.ng = min(GROUPS, p.n_groups - x.g0);
-  x.b_begin = it.ks * p.boxes_per_split;
-  x.b_end = min(x.b_begin + p.boxes_per_split, p.pos_boxes);
-#pragma unroll
-  for (int g = 0; g < GROUPS; g++) {
-    const int gg = min(x.g0 + g, p.n_groups - 1);
-    const int t = gg / p.cin_blocks;
-    const ConvTap tap = p.taps[t];
-    x.map[g] = tap.map;
-    x.dd[g] = tap.dd;
-    x.dh[g] = tap.dh;
-    x.dw[g] = tap.dw;
-    x.c0[g] = (gg - t * p.cin_blocks) * 64;
-  }
-  return x;
-}
-// Position-box iterator without div/mod in the loop.
-struct BoxIter {
-  int n, td, th, tw;
-  __device__ __forceinline__ void init(const WgradParams& p, int b) {
-    tw = b % p.tiles_w;
-    b /= p.tiles_w;
-    th = b % p.tiles_h;
-    b /= p.tiles_h;
-    td = b % p.tiles_d;
-    n = b / p.tiles_d;
-  }
-  __device__ __forceinline__ void next(const WgradParams& p) {
-    if (++tw == p.tiles_w) {
-      tw = 0;
-      if (++th == p.tiles_h) {
-        th = 0;
-        if (++td == p.tiles_d) {
-          td = 0;
-          ++n;
-        }
-      }
-    }
-  }
-};
-template <int GROUPS>
-__device__ __forceinline__ bool wgrad_box_active(const WgradParams& p, const WItemCtx<GROUPS>& x, int d0, int h0,
-                                                 int w0) {
-  bool any = false;
-#pragma unroll
-  for (int g = 0; g < GROUPS; g++)
-    any |= (g < x.ng) &&
-           box_in_range(p.x_ext[x.map[g]], d0 + x.dd[g], h0 + x.dh[g], w0 + x.dw[g], p.bd, p.bh, p.bw);
-  return any;
-}
-
-template <int GROUPS, int STAGES>
-__global__ void __launch_bounds__(kIgemmThreads, 1) wgrad_mnmajor_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = WgradCfg<GROUPS, STAGES>;
-  constexpr int BLOCK_N = Cfg::BLOCK_N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_items = p.m_tiles * p.n_tiles * p.splits;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; i++) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer: the whole warp walks the loop, lane l issues box l =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.dy_map);
-      tma_prefetch_desc(&p.x_maps[0]);
-    }
-    int st = 0;
-    uint32_t ph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
-      const uint32_t tx_bytes = static_cast<uint32_t>(2 + x.ng) * Cfg::BOX_BYTES;
-      // this lane's box: lanes 0,1 = dY channel halves, lanes 2.. = X groups
-      const int g = lane - 2;
-      int my_map = 0, my_dd = 0, my_dh = 0, my_dw = 0, my_c0 = 0;
-#pragma unroll
-      for (int gi = 0; gi < GROUPS; gi++)
-        if (g == gi) {
-          my_map = x.map[gi];
-          my_dd = x.dd[gi];
-          my_dh = x.dh[gi];
-          my_dw = x.dw[gi];
-          my_c0 = x.c0[gi];
-        }
-      BoxIter bi;
-      bi.init(p, x.b_begin);
-      for (int b = x.b_begin; b < x.b_end; b++, bi.next(p)) {
-        const int d0 = bi.td * p.bd, h0 = bi.th * p.bh, w0 = bi.tw * p.bw;
-        if (!wgrad_box_active<GROUPS>(p, x, d0, h0, w0)) continue;
-        if (lane == 0) {
-          mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], tx_bytes);
-        }
-        __syncwarp();
-        if (lane < 2) {
-          tma_load_5d(smem_a + st * Cfg::A_BYTES + lane * Cfg::BOX_BYTES, &p.dy_map, &full[st], x.mt * 128 + lane * 64,
-                      w0, h0, d0, bi.n);
-        } else if (g < x.ng) {
-          tma_load_5d(smem_b + st * Cfg::B_BYTES + g * Cfg::BOX_BYTES, &p.x_maps[my_map], &full[st], my_c0, w0 + my_dw,
-                      h0 + my_dh, d0 + my_dd, bi.n);
-        }
-        if (++st == STAGES) {
-          st = 0;
-          ph ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, true, true);
-      int st = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t accph = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
-        mbar_wait(&tempty[acc], accph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        uint32_t accum = 0;
-        BoxIter bi;
-        bi.init(p, x.b_begin);
-        for (int b = x.b_begin; b < x.b_end; b++, bi.next(p)) {
-          if (!wgrad_box_active<GROUPS>(p, x, bi.td * p.bd, bi.th * p.bh, bi.tw * p.bw)) continue;
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + st * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + st * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            // 16 positions per MMA = 2 groups of 8 rows (SBO 1024 B); channel groups Cfg::BOX_BYTES apart (LBO)
-            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, Cfg::BOX_BYTES, 1024);
-            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, Cfg::BOX_BYTES, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, accum | static_cast<uint32_t>(k));
-          }
-          accum = 1;
-          umma_commit(&empty[st]);
-          if (++st == STAGES) {
-            st = 0;
-            ph ^= 1;
-          }
-        }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1;
-        }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    int acc = 0;
-    uint32_t accph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WItemCtx<GROUPS> x = make_item_ctx<GROUPS>(p, item);
-      const int g0 = x.g0, ng = x.ng;
-      bool has_k = false;
-      {
-        BoxIter bi;
-        bi.init(p, x.b_begin);
-        for (int b = x.b_begin; b < x.b_end && !has_k; b++, bi.next(p))
-          has_k = wgrad_box_active<GROUPS>(p, x, bi.td * p.bd, bi.th * p.bh, bi.tw * p.bw);
-      }
-      const int co = x.mt * 128 + row;
-      float* dst = p.dw + static_cast<long long>(co) * p.k_total + static_cast<long long>(g0) * 64;
-      mbar_wait(&tfull[acc], accph);
-      tc_fence_after();
-      if (has_k) {
-#pragma unroll 1
-        for (int chunk = 0; chunk < ng * 2; chunk++) {
-          uint32_t v[32];
-          tmem_ld_32x32(
-              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + chunk * 32), v);
-          tmem_ld_wait();
-          if (co < p.cout) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              float4 val;
-              val.x = __uint_as_float(v[j4 * 4 + 0]);
-              val.y = __uint_as_float(v[j4 * 4 + 1]);
-              val.z = __uint_as_float(v[j4 * 4 + 2]);
-              val.w = __uint_as_float(v[j4 * 4 + 3]);
-              atomicAdd(reinterpret_cast<float4*>(dst + chunk * 32 + j4 * 4), val);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        accph ^= 1;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-// =================================================================================================
 // Launchers
 // =================================================================================================
 extern void count_launch();
@@ -634,37 +339,6 @@ int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream) {
       return launch_igemm_t<256, 4>(p, stream);
     default:
       set_error("igemm: unsupported BLOCK_N %d", block_n);
-      return ADNI_ENOTSUP;
-  }
-}
-
-template <int GROUPS, int STAGES>
-static int launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
-  using Cfg = WgradCfg<GROUPS, STAGES>;
-  auto kern = wgrad_mnmajor_kernel<GROUPS, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
-  count_launch();
-  ADNI_LAUNCH_CHECK("wgrad_mnmajor_kernel");
-  return ADNI_OK;
-}
-
-int launch_wgrad(const WgradParams& p, int groups, cudaStream_t stream) {
-  switch (groups) {
-    case 1:
-      return launch_wgrad_t<1, 8>(p, stream);
-    case 2:
-      return launch_wgrad_t<2, 6>(p, stream);
-    case 4:
-      return launch_wgrad_t<4, 4>(p, stream);
-    default:
-      set_error("wgrad: unsupported group count %d", groups);
       return ADNI_ENOTSUP;
   }
 }

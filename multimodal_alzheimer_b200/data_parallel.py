@@ -68,17 +68,26 @@ class PeerReducer:
 
 
 _PEER_REDUCERS = {}
-# On by default (ADNI_PEER_REDUCE=0 selects NCCL).  Measured on 2 x B200: bit-identical to NCCL on 200 test vectors,
-# 2252-2264 volumes/s against 2106 through NCCL (+7 %), 4 of 4 runs clean.  (Two earlier failures next to it were the
-# barrier-phase aliasing bug of the dual-issuer conv kernel, fixed in conv_halo.cu.)  The spinning exchange CTA can
+# ADNI_PEER_REDUCE: "1" (default) = the one-shot NVLink kernel, and if symmetric memory cannot be set up on this box the
+# exchange goes through NCCL with a warning on EVERY rank's stderr and `exchange_status()` says so (bench.py prints
+# it in its JSON line - never a silent switch); "require" = raise instead; "0" = NCCL for everything.
+# Measured on 2 x B200: bit-identical to NCCL on 200 test vectors, +7 % volumes/s.  The spinning exchange CTA can
 # delay, not block, a persistent conv grid: conv CTAs own disjoint work ranges, so the CTA that finds the SM taken
 # runs on the first SM another CTA of its grid vacates.
-_PEER_DISABLED = [os.environ.get("ADNI_PEER_REDUCE", "1") == "0"]
+_PEER_MODE = os.environ.get("ADNI_PEER_REDUCE", "1")
+_PEER_DISABLED = [_PEER_MODE == "0"]
+_PEER_STATUS = {"mode": "nccl (ADNI_PEER_REDUCE=0)" if _PEER_MODE == "0" else "unused", "error": None}
+
+
+def exchange_status():
+    """Which path the sync-BN / loss-normaliser sums take: 'peer' (csrc/peer_reduce.cu), 'nccl (...)' with the reason,
+    or 'unused' (single rank so far)."""
+    return dict(_PEER_STATUS)
 
 
 def peer_reducer(channel, device):
     """The PeerReducer of a channel (None = default group, else one of the per-branch groups), created on first use;
-    None when symmetric memory is unavailable (callers fall back to NCCL)."""
+    None when disabled or when symmetric memory is unavailable (callers use NCCL; see ADNI_PEER_REDUCE above)."""
     if _PEER_DISABLED[0] or not torch.cuda.is_available():
         return None
     key = (id(channel) if channel is not None else 0, device.index)
@@ -88,10 +97,15 @@ def peer_reducer(channel, device):
             return None  # collective construction cannot be captured: this call goes through NCCL
         try:
             red = _PEER_REDUCERS[key] = PeerReducer(device)
-        except Exception as e:  # noqa: BLE001 - optional fast path
+            _PEER_STATUS["mode"] = "peer"
+        except Exception as e:  # noqa: BLE001 - reported, never silent
+            if _PEER_MODE == "require":
+                raise
             _PEER_DISABLED[0] = True
-            if dist.get_rank() == 0:
-                print(f"[adni_b200] peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+            _PEER_STATUS.update(mode=f"nccl (peer all-reduce unavailable: {type(e).__name__})", error=str(e))
+            import sys
+            print(f"[adni_b200 rank {dist.get_rank()}] WARNING: one-shot NVLink all-reduce unavailable "
+                  f"({type(e).__name__}: {e}); sync-BN sums go through NCCL", file=sys.stderr, flush=True)
             return None
     return red
 
