@@ -373,19 +373,19 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
   return ADNI_OK;
 }
 
-int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
-             cudaStream_t stream) {
+// Geometry half of the wgrad plan (everything except the tensor maps and pointers): shared by tc_wgrad and the
+// planner query.  Returns the M-tile configuration; fills the box and every integer field of `p`.
+int plan_wgrad_geometry(const adni_conv3d_geom& g, WgradParams& p, Box& b) {
   const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
   const int Ho = out_extent(g.H, g.k, g.stride, g.pad, g.dil);
   const int Wo = out_extent(g.W, g.k, g.stride, g.pad, g.dil);
   const int taps = g.k * g.k * g.k;
-  const std::vector<View> views = parity_views(x, g.D, g.H, g.W, g.Cin, g.stride);
   const std::vector<AxisTap> at = fwd_axis_taps(g.k, g.stride, g.pad, g.dil);
   std::vector<int> ext_d, ext_h, ext_w;
-  for (int p = 0; p < g.stride; p++) {
-    ext_d.push_back((g.D - p + g.stride - 1) / g.stride);
-    ext_h.push_back((g.H - p + g.stride - 1) / g.stride);
-    ext_w.push_back((g.W - p + g.stride - 1) / g.stride);
+  for (int q = 0; q < g.stride; q++) {
+    ext_d.push_back((g.D - q + g.stride - 1) / g.stride);
+    ext_h.push_back((g.H - q + g.stride - 1) / g.stride);
+    ext_w.push_back((g.W - q + g.stride - 1) / g.stride);
   }
   // one CTA owns all 512 TMEM columns: mt_cfg accumulators of 128 Cout rows x (512/mt_cfg) K_total columns
   int mt_cfg = g.Cout >= 256 ? 2 : 1;  // measured best on B200 (tools/wgrad_probe.py)
@@ -394,28 +394,7 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     if (v == 1 || v == 2 || v == 4) mt_cfg = v;
   }
   const int box_rows = wgrad2_box_rows(mt_cfg);
-  const Box b = plan_box(Do, Ho, Wo, box_rows, true, at, at, at, ext_d, ext_h, ext_w);
-
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
-  View dyv;
-  dyv.base = dy;
-  dyv.D = Do;
-  dyv.H = Ho;
-  dyv.W = Wo;
-  dyv.sw = g.Cout;
-  dyv.sh = (long long)Wo * g.Cout;
-  dyv.sd = (long long)Ho * Wo * g.Cout;
-  dyv.sn = (long long)Do * Ho * Wo * g.Cout;
-  int rc = encode_view(&p.dy_map, dyv, g.Cout, b, g.N);
-  if (rc) return rc;
-  for (size_t i = 0; i < views.size(); i++) {
-    rc = encode_view(&p.x_maps[i], views[i], g.Cin, b, g.N);
-    if (rc) return rc;
-    p.x_ext[i][0] = views[i].D;
-    p.x_ext[i][1] = views[i].H;
-    p.x_ext[i][2] = views[i].W;
-  }
+  b = plan_box(Do, Ho, Wo, box_rows, true, at, at, at, ext_d, ext_h, ext_w);
   int t = 0;
   for (int kd = 0; kd < g.k; kd++)
     for (int kh = 0; kh < g.k; kh++)
@@ -426,6 +405,14 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
         tp.dh = int8_t(at[kh].off);
         tp.dw = int8_t(at[kw].off);
         tp.kofs = t * g.Cin;
+      }
+  int v = 0;
+  for (int pd = 0; pd < g.stride; pd++)
+    for (int ph = 0; ph < g.stride; ph++)
+      for (int pw = 0; pw < g.stride; pw++, v++) {
+        p.x_ext[v][0] = ext_d[pd];
+        p.x_ext[v][1] = ext_h[ph];
+        p.x_ext[v][2] = ext_w[pw];
       }
   p.ntaps = taps;
   p.cin_blocks = g.Cin / 64;
@@ -452,6 +439,54 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
   p.splits = (p.pos_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = g.Cout;
   p.k_total = p.n_groups * 64;
+  return mt_cfg;
+}
+
+// Fraction of the (position box, 64-column group) MMA blocks wgrad2 issues: a box is skipped for an N tile when the
+// shifted boxes of ALL the tile's taps lie in the zero padding (conv_wgrad2.cu box_active).
+double wgrad_executed_fraction(const WgradParams& p, int mt_cfg) {
+  const int groups = 8 / mt_cfg;
+  long long issued = 0;
+  for (int nt = 0; nt < p.n_tiles; nt++) {
+    const int g0 = nt * groups, ng = std::min(groups, p.n_groups - g0);
+    for (int td = 0; td < p.tiles_d; td++)
+      for (int th = 0; th < p.tiles_h; th++)
+        for (int tw = 0; tw < p.tiles_w; tw++) {
+          bool any = false;
+          for (int gi = 0; gi < ng && !any; gi++) {
+            const ConvTap& tp = p.taps[(g0 + gi) / p.cin_blocks];
+            const int* ext = p.x_ext[tp.map];
+            const int d = td * p.bd + tp.dd, h = th * p.bh + tp.dh, w = tw * p.bw + tp.dw;
+            any = d + p.bd > 0 && d < ext[0] && h + p.bh > 0 && h < ext[1] && w + p.bw > 0 && w < ext[2];
+          }
+          if (any) issued += ng;
+        }
+  }
+  return double(issued) / (double(p.n_groups) * p.tiles_d * p.tiles_h * p.tiles_w);
+}
+
+int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
+             cudaStream_t stream) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  Box b;
+  const int mt_cfg = plan_wgrad_geometry(g, p, b);
+  const std::vector<View> views = parity_views(x, g.D, g.H, g.W, g.Cin, g.stride);
+  View dyv;
+  dyv.base = dy;
+  dyv.D = p.Do;
+  dyv.H = p.Ho;
+  dyv.W = p.Wo;
+  dyv.sw = g.Cout;
+  dyv.sh = (long long)p.Wo * g.Cout;
+  dyv.sd = (long long)p.Ho * p.Wo * g.Cout;
+  dyv.sn = (long long)p.Do * p.Ho * p.Wo * g.Cout;
+  int rc = encode_view(&p.dy_map, dyv, g.Cout, b, g.N);
+  if (rc) return rc;
+  for (size_t i = 0; i < views.size(); i++) {
+    rc = encode_view(&p.x_maps[i], views[i], g.Cin, b, g.N);
+    if (rc) return rc;
+  }
   p.dw = dw;
   return launch_wgrad2(p, mt_cfg, stream);
 }
@@ -502,7 +537,18 @@ int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind,
     return ADNI_OK;
   }
   *engine_kind = 1;
-  if (pass == 2) return ADNI_OK;  // wgrad: split-K over position boxes, reported as issued
+  if (pass == 2) {
+    if (wgrad_halo_supported(*g)) {  // layer1 halo-plane wgrad: the kd = 0 / 2 taps of the first / last plane are skipped
+      *executed_fraction = (3.0 * g->D - 2.0) / (3.0 * g->D);
+      return ADNI_OK;
+    }
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    Box wb;
+    const int mt_cfg = plan_wgrad_geometry(*g, wp, wb);
+    *executed_fraction = wgrad_executed_fraction(wp, mt_cfg);
+    return ADNI_OK;
+  }
   if (halo_supported(*g)) {
     *engine_kind = 2;
     *executed_fraction = (3.0 * g->D - 2.0) / (3.0 * g->D);  // the kd = 0 / 2 taps of the first / last plane

@@ -85,7 +85,7 @@ def _engine_tag(g, pass_, engine):
         if engine == ENGINE_DIRECT or kind.value == 0:
             hit = ("direct", 1.0)
         elif pass_ == 2:
-            hit = ("tc_wgrad", 1.0)
+            hit = ("tc_wgrad", float(frac.value))
         else:
             hit = ("tc_halo" if kind.value == 2 else "tc_kmajor", float(frac.value))
         _PLAN_CACHE[key] = hit
