@@ -52,12 +52,8 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--depth", type=int, default=18)
     args = ap.parse_args()
-    from bench import hparams_for
     from multimodal_alzheimer_b200 import staging
-    from multimodal_alzheimer_b200.optim import Adam
-    from multimodal_alzheimer_b200.pkg.models.fusion_models.anat_pet_fusion import Anat_PET_CNN, ResNet_PET_Trunk
-    from multimodal_alzheimer_b200.pkg.models.mri_models.anat_cnn import Anat_CNN
-    from multimodal_alzheimer_b200.pkg.models.pet_models.pet_resnet_cnn import PET_CNN_ResNet
+    from multimodal_alzheimer_b200 import workloads as W
     from multimodal_alzheimer_b200.pkg.utils.dataloader import MultiModalDataset, StagedLoader
 
     dev = torch.device("cuda:0")
@@ -71,11 +67,9 @@ def main():
                            normalize_mri={"per_scan_norm": "min_max"}, quantile=0.98)
     assert len(ds) == args.pairs, (len(ds), args.pairs)
 
-    enc, fus = hparams_for("pet_mri_fusion_r18", args.depth)
-    torch.manual_seed(15)
-    model = Anat_PET_CNN(dict(fus), model_mri=Anat_CNN(dict(enc)), pet_trunk=ResNet_PET_Trunk(PET_CNN_ResNet(dict(enc))))
+    model = W.build_model(W.product_namespace(), "pet_mri_fusion_r18", depth=args.depth)   # the bench workload's model
     model.to(dev).train()
-    opt = Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+    opt = model.configure_optimizers()
 
     def epoch(loader):
         torch.cuda.synchronize()
