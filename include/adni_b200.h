@@ -36,7 +36,8 @@ typedef uint16_t adni_bf16;
 /* Conv engine selector (tests force one; product code passes AUTO). */
 #define ADNI_ENGINE_AUTO 0
 #define ADNI_ENGINE_TCGEN05 1 /* implicit GEMM on tcgen05/TMEM fed by TMA            */
-#define ADNI_ENGINE_DIRECT 2  /* CUDA-core direct convolution (small channel counts) */
+#define ADNI_ENGINE_DIRECT 2  /* CUDA-core direct convolution (odd shapes, strided small-channel convs) */
+#define ADNI_ENGINE_MMA_SYNC 3 /* warp-level tensor-core engine for the small-channel stacks (Cin 1/8..64, Cout 8..64) */
 
 const char* adni_last_error_string(void);
 int adni_version(void);
@@ -62,7 +63,8 @@ typedef struct {
 int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil);
 
 /* Planner query (measurement only): which engine a geometry is routed to for pass 0 = fprop, 1 = dgrad, 2 = wgrad
- * (engine_kind 0 = direct CUDA-core, 1 = tcgen05 tap-per-box implicit GEMM, 2 = tcgen05 halo-resident) and the
+ * (engine_kind 0 = direct CUDA-core, 1 = tcgen05 tap-per-box implicit GEMM, 2 = tcgen05 halo-resident, 3 = mma.sync
+ * small-channel engine) and the
  * fraction of the (tile, tap) MMA blocks that are actually issued - taps whose shifted box lies entirely in the
  * zero padding are skipped, so executed FLOPs = algorithmic FLOPs x executed_fraction. */
 int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind, double* executed_fraction);

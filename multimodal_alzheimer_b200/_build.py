@@ -19,6 +19,7 @@ SOURCES = [
     "conv_wgrad_halo.cu",
     "conv_api.cu",
     "conv_direct.cu",
+    "conv_small.cu",
     "conv_stem.cu",
     "stem_fused.cu",
     "elementwise.cu",

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libadni_b200.so")
 
-ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_DIRECT = 0, 1, 2
+ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_DIRECT, ENGINE_MMA_SYNC = 0, 1, 2, 3
 
 _lib = None
 

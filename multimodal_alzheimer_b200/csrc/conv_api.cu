@@ -23,6 +23,15 @@ int halo_pitch();
 int halo_rows();
 int launch_igemm_halo(const HaloParams& p, int channels, cudaStream_t stream);
 
+// conv_small.cu: warp-level tensor-core engine (mma.sync) for the small-channel stacks (Small_PET_CNN & co.)
+bool small_conv_supported(const adni_conv3d_geom& g, int pass);
+int small_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,
+                     __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
+int small_conv_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito, __nv_bfloat16* dx,
+                     cudaStream_t stream);
+int small_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
+                     cudaStream_t stream);
+
 int direct_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti,
                       const float* bias, __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream);
 int direct_conv_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
@@ -503,14 +512,29 @@ int check_geom(const adni_conv3d_geom* g) {
   return ADNI_OK;
 }
 
-int resolve_engine(const adni_conv3d_geom& g, int engine, int* out) {
-  if (engine == ADNI_ENGINE_AUTO) engine = tc_supported(g) ? ADNI_ENGINE_TCGEN05 : ADNI_ENGINE_DIRECT;
+bool small_enabled() {
+  static const bool on = env_int("ADNI_SMALL_CONV", 1) != 0;
+  return on;
+}
+
+// AUTO: tcgen05 when the channel counts fill its tiles, else the mma.sync small-channel engine, else CUDA cores.
+int resolve_engine(const adni_conv3d_geom& g, int pass, bool has_addend, int engine, int* out) {
+  if (engine == ADNI_ENGINE_AUTO) {
+    if (tc_supported(g)) engine = ADNI_ENGINE_TCGEN05;
+    else if (small_enabled() && !has_addend && small_conv_supported(g, pass)) engine = ADNI_ENGINE_MMA_SYNC;
+    else engine = ADNI_ENGINE_DIRECT;
+  }
   if (engine == ADNI_ENGINE_TCGEN05 && !tc_supported(g)) {
     set_error("conv3d: tcgen05 engine needs Cin,Cout multiples of 64, stride 1|2, k^3 <= 64 (Cin=%d Cout=%d k=%d s=%d)",
               g.Cin, g.Cout, g.k, g.stride);
     return ADNI_ENOTSUP;
   }
-  if (engine != ADNI_ENGINE_TCGEN05 && engine != ADNI_ENGINE_DIRECT) {
+  if (engine == ADNI_ENGINE_MMA_SYNC && (has_addend || !small_conv_supported(g, pass))) {
+    set_error("conv3d: the small-channel engine needs stride 1, dilation 1, Cin in {1,8,16,32,64}, Cout in {8,16,32,64}, "
+              "no addend (Cin=%d Cout=%d k=%d s=%d d=%d)", g.Cin, g.Cout, g.k, g.stride, g.dil);
+    return ADNI_ENOTSUP;
+  }
+  if (engine != ADNI_ENGINE_TCGEN05 && engine != ADNI_ENGINE_DIRECT && engine != ADNI_ENGINE_MMA_SYNC) {
     set_error("conv3d: unknown engine %d", engine);
     return ADNI_EINVAL;
   }
@@ -533,7 +557,7 @@ int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind,
   ADNI_REQUIRE(engine_kind && executed_fraction && pass >= 0 && pass <= 2, ADNI_EINVAL, "conv3d_plan_info: bad arguments");
   *executed_fraction = 1.0;
   if (!tc_supported(*g)) {
-    *engine_kind = 0;
+    *engine_kind = (small_enabled() && small_conv_supported(*g, pass)) ? 3 : 0;
     return ADNI_OK;
   }
   *engine_kind = 1;
@@ -592,13 +616,17 @@ int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
   ADNI_REQUIRE(x && w_oti && y, ADNI_EINVAL, "conv3d_fprop: null pointer");
   ADNI_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), ADNI_EINVAL, "conv3d_fprop: stats need both buffers");
   int eng;
-  rc = resolve_engine(*g, engine, &eng);
+  rc = resolve_engine(*g, 0, false, engine, &eng);
   if (rc) return rc;
   auto xs = reinterpret_cast<const __nv_bfloat16*>(x);
   auto ws = reinterpret_cast<const __nv_bfloat16*>(w_oti);
   auto ys = reinterpret_cast<__nv_bfloat16*>(y);
   if (eng == ADNI_ENGINE_TCGEN05)
     return tc_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
+  if (eng == ADNI_ENGINE_MMA_SYNC) {
+    rc = small_conv_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
+    if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;   // AUTO: tile too large for shared memory
+  }
   return direct_conv_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
 }
 
@@ -608,13 +636,17 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
   if (rc) return rc;
   ADNI_REQUIRE(dy && w_ito && dx, ADNI_EINVAL, "conv3d_dgrad: null pointer");
   int eng;
-  rc = resolve_engine(*g, engine, &eng);
+  rc = resolve_engine(*g, 1, addend != nullptr, engine, &eng);
   if (rc) return rc;
   auto dys = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto ws = reinterpret_cast<const __nv_bfloat16*>(w_ito);
   auto as = reinterpret_cast<const __nv_bfloat16*>(addend);
   auto dxs = reinterpret_cast<__nv_bfloat16*>(dx);
   if (eng == ADNI_ENGINE_TCGEN05) return tc_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
+  if (eng == ADNI_ENGINE_MMA_SYNC) {
+    rc = small_conv_dgrad(*g, dys, ws, dxs, static_cast<cudaStream_t>(stream));
+    if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;
+  }
   return direct_conv_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
 }
 
@@ -629,10 +661,15 @@ int adni_conv3d_wgrad(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
   if (rc) return rc;
   ADNI_REQUIRE(x && dy && dw_oti, ADNI_EINVAL, "conv3d_wgrad: null pointer");
   int eng;
-  rc = resolve_engine(*g, engine, &eng);
+  rc = resolve_engine(*g, 2, false, engine, &eng);
   if (rc) return rc;
   auto xs = reinterpret_cast<const __nv_bfloat16*>(x);
   auto dys = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (eng == ADNI_ENGINE_MMA_SYNC) {
+    ADNI_REQUIRE(dbias == nullptr, ADNI_ENOTSUP, "conv3d_wgrad: the small-channel engine has no bias gradient (use channel_stats)");
+    rc = small_conv_wgrad(*g, xs, dys, dw_oti, static_cast<cudaStream_t>(stream));
+    if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;
+  }
   if (eng == ADNI_ENGINE_TCGEN05) {
     ADNI_REQUIRE(dbias == nullptr, ADNI_ENOTSUP, "conv3d_wgrad: tcgen05 engine has no bias gradient (use channel_stats)");
     if (scratch != nullptr && wgrad_halo_supported(*g))

@@ -7,7 +7,7 @@ libadni_b200.so; no arithmetic happens in Python and nothing here falls back to 
 import torch
 
 from . import _lib
-from ._lib import ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05, call, geom, out_extent, ptr, stream_ptr  # noqa: F401
+from ._lib import ENGINE_AUTO, ENGINE_DIRECT, ENGINE_MMA_SYNC, ENGINE_TCGEN05, call, geom, out_extent, ptr, stream_ptr  # noqa: F401
 
 BF16 = torch.bfloat16
 
@@ -71,25 +71,31 @@ def call_hbm(tag, nbytes, name, *args):
 _PLAN_CACHE = {}
 
 
-def _engine_tag(g, pass_, engine):
-    """(kernel-family tag, executed fraction of the algorithmic FLOPs) for bench.py's per-kernel roofline: asks the
-    library's own planner (adni_conv3d_plan_info) which engine the geometry is routed to."""
-    if not PROFILE.on:
-        return "", 1.0
-    key = (g.N, g.D, g.H, g.W, g.Cin, g.Cout, g.k, g.stride, g.pad, g.dil, pass_, engine)
+def _plan(g, pass_):
+    """(engine kind, executed fraction) the library's planner reports for a geometry (cached):
+    0 = direct CUDA-core, 1 = tcgen05 tap-per-box, 2 = tcgen05 halo-resident, 3 = mma.sync small-channel engine."""
+    key = (g.N, g.D, g.H, g.W, g.Cin, g.Cout, g.k, g.stride, g.pad, g.dil, pass_)
     hit = _PLAN_CACHE.get(key)
     if hit is None:
         import ctypes
         kind, frac = ctypes.c_int(0), ctypes.c_double(1.0)
         call("adni_conv3d_plan_info", g, pass_, ctypes.byref(kind), ctypes.byref(frac))
-        if engine == ENGINE_DIRECT or kind.value == 0:
-            hit = ("direct", 1.0)
-        elif pass_ == 2:
-            hit = ("tc_wgrad", float(frac.value))
-        else:
-            hit = ("tc_halo" if kind.value == 2 else "tc_kmajor", float(frac.value))
-        _PLAN_CACHE[key] = hit
+        hit = _PLAN_CACHE[key] = (kind.value, float(frac.value))
     return hit
+
+
+def _engine_tag(g, pass_, engine):
+    """(kernel-family tag, executed fraction of the algorithmic FLOPs) for bench.py's per-kernel roofline."""
+    if not PROFILE.on:
+        return "", 1.0
+    kind, frac = _plan(g, pass_)
+    if engine == ENGINE_DIRECT or kind == 0:
+        return "direct", 1.0
+    if engine == ENGINE_MMA_SYNC or kind == 3:
+        return "tc_small", 1.0
+    if pass_ == 2:
+        return "tc_wgrad", frac
+    return ("tc_halo" if kind == 2 else "tc_kmajor"), frac
 
 
 def _chk(t, dtype, name):
@@ -286,7 +292,7 @@ def conv3d_wgrad(x, dy, k, stride, pad, dil, want_dbias=False, engine=ENGINE_AUT
     dw = zeros_f32((Cout, k * k * k, Cin), x.device)
     db = None
     if want_dbias:
-        if engine == ENGINE_DIRECT or (Cin % 64 != 0 or Cout % 64 != 0):
+        if engine == ENGINE_DIRECT or (engine == ENGINE_AUTO and _plan(g, 2)[0] == 0):
             db = torch.zeros((Cout,), dtype=torch.float32, device=x.device)
             ev = PROFILE.begin()
             call("adni_conv3d_wgrad", g, ptr(x), ptr(dy), ptr(dw), ptr(db), None, ENGINE_DIRECT, stream_ptr())

@@ -137,3 +137,29 @@ def test_planner_routes_every_encoder_conv_to_a_tensor_core_engine(depth, shape,
             assert rc == 0, ((D, H, W, Ci, Co, k, s, p, d), pass_, lib.adni_last_error_string())
             assert kind.value in (1, 2), ((D, H, W, Ci, Co, k, s, p, d), pass_, kind.value)
             assert 0.0 < frac.value <= 1.0
+
+
+def test_planner_routes_small_stacks_to_tensor_cores():
+    """Every conv of the reference's small-CNN search space (train_pet_cnn.py:43-59) is planned onto a tensor-core
+    engine for all three passes (host-side query, no kernel launch)."""
+    import ctypes
+    from multimodal_alzheimer_b200 import _lib
+    lib = _lib.load()
+    for first in (8, 16, 32):
+        for n in (3, 4):
+            chans = [1] + [first * 2 ** i for i in range(n)]
+            for filt in ((5, 5, 3, 3), (7, 5, 3, 3), (5, 5, 5, 3), (3, 3, 3, 3)):
+                ext = 128
+                for i in range(n):
+                    k = filt[i]
+                    g = _lib.geom(2, ext, ext, ext, chans[i], chans[i + 1], k, 1, (k - 1) // 2, 1)
+                    for pass_ in (0, 1, 2):
+                        if pass_ == 1 and i == 0:
+                            continue                       # no input gradient for the first layer
+                        kind, frac = ctypes.c_int(-1), ctypes.c_double(0)
+                        assert lib.adni_conv3d_plan_info(ctypes.byref(g), pass_, ctypes.byref(kind), ctypes.byref(frac)) == 0
+                        if (chans[i], chans[i + 1], k) == (64, 128, 5):
+                            assert kind.value == 0      # 125 taps exceed the tcgen05 tap mask, 128 > the small engine
+                            continue
+                        assert kind.value in (1, 2, 3), (chans[i], chans[i + 1], k, pass_, kind.value)
+                    ext //= 2

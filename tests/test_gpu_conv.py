@@ -136,12 +136,59 @@ def test_direct_conv(cuda_dev, shape):
     assert_close(db, b_ref.grad, 2e-4, f"direct dbias {shape}")
 
 
+SMALL = 3
+# the small-channel stacks (pet_cnn.py:18-28, early_fusion.py:34-44, anat_pet_featuremapfusion.py:40-64) on the
+# mma.sync engine: every (Cin, Cout, k) of conv_out in {(8,16,32,64), (16,32,64,..), (32,64,..)} x filter sizes {3,5,7}
+SMALL_SHAPES = [
+    (2, 16, 16, 16, 1, 8, 5, 1, 2, 1),     # Small_PET_CNN conv1 (on-chip window expansion)
+    (1, 12, 20, 33, 1, 16, 7, 1, 3, 1),    # first layer with filter 7, ragged extents, two w tiles + tail
+    (2, 9, 10, 17, 1, 32, 3, 1, 1, 1),     # first layer, filter 3
+    (2, 8, 8, 16, 8, 16, 5, 1, 2, 1),      # conv2
+    (1, 13, 11, 19, 8, 16, 5, 1, 2, 1),    # conv2, ragged
+    (1, 8, 8, 8, 16, 32, 3, 1, 1, 1),      # conv3
+    (2, 6, 9, 20, 16, 32, 5, 1, 2, 1),     # filter (5,5,5,3): third layer with k = 5
+    (1, 8, 8, 8, 32, 64, 3, 1, 1, 1),      # conv4
+    (3, 5, 7, 18, 32, 64, 3, 1, 1, 1),     # conv4, ragged
+    (1, 7, 8, 16, 64, 64, 3, 1, 1, 1),     # 64 channels on both sides (forced: AUTO sends this shape to tcgen05)
+    (2, 9, 9, 17, 8, 8, 4, 1, 2, 1),       # even kernel after the high-side pad (output extent = input - 1 + ... )
+]
+
+
+@pytest.mark.parametrize("shape", SMALL_SHAPES)
+def test_small_channel_engine(cuda_dev, shape):
+    """fprop (+bias, +BatchNorm sums), dgrad and wgrad of the mma.sync engine vs torch fp32 on the same bf16 operands."""
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev, seed=3)
+    bias = torch.randn(Cout, device=cuda_dev)
+    oti, ito = K.weights_to_kernel_layout(w)
+    x_ref.requires_grad_(True)
+    w_ref.requires_grad_(True)
+    ref = F.conv3d(x_ref, w_ref, bias, s, p, d)
+    y, st = K.conv3d_fprop(x_b, oti, bias, k, s, p, d, stats=True, engine=SMALL)
+    torch.cuda.synchronize()
+    assert_close(to_ncdhw_f32(y), ref.detach(), 6e-3, f"small fprop {shape}")
+    assert_close(st[0], ref.detach().double().sum(dim=(0, 2, 3, 4)), 1e-3, f"small stats sum {shape}")
+    assert_close(st[1], (ref.detach().double() ** 2).sum(dim=(0, 2, 3, 4)), 1e-4, f"small stats sqsum {shape}")
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref))
+    ref.backward(to_ncdhw_f32(dy_b))
+    if Cin != 1:
+        dx = K.conv3d_dgrad(dy_b, ito, tuple(x_b.shape), k, s, p, d, engine=SMALL)
+        assert_close(to_ncdhw_f32(dx), x_ref.grad, 6e-3, f"small dgrad {shape}")
+    dw, db = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, want_dbias=True, engine=SMALL)
+    torch.cuda.synchronize()
+    assert_close(K.wgrad_to_param_layout(dw, tuple(w.shape)), w_ref.grad, 2e-4, f"small wgrad {shape}")
+    assert_close(db, to_ncdhw_f32(dy_b).sum(dim=(0, 2, 3, 4)), 2e-4, f"small dbias {shape}")
+
+
 def test_engine_rejects_unsupported(cuda_dev):
     from multimodal_alzheimer_b200 import kernels as K
     x = torch.zeros((1, 4, 4, 4, 8), dtype=torch.bfloat16, device=cuda_dev)
     w = torch.zeros((8, 27, 8), dtype=torch.bfloat16, device=cuda_dev)
     with pytest.raises(NotImplementedError):
         K.conv3d_fprop(x, w, None, 3, 1, 1, 1, engine=TC)
+    with pytest.raises(NotImplementedError):                       # the small-channel engine is stride 1 only
+        K.conv3d_fprop(x, w, None, 3, 2, 1, 1, engine=SMALL)
 
 
 STEM_SHAPES = [(2, 16, 16, 16), (1, 32, 24, 40), (1, 18, 20, 22), (3, 9, 11, 13), (1, 128, 128, 128)]
