@@ -80,6 +80,18 @@ int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
 int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito,
                       const adni_bf16* addend, adni_bf16* dx, int engine, void* stream);
 
+/* adni_conv3d_dgrad whose epilogue also performs the BatchNorm-backward reduction of the layer that PRODUCED dx's
+ * tensor (MedicalNet blocks: conv -> bn -> relu; the dx of one conv is the `dout` of the preceding BatchNorm3d):
+ *   sum_g[c] += sum g,  sum_gy[c] += sum g * bn_y   with g = the bf16 value stored in dx, masked by that layer's ReLU:
+ *   bn_relu_out > 0 (the layer's stored output; blocks ending in bn -> (+ residual) -> relu), or
+ *   bn_y * bn_scale[c] + bn_shift[c] > 0 (recomputed; conv -> bn -> relu), or no mask (all three null).
+ * bn_y / bn_relu_out have dx's shape.  sum g*xhat = invstd * (sum_gy - mean * sum_g): adni_bn_bwd_apply takes the
+ * sums in this form (red_form 1).  Replaces one full read of dx and bn_y per BatchNorm layer (adni_bn_bwd_reduce).
+ * tcgen05 engines only (ADNI_ENOTSUP otherwise: call adni_conv3d_dgrad + adni_bn_bwd_reduce). */
+int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
+                            adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
+                            const float* bn_shift, double* sum_g, double* sum_gy, void* stream);
+
 /* dw_oti[Cout][taps][Cin] (fp32) += sum over positions of dy^T * im2col(x).  The caller zeroes dw
  * (the split-K partial sums are accumulated with red.global.add). dbias[Cout] (fp32, may be null) +=
  * sum(dy).  `scratch` (nullable): adni_conv3d_wgrad_scratch_floats(g) ZEROED floats; when given and non-empty the
@@ -150,11 +162,13 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
  * dres (nullable) = g (the gradient flowing into the residual input); dgamma = red_gx * param_grad_scale, dbeta =
  * red_g * param_grad_scale are written (fp32) when non-null.  `count` is the GLOBAL element count per channel
  * (sync-BN); with all-reduced sums pass param_grad_scale = 1 / world_size so that the SUM of the ranks' parameter
- * gradients (the data-parallel gradient all-reduce) is the full-batch gradient. */
+ * gradients (the data-parallel gradient all-reduce) is the full-batch gradient.
+ * red_form 0: red = [sum g | sum g*xhat] (adni_bn_bwd_reduce); 1: red = [sum g | sum g*y] as accumulated by the
+ * epilogue of adni_conv3d_dgrad_bnred (sum g*xhat = invstd * (sum g*y - mean * sum g), evaluated in fp64). */
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
                       const float* invstd, const float* gamma, const float* scale, const float* shift,
                       const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
-                      float* dgamma, float* dbeta, double param_grad_scale, void* stream);
+                      float* dgamma, float* dbeta, double param_grad_scale, int red_form, void* stream);
 
 /* Training-mode BatchNorm forward in ONE launch (adni_bn_finalize + adni_bn_apply): scale / shift are derived from the
  * fp64 batch sums inside the apply kernel; bnp (fp32 [4][C]: mean, invstd, scale, shift) is written for the backward

@@ -12,12 +12,21 @@ Data parallelism: when torch.distributed is initialised with wo
 statistic sums (forward: sum x, sum x^2; backward: sum g, sum g*xhat) and the loss normaliser are
 all-reduced so that N ranks on shards of a batch reproduce the single-process full-batch step.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import kernels as K
 
 BF16 = torch.bfloat16
+
+# BatchNorm-backward sums fused into the epilogue of the dgrad that produces the BatchNorm's output gradient
+# (adni_conv3d_dgrad_bnred): on by default, ADNI_FUSE_BN_REDUCE=0 restores the separate reduction kernel.
+_FUSE_BNRED = os.environ.get("ADNI_FUSE_BN_REDUCE", "1") != "0"
+# sums a block's last dgrad computed for the PRECEDING block's final BatchNorm, keyed by the address of the gradient
+# tensor it hands to that block (consumed - popped - by that block's backward within the same backward pass)
+_PENDING_RED = {}
 
 
 # --------------------------------------------------------------------------------------------- DP helpers
@@ -121,21 +130,55 @@ def _bn_forward(y, stats, gamma, beta, bn, residual, relu):
     return out, None, rows
 
 
-def _bn_backward(dout, out, y, bnp, gamma, count, relu, want_dres, want_pg):
-    """out=None with relu=True: the forward had no residual, the ReLU mask is recomputed from y*scale+shift."""
+def _bn_backward(dout, out, y, bnp, gamma, count, relu, want_dres, want_pg, red=None):
+    """out=None with relu=True: the forward had no residual, the ReLU mask is recomputed from y*scale+shift.
+    `red`: the sums [sum g | sum g*y] a dgrad epilogue already accumulated for this layer (no reduction pass then)."""
     if bnp is None:
         raise NotImplementedError("BatchNorm backward in eval mode is outside the training hot path")
     mean, invstd, scale, shift = bnp[0], bnp[1], bnp[2], bnp[3]
     if not relu or out is not None:
         scale = shift = None
-    red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale, shift)
+    red_form = 1
+    if red is None:
+        red = K.bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale, shift)
+        red_form = 0
     _allreduce_(red)
     # dgamma / dbeta are written by the apply kernel from the all-reduced sums scaled by 1 / world_size: the gradient
     # all-reduce that follows the backward pass SUMS the ranks' parameter gradients, which restores the global sums
     # (handing every rank the full sums would count them world_size times).
     dy, dres, dgamma, dbeta = K.bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_pg,
-                                             scale, shift, param_grad_scale=1.0 / _world())
+                                             scale, shift, param_grad_scale=1.0 / _world(), red_form=red_form)
     return dy, dres, dgamma, dbeta
+
+
+def _dgrad_bnred(dy, w_ito, in_shape, cfg, bn_y, bnp, relu_out=None, addend=None):
+    """dx = dgrad(dy) (+ addend) and, fused into its epilogue when the tcgen05 engines take the shape, the backward
+    sums of the conv -> bn -> relu layer whose output dx is the gradient of: (dx, red | None).  relu_out: that layer's
+    stored output (mask = > 0); None = the mask is recomputed from bn_y * scale + shift."""
+    if (_FUSE_BNRED and bnp is not None and bn_y is not None
+            and K.dgrad_bnred_supported(in_shape[-1], dy.shape[-1], cfg.k, cfg.stride)):
+        scale, shift = (None, None) if relu_out is not None else (bnp[2], bnp[3])
+        return K.conv3d_dgrad_bnred(dy, w_ito, in_shape, cfg.k, cfg.stride, cfg.pad, cfg.dil, bn_y, bn_relu_out=relu_out,
+                                    bn_scale=scale, bn_shift=shift, addend=addend)
+    return K.conv3d_dgrad(dy, w_ito, in_shape, cfg.k, cfg.stride, cfg.pad, cfg.dil, addend=addend), None
+
+
+def _block_input_grad(ctx_tail, x, dy1, w1_ito, c1, addend):
+    """The gradient a residual block returns for its input x.  When x is the output of a preceding block (its final
+    bn -> + residual -> relu is described by ctx_tail = (y_last, bnp_last)), that BatchNorm's backward sums ride in the
+    epilogue and are parked for the preceding block's backward."""
+    tail_y, tail_p = ctx_tail
+    dx, red = _dgrad_bnred(dy1, w1_ito, tuple(x.shape), c1, tail_y, tail_p, relu_out=x, addend=addend)
+    if red is not None:
+        _PENDING_RED[dx.data_ptr()] = (red, dx.numel())
+    return dx
+
+
+def _take_pending_red(dout):
+    hit = _PENDING_RED.pop(dout.data_ptr(), None)
+    if hit is not None and hit[1] == dout.numel():
+        return hit[0]
+    return None
 
 
 class ConvCfg:
@@ -274,10 +317,12 @@ class StemFn(torch.autograd.Function):
 
 # --------------------------------------------------------------------------------------------- residual blocks
 class BasicBlockFn(torch.autograd.Function):
-    """MedicalNet BasicBlock: conv3-bn-relu-conv3-bn (+ downsample(x) | x) - relu."""
+    """MedicalNet BasicBlock: conv3-bn-relu-conv3-bn (+ downsample(x) | x) - relu.  Returns (out, y2, bnp2): the raw
+    output of conv2 and bn2's parameters describe the block's final bn -> relu to the NEXT block, whose last dgrad
+    computes bn2's backward sums in its epilogue (tail_y / tail_p are the same pair of the PRECEDING block)."""
 
     @staticmethod
-    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, bn1, bn2, bnd, c1, c2, cd):
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, bn1, bn2, bnd, c1, c2, cd, tail_y=None, tail_p=None):
         ctx.dp_group = _GROUP[0]
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
@@ -291,21 +336,24 @@ class BasicBlockFn(torch.autograd.Function):
             nd = 0
             r = x
         out, p2, n2 = _bn_forward(y2, st2, g2, b2, bn2, r, True)
-        ctx.save_for_backward(x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito)
+        ctx.save_for_backward(x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito, tail_y, tail_p)
         ctx.cfg = (c1, c2, cd, n1, n2, nd, w1.shape, w2.shape, None if wd is None else wd.shape, need_dx)
-        return out
+        if p2 is None:
+            p2 = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(y2, p2)
+        return out, y2, p2
 
     @staticmethod
     @_with_forward_group
-    def backward(ctx, dout):
-        x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito = ctx.saved_tensors
+    def backward(ctx, dout, _dy2, _dp2):
+        x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito, tail_y, tail_p = ctx.saved_tensors
         c1, c2, cd, n1, n2, nd, ws1, ws2, wsd, need_dx = ctx.cfg
         dout = dout.contiguous()
-        dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, p2, g2, n2, True, True, True)
+        dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, p2, g2, n2, True, True, True, red=_take_pending_red(dout))
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
-        da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
+        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1)
         del dy2
-        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True)
+        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True, red=red1)
         del da1
         dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
         dwd = dgd = dbd = None
@@ -315,17 +363,19 @@ class BasicBlockFn(torch.autograd.Function):
             dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
             if need_dx:
                 dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
-                dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dxd)
+                dx = _block_input_grad((tail_y, tail_p), x, dy1, w1_ito, c1, dxd)
         elif need_dx:
-            dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dres)
-        return (dx, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd) + (None,) * 6
+            dx = _block_input_grad((tail_y, tail_p), x, dy1, w1_ito, c1, dres)
+        return (dx, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd) + (None,) * 8
 
 
 class BottleneckFn(torch.autograd.Function):
-    """MedicalNet Bottleneck: 1x1-bn-relu, 3x3(stride,dil)-bn-relu, 1x1-bn (+ downsample(x) | x) - relu."""
+    """MedicalNet Bottleneck: 1x1-bn-relu, 3x3(stride,dil)-bn-relu, 1x1-bn (+ downsample(x) | x) - relu.
+    Returns (out, y3, bnp3) / takes (tail_y, tail_p) like BasicBlockFn."""
 
     @staticmethod
-    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, wd, gd, bd, bn1, bn2, bn3, bnd, c1, c2, c3, cd):
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, wd, gd, bd, bn1, bn2, bn3, bnd, c1, c2, c3, cd, tail_y=None,
+                tail_p=None):
         ctx.dp_group = _GROUP[0]
         need_dx = ctx.needs_input_grad[0]
         y1, st1, w1_ito = _conv_fwd(x, w1, c1, need_ito=need_dx)
@@ -342,28 +392,31 @@ class BottleneckFn(torch.autograd.Function):
             r = x
         out, p3, n3 = _bn_forward(y3, st3, g3, b3, bn3, r, True)
         ctx.save_for_backward(x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
-                              wd_ito)
+                              wd_ito, tail_y, tail_p)
         ctx.cfg = (c1, c2, c3, cd, n1, n2, n3, nd, w1.shape, w2.shape, w3.shape, None if wd is None else wd.shape,
                    need_dx)
-        return out
+        if p3 is None:
+            p3 = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(y3, p3)
+        return out, y3, p3
 
     @staticmethod
     @_with_forward_group
-    def backward(ctx, dout):
-        (x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
-         wd_ito) = ctx.saved_tensors
+    def backward(ctx, dout, _dy3, _dp3):
+        (x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito, wd_ito, tail_y,
+         tail_p) = ctx.saved_tensors
         c1, c2, c3, cd, n1, n2, n3, nd, ws1, ws2, ws3, wsd, need_dx = ctx.cfg
         dout = dout.contiguous()
-        dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, p3, g3, n3, True, True, True)
+        dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, p3, g3, n3, True, True, True, red=_take_pending_red(dout))
         dw3, _ = _conv_wgrad(a2, dy3, c3, ws3)
-        da2 = K.conv3d_dgrad(dy3, w3_ito, tuple(a2.shape), c3.k, c3.stride, c3.pad, c3.dil)
+        da2, red2 = _dgrad_bnred(dy3, w3_ito, tuple(a2.shape), c3, y2, p2)
         del dy3
-        dy2, _, dg2, db2 = _bn_backward(da2, None, y2, p2, g2, n2, True, False, True)
+        dy2, _, dg2, db2 = _bn_backward(da2, None, y2, p2, g2, n2, True, False, True, red=red2)
         del da2
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
-        da1 = K.conv3d_dgrad(dy2, w2_ito, tuple(a1.shape), c2.k, c2.stride, c2.pad, c2.dil)
+        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1)
         del dy2
-        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True)
+        dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True, red=red1)
         del da1
         dw1, _ = _conv_wgrad(x, dy1, c1, ws1)
         dwd = dgd = dbd = None
@@ -373,10 +426,10 @@ class BottleneckFn(torch.autograd.Function):
             dwd, _ = _conv_wgrad(x, dyd, cd, wsd)
             if need_dx:
                 dxd = K.conv3d_dgrad(dyd, wd_ito, tuple(x.shape), cd.k, cd.stride, cd.pad, cd.dil)
-                dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dxd)
+                dx = _block_input_grad((tail_y, tail_p), x, dy1, w1_ito, c1, dxd)
         elif need_dx:
-            dx = K.conv3d_dgrad(dy1, w1_ito, tuple(x.shape), c1.k, c1.stride, c1.pad, c1.dil, addend=dres)
-        return (dx, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dwd, dgd, dbd) + (None,) * 8
+            dx = _block_input_grad((tail_y, tail_p), x, dy1, w1_ito, c1, dres)
+        return (dx, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dwd, dgd, dbd) + (None,) * 10
 
 
 # --------------------------------------------------------------------------------------------- stand-alone ops

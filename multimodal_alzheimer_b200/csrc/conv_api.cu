@@ -163,7 +163,8 @@ bool halo_supported(const adni_conv3d_geom& g) {
 // `a` is the tensor the taps slide over (x for fprop, dy for dgrad), `w` the matching K-major weight copy
 // (OTI / ITO), `mirror` selects dgrad's flipped tap order.  Returns ADNI_ENOTSUP when the tile set does not fit.
 int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat16* w, bool mirror, const float* bias,
-            const __nv_bfloat16* addend, __nv_bfloat16* out, double* ssum, double* ssq, cudaStream_t stream) {
+            const __nv_bfloat16* addend, __nv_bfloat16* out, double* ssum, double* ssq, cudaStream_t stream,
+            const BnReduceEpilogue* red = nullptr) {
   const int C = g.Cin;
   HaloParams p;
   memset(&p, 0, sizeof(p));
@@ -201,6 +202,14 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
   p.bias = bias;
   p.stat_sum = ssum;
   p.stat_sq = ssq;
+  if (red != nullptr) {  // dx has the layout of the tensor the BatchNorm normalised: same offsets
+    p.red_y = red->y;
+    p.red_mask = red->mask;
+    p.red_scale = red->scale;
+    p.red_shift = red->shift;
+    p.stat_sum = red->sum_g;
+    p.stat_sq = red->sum_gy;
+  }
   return launch_igemm_halo(p, C, stream);
 }
 
@@ -284,9 +293,9 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
 
 // dx = sum_k dy[(i + pad - k*dil)/stride] * w[k]^T, one launch per parity class of dx when stride > 1.
 int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
-             const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream) {
+             const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream, const BnReduceEpilogue* red = nullptr) {
   if (halo_supported(g)) {
-    const int rc = tc_halo(g, dy, w_ito, true, nullptr, addend, dx, nullptr, nullptr, stream);
+    const int rc = tc_halo(g, dy, w_ito, true, nullptr, addend, dx, nullptr, nullptr, stream, red);
     if (rc != ADNI_ENOTSUP) return rc;
   }
   const int Do = out_extent(g.D, g.k, g.stride, g.pad, g.dil);
@@ -376,6 +385,15 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
         p.out_sw = ov.sw;
         p.out = const_cast<__nv_bfloat16*>(ov.base);
         p.addend = addend ? adds[cls].base : nullptr;
+        if (red != nullptr) {  // y / mask share dx's layout: the parity class is the same element offset into them
+          const long long cls_off = ov.base - dx;
+          p.red_y = red->y + cls_off;
+          p.red_mask = red->mask ? red->mask + cls_off : nullptr;
+          p.red_scale = red->scale;
+          p.red_shift = red->shift;
+          p.stat_sum = red->sum_g;
+          p.stat_sq = red->sum_gy;
+        }
         rc = launch_igemm(p, block_n, stream);
         if (rc) return rc;
       }
@@ -648,6 +666,28 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
     if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;
   }
   return direct_conv_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
+}
+
+int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
+                            adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
+                            const float* bn_shift, double* sum_g, double* sum_gy, void* stream) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(dy && w_ito && dx && bn_y && sum_g && sum_gy, ADNI_EINVAL, "conv3d_dgrad_bnred: null pointer");
+  ADNI_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), ADNI_EINVAL, "conv3d_dgrad_bnred: scale and shift go together");
+  ADNI_REQUIRE(!(bn_relu_out && bn_scale), ADNI_EINVAL, "conv3d_dgrad_bnred: one ReLU mask source at most");
+  ADNI_REQUIRE(tc_supported(*g), ADNI_ENOTSUP, "conv3d_dgrad_bnred: the fused reduction lives in the tcgen05 epilogues (Cin=%d Cout=%d)",
+               g->Cin, g->Cout);
+  BnReduceEpilogue red;
+  red.y = reinterpret_cast<const __nv_bfloat16*>(bn_y);
+  red.mask = reinterpret_cast<const __nv_bfloat16*>(bn_relu_out);
+  red.scale = bn_scale;
+  red.shift = bn_shift;
+  red.sum_g = sum_g;
+  red.sum_gy = sum_gy;
+  return tc_dgrad(*g, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(w_ito),
+                  reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(dx),
+                  static_cast<cudaStream_t>(stream), &red);
 }
 
 long long adni_conv3d_wgrad_scratch_floats(const adni_conv3d_geom* g) {

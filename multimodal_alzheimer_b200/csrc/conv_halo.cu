@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
     const int et = threadIdx.x - 64;  // 0..127
     const int row = q4 * 32 + lane;
     const int rh = row / kHaloBoxW, rw = row % kHaloBoxW;
-    const bool do_stats = p.stat_sum != nullptr;
+    const bool do_red = p.red_y != nullptr;                  // BatchNorm-BACKWARD sums fused into a dgrad call
+    const bool do_fwd_stats = p.stat_sum != nullptr && !do_red;
+    const bool do_stats = do_fwd_stats || do_red;            // either way: two per-channel sums into stat_sum / stat_sq
     // BatchNorm sums.  BLOCK_N = 64: every thread owns one tile row and keeps fp32 partial sums of its 64 channels in
     // registers for the whole CTA; one transpose-reduce and one fp64 atomic per channel at the end.  BLOCK_N = 128:
     // per-piece transpose-reduce into per-CTA fp64 sums (the register file does not hold 256 accumulators).
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
 #pragma unroll
               for (int j = 0; j < 32; j++) f[j] += __ldg(p.bias + chunk * 32 + j);
             }
-            if (do_stats) {
+            if (do_fwd_stats) {   // forward sums: y, y^2 (before any addend)
               if constexpr (REG_STATS) {
                 if (valid) {
 #pragma unroll
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
                 stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
               }
             }
+            uint32_t packed[16];
             if (valid) {
               if (p.addend != nullptr) {
                 const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
@@ -428,15 +431,60 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
                   }
                 }
               }
+#pragma unroll
+              for (int j2 = 0; j2 < 16; j2++) packed[j2] = pack_bf16x2(f[2 * j2], f[2 * j2 + 1]);
               uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
 #pragma unroll
-              for (int j4 = 0; j4 < 4; j4++) {
-                uint4 o;
-                o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-                o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-                o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-                o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
-                op[j4] = o;
+              for (int j4 = 0; j4 < 4; j4++)
+                op[j4] = make_uint4(packed[4 * j4], packed[4 * j4 + 1], packed[4 * j4 + 2], packed[4 * j4 + 3]);
+            }
+            if (do_red) {  // backward sums of the STORED gradient, masked by the preceding layer's ReLU: g, g*y
+              float s1[REG_STATS ? 1 : 32], s2[REG_STATS ? 1 : 32];
+              if constexpr (!REG_STATS) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) s1[j] = s2[j] = 0.f;
+              }
+              if (valid) {
+                const uint4* yp = reinterpret_cast<const uint4*>(p.red_y + off + chunk * 32);
+                const uint4* mp =
+                    p.red_mask != nullptr ? reinterpret_cast<const uint4*>(p.red_mask + off + chunk * 32) : nullptr;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                  const uint4 yv = __ldg(yp + j4);
+                  const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+                  uint32_t mw[4] = {0u, 0u, 0u, 0u};
+                  if (mp != nullptr) {
+                    const uint4 mv = __ldg(mp + j4);
+                    mw[0] = mv.x, mw[1] = mv.y, mw[2] = mv.z, mw[3] = mv.w;
+                  }
+#pragma unroll
+                  for (int e = 0; e < 4; e++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                      const int j = j4 * 8 + e * 2 + h;
+                      const float y = h ? bf16_hi(yw[e]) : bf16_lo(yw[e]);
+                      float gq = h ? bf16_hi(packed[j >> 1]) : bf16_lo(packed[j >> 1]);
+                      if (mp != nullptr) {
+                        gq = (h ? bf16_hi(mw[e]) : bf16_lo(mw[e])) > 0.f ? gq : 0.f;
+                      } else if (p.red_scale != nullptr) {
+                        gq = fmaf(y, __ldg(p.red_scale + chunk * 32 + j), __ldg(p.red_shift + chunk * 32 + j)) > 0.f ? gq : 0.f;
+                      }
+                      if constexpr (REG_STATS) {
+                        rs1[chunk * 32 + j] += gq;
+                        rs2[chunk * 32 + j] = fmaf(gq, y, rs2[chunk * 32 + j]);
+                      } else {
+                        s1[j] = gq;
+                        s2[j] = gq * y;
+                      }
+                    }
+                  }
+                }
+              }
+              if constexpr (!REG_STATS) {
+                const float cs1 = warp_column_sums(s1, lane);
+                const float cs2 = warp_column_sums(s2, lane);
+                stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
+                stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
               }
             }
           }

@@ -34,6 +34,13 @@ struct IgemmParams {
   const float* bias;            // [N_total], nullable
   double* stat_sum;             // [N_total], nullable
   double* stat_sq;
+  // BatchNorm-backward sums fused into a dgrad epilogue (the gradient this kernel writes is the `dout` of a preceding
+  // BatchNorm): with red_y set, stat_sum / stat_sq receive  sum g  and  sum g*y  per channel, g = the bf16 value stored
+  // in `out`, masked by that layer's ReLU: red_mask > 0 (its stored output), or y*red_scale + red_shift > 0, or no mask.
+  const __nv_bfloat16* red_y;     // same view as out
+  const __nv_bfloat16* red_mask;  // same view as out, nullable
+  const float* red_scale;         // [N_total], nullable
+  const float* red_shift;
   int debug;  // diagnostics only (ADNI_DEBUG_MODE): 1 = no MMA issue, 2 = no TMA loads, 3 = no epilogue stores
 };
 
@@ -75,6 +82,20 @@ struct HaloParams {
   const float* bias;
   double* stat_sum;
   double* stat_sq;
+  const __nv_bfloat16* red_y;     // fused BatchNorm-backward sums, as in IgemmParams
+  const __nv_bfloat16* red_mask;
+  const float* red_scale;
+  const float* red_shift;
+};
+
+// Optional epilogue of a dgrad call: the BatchNorm-backward reduction of the layer whose output gradient it produces.
+struct BnReduceEpilogue {
+  const __nv_bfloat16* y;      // raw conv output that BatchNorm normalised (same shape as dx)
+  const __nv_bfloat16* mask;   // the layer's ReLU output (mask = > 0) or null
+  const float* scale;          // or the BatchNorm scale / shift to recompute the mask from y; null = no ReLU
+  const float* shift;
+  double* sum_g;               // [C] += sum g
+  double* sum_gy;              // [C] += sum g*y
 };
 
 }  // namespace adni

@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
     const int ew = warp - 2;
     const int et = threadIdx.x - 64;  // 0..127
     const int row = q * 32 + lane;
-    const bool do_stats = p.stat_sum != nullptr;
+    const bool do_red = p.red_y != nullptr;                       // BatchNorm-backward sums (dgrad calls)
+    const bool do_stats = p.stat_sum != nullptr && !do_red;       // BatchNorm-forward sums (fprop calls)
     int acc = 0;
     uint32_t accph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
           stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
           stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
         }
-        if (valid && p.debug != 3) {
+        uint32_t packed[16];
+        if (valid) {
           if (p.addend != nullptr) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + chunk * 32);
 #pragma unroll
@@ -262,16 +264,55 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
               }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; j4++) {
-            uint4 o;
-            o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-            o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-            o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-            o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
-            op[j4] = o;
+          for (int j2 = 0; j2 < 16; j2++) packed[j2] = pack_bf16x2(f[2 * j2], f[2 * j2 + 1]);
+          if (p.debug != 3) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + off + chunk * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) op[j4] = make_uint4(packed[4 * j4], packed[4 * j4 + 1], packed[4 * j4 + 2], packed[4 * j4 + 3]);
           }
+        }
+        if (do_red) {
+          // sums of the STORED gradient (bf16), masked by the preceding layer's ReLU
+          float s1[32], s2[32];
+          if (valid) {
+            const uint4* yp = reinterpret_cast<const uint4*>(p.red_y + off + chunk * 32);
+            const uint4* mp = p.red_mask != nullptr ? reinterpret_cast<const uint4*>(p.red_mask + off + chunk * 32) : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+              const uint4 yv = __ldg(yp + j4);
+              const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+              uint32_t mw[4] = {0u, 0u, 0u, 0u};
+              if (mp != nullptr) {
+                const uint4 mv = __ldg(mp + j4);
+                mw[0] = mv.x, mw[1] = mv.y, mw[2] = mv.z, mw[3] = mv.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const int j = j4 * 8 + e * 2 + h;
+                  const float y = h ? bf16_hi(yw[e]) : bf16_lo(yw[e]);
+                  float g = h ? bf16_hi(packed[j >> 1]) : bf16_lo(packed[j >> 1]);
+                  if (mp != nullptr) {
+                    g = (h ? bf16_hi(mw[e]) : bf16_lo(mw[e])) > 0.f ? g : 0.f;
+                  } else if (p.red_scale != nullptr) {
+                    const int ch = c.n0 + chunk * 32 + j;
+                    g = fmaf(y, __ldg(p.red_scale + ch), __ldg(p.red_shift + ch)) > 0.f ? g : 0.f;
+                  }
+                  s1[j] = g;
+                  s2[j] = g * y;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) s1[j] = s2[j] = 0.f;
+          }
+          const float cs1 = warp_column_sums(s1, lane);
+          const float cs2 = warp_column_sums(s2, lane);
+          stat_smem[(ew * 2 + 0) * BLOCK_N + chunk * 32 + lane] = cs1;
+          stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
         }
       }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
@@ -282,7 +323,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
         acc = 0;
         accph ^= 1;
       }
-      if (do_stats) {
+      if (do_stats || do_red) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int col = et; col < BLOCK_N; col += 128) {
           float a = 0.f, b = 0.f;

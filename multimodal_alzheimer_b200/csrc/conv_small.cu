@@ -184,11 +184,12 @@ __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int taps = p.k * p.k * p.k;
+  const int co0 = blockIdx.y * NT * 8;   // output-channel chunk of this CTA (wide layers with long K are split over y)
 
   // ---- B fragments: wfrag[(s*NT + j)*32 + lane] = {B[16s+2t..+1][8j+g], B[16s+8+2t..+1][8j+g]} -----------------
   for (int i = threadIdx.x; i < p.S * NT * 32; i += kThreads) {
     const int l = i & 31, sj = i >> 5, j = sj % NT, s = sj / NT;
-    const int n = 8 * j + (l >> 2), tt = l & 3;
+    const int n = co0 + 8 * j + (l >> 2), tt = l & 3;
     uint32_t regs[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams
         const bool ok = row_ok && ow < p.Wo;
 #pragma unroll
         for (int j = 0; j < NT; j++) {
-          const int ch = 8 * j + 2 * t;
+          const int ch = co0 + 8 * j + 2 * t;
           float v0 = acc[i][j][2 * half], v1 = acc[i][j][2 * half + 1];
           if (p.bias != nullptr && ch < p.Co) {
             v0 += __ldg(p.bias + ch);
@@ -315,9 +316,9 @@ __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams
   }
   if (do_stats) {
     __syncthreads();
-    if (threadIdx.x < NT * 8 && threadIdx.x < p.Co) {
-      atomicAdd(p.ssum + threadIdx.x, stat_s[threadIdx.x * 2 + 0]);
-      atomicAdd(p.ssq + threadIdx.x, stat_s[threadIdx.x * 2 + 1]);
+    if (threadIdx.x < NT * 8 && co0 + threadIdx.x < p.Co) {
+      atomicAdd(p.ssum + co0 + threadIdx.x, stat_s[threadIdx.x * 2 + 0]);
+      atomicAdd(p.ssq + co0 + threadIdx.x, stat_s[threadIdx.x * 2 + 1]);
     }
   }
 }
@@ -478,7 +479,7 @@ size_t fprop_smem(const SmallParams& p, int NT) {
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int NT, int R, bool C1>
-int launch_fprop_t(const SmallParams& p, size_t smem, cudaStream_t st) {
+int launch_fprop_t(const SmallParams& p, size_t smem, int ysplit, cudaStream_t st) {
   auto kern = small_fprop_kernel<NT, R, C1>;
   static size_t attr = 0;
   if (smem > attr) {
@@ -486,33 +487,50 @@ int launch_fprop_t(const SmallParams& p, size_t smem, cudaStream_t st) {
     attr = smem;
   }
   const int per_sm = std::max<size_t>(1, std::min<size_t>(3, kSmemLimit / (smem + 1024)));
-  const long long want = static_cast<long long>(num_sms()) * per_sm;
-  const int grid = static_cast<int>(std::min<long long>(p.total_tiles, want));
+  const long long want = std::max<long long>(1, static_cast<long long>(num_sms()) * per_sm / ysplit);
+  dim3 grid(static_cast<unsigned>(std::min<long long>(p.total_tiles, want)), static_cast<unsigned>(ysplit));
   kern<<<grid, kThreads, smem, st>>>(p);
   count_launch();
   ADNI_LAUNCH_CHECK("small_fprop_kernel");
   return ADNI_OK;
 }
 
+// Tile depth (R = 4 rows per warp when it fits, else 2) and output-channel chunk (NT n-tiles of 8 per CTA; the rest
+// of a wide layer goes to blockIdx.y) such that B fragments + halo tile fit shared memory.
+bool pick_small_cfg(const SmallParams& p4, const SmallParams& p2, int nt_total, int* nt, bool* r4) {
+  for (int n = nt_total; n >= 1; n >>= 1) {
+    if (n <= 4 && fprop_smem(p4, n) <= kSmemLimit) {
+      *nt = n, *r4 = true;
+      return true;
+    }
+    if (fprop_smem(p2, n) <= kSmemLimit) {
+      *nt = n, *r4 = false;
+      return true;
+    }
+  }
+  return false;
+}
+
 template <bool C1>
-int launch_fprop_nt(const SmallParams& p4, const SmallParams& p2, int NT, cudaStream_t st) {
-  // R = 4 rows per warp (tile depth 4) when it fits shared memory and registers, else R = 2
-  const bool r4 = NT <= 4 && fprop_smem(p4, NT) <= kSmemLimit;
-  const SmallParams& p = r4 ? p4 : p2;
-  const size_t smem = fprop_smem(p, NT);
-  if (smem > kSmemLimit) {
-    set_error("small conv: %zu bytes of shared memory needed (Cin=%d Cout=%d k=%d)", smem, p.Ci, p.Co, p.k);
+int launch_fprop_nt(const SmallParams& p4, const SmallParams& p2, int nt_total, cudaStream_t st) {
+  int NT = 0;
+  bool r4 = false;
+  if (!pick_small_cfg(p4, p2, nt_total, &NT, &r4)) {
+    set_error("small conv: tile + weights exceed shared memory (Cin=%d Cout=%d k=%d)", p4.Ci, p4.Co, p4.k);
     return ADNI_ENOTSUP;
   }
+  const SmallParams& p = r4 ? p4 : p2;
+  const size_t smem = fprop_smem(p, NT);
+  const int ysplit = nt_total / NT;
   switch (NT) {
     case 1:
-      return r4 ? launch_fprop_t<1, 4, C1>(p, smem, st) : launch_fprop_t<1, 2, C1>(p, smem, st);
+      return r4 ? launch_fprop_t<1, 4, C1>(p, smem, ysplit, st) : launch_fprop_t<1, 2, C1>(p, smem, ysplit, st);
     case 2:
-      return r4 ? launch_fprop_t<2, 4, C1>(p, smem, st) : launch_fprop_t<2, 2, C1>(p, smem, st);
+      return r4 ? launch_fprop_t<2, 4, C1>(p, smem, ysplit, st) : launch_fprop_t<2, 2, C1>(p, smem, ysplit, st);
     case 4:
-      return r4 ? launch_fprop_t<4, 4, C1>(p, smem, st) : launch_fprop_t<4, 2, C1>(p, smem, st);
+      return r4 ? launch_fprop_t<4, 4, C1>(p, smem, ysplit, st) : launch_fprop_t<4, 2, C1>(p, smem, ysplit, st);
     default:
-      return launch_fprop_t<8, 2, C1>(p, smem, st);
+      return launch_fprop_t<8, 2, C1>(p, smem, ysplit, st);
   }
 }
 
@@ -555,10 +573,21 @@ bool small_conv_supported(const adni_conv3d_geom& g, int pass) {
   auto pow2 = [](int v, int lo, int hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; };
   if (g.stride != 1 || g.dil != 1 || g.k < 1 || g.k > 7 || g.pad > g.k - 1) return false;
   if (!pow2(g.Cout, 8, 64)) return false;
-  if (g.Cin == 1) return pass != 1;                        // the first layer: on-chip window expansion, no dgrad
-  if (!pow2(g.Cin, 8, 64)) return false;
+  if (g.Cin != 1 && !pow2(g.Cin, 8, 64)) return false;
+  if (g.Cin == 1 && pass == 1) return false;               // the first layer (on-chip window expansion) has no dgrad
   const int slide = pass == 1 ? g.Cout : g.Cin;            // channels of the tensor the taps slide over
-  return g.k * g.k * g.k * (slide / 8) <= kMaxQ;
+  const int outc = pass == 1 ? g.Cin : g.Cout;
+  if (slide != 1 && g.k * g.k * g.k * (slide / 8) > kMaxQ) return false;
+  if (pass == 2) return true;                              // wgrad tiles always fit (<= 64 channels on both sides)
+  // fprop / dgrad keep every B fragment in shared memory next to the halo tile: must fit with the shallow tile (R = 2)
+  SmallParams p4, p2;
+  memset(&p4, 0, sizeof(p4));
+  memset(&p2, 0, sizeof(p2));
+  plan_small(p4, 1, 8, 8, 16, slide, 8, 8, 16, outc, g.k, 0, 0, 4);
+  plan_small(p2, 1, 8, 8, 16, slide, 8, 8, 16, outc, g.k, 0, 0, 2);
+  int nt = 0;
+  bool r4 = false;
+  return pick_small_cfg(p4, p2, nt_for(outc), &nt, &r4);
 }
 
 int small_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,

@@ -356,11 +356,16 @@ __global__ void __launch_bounds__(kEwThreads)
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const double* __restrict__ red, double inv_count, long long nvec, int vpr, int C, int relu,
                         __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, double pg_scale) {
+                        float* __restrict__ dbeta, double pg_scale, int red_form) {
+  // red_form 0: red[C + c] = sum g*xhat;  1: red[C + c] = sum g*y (a conv epilogue produced it, adni_conv3d_dgrad_bnred):
+  // sum g*xhat = invstd * (sum g*y - mean * sum g), evaluated in fp64
+  auto sum_gx = [&](int c) -> double {
+    return red_form ? (double)invstd[c] * (red[C + c] - (double)mean[c] * red[c]) : red[C + c];
+  };
   if (blockIdx.x == 0 && (dgamma || dbeta)) {  // dgamma = sum g*xhat, dbeta = sum g (x pg_scale, see the C-ABI comment)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (dbeta) dbeta[c] = (float)(red[c] * pg_scale);
-      if (dgamma) dgamma[c] = (float)(red[C + c] * pg_scale);
+      if (dgamma) dgamma[c] = (float)(sum_gx(c) * pg_scale);
     }
   }
   extern __shared__ float coef[];  // [5][C]: A, B, K, scale, shift (only used when the channel vector is not fixed)
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kEwThreads)
     const float gm = gamma ? gamma[c] : 1.f;
     const float is = invstd[c], mu = mean[c];
     const float mg = (float)(red[c] * inv_count);
-    const float mgx = (float)(red[C + c] * inv_count);
+    const float mgx = (float)(sum_gx(c) * inv_count);
     a = gm * is;
     b = -a * is * mgx;
     k = -a * mg - b * mu;
@@ -925,9 +930,9 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
 int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf16* y, const float* mean,
                       const float* invstd, const float* gamma, const float* scale, const float* shift,
                       const double* red, double count, long long rows, int C, int relu, adni_bf16* dy, adni_bf16* dres,
-                      float* dgamma, float* dbeta, double param_grad_scale, void* stream) {
-  ADNI_REQUIRE(dout && y && mean && invstd && red && dy && rows > 0 && count > 0, ADNI_EINVAL,
-               "bn_bwd_apply: bad arguments");
+                      float* dgamma, float* dbeta, double param_grad_scale, int red_form, void* stream) {
+  ADNI_REQUIRE(dout && y && mean && invstd && red && dy && rows > 0 && count > 0 && (red_form == 0 || red_form == 1),
+               ADNI_EINVAL, "bn_bwd_apply: bad arguments");
   ADNI_REQUIRE(!relu || out || (scale && shift), ADNI_EINVAL,
                "bn_bwd_apply: relu mask needs the forward output or scale/shift");
   if (relu) relu = out ? 1 : 2;
@@ -936,7 +941,7 @@ int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf
   ADNI_REQUIRE(C <= 2048, ADNI_ENOTSUP, "bn_bwd_apply: C=%d > 2048", C);
   bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 5 * C * sizeof(float), ST(stream)>>>(
       CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, scale, shift, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy),
-      BF(dres), dgamma, dbeta, param_grad_scale);
+      BF(dres), dgamma, dbeta, param_grad_scale, red_form);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return ADNI_OK;

@@ -272,6 +272,34 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
     return dx
 
 
+def conv3d_dgrad_bnred(dy, w_ito, in_shape, k, stride, pad, dil, bn_y, bn_relu_out=None, bn_scale=None, bn_shift=None,
+                       addend=None):
+    """conv3d_dgrad whose epilogue also accumulates the BatchNorm-backward sums of the layer that produced dx's tensor
+    (adni_conv3d_dgrad_bnred).  Returns (dx, red) with red fp64 [2, Cin] = [sum g | sum g*y]  (bn_bwd_apply red_form 1)."""
+    _chk(dy, BF16, "dy")
+    _chk(w_ito, BF16, "w_ito")
+    _chk(bn_y, BF16, "bn_y")
+    N, D, H, W, Cin = in_shape
+    Cout = dy.shape[-1]
+    if tuple(bn_y.shape) != tuple(in_shape):
+        raise ValueError(f"conv3d_dgrad_bnred: bn_y {tuple(bn_y.shape)} must have dx's shape {tuple(in_shape)}")
+    g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    red = zeros_f64((2, Cin), dy.device)
+    ev = PROFILE.begin()
+    call("adni_conv3d_dgrad_bnred", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), ptr(bn_y), ptr(bn_relu_out),
+         ptr(bn_scale), ptr(bn_shift), ptr(red[0]), ptr(red[1]), stream_ptr())
+    tag, frac = _engine_tag(g, 1, ENGINE_AUTO)
+    PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
+                f"dgrad+bnred N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
+    return dx, red
+
+
+def dgrad_bnred_supported(Cin, Cout, k, stride):
+    """The fused reduction lives in the tcgen05 epilogues (csrc/conv_api.cu tc_supported)."""
+    return Cin % 64 == 0 and Cout % 64 == 0 and stride in (1, 2) and k ** 3 <= 64
+
+
 _SCRATCH_CACHE = {}
 
 
@@ -464,7 +492,7 @@ def bn_bwd_reduce(dout, out, y, mean, invstd, relu, scale=None, shift=None):
 
 
 def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres, want_param_grads=True, scale=None,
-                 shift=None, param_grad_scale=1.0):
+                 shift=None, param_grad_scale=1.0, red_form=0):
     C = y.shape[-1]
     rows = y.numel() // C
     dy = torch.empty_like(y)
@@ -474,7 +502,7 @@ def bn_bwd_apply(dout, out, y, mean, invstd, gamma, red, count, relu, want_dres,
     call_hbm("hbm_bn_bwd_apply", 2 * y.numel() * n_tensors, "adni_bn_bwd_apply", ptr(dout),
              ptr(out) if relu else None, ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale), ptr(shift), ptr(red),
              float(count), rows, C, int(relu), ptr(dy), ptr(dres), ptr(pg[0]) if want_param_grads else None,
-             ptr(pg[1]) if want_param_grads else None, float(param_grad_scale), stream_ptr())
+             ptr(pg[1]) if want_param_grads else None, float(param_grad_scale), int(red_form), stream_ptr())
     if want_param_grads:
         return dy, dres, pg[0], pg[1]
     return dy, dres, None, None

@@ -25,6 +25,19 @@ def _ds_args(downsample):
     return conv.weight, bn.weight, bn.bias, bn.state(), conv.cfg
 
 
+def _with_tail(out, y_last, bnp_last):
+    """Tag a block's output with the description of the bn -> (+ residual) -> relu that produced it (raw conv output,
+    BatchNorm parameters): the next block's last dgrad folds that BatchNorm's backward sums into its epilogue
+    (autograd._block_input_grad).  Training-mode batches only (eval mode has no BatchNorm backward)."""
+    if bnp_last.numel():
+        out._adni_tail = (y_last, bnp_last)
+    return out
+
+
+def _tail_of(x):
+    return getattr(x, "_adni_tail", (None, None))
+
+
 class BasicBlock(tnn.Module):
     expansion = 1
 
@@ -41,9 +54,11 @@ class BasicBlock(tnn.Module):
 
     def forward(self, x):
         wd, gd, bd, bnd, cd = _ds_args(self.downsample)
-        return A.BasicBlockFn.apply(bnn.as_volume(x), self.conv1.weight, self.bn1.weight, self.bn1.bias,
-                                    self.conv2.weight, self.bn2.weight, self.bn2.bias, wd, gd, bd, self.bn1.state(),
-                                    self.bn2.state(), bnd, self.conv1.cfg, self.conv2.cfg, cd)
+        tail_y, tail_p = _tail_of(x)
+        out, y2, p2 = A.BasicBlockFn.apply(bnn.as_volume(x), self.conv1.weight, self.bn1.weight, self.bn1.bias,
+                                           self.conv2.weight, self.bn2.weight, self.bn2.bias, wd, gd, bd, self.bn1.state(),
+                                           self.bn2.state(), bnd, self.conv1.cfg, self.conv2.cfg, cd, tail_y, tail_p)
+        return _with_tail(out, y2, p2)
 
 
 class Bottleneck(tnn.Module):
@@ -64,10 +79,13 @@ class Bottleneck(tnn.Module):
 
     def forward(self, x):
         wd, gd, bd, bnd, cd = _ds_args(self.downsample)
-        return A.BottleneckFn.apply(bnn.as_volume(x), self.conv1.weight, self.bn1.weight, self.bn1.bias,
-                                    self.conv2.weight, self.bn2.weight, self.bn2.bias, self.conv3.weight,
-                                    self.bn3.weight, self.bn3.bias, wd, gd, bd, self.bn1.state(), self.bn2.state(),
-                                    self.bn3.state(), bnd, self.conv1.cfg, self.conv2.cfg, self.conv3.cfg, cd)
+        tail_y, tail_p = _tail_of(x)
+        out, y3, p3 = A.BottleneckFn.apply(bnn.as_volume(x), self.conv1.weight, self.bn1.weight, self.bn1.bias,
+                                           self.conv2.weight, self.bn2.weight, self.bn2.bias, self.conv3.weight,
+                                           self.bn3.weight, self.bn3.bias, wd, gd, bd, self.bn1.state(), self.bn2.state(),
+                                           self.bn3.state(), bnd, self.conv1.cfg, self.conv2.cfg, self.conv3.cfg, cd,
+                                           tail_y, tail_p)
+        return _with_tail(out, y3, p3)
 
 
 class ResNet(tnn.Module):

@@ -158,8 +158,10 @@ def test_planner_routes_small_stacks_to_tensor_cores():
                             continue                       # no input gradient for the first layer
                         kind, frac = ctypes.c_int(-1), ctypes.c_double(0)
                         assert lib.adni_conv3d_plan_info(ctypes.byref(g), pass_, ctypes.byref(kind), ctypes.byref(frac)) == 0
-                        if (chans[i], chans[i + 1], k) == (64, 128, 5):
-                            assert kind.value == 0      # 125 taps exceed the tcgen05 tap mask, 128 > the small engine
+                        if (chans[i], chans[i + 1], k) == (64, 128, 5) or (chans[i], chans[i + 1], k, pass_) == (32, 64, 5, 1):
+                            # 125 taps exceed the tcgen05 tap mask and 128 channels the small engine; the dgrad of
+                            # 32 -> 64 at k = 5 (a 64-channel halo tile + 125 x 64-deep weights) exceeds shared memory
+                            assert kind.value == 0
                             continue
                         assert kind.value in (1, 2, 3), (chans[i], chans[i + 1], k, pass_, kind.value)
                     ext //= 2

@@ -95,6 +95,41 @@ def test_tc_wgrad(cuda_dev, shape):
     assert_close(g, w_ref.grad, 2e-4, f"wgrad {shape}")
 
 
+BNRED_SHAPES = [TC_SHAPES[1], TC_SHAPES[2], TC_SHAPES[4], TC_SHAPES[5], TC_SHAPES[6], TC_SHAPES[9], TC_SHAPES[10],
+                (2, 10, 12, 10, 256, 64, 1, 1, 0, 1)]   # + a Bottleneck 1x1 reduce conv (dx has 256 channels)
+
+
+@pytest.mark.parametrize("mask_mode", ["relu_out", "recompute", "none"])
+@pytest.mark.parametrize("shape", BNRED_SHAPES)
+def test_tc_dgrad_with_fused_bn_backward_sums(cuda_dev, shape, mask_mode):
+    """adni_conv3d_dgrad_bnred: dx is bit-identical to adni_conv3d_dgrad, and the epilogue's per-channel sums equal
+    sum g and sum g*y over the STORED bf16 dx with the preceding layer's ReLU mask (fp64 reference)."""
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    _, ito = K.weights_to_kernel_layout(w)
+    Do, Ho, Wo = (K.out_extent(v, k, s, p, d) for v in (D, H, W))
+    g = torch.Generator().manual_seed(5)
+    dy_b = torch.randn((N, Do, Ho, Wo, Cout), generator=g).to(cuda_dev).to(torch.bfloat16)
+    add = torch.randn((N, D, H, W, Cin), generator=g).to(cuda_dev).to(torch.bfloat16)
+    bn_y = (torch.randn((N, D, H, W, Cin), generator=g) * 1.5 + 0.3).to(cuda_dev).to(torch.bfloat16)
+    scale = (torch.rand(Cin, generator=g) * 2 - 0.5).to(cuda_dev)         # some negative scales
+    shift = (torch.randn(Cin, generator=g) * 0.5).to(cuda_dev)
+    relu_out = torch.relu(torch.randn((N, D, H, W, Cin), generator=g)).to(cuda_dev).to(torch.bfloat16)
+    kw = dict(relu_out=dict(bn_relu_out=relu_out), recompute=dict(bn_scale=scale, bn_shift=shift), none={})[mask_mode]
+    dx_ref = K.conv3d_dgrad(dy_b, ito, tuple(x_b.shape), k, s, p, d, addend=add)
+    dx, red = K.conv3d_dgrad_bnred(dy_b, ito, tuple(x_b.shape), k, s, p, d, bn_y, addend=add, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_ref)
+    gq, yq = dx.double(), bn_y.double()
+    if mask_mode == "relu_out":
+        gq = gq * (relu_out > 0)
+    elif mask_mode == "recompute":
+        gq = gq * (torch.addcmul(shift, bn_y.float(), scale) > 0)          # fmaf(y, scale, shift) in fp32, like the kernel
+    assert_close(red[0], gq.sum(dim=(0, 1, 2, 3)), 2e-5, f"sum g {shape} {mask_mode}")
+    assert_close(red[1], (gq * yq).sum(dim=(0, 1, 2, 3)), 2e-5, f"sum g*y {shape} {mask_mode}")
+
+
 @pytest.mark.parametrize("shape", TINY_SHAPES)
 def test_tc_tiny_feature_maps(cuda_dev, shape):
     """fprop + dgrad + wgrad on feature maps smaller than one tile, through the planner's own engine choice."""
@@ -149,7 +184,8 @@ SMALL_SHAPES = [
     (2, 6, 9, 20, 16, 32, 5, 1, 2, 1),     # filter (5,5,5,3): third layer with k = 5
     (1, 8, 8, 8, 32, 64, 3, 1, 1, 1),      # conv4
     (3, 5, 7, 18, 32, 64, 3, 1, 1, 1),     # conv4, ragged
-    (1, 7, 8, 16, 64, 64, 3, 1, 1, 1),     # 64 channels on both sides (forced: AUTO sends this shape to tcgen05)
+    (1, 7, 8, 16, 64, 32, 3, 1, 1, 1),     # 64 sliding channels (the dgrad of conv4 seen as a forward conv)
+    (1, 6, 9, 17, 32, 64, 5, 1, 2, 1),     # long K (125 taps x 32 channels): output channels split over blockIdx.y
     (2, 9, 9, 17, 8, 8, 4, 1, 2, 1),       # even kernel after the high-side pad (output extent = input - 1 + ... )
 ]
 
