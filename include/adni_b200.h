@@ -88,6 +88,9 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
  * bn_y / bn_relu_out have dx's shape.  sum g*xhat = invstd * (sum_gy - mean * sum_g): adni_bn_bwd_apply takes the
  * sums in this form (red_form 1).  Replaces one full read of dx and bn_y per BatchNorm layer (adni_bn_bwd_reduce).
  * tcgen05 engines only (ADNI_ENOTSUP otherwise: call adni_conv3d_dgrad + adni_bn_bwd_reduce). */
+/* 1 when the fused form is the faster one for this geometry (long main loops hide the epilogue's extra reads; host-side
+ * query, no launch): callers use adni_conv3d_dgrad + adni_bn_bwd_reduce otherwise. */
+int adni_conv3d_dgrad_bnred_profitable(const adni_conv3d_geom* g);
 int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
                             adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
                             const float* bn_shift, double* sum_g, double* sum_gy, void* stream);

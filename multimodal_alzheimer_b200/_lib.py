@@ -65,6 +65,7 @@ _SIGNATURES = {
     "adni_bn_apply": [_P, _P, _P, _P, _P, _LL, _I, _I, _P, _P, _P],
     "adni_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P],
     "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _D, _I, _P],
+    "adni_conv3d_dgrad_bnred_profitable": [ctypes.POINTER(ConvGeom)],
     "adni_conv3d_dgrad_bnred": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "adni_bn_train_apply": [_P, _P, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _LL, _I, _I, _P],
     "adni_channel_stats": [_P, _LL, _I, _P, _P, _P],

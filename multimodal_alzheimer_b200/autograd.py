@@ -156,7 +156,7 @@ def _dgrad_bnred(dy, w_ito, in_shape, cfg, bn_y, bnp, relu_out=None, addend=None
     sums of the conv -> bn -> relu layer whose output dx is the gradient of: (dx, red | None).  relu_out: that layer's
     stored output (mask = > 0); None = the mask is recomputed from bn_y * scale + shift."""
     if (_FUSE_BNRED and bnp is not None and bn_y is not None
-            and K.dgrad_bnred_supported(in_shape[-1], dy.shape[-1], cfg.k, cfg.stride)):
+            and K.dgrad_bnred_profitable(in_shape, dy.shape[-1], cfg.k, cfg.stride, cfg.pad, cfg.dil)):
         scale, shift = (None, None) if relu_out is not None else (bnp[2], bnp[3])
         return K.conv3d_dgrad_bnred(dy, w_ito, in_shape, cfg.k, cfg.stride, cfg.pad, cfg.dil, bn_y, bn_relu_out=relu_out,
                                     bn_scale=scale, bn_shift=shift, addend=addend)
@@ -351,7 +351,7 @@ class BasicBlockFn(torch.autograd.Function):
         dout = dout.contiguous()
         dy2, dres, dg2, db2 = _bn_backward(dout, out, y2, p2, g2, n2, True, True, True, red=_take_pending_red(dout))
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
-        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1)
+        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1, relu_out=a1)
         del dy2
         dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True, red=red1)
         del da1
@@ -409,12 +409,12 @@ class BottleneckFn(torch.autograd.Function):
         dout = dout.contiguous()
         dy3, dres, dg3, db3 = _bn_backward(dout, out, y3, p3, g3, n3, True, True, True, red=_take_pending_red(dout))
         dw3, _ = _conv_wgrad(a2, dy3, c3, ws3)
-        da2, red2 = _dgrad_bnred(dy3, w3_ito, tuple(a2.shape), c3, y2, p2)
+        da2, red2 = _dgrad_bnred(dy3, w3_ito, tuple(a2.shape), c3, y2, p2, relu_out=a2)
         del dy3
         dy2, _, dg2, db2 = _bn_backward(da2, None, y2, p2, g2, n2, True, False, True, red=red2)
         del da2
         dw2, _ = _conv_wgrad(a1, dy2, c2, ws2)
-        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1)
+        da1, red1 = _dgrad_bnred(dy2, w2_ito, tuple(a1.shape), c2, y1, p1, relu_out=a1)
         del dy2
         dy1, _, dg1, db1 = _bn_backward(da1, None, y1, p1, g1, n1, True, False, True, red=red1)
         del da1

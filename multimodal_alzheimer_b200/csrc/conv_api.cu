@@ -668,6 +668,15 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
   return direct_conv_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
 }
 
+int adni_conv3d_dgrad_bnred_profitable(const adni_conv3d_geom* g) {
+  // Measured on B200 (profiles/r02_bnred_ab.md): the extra rows the epilogue reads are hidden only under a long main
+  // loop - the tap-per-box engine with >= 54 K blocks per tile (3x3x3, stride 1, >= 128 channels: layers 3 / 4 and
+  // the Bottleneck conv2s).  1x1x1 convs are epilogue-bound already (2.5-3x slower with the sums), and the halo
+  // engine's four epilogue warps have no slack either (layer1 dgrad 0.36 -> 0.89 ms).
+  if (g == nullptr || check_geom(g) != ADNI_OK || !tc_supported(*g) || halo_supported(*g)) return 0;
+  return (g->k == 3 && g->stride == 1 && g->Cout >= 128) ? 1 : 0;
+}
+
 int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
                             adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
                             const float* bn_shift, double* sum_g, double* sum_gy, void* stream) {

@@ -215,10 +215,35 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
       const bool valid = rd < p.bd && od < p.Do && oh < p.Ho && ow < p.Wo;
       const long long off = c.n * p.out_sn + od * p.out_sd + oh * p.out_sh + ow * p.out_sw + c.n0;
 
+      // fused BatchNorm-backward sums: the y / mask rows of chunk c+1 are in flight while chunk c is processed, and
+      // those of chunk 0 while this thread still waits for the accumulator (they do not depend on the MMA result)
+      uint4 y_nxt[4], m_nxt[4];
+      const bool red_row = do_red && valid;
+      const bool red_mask = red_row && p.red_mask != nullptr;
+      auto red_prefetch = [&](int chunk) {
+        if (red_row) {
+          const uint4* yp = reinterpret_cast<const uint4*>(p.red_y + off + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) y_nxt[j4] = __ldg(yp + j4);
+          if (red_mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.red_mask + off + chunk * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) m_nxt[j4] = __ldg(mp + j4);
+          }
+        }
+      };
+      red_prefetch(0);
       mbar_wait_spin(&tfull[acc], accph, 2217);
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
+        uint4 y_cur[4], m_cur[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) {
+          y_cur[j4] = y_nxt[j4];
+          m_cur[j4] = m_nxt[j4];
+        }
+        if (chunk + 1 < BLOCK_N / 32) red_prefetch(chunk + 1);
         uint32_t v[32];
         if (has_k) {
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -276,17 +301,10 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
           // sums of the STORED gradient (bf16), masked by the preceding layer's ReLU
           float s1[32], s2[32];
           if (valid) {
-            const uint4* yp = reinterpret_cast<const uint4*>(p.red_y + off + chunk * 32);
-            const uint4* mp = p.red_mask != nullptr ? reinterpret_cast<const uint4*>(p.red_mask + off + chunk * 32) : nullptr;
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++) {
-              const uint4 yv = __ldg(yp + j4);
-              const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-              uint32_t mw[4] = {0u, 0u, 0u, 0u};
-              if (mp != nullptr) {
-                const uint4 mv = __ldg(mp + j4);
-                mw[0] = mv.x, mw[1] = mv.y, mw[2] = mv.z, mw[3] = mv.w;
-              }
+              const uint32_t yw[4] = {y_cur[j4].x, y_cur[j4].y, y_cur[j4].z, y_cur[j4].w};
+              const uint32_t mw[4] = {m_cur[j4].x, m_cur[j4].y, m_cur[j4].z, m_cur[j4].w};
 #pragma unroll
               for (int e = 0; e < 4; e++) {
 #pragma unroll
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
                   const int j = j4 * 8 + e * 2 + h;
                   const float y = h ? bf16_hi(yw[e]) : bf16_lo(yw[e]);
                   float g = h ? bf16_hi(packed[j >> 1]) : bf16_lo(packed[j >> 1]);
-                  if (mp != nullptr) {
+                  if (red_mask) {
                     g = (h ? bf16_hi(mw[e]) : bf16_lo(mw[e])) > 0.f ? g : 0.f;
                   } else if (p.red_scale != nullptr) {
                     const int ch = c.n0 + chunk * 32 + j;

@@ -230,6 +230,8 @@ def wgrad_to_param_layout(dw_oti, shape, out=None):
     """fp32 [Cout, taps, Cin] -> fp32 parameter-shaped gradient [Cout, Cin, kd, kh, kw]."""
     cout, cin = shape[0], shape[1]
     taps = dw_oti.shape[1]
+    if taps == 1 and out is None:      # 1x1x1 convs: [Cout][1][Cin] IS the parameter layout - no copy
+        return dw_oti.view(shape)
     accumulate = out is not None
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=dw_oti.device)
@@ -295,9 +297,18 @@ def conv3d_dgrad_bnred(dy, w_ito, in_shape, k, stride, pad, dil, bn_y, bn_relu_o
     return dx, red
 
 
-def dgrad_bnred_supported(Cin, Cout, k, stride):
-    """The fused reduction lives in the tcgen05 epilogues (csrc/conv_api.cu tc_supported)."""
-    return Cin % 64 == 0 and Cout % 64 == 0 and stride in (1, 2) and k ** 3 <= 64
+_BNRED_CACHE = {}
+
+
+def dgrad_bnred_profitable(in_shape, Cout, k, stride, pad, dil):
+    """Whether the library prefers the fused dgrad + BatchNorm-backward sums for this geometry
+    (adni_conv3d_dgrad_bnred_profitable: long main loops only)."""
+    key = (tuple(in_shape), Cout, k, stride, pad, dil)
+    hit = _BNRED_CACHE.get(key)
+    if hit is None:
+        N, D, H, W, Cin = in_shape
+        hit = _BNRED_CACHE[key] = bool(_lib.load().adni_conv3d_dgrad_bnred_profitable(geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)))
+    return hit
 
 
 _SCRATCH_CACHE = {}
