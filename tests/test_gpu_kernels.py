@@ -381,7 +381,8 @@ def test_conv_plan_info(cuda_dev):
     assert k4 == 1 and 0.5 < f4 < 0.9                                                  # dilation 4: ~31 % of the taps skipped
     assert info(2, 16, 256, 2, 1)[0] == 1 and 0.7 < info(2, 16, 256, 2, 1)[1] <= 1.0
     assert info(2, 16, 512, 4, 2)[0] == 1 and 0.4 < info(2, 16, 512, 4, 2)[1] < 0.8        # wgrad: all-padding (box, tap group) blocks skipped
-    assert info(2, 8, 8, 1, 0)[0] == 0                                                 # small channels: direct engine
+    assert info(2, 8, 8, 1, 0)[0] == 3                                                 # small channels: the mma.sync engine
+    assert info(2, 8, 24, 1, 0)[0] == 0                                                # odd channel counts: CUDA cores
 
 
 def test_adam_multi_tensor_matches_torch_adam(cuda_dev):
