@@ -16,7 +16,7 @@
 namespace adni {
 
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream, const SkSched* sk = nullptr);
-int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream);
+int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream, const W2Sched* sk = nullptr);
 int wgrad2_box_rows(int mt_cfg);
 bool wgrad_halo_supported(const adni_conv3d_geom& g);
 int launch_wgrad_halo(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tic, float* dw_oti,
@@ -602,6 +602,82 @@ double wgrad_executed_fraction(const WgradParams& p, int mt_cfg) {
   return double(issued) / (double(p.n_groups) * p.tiles_d * p.tiles_h * p.tiles_w);
 }
 
+// Stream-K plan for wgrad2 (cached per geometry): equal numbers of ACTIVE (position box, output tile) blocks per CTA.
+// The static split-K schedule leaves the slowest CTA 20-35 % above the mean on the dilated layers (boxes whose taps all
+// lie in the padding are skipped, and 594-648 items fall unevenly on 148 SMs); partial sums already go through
+// red.global.add, so cutting tiles at arbitrary box boundaries needs no fix-up pass.
+struct W2Plan {
+  bool use = false;
+  W2Sched sched;
+};
+
+const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
+  static std::mutex mu;
+  static std::map<std::vector<int>, W2Plan> cache;
+  std::vector<int> key = {p.ntaps, p.cin_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.m_tiles, p.n_tiles, mt_cfg, num_sms()};
+  for (int t = 0; t < p.ntaps; t++)
+    key.push_back((int(p.taps[t].map) << 24) ^ ((p.taps[t].dd & 0xff) << 16) ^ ((p.taps[t].dh & 0xff) << 8) ^ (p.taps[t].dw & 0xff));
+  for (int m = 0; m < kMaxMaps; m++)
+    for (int a = 0; a < 3; a++) key.push_back(p.x_ext[m][a]);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  W2Plan plan;
+  memset(&plan.sched, 0, sizeof(plan.sched));
+  static const int enabled = env_int("ADNI_STREAM_K", 1);
+  const int groups = 8 / mt_cfg;
+  const int per_sample = p.tiles_d * p.tiles_h * p.tiles_w;
+  const int G = std::min(num_sms(), kSkMaxCtas);
+  if (enabled && per_sample > 0 && p.N > 0) {
+    // cum[nt][r] = active boxes among the first r boxes of one sample for N tile nt (the pattern repeats per sample)
+    std::vector<std::vector<int>> cum(static_cast<size_t>(p.n_tiles), std::vector<int>(static_cast<size_t>(per_sample) + 1, 0));
+    for (int nt = 0; nt < p.n_tiles; nt++) {
+      const int g0 = nt * groups, ng = std::min(groups, p.n_groups - g0);
+      int r = 0;
+      for (int td = 0; td < p.tiles_d; td++)
+        for (int th = 0; th < p.tiles_h; th++)
+          for (int tw = 0; tw < p.tiles_w; tw++, r++) {
+            bool any = false;
+            for (int gi = 0; gi < ng && !any; gi++) {
+              const ConvTap& tp = p.taps[(g0 + gi) / p.cin_blocks];
+              const int* ext = p.x_ext[tp.map];
+              const int d = td * p.bd + tp.dd, h = th * p.bh + tp.dh, w = tw * p.bw + tp.dw;
+              any = d + p.bd > 0 && d < ext[0] && h + p.bh > 0 && h < ext[1] && w + p.bw > 0 && w < ext[2];
+            }
+            cum[nt][r + 1] = cum[nt][r] + (any ? 1 : 0);
+          }
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    std::vector<long long> prefix(static_cast<size_t>(tiles) + 1, 0);   // active blocks before tile t (tile = mt * n_tiles + nt)
+    for (int t = 0; t < tiles; t++) prefix[t + 1] = prefix[t] + static_cast<long long>(cum[t % p.n_tiles][per_sample]) * p.N;
+    const long long T = prefix[tiles];
+    if (T >= 8LL * G) {
+      // raw box index (over all samples) of the a-th active box (0-based) of N tile nt
+      auto raw_of = [&](int nt, long long a) -> int {
+        const int per = cum[nt][per_sample];
+        const long long n = a / per;
+        const int rem = int(a % per);
+        int r = int(std::upper_bound(cum[nt].begin(), cum[nt].end(), rem) - cum[nt].begin()) - 1;   // cum[r] <= rem < cum[r+1]
+        return int(n * per_sample + r);
+      };
+      plan.use = true;
+      plan.sched.ctas = G;
+      int tile = 0;
+      for (int c = 0; c < G; c++) {
+        const long long start = T * c / G, end = T * (c + 1) / G;   // end > start
+        while (prefix[tile + 1] <= start) tile++;
+        plan.sched.tile_begin[c] = tile;
+        plan.sched.box_begin[c] = raw_of(tile % p.n_tiles, start - prefix[tile]);
+        int last = tile;
+        while (prefix[last + 1] < end) last++;
+        plan.sched.tile_last[c] = last;
+        plan.sched.box_end[c] = raw_of(last % p.n_tiles, end - 1 - prefix[last]) + 1;
+      }
+    }
+  }
+  return cache.emplace(key, plan).first->second;
+}
+
 int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
              cudaStream_t stream) {
   WgradParams p;
@@ -625,7 +701,8 @@ int tc_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     if (rc) return rc;
   }
   p.dw = dw;
-  return launch_wgrad2(p, mt_cfg, stream);
+  const W2Plan& plan = plan_wgrad_stream_k(p, mt_cfg);
+  return launch_wgrad2(p, mt_cfg, stream, plan.use ? &plan.sched : nullptr);
 }
 
 int check_geom(const adni_conv3d_geom* g) {

@@ -84,6 +84,18 @@ struct WgradParams {
   float* dw;    // [Cout][K_total] fp32, accumulated with red.add
 };
 
+// Stream-K schedule of wgrad2 (conv_wgrad2.cu): the active (position box x output tile) blocks of all output tiles form
+// one sequence cut into equal ranges.  Tile = mt_outer * n_tiles + nt; CTA b walks tiles tile_begin[b] .. tile_last[b]
+// and, inside its first / last tile, the raw position boxes from box_begin[b] / up to box_end[b].  Partial sums go to
+// dw through red.global.add as in the static schedule, so a tile may be shared by any number of CTAs.
+struct W2Sched {
+  int tile_begin[kSkMaxCtas];
+  int box_begin[kSkMaxCtas];
+  int tile_last[kSkMaxCtas];
+  int box_end[kSkMaxCtas];
+  int ctas;
+};
+
 // Halo-resident fprop / dgrad for 3x3x3, stride 1, dilation 1, pad 1 convs with Cin == Cout in {64, 128}
 // (ResNet layer1 / layer2), see conv_halo.cu: the M tile is one output plane piece of 8 (w) x 16 (h) positions; the
 // CTA walks a column of such pieces along d and keeps the (10 x 18)-position input planes in a shared-memory ring.

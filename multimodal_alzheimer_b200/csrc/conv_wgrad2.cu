@@ -8,6 +8,8 @@
 //   dW[Cout][K_total] += sum over position boxes (32 positions each)  dY[pos][Cout]^T * X[pos + tap][Cin slice]
 // Operands are MN-major for this GEMM (channels contiguous): TMA boxes of 32 positions x 64 channels with the
 // 128-byte swizzle are consumed through MN-major UMMA descriptors.
+#include <type_traits>
+
 #include "conv_igemm.cuh"
 
 namespace adni {
@@ -47,17 +49,37 @@ struct ItemCtx {
   int ng, b_begin, b_end, mt_outer, g0;
 };
 
-template <int NG>
-__device__ __forceinline__ ItemCtx<NG> make_ctx(const WgradParams& p, int item) {
+// Work walk of a CTA: items blockIdx.x, + gridDim.x, ... of the static split-K schedule, or the tiles of its stream-K
+// range (W2Sched).  `cur` is the item / tile index; ctx() resolves it to (N tile, M tile, position-box range).
+template <bool SK, typename SchedT>
+__device__ __forceinline__ void w2_range(const WgradParams& p, const SchedT& sk, int& cur, int& stop, int& step) {
+  if constexpr (SK) {
+    cur = sk.tile_begin[blockIdx.x];
+    stop = sk.tile_last[blockIdx.x] + 1;
+    step = 1;
+  } else {
+    cur = blockIdx.x;
+    stop = p.m_tiles * p.n_tiles * p.splits;
+    step = gridDim.x;
+  }
+}
+
+template <int NG, bool SK, typename SchedT>
+__device__ __forceinline__ ItemCtx<NG> make_ctx(const WgradParams& p, const SchedT& sk, int item) {
   ItemCtx<NG> x;
   const int nt = item % p.n_tiles;
   const int r = item / p.n_tiles;
   x.mt_outer = r % p.m_tiles;
-  const int ks = r / p.m_tiles;
   x.g0 = nt * NG;
   x.ng = min(NG, p.n_groups - x.g0);
-  x.b_begin = ks * p.boxes_per_split;
-  x.b_end = min(x.b_begin + p.boxes_per_split, p.pos_boxes);
+  if constexpr (SK) {
+    x.b_begin = item == sk.tile_begin[blockIdx.x] ? sk.box_begin[blockIdx.x] : 0;
+    x.b_end = item == sk.tile_last[blockIdx.x] ? sk.box_end[blockIdx.x] : p.pos_boxes;
+  } else {
+    const int ks = r / p.m_tiles;
+    x.b_begin = ks * p.boxes_per_split;
+    x.b_end = min(x.b_begin + p.boxes_per_split, p.pos_boxes);
+  }
 #pragma unroll
   for (int g = 0; g < NG; g++) {
     const int gg = min(x.g0 + g, p.n_groups - 1);
@@ -105,9 +127,12 @@ __device__ __forceinline__ bool box_active(const WgradParams& p, const ItemCtx<N
   return any;
 }
 
-template <int MT>
-__global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_constant__ WgradParams p) {
+template <int MT, bool SK>
+__global__ void __launch_bounds__(kThreads, 1)
+    wgrad2_kernel(const __grid_constant__ WgradParams p,
+                  const __grid_constant__ typename std::conditional<SK, W2Sched, SkNone>::type sk) {
   using Cfg = W2Cfg<MT>;
+  using SchedT = typename std::conditional<SK, W2Sched, SkNone>::type;
   constexpr int NG = Cfg::NG;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int kBoxRows = Cfg::ROWS;
@@ -121,7 +146,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = p.m_tiles * p.n_tiles * p.splits;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) {
@@ -147,8 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
     // box are then broadcast with shuffles, so the per-K-block path has no divisions and no table lookups.
     int st = 0;
     uint32_t ph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const ItemCtx<NG> x = make_ctx<NG>(p, item);
+    int item, item_stop, item_step;
+    w2_range<SK, SchedT>(p, sk, item, item_stop, item_step);
+    for (; item < item_stop; item += item_step) {
+      const ItemCtx<NG> x = make_ctx<NG, SK, SchedT>(p, sk, item);
       const uint32_t tx_bytes = static_cast<uint32_t>(Cfg::A_BOXES + x.ng) * kBoxBytes;
       const int g = lane - Cfg::A_BOXES;
       int my_map = 0, my_dd = 0, my_dh = 0, my_dw = 0, my_c0 = 0;
@@ -201,8 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
     const uint32_t desc_lo_base = static_cast<uint32_t>(umma_smem_desc_sw128(0, kBoxBytes, 1024) & 0xFFFFFFFFull);
     int st = 0;
     uint32_t ph = 0, accph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const ItemCtx<NG> x = make_ctx<NG>(p, item);
+    int item, item_stop, item_step;
+    w2_range<SK, SchedT>(p, sk, item, item_stop, item_step);
+    for (; item < item_stop; item += item_step) {
+      const ItemCtx<NG> x = make_ctx<NG, SK, SchedT>(p, sk, item);
       if (lane == 0) {
         mbar_wait(tempty, accph ^ 1);
         tc_fence_after();
@@ -254,8 +282,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t accph = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const ItemCtx<NG> x = make_ctx<NG>(p, item);
+    int item, item_stop, item_step;
+    w2_range<SK, SchedT>(p, sk, item, item_stop, item_step);
+    for (; item < item_stop; item += item_step) {
+      const ItemCtx<NG> x = make_ctx<NG, SK, SchedT>(p, sk, item);
       bool has_k = false;
       {
         BoxWalk bi;
@@ -307,17 +337,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_kernel(const __grid_consta
 }
 
 template <int MT>
-int launch_t(const WgradParams& p, cudaStream_t stream) {
+int launch_t(const WgradParams& p, const W2Sched* sk, cudaStream_t stream) {
   using Cfg = W2Cfg<MT>;
-  auto kern = wgrad2_kernel<MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+  if (sk != nullptr) {
+    auto kern = wgrad2_kernel<MT, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      attr_set = true;
+    }
+    kern<<<sk->ctas, kThreads, Cfg::SMEM_BYTES, stream>>>(p, *sk);
+  } else {
+    auto kern = wgrad2_kernel<MT, false>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(p, SkNone{0});
   }
-  const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   ADNI_LAUNCH_CHECK("wgrad2_kernel");
   return ADNI_OK;
@@ -329,14 +369,14 @@ int launch_t(const WgradParams& p, cudaStream_t stream) {
 int wgrad2_groups_per_tile(int mt_cfg) { return 8 / mt_cfg; }
 int wgrad2_box_rows(int mt_cfg) { return wgrad2_box_rows_c(mt_cfg); }
 
-int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream) {
+int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream, const W2Sched* sk) {
   switch (mt_cfg) {
     case 1:
-      return launch_t<1>(p, stream);
+      return launch_t<1>(p, sk, stream);
     case 2:
-      return launch_t<2>(p, stream);
+      return launch_t<2>(p, sk, stream);
     case 4:
-      return launch_t<4>(p, stream);
+      return launch_t<4>(p, sk, stream);
     default:
       set_error("wgrad2: unsupported M-tile count %d", mt_cfg);
       return ADNI_ENOTSUP;
