@@ -246,7 +246,7 @@ const SkPlan& plan_stream_k(const IgemmParams& p) {
   const long long boxes = (long long)p.N * p.tiles_d * p.tiles_h * p.tiles_w;
   const long long total = boxes * p.n_tiles;
   plan.total_tiles = int(total);
-  const int G = int(std::min<long long>(num_sms(), total));
+  const int G = std::min(num_sms(), kSkMaxCtas);   // every SM gets a range, however few tiles there are
   static const int enabled = env_int("ADNI_STREAM_K", 1);
   if (enabled && total > 0 && total <= kSkMaxTiles && G <= kSkMaxCtas && p.ntaps > 0) {
     // iterations per tile (same test as the kernel's tap mask); tile index = box * n_tiles + nt, box = ((n*td+d)*th+h)*tw+w
@@ -272,11 +272,15 @@ const SkPlan& plan_stream_k(const IgemmParams& p) {
           }
     if (all_nonzero) {
       // static schedule's slowest CTA vs the ideal
-      std::vector<long long> load(static_cast<size_t>(G), 0);
-      for (size_t i = 0; i < iters.size(); i++) load[i % G] += iters[i];
+      const size_t Gs = static_cast<size_t>(std::min<long long>(G, total));   // the static grid
+      std::vector<long long> load(Gs, 0);
+      for (size_t i = 0; i < iters.size(); i++) load[i % Gs] += iters[i];
       const long long worst = *std::max_element(load.begin(), load.end());
-      const double eff = double(T) / G / double(worst);
-      if (eff < 0.93 && T / G >= 16) {
+      // a K iteration (64-deep block, N = 256) is ~0.27 us; parking + finishing a shared tile costs a CTA ~10 us at the
+      // end of its range: worth it only if the slowest CTA of the static schedule is >= 64 iterations above the mean
+      // (static: when fewer tiles than SMs, the idle SMs count too)
+      const long long ideal = T / G;
+      if (worst - ideal >= 64 && ideal >= 64) {
         plan.use = true;
         plan.sched.ctas = G;
         std::vector<long long> prefix(iters.size() + 1, 0);
@@ -301,8 +305,7 @@ const SkPlan& plan_stream_k(const IgemmParams& p) {
 // bytes of workspace a stream-K launch needs: arrival counters (one int per tile) + two partial-tile slots per CTA
 size_t sk_workspace_bytes(const SkPlan& plan, int block_n) {
   if (!plan.use) return 0;
-  const size_t counters = (static_cast<size_t>(plan.total_tiles) * 4 + 255) & ~size_t(255);
-  return counters + static_cast<size_t>(2) * plan.sched.ctas * 128 * block_n * 4;
+  return static_cast<size_t>(kSkMaxTiles) * 4 + static_cast<size_t>(2) * plan.sched.ctas * 128 * block_n * 4;
 }
 
 // Launch with the stream-K schedule when the plan wants one and the caller's workspace holds it, else statically.
@@ -313,8 +316,8 @@ int launch_igemm_planned(const IgemmParams& p, int block_n, void* workspace, siz
     if (plan.use && need <= ws_bytes && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0) {
       SkSched sched = plan.sched;
       sched.counters = static_cast<int*>(workspace);
-      sched.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) +
-                                               ((static_cast<size_t>(plan.total_tiles) * 4 + 255) & ~size_t(255)));
+      // fixed offset: a launch with few tiles must not leave partial sums where a later launch keeps its counters
+      sched.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + static_cast<size_t>(kSkMaxTiles) * 4);
       return launch_igemm(p, block_n, stream, &sched);
     }
   }
@@ -624,7 +627,7 @@ const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
   if (it != cache.end()) return it->second;
   W2Plan plan;
   memset(&plan.sched, 0, sizeof(plan.sched));
-  static const int enabled = env_int("ADNI_STREAM_K", 1);
+  static const int enabled = env_int("ADNI_STREAM_K_WGRAD", 1);
   const int groups = 8 / mt_cfg;
   const int per_sample = p.tiles_d * p.tiles_h * p.tiles_w;
   const int G = std::min(num_sms(), kSkMaxCtas);

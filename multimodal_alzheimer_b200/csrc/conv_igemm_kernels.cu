@@ -303,6 +303,14 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
               d4[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]),
                                    __uint_as_float(v[4 * j4 + 3]));
           }
+          // the accumulator is parked: hand the TMEM buffer back at once (the fix-up below runs under the next main loop)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            accph ^= 1;
+          }
           __threadfence();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           int* ticket_s = reinterpret_cast<int*>(stat_smem);   // free here: the statistic slots are written later
@@ -319,19 +327,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
           asm volatile("bar.sync 1, 128;" ::: "memory");
           from_scratch = *ticket_s != 0;
           asm volatile("bar.sync 1, 128;" ::: "memory");       // ticket_s is read before the statistic slots are reused
-          if (from_scratch) __threadfence();
+          if (!from_scratch) continue;                         // the tile is finished by a later arriver
+          __threadfence();
         }
-      }
-      if (SK && u.partial && !from_scratch) {
-        // this CTA's share is parked; the tile is finished by a later arriver
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1;
-        }
-        continue;
       }
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
@@ -347,17 +345,38 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; j++) f[j] = 0.f;
           if constexpr (SK) {
-            for (int cc = c_first; cc <= c_last; cc++) {
+            // contributions are added in CTA order (deterministic); two contributors' rows are in flight at a time
+            auto slot_ptr = [&](int cc) {
               const int slot = 2 * cc + ((tile == sk.tile_last[cc] && tile != sk.tile_begin[cc]) ? 1 : 0);
-              const float4* s4 = reinterpret_cast<const float4*>(sk.scratch + static_cast<size_t>(slot) * (128 * BLOCK_N) +
-                                                                 chunk * (128 * 32) + row * 32);
+              return reinterpret_cast<const float4*>(sk.scratch + static_cast<size_t>(slot) * (128 * BLOCK_N) +
+                                                     chunk * (128 * 32) + row * 32);
+            };
+            for (int cc = c_first; cc <= c_last; cc += 2) {
+              const bool two = cc + 1 <= c_last;
+              const float4* s4a = slot_ptr(cc);
+              const float4* s4b = slot_ptr(two ? cc + 1 : cc);
+              float4 ta[8], tb[8];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; j4++) ta[j4] = __ldcg(s4a + j4);
+              if (two) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) tb[j4] = __ldcg(s4b + j4);
+              }
 #pragma unroll
               for (int j4 = 0; j4 < 8; j4++) {
-                const float4 t4 = __ldcg(s4 + j4);
-                f[4 * j4 + 0] += t4.x;
-                f[4 * j4 + 1] += t4.y;
-                f[4 * j4 + 2] += t4.z;
-                f[4 * j4 + 3] += t4.w;
+                f[4 * j4 + 0] += ta[j4].x;
+                f[4 * j4 + 1] += ta[j4].y;
+                f[4 * j4 + 2] += ta[j4].z;
+                f[4 * j4 + 3] += ta[j4].w;
+              }
+              if (two) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                  f[4 * j4 + 0] += tb[j4].x;
+                  f[4 * j4 + 1] += tb[j4].y;
+                  f[4 * j4 + 2] += tb[j4].z;
+                  f[4 * j4 + 3] += tb[j4].w;
+                }
               }
             }
           }
@@ -451,13 +470,15 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
           stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
         }
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        accph ^= 1;
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp (a partial unit did so when it parked)
+      if (!(SK && u.partial)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          accph ^= 1;
+        }
       }
       if (do_stats || do_red) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
