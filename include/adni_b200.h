@@ -225,6 +225,16 @@ int adni_maxpool3d_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, in
                        adni_bf16* y, uint8_t* argmax, void* stream);
 int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D, int H, int W, int C, int k,
                        int stride, int pad, adni_bf16* dx, void* stream);
+
+/* ReLU -> MaxPool3d(k) with non-overlapping windows (kernel == stride, no padding; k in {2, 3}) in one pass:
+ * Conv3d -> ReLU -> MaxPool3d(2) of the small-CNN stacks (pet_cnn.py:21-25, early_fusion.py:37-41).
+ * y = relu(max_window x) (relu = 0: plain max pool); argmax = first maximum of x in (d, h, w) order.  The backward pass
+ * writes dx[i] = dy[window] where i is the arg-max and (pooled == NULL or pooled[window] > 0), else 0: MaxPool backward
+ * and ReLU backward together - the ReLU output is never stored.  floor mode: a ragged axis tail gets no gradient. */
+int adni_relu_maxpool_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, int k, int relu, adni_bf16* y,
+                          uint8_t* argmax, void* stream);
+int adni_relu_maxpool_bwd(const adni_bf16* dy, const uint8_t* argmax, const adni_bf16* pooled, int N, int D, int H, int W,
+                          int C, int k, adni_bf16* dx, void* stream);
 /* Fused stem tail  bn1 -> ReLU -> MaxPool3d(3,2,1)  (MedicalNet ResNet.forward) and its backward, without
  * materialising the activated 64-channel tensor or its gradient:
  *   fwd   : p, argmax = maxpool(relu(y*scale + shift))            y: raw conv1 output [N][D][H][W][C]

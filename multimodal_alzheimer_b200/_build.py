@@ -24,6 +24,7 @@ SOURCES = [
     "stem_fused.cu",
     "elementwise.cu",
     "dropout.cu",
+    "pool_small.cu",
     "head_loss.cu",
     "metrics.cu",
     "normalize.cu",

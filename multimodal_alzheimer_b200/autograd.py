@@ -538,6 +538,24 @@ class MaxPoolFn(torch.autograd.Function):
         return K.maxpool3d_bwd(dy.contiguous(), am, shape, k, stride, pad), None, None, None
 
 
+class ReluMaxPoolFn(torch.autograd.Function):
+    """nn.ReLU -> nn.MaxPool3d(k) with non-overlapping windows as one pass each way (csrc/pool_small.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        x = x.contiguous()
+        y, am = K.relu_maxpool_fwd(x, k, relu=True)
+        ctx.save_for_backward(am, y)
+        ctx.cfg = (tuple(x.shape), k)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        am, y = ctx.saved_tensors
+        shape, k = ctx.cfg
+        return K.relu_maxpool_bwd(dy.contiguous(), am, y, shape, k), None
+
+
 class GapFn(torch.autograd.Function):
     """AdaptiveAvgPool3d(1): bf16 [N,D,H,W,C] -> fp32 [N,C,1,1,1]."""
 

@@ -126,16 +126,31 @@ __device__ __forceinline__ void load_tile_vec(const SmallParams& p, const TileOr
 // 16-byte "pixel" of its 8 inputs w - pad .. w - pad + 7.
 __device__ __forceinline__ void load_tile_c1(const SmallParams& p, const TileOrigin& o, uint8_t* tile_s,
                                              __nv_bfloat16* raw_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = p.HD * p.HH;
-  for (int i = threadIdx.x; i < rows * p.RAWW; i += kThreads) {
-    const int r = i / p.RAWW, x = i - r * p.RAWW;
-    const int hd = r / p.HH, hh = r - hd * p.HH;
-    const int id = o.d0 + hd - p.pad, ih = o.h0 + hh - p.pad, iw = o.w0 + x - p.pad;
-    const bool ok = id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi;
-    raw_s[i] = ok ? p.in[((static_cast<long long>(o.n) * p.Di + id) * p.Hi + ih) * p.Wi + iw] : __float2bfloat16(0.f);
+  // a warp per halo row (RAWW = 23 <= 32 inputs: one coalesced load), four rows in flight per warp
+  const int iw = o.w0 + lane - p.pad;
+  const bool col_ok = lane < p.RAWW && iw >= 0 && iw < p.Wi;
+  const uint16_t* in16 = reinterpret_cast<const uint16_t*>(p.in);
+  uint16_t* raw16 = reinterpret_cast<uint16_t*>(raw_s);
+  for (int r0 = warp; r0 < rows; r0 += 4 * (kThreads / 32)) {
+    uint16_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + u * (kThreads / 32);
+      const int hd = r / p.HH, hh = r - hd * p.HH;
+      const int id = o.d0 + hd - p.pad, ih = o.h0 + hh - p.pad;
+      const bool ok = r < rows && col_ok && id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi;
+      v[u] = ok ? __ldg(in16 + ((static_cast<long long>(o.n) * p.Di + id) * p.Hi + ih) * p.Wi + iw) : uint16_t(0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + u * (kThreads / 32);
+      if (r < rows && lane < p.RAWW) raw16[r * p.RAWW + lane] = v[u];
+    }
   }
   __syncthreads();
-  const uint16_t* raw = reinterpret_cast<const uint16_t*>(raw_s);
+  const uint16_t* raw = raw16;
   for (int i = threadIdx.x; i < rows * TW; i += kThreads) {
     const int r = i >> 4, hw = i & 15;
     const uint16_t* s = raw + r * p.RAWW + hw;
@@ -486,7 +501,7 @@ int launch_fprop_t(const SmallParams& p, size_t smem, int ysplit, cudaStream_t s
     ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
-  const int per_sm = std::max<size_t>(1, std::min<size_t>(3, kSmemLimit / (smem + 1024)));
+  const int per_sm = std::max<size_t>(1, std::min<size_t>(4, kSmemLimit / (smem + 1024)));
   const long long want = std::max<long long>(1, static_cast<long long>(num_sms()) * per_sm / ysplit);
   dim3 grid(static_cast<unsigned>(std::min<long long>(p.total_tiles, want)), static_cast<unsigned>(ysplit));
   kern<<<grid, kThreads, smem, st>>>(p);
@@ -556,7 +571,7 @@ int launch_wgrad_t(SmallWgradParams& wp, cudaStream_t st) {
   }
   wp.nt_per_cta = 8 * NW;
   const int ysplit = (wp.n_tiles_total + wp.nt_per_cta - 1) / wp.nt_per_cta;
-  const int per_sm = std::max<size_t>(1, std::min<size_t>(2, kSmemLimit / (smem + 1024)));
+  const int per_sm = std::max<size_t>(1, std::min<size_t>(NW <= 4 ? 4 : 2, kSmemLimit / (smem + 1024)));
   const long long want = std::max<long long>(1, static_cast<long long>(num_sms()) * per_sm / ysplit);
   dim3 grid(static_cast<unsigned>(std::min<long long>(p.total_tiles, want)), static_cast<unsigned>(ysplit));
   kern<<<grid, kThreads, smem, st>>>(wp);
@@ -637,7 +652,9 @@ int small_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
   wp.n_tiles_total = wp.x.Q;
   const bool c1 = g.Cin == 1;
   const int MT = (g.Cout + 15) / 16;
-  if (MT == 1) return c1 ? launch_wgrad_t<1, 16, true>(wp, stream) : launch_wgrad_t<1, 16, false>(wp, stream);
+  // the first layer has k*k <= 49 N-tiles: 4 (k = 5) or 7 per warp keep the kernel at <= 64 registers, 4 CTAs per SM
+  if (MT == 1 && c1) return wp.x.Q <= 32 ? launch_wgrad_t<1, 4, true>(wp, stream) : launch_wgrad_t<1, 8, true>(wp, stream);
+  if (MT == 1) return launch_wgrad_t<1, 16, false>(wp, stream);
   if (MT == 2) return c1 ? launch_wgrad_t<2, 8, true>(wp, stream) : launch_wgrad_t<2, 8, false>(wp, stream);
   return c1 ? launch_wgrad_t<4, 4, true>(wp, stream) : launch_wgrad_t<4, 4, false>(wp, stream);
 }

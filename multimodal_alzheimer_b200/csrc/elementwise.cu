@@ -828,6 +828,10 @@ __global__ void __launch_bounds__(256) weights_multi_kernel(const WeightJob* __r
 }
 
 }  // namespace
+
+// pool_small.cu
+int launch_pool_nonoverlap_bwd(const __nv_bfloat16* dy, const uint8_t* am, const __nv_bfloat16* pooled, int N, int D, int H,
+                               int W, int C, int k, __nv_bfloat16* dx, cudaStream_t st);
 }  // namespace adni
 
 using namespace adni;
@@ -990,6 +994,8 @@ int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D,
   ADNI_REQUIRE(dy && dx && argmax, ADNI_EINVAL, "maxpool3d_bwd: null pointer");
   ADNI_REQUIRE(C % 8 == 0 && k >= 1 && k * k * k <= 255 && stride >= 1 && 2 * pad <= k, ADNI_ENOTSUP,
                "maxpool3d_bwd: unsupported C=%d k=%d stride=%d pad=%d", C, k, stride, pad);
+  if (stride == k && pad == 0)   // non-overlapping windows (MaxPool3d(2)): one thread per input vector, pool_small.cu
+    return launch_pool_nonoverlap_bwd(CBF(dy), argmax, nullptr, N, D, H, W, C, k, BF(dx), ST(stream));
   const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long total = (long long)N * D * H * W * (C / 8);
   // windows that can touch an 8-voxel tile edge: (8 + k - 2)/s + 1 (+1 for unaligned tiles when s does not divide 8)

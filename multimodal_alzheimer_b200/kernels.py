@@ -558,6 +558,32 @@ def maxpool3d_bwd(dy, argmax, in_shape, k, stride, pad):
     return dx
 
 
+def relu_maxpool_supported(k, stride, pad):
+    return k in (2, 3) and stride == k and pad == 0
+
+
+def relu_maxpool_fwd(x, k, relu=True):
+    """relu(maxpool_k(x)) for non-overlapping windows in one pass; returns (pooled, argmax)."""
+    _chk(x, BF16, "x")
+    N, D, H, W, C = x.shape
+    Do, Ho, Wo = D // k, H // k, W // k
+    y = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=x.device)
+    am = torch.empty((N, Do, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+    call_hbm("hbm_relu_pool", 2 * x.numel() + 3 * y.numel(), "adni_relu_maxpool_fwd", ptr(x), N, D, H, W, C, k, int(relu),
+             ptr(y), ptr(am), stream_ptr())
+    return y, am
+
+
+def relu_maxpool_bwd(dy, argmax, pooled, in_shape, k):
+    """Gradient of relu_maxpool_fwd w.r.t. x (pooled = the forward output: ReLU mask; None = plain max pool)."""
+    _chk(dy, BF16, "dy")
+    N, D, H, W, C = in_shape
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    call_hbm("hbm_relu_pool", 2 * dx.numel() + 5 * dy.numel(), "adni_relu_maxpool_bwd", ptr(dy), ptr(argmax), ptr(pooled),
+             N, D, H, W, C, k, ptr(dx), stream_ptr())
+    return dx
+
+
 def fused_pool_supported(k, stride, pad):
     return (k, stride, pad) == (3, 2, 1)
 

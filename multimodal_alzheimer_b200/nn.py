@@ -220,6 +220,10 @@ class Sequential(tnn.Sequential):
                 else:
                     x = nxt(y, stats=st)
                     i += 2
+            elif (isinstance(m, ReLU) and isinstance(nxt, MaxPool3d) and x.dtype == BF16 and x.dim() == 5
+                  and A.K.relu_maxpool_supported(nxt.kernel_size, nxt.stride, nxt.padding)):
+                x = A.ReluMaxPoolFn.apply(x, nxt.kernel_size)      # conv -> ReLU -> MaxPool3d(2): one pass each way
+                i += 2
             elif isinstance(m, BatchNorm3d) and isinstance(nxt, ReLU):
                 x = m(x, relu=True)
                 i += 2

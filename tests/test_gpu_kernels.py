@@ -95,6 +95,31 @@ def test_maxpool(cuda_dev, cfg):
     assert torch.equal(to_ncdhw_f32(dx).cpu(), xr.grad)
 
 
+@pytest.mark.parametrize("cfg", [((2, 8, 8, 16, 8), 2), ((1, 9, 7, 11, 16), 2), ((2, 6, 9, 12, 32), 3), ((1, 4, 4, 4, 64), 2)])
+def test_relu_maxpool_fused(cuda_dev, cfg):
+    """ReLU -> MaxPool3d(k) (non-overlapping, floor mode incl. ragged tails) in one pass each way vs torch on the CPU:
+    pooled values and the input gradient bit-exact, ties and all-negative windows included (relu'(0) = 0)."""
+    from multimodal_alzheimer_b200 import kernels as K
+    shape, k = cfg
+    x = (torch.randint(0, 7, shape, generator=torch.Generator().manual_seed(5)).float() - 3).to(cuda_dev).to(BF)
+    y, am = K.relu_maxpool_fwd(x, k, relu=True)
+    xr = to_ncdhw_f32(x).cpu().requires_grad_(True)
+    ref = F.max_pool3d(torch.relu(xr), k)
+    assert torch.equal(to_ncdhw_f32(y).cpu(), ref.detach())
+    dy = torch.randint(-3, 4, ref.shape, generator=torch.Generator().manual_seed(6)).float()
+    ref.backward(dy)
+    dx = K.relu_maxpool_bwd(to_ndhwc_bf16(dy).to(cuda_dev), am, y, tuple(x.shape), k)
+    assert torch.equal(to_ncdhw_f32(dx).cpu(), xr.grad)
+    # plain max pool through the same kernels (relu = 0 / no mask) == the generic entry point's results
+    y2, am2 = K.relu_maxpool_fwd(x, k, relu=False)
+    y3, am3 = K.maxpool3d_fwd(x, k, k, 0)
+    assert torch.equal(y2, y3) and torch.equal(am2, am3)
+    dxa = K.maxpool3d_bwd(to_ndhwc_bf16(dy).to(cuda_dev), am3, tuple(x.shape), k, k, 0)
+    xr2 = to_ncdhw_f32(x).cpu().requires_grad_(True)
+    F.max_pool3d(xr2, k).backward(dy)
+    assert torch.equal(to_ncdhw_f32(dxa).cpu(), xr2.grad)
+
+
 def test_gap(cuda_dev):
     from multimodal_alzheimer_b200 import kernels as K
     x = _rand_act((3, 5, 6, 7, 512), cuda_dev)
