@@ -72,21 +72,13 @@ int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind,
 /* y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_oti) (+bias).  If stat_sum/stat_sqsum are non-null,
  * per-channel sum(y) and sum(y*y) (fp64, from the fp32 accumulators) are ADDED into them: the
  * BatchNorm3d batch statistics fused into the conv epilogue (MedicalNet bn1/bn2/bn3). */
-/* Workspace of the conv entry points below: `workspace` (DEVICE memory, 256-byte aligned, ws_bytes >=
- * adni_conv3d_workspace_bytes()) must be ZERO when first handed in and may be reused by later calls on the SAME stream
- * (every kernel leaves it zeroed where it must be); one workspace per concurrently used stream.  With it the tap-per-box
- * engine balances tiles of unequal cost over the SMs (stream-K: tiles cut at K-iteration granularity, partial tiles
- * summed in a fixed order by the last CTA to arrive - deterministic).  NULL = the static tile round-robin. */
-size_t adni_conv3d_workspace_bytes(void);
-
 int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* w_oti, const float* bias,
-                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* workspace, size_t ws_bytes,
-                      void* stream);
+                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* stream);
 
 /* dx[N,D,H,W,Cin] = conv_transpose(dy[N,Do,Ho,Wo,Cout], w) (+ addend, same shape as dx, may be null).
  * w_ito is the [Cin][taps][Cout] copy of the weights. */
 int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito,
-                      const adni_bf16* addend, adni_bf16* dx, int engine, void* workspace, size_t ws_bytes, void* stream);
+                      const adni_bf16* addend, adni_bf16* dx, int engine, void* stream);
 
 /* adni_conv3d_dgrad whose epilogue also performs the BatchNorm-backward reduction of the layer that PRODUCED dx's
  * tensor (MedicalNet blocks: conv -> bn -> relu; the dx of one conv is the `dout` of the preceding BatchNorm3d):
@@ -101,8 +93,7 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
 int adni_conv3d_dgrad_bnred_profitable(const adni_conv3d_geom* g);
 int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
                             adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
-                            const float* bn_shift, double* sum_g, double* sum_gy, void* workspace, size_t ws_bytes,
-                            void* stream);
+                            const float* bn_shift, double* sum_g, double* sum_gy, void* stream);
 
 /* dw_oti[Cout][taps][Cin] (fp32) += sum over positions of dy^T * im2col(x).  The caller zeroes dw
  * (the split-K partial sums are accumulated with red.global.add). dbias[Cout] (fp32, may be null) +=

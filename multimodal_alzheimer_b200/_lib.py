@@ -36,9 +36,8 @@ _SZ = ctypes.c_size_t
 _SIGNATURES = {
     "adni_conv3d_out_extent": [_I, _I, _I, _I, _I],
     "adni_conv3d_plan_info": [ctypes.POINTER(ConvGeom), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
-    "adni_conv3d_workspace_bytes": [],
-    "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P, _SZ, _P],
-    "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P, _SZ, _P],
+    "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P],
+    "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
     "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _I, _P],
     "adni_conv3d_wgrad_scratch_floats": [ctypes.POINTER(ConvGeom)],
     "adni_stem_x8_elems": [_I, _I, _I, _I],
@@ -67,7 +66,7 @@ _SIGNATURES = {
     "adni_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P],
     "adni_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _LL, _I, _I, _P, _P, _P, _P, _D, _I, _P],
     "adni_conv3d_dgrad_bnred_profitable": [ctypes.POINTER(ConvGeom)],
-    "adni_conv3d_dgrad_bnred": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    "adni_conv3d_dgrad_bnred": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "adni_bn_train_apply": [_P, _P, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _LL, _I, _I, _P],
     "adni_channel_stats": [_P, _LL, _I, _P, _P, _P],
     "adni_maxpool3d_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
@@ -111,7 +110,6 @@ _RESTYPES = {
     "adni_stem_x8_elems": ctypes.c_longlong,
     "adni_quantile_workspace_bytes": ctypes.c_size_t,
     "adni_peer_buffer_bytes": ctypes.c_size_t,
-    "adni_conv3d_workspace_bytes": ctypes.c_size_t,
     "adni_conv3d_wgrad_scratch_floats": ctypes.c_longlong,
 }
 

@@ -15,7 +15,7 @@
 
 namespace adni {
 
-int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream, const SkSched* sk = nullptr);
+int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream, const W2Sched* sk = nullptr);
 int wgrad2_box_rows(int mt_cfg);
 bool wgrad_halo_supported(const adni_conv3d_geom& g);
@@ -215,118 +215,8 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
   return launch_igemm_halo(p, C, stream);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Stream-K schedule for the tap-per-box kernel.  The static schedule hands tile i to CTA i mod 148; tiles differ in
-// cost (taps whose shifted box lies in the padding are skipped: a corner tile of a dilation-4 conv runs 8 of 27 taps)
-// and at small per-GPU batches there are fewer than two tiles per SM (4 samples: 256 tiles on 148 SMs), so the slowest
-// CTA does up to 1.4x the average work.  Stream-K cuts the sequence of all K iterations into 148 equal ranges instead.
-// The plan depends only on the geometry: cached.
-constexpr long long kSkMaxTiles = 65536;   // bounds the arrival-counter block of the workspace (256 KB)
-struct SkPlan {
-  bool use = false;
-  int total_tiles = 0;
-  SkSched sched;
-};
-
-const SkPlan& plan_stream_k(const IgemmParams& p) {
-  static std::mutex mu;
-  static std::map<std::vector<int>, SkPlan> cache;
-  std::vector<int> key = {p.ntaps, p.kc_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.tiles_d, p.tiles_h, p.tiles_w,
-                          p.n_tiles, num_sms()};
-  for (int t = 0; t < p.ntaps; t++) {
-    key.push_back((int(p.taps[t].map) << 24) ^ ((p.taps[t].dd & 0xff) << 16) ^ ((p.taps[t].dh & 0xff) << 8) ^ (p.taps[t].dw & 0xff));
-  }
-  for (int m = 0; m < kMaxMaps; m++)
-    for (int a = 0; a < 3; a++) key.push_back(p.a_ext[m][a]);
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) return it->second;
-  SkPlan plan;
-  memset(&plan.sched, 0, sizeof(plan.sched));
-  const long long boxes = (long long)p.N * p.tiles_d * p.tiles_h * p.tiles_w;
-  const long long total = boxes * p.n_tiles;
-  plan.total_tiles = int(total);
-  const int G = std::min(num_sms(), kSkMaxCtas);   // every SM gets a range, however few tiles there are
-  static const int enabled = env_int("ADNI_STREAM_K", 1);
-  if (enabled && total > 0 && total <= kSkMaxTiles && G <= kSkMaxCtas && p.ntaps > 0) {
-    // iterations per tile (same test as the kernel's tap mask); tile index = box * n_tiles + nt, box = ((n*td+d)*th+h)*tw+w
-    std::vector<int> iters(static_cast<size_t>(total));
-    bool all_nonzero = true;
-    long long T = 0;
-    size_t idx = 0;
-    for (int n = 0; n < p.N; n++)
-      for (int td = 0; td < p.tiles_d; td++)
-        for (int th = 0; th < p.tiles_h; th++)
-          for (int tw = 0; tw < p.tiles_w; tw++) {
-            int valid = 0;
-            for (int t = 0; t < p.ntaps; t++) {
-              const int* ext = p.a_ext[p.taps[t].map];
-              const int d = td * p.bd + p.taps[t].dd, h = th * p.bh + p.taps[t].dh, w = tw * p.bw + p.taps[t].dw;
-              if (d + p.bd > 0 && d < ext[0] && h + p.bh > 0 && h < ext[1] && w + p.bw > 0 && w < ext[2]) valid++;
-            }
-            if (valid == 0) all_nonzero = false;
-            for (int nt = 0; nt < p.n_tiles; nt++) {
-              iters[idx++] = valid * p.kc_blocks;
-              T += valid * p.kc_blocks;
-            }
-          }
-    if (all_nonzero) {
-      // static schedule's slowest CTA vs the ideal
-      const size_t Gs = static_cast<size_t>(std::min<long long>(G, total));   // the static grid
-      std::vector<long long> load(Gs, 0);
-      for (size_t i = 0; i < iters.size(); i++) load[i % Gs] += iters[i];
-      const long long worst = *std::max_element(load.begin(), load.end());
-      // a K iteration (64-deep block, N = 256) is ~0.27 us; parking + finishing a shared tile costs a CTA ~10 us at the
-      // end of its range: worth it only if the slowest CTA of the static schedule is >= 64 iterations above the mean
-      // (static: when fewer tiles than SMs, the idle SMs count too)
-      const long long ideal = T / G;
-      if (worst - ideal >= 64 && ideal >= 64) {
-        plan.use = true;
-        plan.sched.ctas = G;
-        std::vector<long long> prefix(iters.size() + 1, 0);
-        for (size_t i = 0; i < iters.size(); i++) prefix[i + 1] = prefix[i] + iters[i];
-        size_t tile = 0;
-        for (int c = 0; c < G; c++) {
-          const long long start = T * c / G, end = T * (c + 1) / G;   // end > start (T >= 16 G)
-          while (prefix[tile + 1] <= start) tile++;
-          plan.sched.tile_begin[c] = int(tile);
-          plan.sched.it_begin[c] = int(start - prefix[tile]);
-          size_t last = tile;
-          while (prefix[last + 1] < end) last++;
-          plan.sched.tile_last[c] = int(last);
-          plan.sched.it_end[c] = int(end - prefix[last]);
-        }
-      }
-    }
-  }
-  return cache.emplace(key, plan).first->second;
-}
-
-// bytes of workspace a stream-K launch needs: arrival counters (one int per tile) + two partial-tile slots per CTA
-size_t sk_workspace_bytes(const SkPlan& plan, int block_n) {
-  if (!plan.use) return 0;
-  return static_cast<size_t>(kSkMaxTiles) * 4 + static_cast<size_t>(2) * plan.sched.ctas * 128 * block_n * 4;
-}
-
-// Launch with the stream-K schedule when the plan wants one and the caller's workspace holds it, else statically.
-int launch_igemm_planned(const IgemmParams& p, int block_n, void* workspace, size_t ws_bytes, cudaStream_t stream) {
-  if (workspace != nullptr) {
-    const SkPlan& plan = plan_stream_k(p);
-    const size_t need = sk_workspace_bytes(plan, block_n);
-    if (plan.use && need <= ws_bytes && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0) {
-      SkSched sched = plan.sched;
-      sched.counters = static_cast<int*>(workspace);
-      // fixed offset: a launch with few tiles must not leave partial sums where a later launch keeps its counters
-      sched.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + static_cast<size_t>(kSkMaxTiles) * 4);
-      return launch_igemm(p, block_n, stream, &sched);
-    }
-  }
-  return launch_igemm(p, block_n, stream, nullptr);
-}
-
 int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,
-             __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream, void* workspace = nullptr,
-             size_t ws_bytes = 0) {
+             __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream) {
   if (halo_supported(g)) {
     const int rc = tc_halo(g, x, w_oti, false, bias, nullptr, y, ssum, ssq, stream);
     if (rc != ADNI_ENOTSUP) return rc;
@@ -400,13 +290,12 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     const char* dbg = getenv("ADNI_DEBUG_MODE");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  return launch_igemm_planned(p, block_n, workspace, ws_bytes, stream);
+  return launch_igemm(p, block_n, stream);
 }
 
 // dx = sum_k dy[(i + pad - k*dil)/stride] * w[k]^T, one launch per parity class of dx when stride > 1.
 int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
-             const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream, const BnReduceEpilogue* red = nullptr,
-             void* workspace = nullptr, size_t ws_bytes = 0) {
+             const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream, const BnReduceEpilogue* red = nullptr) {
   if (halo_supported(g)) {
     const int rc = tc_halo(g, dy, w_ito, true, nullptr, addend, dx, nullptr, nullptr, stream, red);
     if (rc != ADNI_ENOTSUP) return rc;
@@ -507,7 +396,7 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
           p.stat_sum = red->sum_g;
           p.stat_sq = red->sum_gy;
         }
-        rc = launch_igemm_planned(p, block_n, workspace, ws_bytes, stream);
+        rc = launch_igemm(p, block_n, stream);
         if (rc) return rc;
       }
   return ADNI_OK;
@@ -817,14 +706,8 @@ int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind,
   return ADNI_OK;
 }
 
-size_t adni_conv3d_workspace_bytes(void) {
-  // arrival counters for <= kSkMaxTiles tiles + two fp32 partial tiles (128 x 256) per CTA, 256-byte aligned
-  return static_cast<size_t>(kSkMaxTiles) * 4 + static_cast<size_t>(2) * kSkMaxCtas * 128 * 256 * 4;
-}
-
 int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_bf16* w_oti, const float* bias,
-                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* workspace, size_t ws_bytes,
-                      void* stream) {
+                      adni_bf16* y, double* stat_sum, double* stat_sqsum, int engine, void* stream) {
   int rc = check_geom(g);
   if (rc) return rc;
   ADNI_REQUIRE(x && w_oti && y, ADNI_EINVAL, "conv3d_fprop: null pointer");
@@ -836,7 +719,7 @@ int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
   auto ws = reinterpret_cast<const __nv_bfloat16*>(w_oti);
   auto ys = reinterpret_cast<__nv_bfloat16*>(y);
   if (eng == ADNI_ENGINE_TCGEN05)
-    return tc_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream), workspace, ws_bytes);
+    return tc_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
   if (eng == ADNI_ENGINE_MMA_SYNC) {
     rc = small_conv_fprop(*g, xs, ws, bias, ys, stat_sum, stat_sqsum, static_cast<cudaStream_t>(stream));
     if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;   // AUTO: tile too large for shared memory
@@ -845,7 +728,7 @@ int adni_conv3d_fprop(const adni_conv3d_geom* g, const adni_bf16* x, const adni_
 }
 
 int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
-                      adni_bf16* dx, int engine, void* workspace, size_t ws_bytes, void* stream) {
+                      adni_bf16* dx, int engine, void* stream) {
   int rc = check_geom(g);
   if (rc) return rc;
   ADNI_REQUIRE(dy && w_ito && dx, ADNI_EINVAL, "conv3d_dgrad: null pointer");
@@ -857,7 +740,7 @@ int adni_conv3d_dgrad(const adni_conv3d_geom* g, const adni_bf16* dy, const adni
   auto as = reinterpret_cast<const __nv_bfloat16*>(addend);
   auto dxs = reinterpret_cast<__nv_bfloat16*>(dx);
   if (eng == ADNI_ENGINE_TCGEN05)
-    return tc_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream), nullptr, workspace, ws_bytes);
+    return tc_dgrad(*g, dys, ws, as, dxs, static_cast<cudaStream_t>(stream));
   if (eng == ADNI_ENGINE_MMA_SYNC) {
     rc = small_conv_dgrad(*g, dys, ws, dxs, static_cast<cudaStream_t>(stream));
     if (rc != ADNI_ENOTSUP || engine == ADNI_ENGINE_MMA_SYNC) return rc;
@@ -876,8 +759,7 @@ int adni_conv3d_dgrad_bnred_profitable(const adni_conv3d_geom* g) {
 
 int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, const adni_bf16* w_ito, const adni_bf16* addend,
                             adni_bf16* dx, const adni_bf16* bn_y, const adni_bf16* bn_relu_out, const float* bn_scale,
-                            const float* bn_shift, double* sum_g, double* sum_gy, void* workspace, size_t ws_bytes,
-                            void* stream) {
+                            const float* bn_shift, double* sum_g, double* sum_gy, void* stream) {
   int rc = check_geom(g);
   if (rc) return rc;
   ADNI_REQUIRE(dy && w_ito && dx && bn_y && sum_g && sum_gy, ADNI_EINVAL, "conv3d_dgrad_bnred: null pointer");
@@ -894,7 +776,7 @@ int adni_conv3d_dgrad_bnred(const adni_conv3d_geom* g, const adni_bf16* dy, cons
   red.sum_gy = sum_gy;
   return tc_dgrad(*g, reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(w_ito),
                   reinterpret_cast<const __nv_bfloat16*>(addend), reinterpret_cast<__nv_bfloat16*>(dx),
-                  static_cast<cudaStream_t>(stream), &red, workspace, ws_bytes);
+                  static_cast<cudaStream_t>(stream), &red);
 }
 
 long long adni_conv3d_wgrad_scratch_floats(const adni_conv3d_geom* g) {

@@ -44,20 +44,7 @@ struct IgemmParams {
   int debug;  // diagnostics only (ADNI_DEBUG_MODE): 1 = no MMA issue, 2 = no TMA loads, 3 = no epilogue stores
 };
 
-// Stream-K schedule of the tap-per-box kernel (conv_igemm_kernels.cu): the K iterations (valid tap x 64-channel block)
-// of all tiles form one sequence that is cut into equal contiguous ranges, one per CTA.  CTA b walks tiles
-// tile_begin[b] .. tile_last[b]; in its first tile it starts at iteration it_begin[b], in its last it stops before
-// it_end[b].  Tiles shared by several CTAs are summed through `scratch` by whichever CTA arrives last (`counters`).
-constexpr int kSkMaxCtas = 160;
-struct SkSched {
-  int tile_begin[kSkMaxCtas];
-  int it_begin[kSkMaxCtas];
-  int tile_last[kSkMaxCtas];
-  int it_end[kSkMaxCtas];
-  int ctas;
-  float* scratch;  // [2 * ctas][BLOCK_N / 32][128][32] fp32 partial tiles
-  int* counters;   // [total tiles], zero on entry; the finalizer of a tile resets its counter
-};
+constexpr int kSkMaxCtas = 160;   // CTAs a stream-K schedule table holds (>= the SM count)
 struct SkNone {
   int unused;
 };

@@ -16,8 +16,6 @@
 // + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bf16 global, fused bias / residual-gradient
 // add / BatchNorm sum & sum-of-squares).  Two TMEM accumulators let the epilogue of tile i overlap the
 // mainloop of tile i+1.
-#include <type_traits>
-
 #include "conv_igemm.cuh"
 
 namespace adni {
@@ -62,40 +60,9 @@ struct IgemmCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-// One work unit of a CTA: K iterations [it0, it1) of `tile` (the whole tile in the static schedule).
-struct WorkUnit {
-  int it0, it1;
-  bool partial;
-};
-template <bool SK, typename SchedT>
-__device__ __forceinline__ void cta_tile_range(const SchedT& sk, int total_tiles, int& tile, int& stop, int& step) {
-  if constexpr (SK) {
-    tile = sk.tile_begin[blockIdx.x];
-    stop = sk.tile_last[blockIdx.x] + 1;
-    step = 1;
-  } else {
-    tile = blockIdx.x;
-    stop = total_tiles;
-    step = gridDim.x;
-  }
-}
-template <bool SK, typename SchedT>
-__device__ __forceinline__ WorkUnit work_unit(const SchedT& sk, int tile, int n_it) {
-  WorkUnit u{0, n_it, false};
-  if constexpr (SK) {
-    if (tile == sk.tile_begin[blockIdx.x]) u.it0 = sk.it_begin[blockIdx.x];
-    if (tile == sk.tile_last[blockIdx.x]) u.it1 = sk.it_end[blockIdx.x];
-    u.partial = u.it0 != 0 || u.it1 != n_it;
-  }
-  return u;
-}
-
-template <int BLOCK_N, int STAGES, bool SK>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
-    igemm_kmajor_kernel(const __grid_constant__ IgemmParams p,
-                        const __grid_constant__ typename std::conditional<SK, SkSched, SkNone>::type sk) {
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N, STAGES>;
-  using SchedT = typename std::conditional<SK, SkSched, SkNone>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -155,21 +122,16 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
     const uint32_t tx_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bd) * 128u + Cfg::B_BYTES;
     int st = 0;
     uint32_t ph = 0;
-    int tile, tile_stop, tile_step;
-    cta_tile_range<SK, SchedT>(sk, total_tiles, tile, tile_stop, tile_step);
-    for (; tile < tile_stop; tile += tile_step) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile<BLOCK_N>(p, tile);
       unsigned long long mask = tap_mask(c);
-      const WorkUnit u = work_unit<SK, SchedT>(sk, tile, __popcll(mask) * p.kc_blocks);
-      int it = 0;
       while (mask) {
         const int t = __ffsll(static_cast<long long>(mask)) - 1;
         mask &= mask - 1;
         const ConvTap tap = p.taps[t];
         const int d = c.d0 + tap.dd, h = c.h0 + tap.dh, w = c.w0 + tap.dw;
         const CUtensorMap* amap = &p.a_maps[tap.map];
-        for (int kb = 0; kb < p.kc_blocks; kb++, it++) {
-          if (SK && (it < u.it0 || it >= u.it1)) continue;   // iterations of this tile that belong to another CTA
+        for (int kb = 0; kb < p.kc_blocks; kb++) {
           if (lane == 0) {
             mbar_wait_spin(&empty[st], ph ^ 1, 2136);
             if (p.debug == 2)
@@ -198,12 +160,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
     uint32_t ph = 0;
     int acc = 0;
     uint32_t accph = 0;
-    int tile, tile_stop, tile_step;
-    cta_tile_range<SK, SchedT>(sk, total_tiles, tile, tile_stop, tile_step);
-    for (; tile < tile_stop; tile += tile_step) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile<BLOCK_N>(p, tile);
-      const WorkUnit u = work_unit<SK, SchedT>(sk, tile, __popcll(tap_mask(c)) * p.kc_blocks);
-      const int nkb = u.it1 - u.it0;
+      const int nkb = __popcll(tap_mask(c)) * p.kc_blocks;
       // The whole warp walks the loop with warp-uniform state (so ptxas keeps stage / descriptor arithmetic on the
       // uniform datapath instead of ELECT + R2UR per operand); one elected lane issues the tcgen05 instructions.
       mbar_wait_spin(&tempty[acc], accph ^ 1, 2168);
@@ -246,13 +205,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
     const bool do_stats = p.stat_sum != nullptr && !do_red;       // BatchNorm-forward sums (fprop calls)
     int acc = 0;
     uint32_t accph = 0;
-    int tile, tile_stop, tile_step;
-    cta_tile_range<SK, SchedT>(sk, total_tiles, tile, tile_stop, tile_step);
-    for (; tile < tile_stop; tile += tile_step) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile<BLOCK_N>(p, tile);
-      const unsigned long long tmask = tap_mask(c);
-      const bool has_k = tmask != 0ull;
-      const WorkUnit u = work_unit<SK, SchedT>(sk, tile, __popcll(tmask) * p.kc_blocks);
+      const bool has_k = tap_mask(c) != 0ull;
       const int rw = row % p.bw;
       const int rh = (row / p.bw) % p.bh;
       const int rd = row / (p.bw * p.bh);
@@ -280,57 +235,6 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
       red_prefetch(0);
       mbar_wait_spin(&tfull[acc], accph, 2217);
       tc_fence_after();
-      // ---- stream-K: a tile shared with other CTAs.  Every contributor parks its partial accumulator in scratch and
-      // takes a ticket; the LAST arriver sums all contributions in CTA order (deterministic, whatever the arrival
-      // order) and runs the epilogue.  Nobody ever waits for another CTA.
-      bool from_scratch = false;
-      int c_first = 0, c_last = 0;
-      if constexpr (SK) {
-        if (u.partial) {
-          const int b = blockIdx.x;
-          const int slot = 2 * b + ((tile == sk.tile_last[b] && tile != sk.tile_begin[b]) ? 1 : 0);
-          float* dst = sk.scratch + static_cast<size_t>(slot) * (128 * BLOCK_N) + row * 32;
-#pragma unroll 1
-          for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                              static_cast<uint32_t>(acc * BLOCK_N + chunk * 32),
-                          v);
-            tmem_ld_wait();
-            float4* d4 = reinterpret_cast<float4*>(dst + chunk * (128 * 32));
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++)
-              d4[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]),
-                                   __uint_as_float(v[4 * j4 + 3]));
-          }
-          // the accumulator is parked: hand the TMEM buffer back at once (the fix-up below runs under the next main loop)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-          if (++acc == 2) {
-            acc = 0;
-            accph ^= 1;
-          }
-          __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          int* ticket_s = reinterpret_cast<int*>(stat_smem);   // free here: the statistic slots are written later
-          c_first = b;
-          while (c_first > 0 && sk.tile_last[c_first - 1] >= tile) c_first--;
-          c_last = b;
-          while (c_last + 1 < sk.ctas && sk.tile_begin[c_last + 1] <= tile) c_last++;
-          if (et == 0) {
-            const int ticket = atomicAdd(sk.counters + tile, 1);
-            const int last = ticket == c_last - c_first;
-            if (last) sk.counters[tile] = 0;                  // ready for the next launch that uses this workspace
-            *ticket_s = last;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          from_scratch = *ticket_s != 0;
-          asm volatile("bar.sync 1, 128;" ::: "memory");       // ticket_s is read before the statistic slots are reused
-          if (!from_scratch) continue;                         // the tile is finished by a later arriver
-          __threadfence();
-        }
-      }
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; chunk++) {
         uint4 y_cur[4], m_cur[4];
@@ -340,60 +244,19 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
           m_cur[j4] = m_nxt[j4];
         }
         if (chunk + 1 < BLOCK_N / 32) red_prefetch(chunk + 1);
-        float f[32];
-        if (SK && from_scratch) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = 0.f;
-          if constexpr (SK) {
-            // contributions are added in CTA order (deterministic); two contributors' rows are in flight at a time
-            auto slot_ptr = [&](int cc) {
-              const int slot = 2 * cc + ((tile == sk.tile_last[cc] && tile != sk.tile_begin[cc]) ? 1 : 0);
-              return reinterpret_cast<const float4*>(sk.scratch + static_cast<size_t>(slot) * (128 * BLOCK_N) +
-                                                     chunk * (128 * 32) + row * 32);
-            };
-            for (int cc = c_first; cc <= c_last; cc += 2) {
-              const bool two = cc + 1 <= c_last;
-              const float4* s4a = slot_ptr(cc);
-              const float4* s4b = slot_ptr(two ? cc + 1 : cc);
-              float4 ta[8], tb[8];
-#pragma unroll
-              for (int j4 = 0; j4 < 8; j4++) ta[j4] = __ldcg(s4a + j4);
-              if (two) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) tb[j4] = __ldcg(s4b + j4);
-              }
-#pragma unroll
-              for (int j4 = 0; j4 < 8; j4++) {
-                f[4 * j4 + 0] += ta[j4].x;
-                f[4 * j4 + 1] += ta[j4].y;
-                f[4 * j4 + 2] += ta[j4].z;
-                f[4 * j4 + 3] += ta[j4].w;
-              }
-              if (two) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) {
-                  f[4 * j4 + 0] += tb[j4].x;
-                  f[4 * j4 + 1] += tb[j4].y;
-                  f[4 * j4 + 2] += tb[j4].z;
-                  f[4 * j4 + 3] += tb[j4].w;
-                }
-              }
-            }
-          }
+        uint32_t v[32];
+        if (has_k) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(acc * BLOCK_N + chunk * 32),
+                        v);
+          tmem_ld_wait();
         } else {
-          uint32_t v[32];
-          if (has_k) {
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                              static_cast<uint32_t>(acc * BLOCK_N + chunk * 32),
-                          v);
-            tmem_ld_wait();
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; j++) v[j] = 0u;
         }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j++) f[j] += __ldg(p.bias + c.n0 + chunk * 32 + j);
@@ -470,15 +333,13 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
           stat_smem[(ew * 2 + 1) * BLOCK_N + chunk * 32 + lane] = cs2;
         }
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp (a partial unit did so when it parked)
-      if (!(SK && u.partial)) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          accph ^= 1;
-        }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        accph ^= 1;
       }
       if (do_stats || do_red) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -511,41 +372,30 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
 extern void count_launch();
 
 template <int BLOCK_N, int STAGES>
-static int launch_igemm_t(const IgemmParams& p, const SkSched* sk, cudaStream_t stream) {
+static int launch_igemm_t(const IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N, STAGES>;
-  const int total_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
-  if (sk != nullptr) {
-    auto kern = igemm_kmajor_kernel<BLOCK_N, STAGES, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-      attr_set = true;
-    }
-    kern<<<sk->ctas, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p, *sk);
-  } else {
-    auto kern = igemm_kmajor_kernel<BLOCK_N, STAGES, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-      attr_set = true;
-    }
-    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p, SkNone{0});
+  auto kern = igemm_kmajor_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
   }
+  const int total_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
   count_launch();
   ADNI_LAUNCH_CHECK("igemm_kmajor_kernel");
   return ADNI_OK;
 }
 
-// sk: a stream-K schedule for this launch (see plan_stream_k in conv_api.cu) or null for the static tile round-robin
-int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream, const SkSched* sk) {
+int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream) {
   switch (block_n) {
     case 64:
-      return launch_igemm_t<64, 8>(p, sk, stream);
+      return launch_igemm_t<64, 8>(p, stream);
     case 128:
-      return launch_igemm_t<128, 6>(p, sk, stream);
+      return launch_igemm_t<128, 6>(p, stream);
     case 256:
-      return launch_igemm_t<256, 4>(p, sk, stream);
+      return launch_igemm_t<256, 4>(p, stream);
     default:
       set_error("igemm: unsupported BLOCK_N %d", block_n);
       return ADNI_ENOTSUP;

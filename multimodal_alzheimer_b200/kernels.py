@@ -239,24 +239,6 @@ def wgrad_to_param_layout(dw_oti, shape, out=None):
     return out
 
 
-_CONV_WS = {}
-
-
-def conv_workspace(device):
-    """(pointer, bytes) of the conv workspace of the CURRENT stream (adni_conv3d_workspace_bytes: stream-K counters and
-    partial-tile slots): zeroed once, then reused by every conv call on that stream - the kernels restore the zeros.
-    Allocated outside CUDA-graph capture (eager warm-up steps come first); a stream that first shows up during capture
-    runs the static schedule."""
-    key = (device.index, stream_ptr().value)
-    ws = _CONV_WS.get(key)
-    if ws is None:
-        if torch.cuda.is_current_stream_capturing():
-            return None, 0
-        n = int(_lib.load().adni_conv3d_workspace_bytes())
-        ws = _CONV_WS[key] = torch.zeros((n + 255) // 8, dtype=torch.int64, device=device)
-    return ptr(ws), ws.numel() * 8
-
-
 def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE_AUTO):
     _chk(x, BF16, "x")
     _chk(w_oti, BF16, "w_oti")
@@ -266,10 +248,9 @@ def conv3d_fprop(x, w_oti, bias, k, stride, pad, dil, stats=False, engine=ENGINE
     Do, Ho, Wo = (out_extent(v, k, stride, pad, dil) for v in (D, H, W))
     y = torch.empty((N, Do, Ho, Wo, Cout), dtype=BF16, device=x.device)
     st = zeros_f64((2, Cout), x.device) if stats else None
-    ws, ws_bytes = conv_workspace(x.device)
     ev = PROFILE.begin()
     call("adni_conv3d_fprop", g, ptr(x), ptr(w_oti), ptr(bias), ptr(y), ptr(st[0]) if stats else None,
-         ptr(st[1]) if stats else None, engine, ws, ws_bytes, stream_ptr())
+         ptr(st[1]) if stats else None, engine, stream_ptr())
     tag, frac = _engine_tag(g, 0, engine)
     PROFILE.end(ev, tag, 2 * N * Do * Ho * Wo * Cout * Cin * k ** 3,
                 f"fprop N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
@@ -285,9 +266,8 @@ def conv3d_dgrad(dy, w_ito, in_shape, k, stride, pad, dil, addend=None, engine=E
     dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
     if addend is not None:
         _chk(addend, BF16, "addend")
-    ws, ws_bytes = conv_workspace(dy.device)
     ev = PROFILE.begin()
-    call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, ws, ws_bytes, stream_ptr())
+    call("adni_conv3d_dgrad", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), engine, stream_ptr())
     tag, frac = _engine_tag(g, 1, engine)
     PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
                 f"dgrad N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)
@@ -308,10 +288,9 @@ def conv3d_dgrad_bnred(dy, w_ito, in_shape, k, stride, pad, dil, bn_y, bn_relu_o
     g = geom(N, D, H, W, Cin, Cout, k, stride, pad, dil)
     dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
     red = zeros_f64((2, Cin), dy.device)
-    ws, ws_bytes = conv_workspace(dy.device)
     ev = PROFILE.begin()
     call("adni_conv3d_dgrad_bnred", g, ptr(dy), ptr(w_ito), ptr(addend), ptr(dx), ptr(bn_y), ptr(bn_relu_out),
-         ptr(bn_scale), ptr(bn_shift), ptr(red[0]), ptr(red[1]), ws, ws_bytes, stream_ptr())
+         ptr(bn_scale), ptr(bn_shift), ptr(red[0]), ptr(red[1]), stream_ptr())
     tag, frac = _engine_tag(g, 1, ENGINE_AUTO)
     PROFILE.end(ev, tag, 2 * dy.numel() * Cin * k ** 3,
                 f"dgrad+bnred N{N} {D}x{H}x{W} {Cin}->{Cout} k{k} s{stride} d{dil}", frac)

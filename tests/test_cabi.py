@@ -48,10 +48,10 @@ def test_out_extent_matches_torch_formula(lib):
 
 def test_bad_arguments_return_einval_without_a_gpu(lib):
     g = _lib.geom(1, 8, 8, 8, 64, 64, 3, 1, 1, 1)
-    assert lib.adni_conv3d_fprop(ctypes.byref(g), None, None, None, None, None, None, 0, None, 0, None) == -1
+    assert lib.adni_conv3d_fprop(ctypes.byref(g), None, None, None, None, None, None, 0, None) == -1
     assert b"null" in lib.adni_last_error_string()
     bad = _lib.geom(1, 8, 8, 8, 64, 64, 3, 0, 1, 1)  # stride 0
-    assert lib.adni_conv3d_fprop(ctypes.byref(bad), None, None, None, None, None, None, 0, None, 0, None) == -1
+    assert lib.adni_conv3d_fprop(ctypes.byref(bad), None, None, None, None, None, None, 0, None) == -1
     assert lib.adni_quantile_workspace_bytes(3) == 3 * lib.adni_quantile_workspace_bytes(1) > 0
     assert lib.adni_loss_fwd(None, 0, 3, None, 4, 3, 1.0, None, None, None, None) == -1
 
@@ -59,7 +59,7 @@ def test_bad_arguments_return_einval_without_a_gpu(lib):
 def test_unsupported_engine_is_enotsup_not_a_fallback(lib):
     g = _lib.geom(1, 8, 8, 8, 8, 8, 3, 1, 1, 1)
     one = ctypes.c_void_p(16)  # never dereferenced: the engine check happens first
-    assert lib.adni_conv3d_fprop(ctypes.byref(g), one, one, None, one, None, None, _lib.ENGINE_TCGEN05, None, 0, None) == -2
+    assert lib.adni_conv3d_fprop(ctypes.byref(g), one, one, None, one, None, None, _lib.ENGINE_TCGEN05, None) == -2
 
 
 def test_cpu_tensors_are_rejected_no_fallback():

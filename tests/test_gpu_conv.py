@@ -130,32 +130,6 @@ def test_tc_dgrad_with_fused_bn_backward_sums(cuda_dev, shape, mask_mode):
     assert_close(red[1], (gq * yq).sum(dim=(0, 1, 2, 3)), 2e-5, f"sum g*y {shape} {mask_mode}")
 
 
-@pytest.mark.parametrize("shape", [TC_SHAPES[3], TC_SHAPES[2], (4, 16, 16, 16, 512, 512, 3, 1, 4, 4)])
-def test_stream_k_is_deterministic_and_restores_its_workspace(cuda_dev, shape):
-    """The tap-per-box engine under the stream-K schedule (tiles of unequal tap counts, fewer than two tiles per SM):
-    results are checked against torch by test_tc_fprop / test_tc_dgrad above; here: two runs are bit-identical (partial
-    tiles are summed in CTA order, whatever the arrival order), statistics included, and the workspace is all zeros
-    again after every call (the next call on the stream reuses it)."""
-    from multimodal_alzheimer_b200 import kernels as K
-    N, D, H, W, Cin, Cout, k, s, p, d = shape
-    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
-    oti, ito = K.weights_to_kernel_layout(w)
-    outs = []
-    for _ in range(3):
-        y, st = K.conv3d_fprop(x_b, oti, None, k, s, p, d, stats=True)
-        dx = K.conv3d_dgrad(y, ito, tuple(x_b.shape), k, s, p, d, addend=x_b)
-        torch.cuda.synchronize()
-        outs.append((y.clone(), st.clone(), dx.clone()))
-        ws = K._CONV_WS[(cuda_dev.index, K.stream_ptr().value)]
-        counters = ws[: (65536 * 4) // 8]
-        assert int(counters.abs().sum()) == 0
-    for y, st, dx in outs[1:]:
-        assert torch.equal(y, outs[0][0]) and torch.equal(dx, outs[0][2])
-        assert_close(st, outs[0][1], 1e-13, "stats")   # fp64 atomics of fp32 tile sums: order changes the last bits at most
-    ref = F.conv3d(x_ref, w_ref, None, s, p, d)
-    assert_close(to_ncdhw_f32(outs[0][0]), ref, 6e-3, f"stream-K fprop {shape}")
-
-
 @pytest.mark.parametrize("shape", TINY_SHAPES)
 def test_tc_tiny_feature_maps(cuda_dev, shape):
     """fprop + dgrad + wgrad on feature maps smaller than one tile, through the planner's own engine choice."""
