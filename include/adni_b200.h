@@ -231,9 +231,14 @@ int adni_relu_maxpool_bwd(const adni_bf16* dy, const uint8_t* argmax, const adni
  *   fwd   : p, argmax = maxpool(relu(y*scale + shift))            y: raw conv1 output [N][D][H][W][C]
  *   reduce: g = relu_mask(y) * maxpool_bwd(dp, argmax);  red[0:C] += sum g, red[C:2C] += sum g*xhat
  *   apply : dy = gamma*invstd*(g - red_g/count - xhat*red_gx/count)
- * bnp is the fp32 [4][C] block (mean, invstd, scale, shift) written by adni_bn_finalize. */
+ * bnp is the fp32 [4][C] block (mean, invstd, scale, shift) written by adni_bn_finalize.
+ * y_at_argmax (nullable, pooled shape): the RAW conv output at every window's arg-max.  With it the backward sums need
+ * no pass over the full-resolution tensor: each window hands its gradient to exactly one voxel, so
+ *   sum g = sum_w dp[w]*mask_w,  sum g*xhat = sum_w dp[w]*mask_w*xhat(y_at_argmax[w])
+ * = adni_bn_bwd_reduce(dout = dp, y = y_at_argmax, scale, shift) over the POOLED tensor (1/8 of the elements). */
 int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float* shift, int N, int D, int H, int W,
-                             int C, int k, int stride, int pad, adni_bf16* p, uint8_t* argmax, void* stream);
+                             int C, int k, int stride, int pad, adni_bf16* p, uint8_t* argmax, adni_bf16* y_at_argmax,
+                             void* stream);
 int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const adni_bf16* y, const float* bnp, int N,
                                int D, int H, int W, int C, int k, int stride, int pad, double* red, void* stream);
 int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const adni_bf16* y, const float* bnp,

@@ -73,7 +73,7 @@ _SIGNATURES = {
     "adni_maxpool3d_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adni_relu_maxpool_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "adni_relu_maxpool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
-    "adni_bn_relu_maxpool_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "adni_bn_relu_maxpool_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "adni_maxpool_bn_bwd_reduce": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adni_maxpool_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adni_gap_fwd": [_P, _I, _LL, _I, _P, _P],

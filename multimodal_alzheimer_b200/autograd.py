@@ -282,13 +282,14 @@ class StemFn(torch.autograd.Function):
             count = (y.numel() // C) * _world()
             bnp = K.bn_finalize(st, count, gamma, beta, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
             _count_batch(bn)
-            p, am = K.bn_relu_maxpool_fwd(y, bnp, *pool)
+            p, am, yraw = K.bn_relu_maxpool_fwd(y, bnp, *pool)
             a_shape = tuple(y.shape)
         else:
             a, bnp, count = _bn_forward(y, st, gamma, beta, bn, None, True)
             p, am = K.maxpool3d_fwd(a, *pool)
             a_shape = tuple(a.shape)
-        ctx.save_for_backward(xs, y, am, bnp, gamma)
+            yraw = None
+        ctx.save_for_backward(xs, y, am, bnp, gamma, yraw)
         ctx.a_shape = a_shape
         ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, w.shape, tc, tuple(x.shape)
         ctx.fused = fused
@@ -297,10 +298,14 @@ class StemFn(torch.autograd.Function):
     @staticmethod
     @_with_forward_group
     def backward(ctx, dp):
-        x, y, am, bnp, gamma = ctx.saved_tensors
+        x, y, am, bnp, gamma, yraw = ctx.saved_tensors
         dp = dp.contiguous()
         if ctx.fused:
-            red = K.maxpool_bn_bwd_reduce(dp, am, y, bnp, *ctx.pool)
+            if yraw is not None:
+                # every window hands its gradient to ONE voxel (its arg-max): the sums run over the pooled tensor
+                red = K.bn_bwd_reduce(dp, None, yraw, bnp[0], bnp[1], True, bnp[2], bnp[3])
+            else:
+                red = K.maxpool_bn_bwd_reduce(dp, am, y, bnp, *ctx.pool)
             dgamma, dbeta = K.bn_param_grads(red)
             _allreduce_(red)
             dy = K.maxpool_bn_bwd_apply(dp, am, y, bnp, gamma, red, ctx.count, *ctx.pool)

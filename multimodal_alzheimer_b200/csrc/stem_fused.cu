@@ -289,8 +289,13 @@ constexpr int kSFh = 2, kSFw = 8, kSFThreads = kSFh * kSFw * 8;  // 2 x 8 pooled
 
 struct PlaneMax {
   float v[8];
-  uint32_t idx;  // 8 nibbles: kh*3 + kw of the winner of every channel
+  uint32_t idx;     // 8 nibbles: kh*3 + kw of the winner of every channel
+  uint32_t raw[4];  // the winner's RAW conv output (bf16 pairs): BatchNorm backward needs xhat at the arg-max only
 };
+// lane (j & 1) of word `dst` <- the same lane of `src`
+__device__ __forceinline__ uint32_t put_lane(uint32_t dst, uint32_t src, int j) {
+  return (j & 1) ? ((dst & 0x0000FFFFu) | (src & 0xFFFF0000u)) : ((dst & 0xFFFF0000u) | (src & 0x0000FFFFu));
+}
 
 // The nine 16-byte vectors of one input plane under a thread's window.  Loading and reducing are separate steps so
 // that the loads of the NEXT plane are in flight while the current one is reduced: with both in one routine a warp
@@ -321,6 +326,8 @@ __device__ __forceinline__ PlaneMax plane_reduce(const PlaneRaw& pr, uint32_t ok
   for (int j = 0; j < 8; j++) m.v[j] = -INFINITY;
   m.idx = 0;
 #pragma unroll
+  for (int k = 0; k < 4; k++) m.raw[k] = 0u;
+#pragma unroll
   for (int t = 0; t < 9; t++) {
     // branch-free: a tap outside the plane (zero vector, border threads only) is computed and then ignored through the
     // predicate of the compare - a per-tap branch cost ~20 reconvergence instructions per tap on every thread
@@ -331,11 +338,13 @@ __device__ __forceinline__ PlaneMax plane_reduce(const PlaneRaw& pr, uint32_t ok
     for (int j = 0; j < 8; j++) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
     float r[8];
     unpack8(pack8(f), r);  // compare what bn_apply would have stored: the bf16-rounded activation
+    const uint32_t rw[4] = {pr.r[t].x, pr.r[t].y, pr.r[t].z, pr.r[t].w};
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       if (ok && r[j] > m.v[j]) {  // first maximum in (kh, kw) order wins
         m.v[j] = r[j];
         m.idx = (m.idx & ~(0xFu << (4 * j))) | (static_cast<uint32_t>(t) << (4 * j));
+        m.raw[j >> 1] = put_lane(m.raw[j >> 1], rw[j >> 1], j);
       }
     }
   }
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
     bn_relu_pool_fwd_stream_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                    const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho, int Wo,
                                    int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
-                                   uint8_t* __restrict__ amax) {
+                                   uint8_t* __restrict__ amax, __nv_bfloat16* __restrict__ yraw) {
   const int vpr = C / 8;
   __shared__ float s_sc[64], s_sh[64];  // the block's 64 channels
   if (threadIdx.x < 64) {
@@ -401,18 +410,21 @@ __global__ void __launch_bounds__(kSFThreads, 3)
     const bool has_odd = od * kS + 1 < D;
     if (has_odd) plane_load(bufB, ys + (long long)(od * kS + 1) * plane, row_stride, C, okmask);
     float best[8];
-    uint32_t bidx[8];
+    uint32_t bidx[8], braw[4];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       best[j] = have_carry ? carry.v[j] : -INFINITY;
       bidx[j] = have_carry ? ((carry.idx >> (4 * j)) & 0xFu) : 0xFFu;
     }
+#pragma unroll
+    for (int k = 0; k < 4; k++) braw[k] = have_carry ? carry.raw[k] : 0u;
     const PlaneMax mid = plane_reduce(bufA, okmask, sc, sh);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       if (mid.v[j] > best[j]) {
         best[j] = mid.v[j];
         bidx[j] = 9u + ((mid.idx >> (4 * j)) & 0xFu);
+        braw[j >> 1] = put_lane(braw[j >> 1], mid.raw[j >> 1], j);
       }
     }
     if (od + 1 < od_end) plane_load(bufA, ys + (long long)((od + 1) * kS) * plane, row_stride, C, okmask);
@@ -424,11 +436,13 @@ __global__ void __launch_bounds__(kSFThreads, 3)
         if (carry.v[j] > best[j]) {
           best[j] = carry.v[j];
           bidx[j] = 18u + ((carry.idx >> (4 * j)) & 0xFu);
+          braw[j >> 1] = put_lane(braw[j >> 1], carry.raw[j >> 1], j);
         }
       }
     }
     const long long oi = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * vpr + cv;
     *reinterpret_cast<uint4*>(p + oi * 8) = pack8(best);
+    if (yraw != nullptr) *reinterpret_cast<uint4*>(yraw + oi * 8) = make_uint4(braw[0], braw[1], braw[2], braw[3]);
     uint2 pk;
     pk.x = (bidx[0] & 255u) | ((bidx[1] & 255u) << 8) | ((bidx[2] & 255u) << 16) | ((bidx[3] & 255u) << 24);
     pk.y = (bidx[4] & 255u) | ((bidx[5] & 255u) << 8) | ((bidx[6] & 255u) << 16) | ((bidx[7] & 255u) << 24);
@@ -445,6 +459,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
 struct PlaneMaxP {
   uint32_t v[4];    // running maxima, two bf16 lanes per word (channels 2k, 2k + 1)
   uint32_t idx[4];  // tap index kh*3 + kw of the winner in each 16-bit lane
+  uint32_t raw[4];  // the winner's raw conv output
 };
 __device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
   return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
@@ -458,6 +473,7 @@ __device__ __forceinline__ PlaneMaxP plane_reduce_packed(const PlaneRaw& pr, uin
   for (int k = 0; k < 4; k++) {
     m.v[k] = kNegInf2;
     m.idx[k] = 0;
+    m.raw[k] = 0;
   }
 #pragma unroll
   for (int t = 0; t < 9; t++) {
@@ -468,12 +484,14 @@ __device__ __forceinline__ PlaneMaxP plane_reduce_packed(const PlaneRaw& pr, uin
     for (int j = 0; j < 8; j++) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
     const uint4 yb = pack8(f);  // what bn_apply would have stored: the bf16-rounded activation
     const uint32_t w[4] = {yb.x, yb.y, yb.z, yb.w};
+    const uint32_t rw[4] = {pr.r[t].x, pr.r[t].y, pr.r[t].z, pr.r[t].w};
     const uint32_t tt = static_cast<uint32_t>(t) * 0x00010001u;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const uint32_t g = gt2_mask(w[k], m.v[k]) & okm;  // strict '>': the first maximum in (kh, kw) order wins
       m.v[k] = (w[k] & g) | (m.v[k] & ~g);
       m.idx[k] = (tt & g) | (m.idx[k] & ~g);
+      m.raw[k] = (rw[k] & g) | (m.raw[k] & ~g);
     }
   }
   return m;
@@ -483,7 +501,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
     bn_relu_pool_fwd_stream_packed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                           const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho,
                                           int Wo, int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
-                                          uint8_t* __restrict__ amax) {
+                                          uint8_t* __restrict__ amax, __nv_bfloat16* __restrict__ yraw) {
   const int vpr = C / 8;
   __shared__ float s_sc[64], s_sh[64];
   if (threadIdx.x < 64) {
@@ -536,11 +554,12 @@ __global__ void __launch_bounds__(kSFThreads, 3)
   for (int od = od_begin; od < od_end; od++) {
     const bool has_odd = od * kS + 1 < D;
     if (has_odd) plane_load(bufB, ys + (long long)(od * kS + 1) * plane, row_stride, C, okmask);
-    uint32_t best[4], bidx[4];
+    uint32_t best[4], bidx[4], braw[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       best[k] = have_carry ? carry.v[k] : kNegInf2;
       bidx[k] = have_carry ? carry.idx[k] : 0x00FF00FFu;
+      braw[k] = have_carry ? carry.raw[k] : 0u;
     }
     const PlaneMaxP mid = plane_reduce_packed(bufA, okmask, sc, sh);
 #pragma unroll
@@ -548,6 +567,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
       const uint32_t g = gt2_mask(mid.v[k], best[k]);  // planes in kd order, strict '>'
       best[k] = (mid.v[k] & g) | (best[k] & ~g);
       bidx[k] = ((mid.idx[k] + 9u * 0x00010001u) & g) | (bidx[k] & ~g);
+      braw[k] = (mid.raw[k] & g) | (braw[k] & ~g);
     }
     if (od + 1 < od_end) plane_load(bufA, ys + (long long)((od + 1) * kS) * plane, row_stride, C, okmask);
     have_carry = has_odd;
@@ -558,10 +578,12 @@ __global__ void __launch_bounds__(kSFThreads, 3)
         const uint32_t g = gt2_mask(carry.v[k], best[k]);
         best[k] = (carry.v[k] & g) | (best[k] & ~g);
         bidx[k] = ((carry.idx[k] + 18u * 0x00010001u) & g) | (bidx[k] & ~g);
+        braw[k] = (carry.raw[k] & g) | (braw[k] & ~g);
       }
     }
     const long long oi = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * vpr + cv;
     *reinterpret_cast<uint4*>(p + oi * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    if (yraw != nullptr) *reinterpret_cast<uint4*>(yraw + oi * 8) = make_uint4(braw[0], braw[1], braw[2], braw[3]);
     uint2 pk;  // bytes 0 and 2 of every index word: channels (0,1,2,3) and (4,5,6,7)
     pk.x = __byte_perm(bidx[0], bidx[1], 0x6420);
     pk.y = __byte_perm(bidx[2], bidx[3], 0x6420);
@@ -738,7 +760,8 @@ typedef __nv_bfloat16 bf16;
 extern "C" {
 
 int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float* shift, int N, int D, int H, int W,
-                             int C, int k, int stride, int pad, adni_bf16* p, uint8_t* argmax, void* stream) {
+                             int C, int k, int stride, int pad, adni_bf16* p, uint8_t* argmax, adni_bf16* y_at_argmax,
+                             void* stream) {
   ADNI_REQUIRE(y && scale && shift && p && argmax && N > 0, ADNI_EINVAL, "bn_relu_maxpool_fwd: bad arguments");
   int rc = check_pool(C, k, stride, pad);
   if (rc) return rc;
@@ -750,18 +773,20 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
     if (pool_variant() == 2) {  // experimental packed-compare variant, same results
       bn_relu_pool_fwd_stream_packed_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(
           reinterpret_cast<const bf16*>(y), scale, shift, D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
-          reinterpret_cast<bf16*>(p), argmax);
+          reinterpret_cast<bf16*>(p), argmax, reinterpret_cast<bf16*>(y_at_argmax));
       count_launch();
       ADNI_LAUNCH_CHECK("bn_relu_pool_fwd_stream_packed_kernel");
       return ADNI_OK;
     }
     bn_relu_pool_fwd_stream_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift,
                                                                         D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
-                                                                        reinterpret_cast<bf16*>(p), argmax);
+                                                                        reinterpret_cast<bf16*>(p), argmax,
+                                                                        reinterpret_cast<bf16*>(y_at_argmax));
     count_launch();
     ADNI_LAUNCH_CHECK("bn_relu_pool_fwd_stream_kernel");
     return ADNI_OK;
   }
+  ADNI_REQUIRE(y_at_argmax == nullptr, ADNI_ENOTSUP, "bn_relu_maxpool_fwd: y_at_argmax needs a streaming variant (ADNI_POOL_STREAM != 0)");
   const int td = (Do + kFT - 1) / kFT, th = (Ho + kFT - 1) / kFT, tw = (Wo + kFT - 1) / kFT;
   dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kFCv - 1) / kFCv)));
   bn_relu_pool_fwd_kernel<<<grid, kThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift, N, D, H, W,

@@ -4,6 +4,8 @@ All activation tensors are bf16 NDHWC (shape [N, D, H, W, C], contiguous).  Thes
 outputs with torch (PyTorch owns device memory and streams — plumbing) and pass raw pointers to
 libadni_b200.so; no arithmetic happens in Python and nothing here falls back to torch ops.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -567,16 +569,22 @@ def fused_pool_supported(k, stride, pad):
     return (k, stride, pad) == (3, 2, 1)
 
 
-def bn_relu_maxpool_fwd(y, bnp, k, stride, pad):
-    """maxpool(relu(y*scale+shift)) without materialising the activation. bnp: fp32 [4, C] from bn_finalize."""
+_POOL_STREAMING = os.environ.get("ADNI_POOL_STREAM", "1") != "0"
+
+
+def bn_relu_maxpool_fwd(y, bnp, k, stride, pad, want_raw=True):
+    """maxpool(relu(y*scale+shift)) without materialising the activation. bnp: fp32 [4, C] from bn_finalize.
+    Returns (pooled, argmax, y_at_argmax): the raw conv output at every window's arg-max (None with the tiled kernels,
+    ADNI_POOL_STREAM=0) lets the BatchNorm backward sums run over the pooled tensor (bn_bwd_reduce)."""
     _chk(y, BF16, "y")
     N, D, H, W, C = y.shape
     Do, Ho, Wo = ((v + 2 * pad - k) // stride + 1 for v in (D, H, W))
     p = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=y.device)
     am = torch.empty((N, Do, Ho, Wo, C), dtype=torch.uint8, device=y.device)
-    call_hbm("hbm_pool_fwd", 2 * y.numel() + 3 * p.numel(), "adni_bn_relu_maxpool_fwd", ptr(y), ptr(bnp[2]),
-             ptr(bnp[3]), N, D, H, W, C, k, stride, pad, ptr(p), ptr(am), stream_ptr())
-    return p, am
+    raw = torch.empty((N, Do, Ho, Wo, C), dtype=BF16, device=y.device) if (want_raw and _POOL_STREAMING) else None
+    call_hbm("hbm_pool_fwd", 2 * y.numel() + (5 if raw is not None else 3) * p.numel(), "adni_bn_relu_maxpool_fwd", ptr(y),
+             ptr(bnp[2]), ptr(bnp[3]), N, D, H, W, C, k, stride, pad, ptr(p), ptr(am), ptr(raw), stream_ptr())
+    return p, am, raw
 
 
 def maxpool_bn_bwd_reduce(dp, argmax, y, bnp, k, stride, pad):

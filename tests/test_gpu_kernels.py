@@ -307,8 +307,20 @@ def test_fused_stem_tail_matches_unfused_kernels(cuda_dev, shape):
     bnp = K.bn_finalize(K.channel_stats(y.view(-1, C)), rows, gamma, beta, 1e-5, 0.1, None, None)
     a = K.bn_apply(y, bnp[2], bnp[3], residual=None, relu=True)
     p_ref, am_ref = K.maxpool3d_fwd(a, 3, 2, 1)
-    p, am = K.bn_relu_maxpool_fwd(y, bnp, 3, 2, 1)
+    p, am, yraw = K.bn_relu_maxpool_fwd(y, bnp, 3, 2, 1)
     assert torch.equal(p, p_ref) and torch.equal(am, am_ref)
+    # the raw conv output at every window's arg-max: gather y at the recorded slot (kd, kh, kw) of window (od, oh, ow)
+    N, D, H, W, _ = shape
+    Do, Ho, Wo = p.shape[1:4]
+    slot = am.long()
+    od, oh, ow = torch.meshgrid(torch.arange(Do), torch.arange(Ho), torch.arange(Wo), indexing="ij")
+    dev = y.device
+    idd = (2 * od.to(dev) - 1)[None, ..., None] + slot // 9
+    ihh = (2 * oh.to(dev) - 1)[None, ..., None] + (slot // 3) % 3
+    iww = (2 * ow.to(dev) - 1)[None, ..., None] + slot % 3
+    nn = torch.arange(N, device=dev)[:, None, None, None, None].expand_as(slot)
+    cc = torch.arange(C, device=dev)[None, None, None, None, :].expand_as(slot)
+    assert torch.equal(yraw, y[nn, idd, ihh, iww, cc])
     dp = _rand_act(tuple(p.shape), cuda_dev, 5)
     da = K.maxpool3d_bwd(dp, am_ref, tuple(a.shape), 3, 2, 1)
     red_ref = K.bn_bwd_reduce(da, a, y, bnp[0], bnp[1], True)
@@ -326,6 +338,10 @@ def test_fused_stem_tail_matches_unfused_kernels(cuda_dev, shape):
     xh = ((y.float().view(-1, C) - bnp[0]) * bnp[1]).double()
     assert_close(red[0], g.sum(0), 1e-5, "fused reduce vs fp32 reference (sum g)")
     assert_close(red[1], (g * xh).sum(0), 1e-5, "fused reduce vs fp32 reference (sum g*xhat)")
+    # the same sums over the POOLED tensor (what StemFn.backward runs): every window feeds exactly one voxel
+    red_p = K.bn_bwd_reduce(dp, None, yraw, bnp[0], bnp[1], True, bnp[2], bnp[3])
+    assert_close(red_p[0], g.sum(0), 1e-5, "pooled reduce vs fp32 reference (sum g)")
+    assert_close(red_p[1], (g * xh).sum(0), 1e-5, "pooled reduce vs fp32 reference (sum g*xhat)")
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 6, 8, 64), (3, 8, 8, 8, 512), (1, 3, 5, 7, 24)])
