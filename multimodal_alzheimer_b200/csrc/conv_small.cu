@@ -90,14 +90,17 @@ __device__ __forceinline__ uint32_t swz(int p, int c, int CH, int sh) {
 struct TileOrigin {
   int n, d0, h0, w0;
 };
-__device__ __forceinline__ TileOrigin tile_origin(const SmallParams& p, long long tile, int TD) {
+__device__ __forceinline__ TileOrigin tile_origin(const SmallParams& p, int tile, int TD) {
+  // 32-bit arithmetic (the host refuses more than 2^31 tiles): four 64-bit divisions per tile and thread cost as much
+  // as the tile's tensor-core work on the 1-channel first layer (131072 tiles of 512 outputs per batch)
   TileOrigin o;
-  o.w0 = static_cast<int>(tile % p.tiles_w) * TW;
-  tile /= p.tiles_w;
-  o.h0 = static_cast<int>(tile % p.tiles_h) * TH;
-  tile /= p.tiles_h;
-  o.d0 = static_cast<int>(tile % p.tiles_d) * TD;
-  o.n = static_cast<int>(tile / p.tiles_d);
+  int t = tile;
+  o.w0 = (t % p.tiles_w) * TW;
+  t /= p.tiles_w;
+  o.h0 = (t % p.tiles_h) * TH;
+  t /= p.tiles_h;
+  o.d0 = (t % p.tiles_d) * TD;
+  o.n = t / p.tiles_d;
   return o;
 }
 
@@ -239,7 +242,8 @@ __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams
   const uint32_t tile_base = smem_u32(tile_s);
   const bool do_stats = p.ssum != nullptr;
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  const int total_tiles = static_cast<int>(p.total_tiles);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileOrigin o = tile_origin(p, tile, R);
     __syncthreads();  // the previous tile's fragments have been read
     if (C1) {
@@ -350,10 +354,9 @@ struct SmallWgradParams {
   int nt_per_cta;            // N-tiles a CTA (blockIdx.y) covers
 };
 
-template <int MT, int NW, bool C1>
+template <int MT, int NW, bool C1, int TD>
 __global__ void __launch_bounds__(kThreads) small_wgrad_kernel(const SmallWgradParams wp) {
   const SmallParams& p = wp.x;
-  constexpr int TD = 4;
   extern __shared__ __align__(16) uint8_t smem[];
   int* tab = reinterpret_cast<int*>(smem);
   size_t off = ((static_cast<size_t>(p.Q) * 4 + 15) / 16) * 16;
@@ -388,7 +391,8 @@ __global__ void __launch_bounds__(kThreads) small_wgrad_kernel(const SmallWgradP
   const int b_row = lane & 15;
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  const int total_tiles = static_cast<int>(p.total_tiles);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileOrigin o = tile_origin(p, tile, TD);
     __syncthreads();
     if (C1) {
@@ -479,7 +483,7 @@ bool plan_small(SmallParams& p, int N, int Di, int Hi, int Wi, int Ci, int Do, i
   p.RAWW = TW + 7;
   p.tiles_d = (Do + TD - 1) / TD, p.tiles_h = (Ho + TH - 1) / TH, p.tiles_w = (Wo + TW - 1) / TW;
   p.total_tiles = static_cast<long long>(N) * p.tiles_d * p.tiles_h * p.tiles_w;
-  return p.Q <= kMaxQ;
+  return p.Q <= kMaxQ && p.total_tiles < (1LL << 31);
 }
 
 size_t fprop_smem(const SmallParams& p, int NT) {
@@ -513,6 +517,7 @@ int launch_fprop_t(const SmallParams& p, size_t smem, int ysplit, cudaStream_t s
 // Tile depth (R = 4 rows per warp when it fits, else 2) and output-channel chunk (NT n-tiles of 8 per CTA; the rest
 // of a wide layer goes to blockIdx.y) such that B fragments + halo tile fit shared memory.
 bool pick_small_cfg(const SmallParams& p4, const SmallParams& p2, int nt_total, int* nt, bool* r4) {
+  // (the 1-channel, 8-output first layer additionally has an R = 8 variant, chosen in small_conv_fprop)
   for (int n = nt_total; n >= 1; n >>= 1) {
     if (n <= 4 && fprop_smem(p4, n) <= kSmemLimit) {
       *nt = n, *r4 = true;
@@ -553,12 +558,12 @@ int nt_for(int Co) { return Co <= 8 ? 1 : (Co <= 16 ? 2 : (Co <= 32 ? 4 : 8)); }
 
 inline int oext(int in, int k, int pad) { return in + 2 * pad - (k - 1); }
 
-template <int MT, int NW, bool C1>
+template <int MT, int NW, bool C1, int TD = 4>
 int launch_wgrad_t(SmallWgradParams& wp, cudaStream_t st) {
   const SmallParams& p = wp.x;
-  auto kern = small_wgrad_kernel<MT, NW, C1>;
+  auto kern = small_wgrad_kernel<MT, NW, C1, TD>;
   size_t smem = ((static_cast<size_t>(p.Q) * 4 + 15) / 16) * 16 + static_cast<size_t>(p.HD) * p.HH * p.HW * p.CH * 16 +
-                static_cast<size_t>(4) * TH * TW * wp.CHo * 16 + 32;   // + slack: Cout = 8 reads one chunk past the dy tile
+                static_cast<size_t>(TD) * TH * TW * wp.CHo * 16 + 32;   // + slack: Cout = 8 reads one chunk past the dy tile
   if (C1) smem += static_cast<size_t>(p.HD) * p.HH * p.RAWW * 2 + 16;
   if (smem > kSmemLimit) {
     set_error("small conv wgrad: %zu bytes of shared memory needed (Cin=%d Cout=%d k=%d)", smem, p.Ci, p.Co, p.k);
@@ -617,6 +622,14 @@ int small_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
     p->in = x, p->w = w_oti, p->bias = bias, p->out = y, p->ssum = ssum, p->ssq = ssq;
   }
   const int NT = nt_for(g.Cout);
+  if (g.Cin == 1 && NT == 1) {   // most tiles, least work per tile: 8 rows per warp (tile depth 8, halo 2.25x instead of 3x)
+    SmallParams p8;
+    memset(&p8, 0, sizeof(p8));
+    plan_small(p8, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, 8);
+    p8.in = x, p8.w = w_oti, p8.bias = bias, p8.out = y, p8.ssum = ssum, p8.ssq = ssq;
+    const size_t smem = fprop_smem(p8, 1);
+    if (smem <= kSmemLimit) return launch_fprop_t<1, 8, true>(p8, smem, 1, stream);
+  }
   return g.Cin == 1 ? launch_fprop_nt<true>(p4, p2, NT, stream) : launch_fprop_nt<false>(p4, p2, NT, stream);
 }
 
@@ -640,7 +653,10 @@ int small_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
   const int Do = oext(g.D, g.k, g.pad), Ho = oext(g.H, g.k, g.pad), Wo = oext(g.W, g.k, g.pad);
   SmallWgradParams wp;
   memset(&wp, 0, sizeof(wp));
-  plan_small(wp.x, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, 4);
+  // the 1-channel first layer has the most tiles and the least work per tile: deeper tiles (8 planes) halve its
+  // per-tile overheads and cut the halo from 3x to 2.25x
+  const int wg_td = (g.Cin == 1 && g.Cout == 8) ? 8 : 4;
+  plan_small(wp.x, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, wg_td);
   wp.x.in = x;
   wp.dy = dy;
   wp.dw = dw;
@@ -653,6 +669,8 @@ int small_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
   const bool c1 = g.Cin == 1;
   const int MT = (g.Cout + 15) / 16;
   // the first layer has k*k <= 49 N-tiles: 4 (k = 5) or 7 per warp keep the kernel at <= 64 registers, 4 CTAs per SM
+  if (MT == 1 && c1 && wg_td == 8)
+    return wp.x.Q <= 32 ? launch_wgrad_t<1, 4, true, 8>(wp, stream) : launch_wgrad_t<1, 8, true, 8>(wp, stream);
   if (MT == 1 && c1) return wp.x.Q <= 32 ? launch_wgrad_t<1, 4, true>(wp, stream) : launch_wgrad_t<1, 8, true>(wp, stream);
   if (MT == 1) return launch_wgrad_t<1, 16, false>(wp, stream);
   if (MT == 2) return c1 ? launch_wgrad_t<2, 8, true>(wp, stream) : launch_wgrad_t<2, 8, false>(wp, stream);
