@@ -127,36 +127,53 @@ __device__ __forceinline__ void load_tile_vec(const SmallParams& p, const TileOr
 
 // C1 mode: raw 1-channel rows (TW + 7 inputs: w0 - pad .. w0 - pad + TW + 6) -> smem, then every position becomes the
 // 16-byte "pixel" of its 8 inputs w - pad .. w - pad + 7.
-__device__ __forceinline__ void load_tile_c1(const SmallParams& p, const TileOrigin& o, uint8_t* tile_s,
-                                             __nv_bfloat16* raw_s) {
+// The raw rows are fetched one tile AHEAD into registers (a warp per halo row, RAWW = 23 <= 32 inputs: one coalesced
+// load per row; <= kC1Rows rows per warp) while the current tile is being computed, then committed to shared memory and
+// expanded: the global-load latency of a tile with ~1 us of tensor work would otherwise be fully exposed.
+constexpr int kC1Rows = 20;   // rows per warp: 12 x 12 halo rows of the k = 5, depth-8 tile / 8 warps = 18 (k = 7 uses depth 4: 17.5)
+struct C1Prefetch {
+  uint32_t v[kC1Rows / 2];    // two bf16 per register
+};
+
+__device__ __forceinline__ void c1_issue(const SmallParams& p, const TileOrigin& o, C1Prefetch& pf) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = p.HD * p.HH;
-  // a warp per halo row (RAWW = 23 <= 32 inputs: one coalesced load), four rows in flight per warp
   const int iw = o.w0 + lane - p.pad;
   const bool col_ok = lane < p.RAWW && iw >= 0 && iw < p.Wi;
   const uint16_t* in16 = reinterpret_cast<const uint16_t*>(p.in);
-  uint16_t* raw16 = reinterpret_cast<uint16_t*>(raw_s);
-  for (int r0 = warp; r0 < rows; r0 += 4 * (kThreads / 32)) {
-    uint16_t v[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int r = r0 + u * (kThreads / 32);
+  for (int u = 0; u < kC1Rows; u += 2) {
+    uint32_t pair = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = warp + (u + h) * (kThreads / 32);
       const int hd = r / p.HH, hh = r - hd * p.HH;
       const int id = o.d0 + hd - p.pad, ih = o.h0 + hh - p.pad;
       const bool ok = r < rows && col_ok && id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi;
-      v[u] = ok ? __ldg(in16 + ((static_cast<long long>(o.n) * p.Di + id) * p.Hi + ih) * p.Wi + iw) : uint16_t(0);
+      const uint32_t val = ok ? __ldg(in16 + ((static_cast<long long>(o.n) * p.Di + id) * p.Hi + ih) * p.Wi + iw) : 0u;
+      pair |= val << (16 * h);
     }
+    pf.v[u / 2] = pair;
+  }
+}
+
+// registers -> raw rows in smem -> (barrier) -> every position's 16-byte pixel of its 8 inputs w - pad .. w - pad + 7
+__device__ __forceinline__ void c1_commit(const SmallParams& p, const C1Prefetch& pf, uint8_t* tile_s,
+                                          __nv_bfloat16* raw_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = p.HD * p.HH;
+  uint16_t* raw16 = reinterpret_cast<uint16_t*>(raw_s);
+  if (lane < p.RAWW) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int r = r0 + u * (kThreads / 32);
-      if (r < rows && lane < p.RAWW) raw16[r * p.RAWW + lane] = v[u];
+    for (int u = 0; u < kC1Rows; u++) {
+      const int r = warp + u * (kThreads / 32);
+      if (r < rows) raw16[r * p.RAWW + lane] = static_cast<uint16_t>(pf.v[u / 2] >> (16 * (u & 1)));
     }
   }
   __syncthreads();
-  const uint16_t* raw = raw16;
   for (int i = threadIdx.x; i < rows * TW; i += kThreads) {
     const int r = i >> 4, hw = i & 15;
-    const uint16_t* s = raw + r * p.RAWW + hw;
+    const uint16_t* s = raw16 + r * p.RAWW + hw;
     uint4 v;
     v.x = s[0] | (static_cast<uint32_t>(s[1]) << 16);
     v.y = s[2] | (static_cast<uint32_t>(s[3]) << 16);
@@ -243,16 +260,20 @@ __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams
   const bool do_stats = p.ssum != nullptr;
 
   const int total_tiles = static_cast<int>(p.total_tiles);
+  C1Prefetch pf;
+  if (C1 && static_cast<int>(blockIdx.x) < total_tiles) c1_issue(p, tile_origin(p, blockIdx.x, R), pf);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileOrigin o = tile_origin(p, tile, R);
     __syncthreads();  // the previous tile's fragments have been read
     if (C1) {
-      load_tile_c1(p, o, tile_s, raw_s);
+      c1_commit(p, pf, tile_s, raw_s);
     } else {
       load_tile_vec(p, o, tile_s);
       cp_async_wait_all();
     }
     __syncthreads();
+    if (C1 && tile + static_cast<int>(gridDim.x) < total_tiles)
+      c1_issue(p, tile_origin(p, tile + gridDim.x, R), pf);   // the next tile's rows are in flight under this tile's MMAs
 
     float acc[R][NT][4];
 #pragma unroll
@@ -392,11 +413,13 @@ __global__ void __launch_bounds__(kThreads) small_wgrad_kernel(const SmallWgradP
   __syncthreads();
 
   const int total_tiles = static_cast<int>(p.total_tiles);
+  C1Prefetch pf;
+  if (C1 && static_cast<int>(blockIdx.x) < total_tiles) c1_issue(p, tile_origin(p, blockIdx.x, TD), pf);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const TileOrigin o = tile_origin(p, tile, TD);
     __syncthreads();
     if (C1) {
-      load_tile_c1(p, o, tile_s, raw_s);
+      c1_commit(p, pf, tile_s, raw_s);
     } else {
       load_tile_vec(p, o, tile_s);
     }
@@ -416,6 +439,7 @@ __global__ void __launch_bounds__(kThreads) small_wgrad_kernel(const SmallWgradP
     }
     cp_async_wait_all();
     __syncthreads();
+    if (C1 && tile + static_cast<int>(gridDim.x) < total_tiles) c1_issue(p, tile_origin(p, tile + gridDim.x, TD), pf);
 
     for (int r = 0; r < TD * TH; r++) {
       const int pr = ((r >> 3) * p.HH + (r & 7)) * p.HW;   // first position of the row inside the halo tile
@@ -483,6 +507,7 @@ bool plan_small(SmallParams& p, int N, int Di, int Hi, int Wi, int Ci, int Do, i
   p.RAWW = TW + 7;
   p.tiles_d = (Do + TD - 1) / TD, p.tiles_h = (Ho + TH - 1) / TH, p.tiles_w = (Wo + TW - 1) / TW;
   p.total_tiles = static_cast<long long>(N) * p.tiles_d * p.tiles_h * p.tiles_w;
+  if (c1 && p.HD * p.HH > kC1Rows * (kThreads / 32)) return false;   // the tile loader's register prefetch holds kC1Rows rows per warp
   return p.Q <= kMaxQ && p.total_tiles < (1LL << 31);
 }
 
@@ -625,10 +650,10 @@ int small_conv_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
   if (g.Cin == 1 && NT == 1) {   // most tiles, least work per tile: 8 rows per warp (tile depth 8, halo 2.25x instead of 3x)
     SmallParams p8;
     memset(&p8, 0, sizeof(p8));
-    plan_small(p8, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, 8);
+    const bool fits = plan_small(p8, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, 8);
     p8.in = x, p8.w = w_oti, p8.bias = bias, p8.out = y, p8.ssum = ssum, p8.ssq = ssq;
     const size_t smem = fprop_smem(p8, 1);
-    if (smem <= kSmemLimit) return launch_fprop_t<1, 8, true>(p8, smem, 1, stream);
+    if (fits && smem <= kSmemLimit) return launch_fprop_t<1, 8, true>(p8, smem, 1, stream);
   }
   return g.Cin == 1 ? launch_fprop_nt<true>(p4, p2, NT, stream) : launch_fprop_nt<false>(p4, p2, NT, stream);
 }
@@ -655,8 +680,12 @@ int small_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __
   memset(&wp, 0, sizeof(wp));
   // the 1-channel first layer has the most tiles and the least work per tile: deeper tiles (8 planes) halve its
   // per-tile overheads and cut the halo from 3x to 2.25x
-  const int wg_td = (g.Cin == 1 && g.Cout == 8) ? 8 : 4;
-  plan_small(wp.x, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, wg_td);
+  int wg_td = (g.Cin == 1 && g.Cout == 8) ? 8 : 4;
+  if (wg_td == 8 && !plan_small(wp.x, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, 8)) wg_td = 4;   // k = 7
+  if (!plan_small(wp.x, g.N, g.D, g.H, g.W, g.Cin, Do, Ho, Wo, g.Cout, g.k, g.pad, 0, wg_td)) {
+    set_error("small conv wgrad: geometry not supported (Cin=%d Cout=%d k=%d)", g.Cin, g.Cout, g.k);
+    return ADNI_ENOTSUP;
+  }
   wp.x.in = x;
   wp.dy = dy;
   wp.dw = dw;

@@ -33,7 +33,7 @@ for d in step:
     a[2] += d.get("dram__bytes_read.sum", 0.0)
     a[3] += d.get("dram__bytes_write.sum", 0.0)
 tot = sum(a[1] for a in agg.values())
-out = [f"# ncu launch list of one training step (`bench.py --steps 1 --warmup 1 --no-graph`, B=32 pairs, 1x B200)",
+out = [f"# ncu launch list of one training step (`bench.py --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline`, B=32 pairs, 1x B200)",
        "", "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
        f"launches in the step: {len(step)}; sum of kernel time: {tot / 1e3:.2f} ms", "",
        "| share | time ms | launches | DRAM read GB | DRAM write GB | kernel |", "|---|---|---|---|---|---|"]
