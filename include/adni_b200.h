@@ -69,6 +69,13 @@ int adni_conv3d_out_extent(int in, int k, int stride, int pad, int dil);
  * zero padding are skipped, so executed FLOPs = algorithmic FLOPs x executed_fraction. */
 int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind, double* executed_fraction);
 
+/* Planner query (host only, no launch; tests / diagnostics): the stream-K schedule the tcgen05 wgrad kernel would run
+ * for this geometry.  header[16] = {used, ctas, chunk_boxes, pos_boxes, m_tiles, n_tiles, groups_per_tile, n_groups,
+ * cin_blocks, bd, bh, bw, tiles_d, tiles_h, tiles_w, m_tile_config}; table[4*c..] = {tile_begin, box_begin, tile_last,
+ * box_end} of CTA c over the chunk-major virtual tiles (chunk * m_tiles * n_tiles + m_tile * n_tiles + n_tile).
+ * Replaces nothing in the reference (cuDNN picks its own wgrad algorithm behind anat_cnn.py:95's backward). */
+int adni_conv3d_wgrad_schedule(const adni_conv3d_geom* g, int* header, int* table, int table_capacity);
+
 /* y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_oti) (+bias).  If stat_sum/stat_sqsum are non-null,
  * per-channel sum(y) and sum(y*y) (fp64, from the fp32 accumulators) are ADDED into them: the
  * BatchNorm3d batch statistics fused into the conv epilogue (MedicalNet bn1/bn2/bn3). */

@@ -36,6 +36,7 @@ _SZ = ctypes.c_size_t
 _SIGNATURES = {
     "adni_conv3d_out_extent": [_I, _I, _I, _I, _I],
     "adni_conv3d_plan_info": [ctypes.POINTER(ConvGeom), _I, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
+    "adni_conv3d_wgrad_schedule": [ctypes.POINTER(ConvGeom), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), _I],
     "adni_conv3d_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _I, _P],
     "adni_conv3d_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _I, _P],
     "adni_conv3d_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _I, _P],

@@ -498,6 +498,11 @@ double wgrad_executed_fraction(const WgradParams& p, int mt_cfg) {
 // The static split-K schedule leaves the slowest CTA 20-35 % above the mean on the dilated layers (boxes whose taps all
 // lie in the padding are skipped, and 594-648 items fall unevenly on 148 SMs); partial sums already go through
 // red.global.add, so cutting tiles at arbitrary box boundaries needs no fix-up pass.
+// The sequence is chunk-major (W2Sched): a plain tile-major sequence spreads the 148 CTAs over ALL positions of dY / X at
+// any moment, and once the two tensors exceed the L2 the kernel streams them from HBM once per output tile
+// (profiles/r02_launch_summary.md: 4.0 GB of DRAM reads per layer4 launch against 0.6 GB under the static schedule, i.e.
+// 4.5 TB/s - the kernel had become HBM-bound).  Chunks of whole samples whose dY + X slices fit ADNI_WGRAD_CHUNK_MB
+// (default 48 MB, well inside the 126 MB L2) keep the balance AND the reuse.
 struct W2Plan {
   bool use = false;
   W2Sched sched;
@@ -506,7 +511,9 @@ struct W2Plan {
 const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
   static std::mutex mu;
   static std::map<std::vector<int>, W2Plan> cache;
-  std::vector<int> key = {p.ntaps, p.cin_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.m_tiles, p.n_tiles, mt_cfg, num_sms()};
+  const int chunk_mb = std::max(1, env_int("ADNI_WGRAD_CHUNK_MB", 48));
+  std::vector<int> key = {p.ntaps, p.cin_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.m_tiles, p.n_tiles, mt_cfg, num_sms(),
+                          p.cout, chunk_mb};
   for (int t = 0; t < p.ntaps; t++)
     key.push_back((int(p.taps[t].map) << 24) ^ ((p.taps[t].dd & 0xff) << 16) ^ ((p.taps[t].dh & 0xff) << 8) ^ (p.taps[t].dw & 0xff));
   for (int m = 0; m < kMaxMaps; m++)
@@ -539,31 +546,47 @@ const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
             cum[nt][r + 1] = cum[nt][r] + (any ? 1 : 0);
           }
     }
+    // position chunks: whole samples whose dY + X slices fit the L2 budget
+    long long x_pos = 0;
+    for (int m = 0; m < kMaxMaps; m++) x_pos += static_cast<long long>(p.x_ext[m][0]) * p.x_ext[m][1] * p.x_ext[m][2];
+    const long long bytes_per_sample =
+        2LL * (static_cast<long long>(p.Do) * p.Ho * p.Wo * p.cout + x_pos * p.cin_blocks * 64);
+    const long long fit = (static_cast<long long>(chunk_mb) << 20) / std::max(1LL, bytes_per_sample);
+    const int chunk_samples = static_cast<int>(std::min<long long>(p.N, std::max(1LL, fit)));
+    const int n_chunks = (p.N + chunk_samples - 1) / chunk_samples;
     const int tiles = p.m_tiles * p.n_tiles;
-    std::vector<long long> prefix(static_cast<size_t>(tiles) + 1, 0);   // active blocks before tile t (tile = mt * n_tiles + nt)
-    for (int t = 0; t < tiles; t++) prefix[t + 1] = prefix[t] + static_cast<long long>(cum[t % p.n_tiles][per_sample]) * p.N;
-    const long long T = prefix[tiles];
-    if (T >= 8LL * G) {
-      // raw box index (over all samples) of the a-th active box (0-based) of N tile nt
-      auto raw_of = [&](int nt, long long a) -> int {
-        const int per = cum[nt][per_sample];
-        const long long n = a / per;
-        const int rem = int(a % per);
-        int r = int(std::upper_bound(cum[nt].begin(), cum[nt].end(), rem) - cum[nt].begin()) - 1;   // cum[r] <= rem < cum[r+1]
-        return int(n * per_sample + r);
-      };
-      plan.use = true;
-      plan.sched.ctas = G;
-      int tile = 0;
-      for (int c = 0; c < G; c++) {
-        const long long start = T * c / G, end = T * (c + 1) / G;   // end > start
-        while (prefix[tile + 1] <= start) tile++;
-        plan.sched.tile_begin[c] = tile;
-        plan.sched.box_begin[c] = raw_of(tile % p.n_tiles, start - prefix[tile]);
-        int last = tile;
-        while (prefix[last + 1] < end) last++;
-        plan.sched.tile_last[c] = last;
-        plan.sched.box_end[c] = raw_of(last % p.n_tiles, end - 1 - prefix[last]) + 1;
+    const long long vtiles_ll = static_cast<long long>(tiles) * n_chunks;
+    if (vtiles_ll < (1LL << 24)) {
+      const int vtiles = static_cast<int>(vtiles_ll);
+      auto samples_of = [&](int chunk) { return std::min(chunk_samples, p.N - chunk * chunk_samples); };
+      std::vector<long long> prefix(static_cast<size_t>(vtiles) + 1, 0);   // active blocks before virtual tile v
+      for (int v = 0; v < vtiles; v++)
+        prefix[v + 1] = prefix[v] + static_cast<long long>(cum[(v % tiles) % p.n_tiles][per_sample]) * samples_of(v / tiles);
+      const long long T = prefix[vtiles];
+      if (T >= 8LL * G) {
+        // raw box index (over all samples) of the a-th active box (0-based) of virtual tile v
+        auto raw_of = [&](int v, long long a) -> int {
+          const int nt = (v % tiles) % p.n_tiles;
+          const int per = cum[nt][per_sample];
+          const long long n = a / per;
+          const int rem = int(a % per);
+          int r = int(std::upper_bound(cum[nt].begin(), cum[nt].end(), rem) - cum[nt].begin()) - 1;   // cum[r] <= rem < cum[r+1]
+          return int((static_cast<long long>(v / tiles) * chunk_samples + n) * per_sample + r);
+        };
+        plan.use = true;
+        plan.sched.ctas = G;
+        plan.sched.chunk_boxes = chunk_samples * per_sample;
+        int tile = 0;
+        for (int c = 0; c < G; c++) {
+          const long long start = T * c / G, end = T * (c + 1) / G;   // end > start
+          while (prefix[tile + 1] <= start) tile++;
+          plan.sched.tile_begin[c] = tile;
+          plan.sched.box_begin[c] = raw_of(tile, start - prefix[tile]);
+          int last = tile;
+          while (prefix[last + 1] < end) last++;
+          plan.sched.tile_last[c] = last;
+          plan.sched.box_end[c] = raw_of(last, end - 1 - prefix[last]) + 1;
+        }
       }
     }
   }
@@ -703,6 +726,31 @@ int adni_conv3d_plan_info(const adni_conv3d_geom* g, int pass, int* engine_kind,
   const double all = double((od + b.bd - 1) / b.bd) * double((oh + b.bh - 1) / b.bh) * double((ow + b.bw - 1) / b.bw) *
                      double(g->k) * g->k * g->k;
   *executed_fraction = done / all;
+  return ADNI_OK;
+}
+
+int adni_conv3d_wgrad_schedule(const adni_conv3d_geom* g, int* header, int* table, int table_capacity) {
+  int rc = check_geom(g);
+  if (rc) return rc;
+  ADNI_REQUIRE(header && table && table_capacity >= 0, ADNI_EINVAL, "conv3d_wgrad_schedule: bad arguments");
+  ADNI_REQUIRE(tc_supported(*g), ADNI_ENOTSUP, "conv3d_wgrad_schedule: not a tcgen05 wgrad geometry (Cin=%d Cout=%d)", g->Cin, g->Cout);
+  WgradParams wp;
+  memset(&wp, 0, sizeof(wp));
+  Box wb;
+  const int mt_cfg = plan_wgrad_geometry(*g, wp, wb);
+  const W2Plan& plan = plan_wgrad_stream_k(wp, mt_cfg);
+  const int h[16] = {plan.use ? 1 : 0, plan.sched.ctas, plan.sched.chunk_boxes, wp.pos_boxes, wp.m_tiles, wp.n_tiles, 8 / mt_cfg,
+                     wp.n_groups, wp.cin_blocks, wp.bd, wp.bh, wp.bw, wp.tiles_d, wp.tiles_h, wp.tiles_w, mt_cfg};
+  memcpy(header, h, sizeof(h));
+  if (plan.use) {
+    ADNI_REQUIRE(table_capacity >= 4 * plan.sched.ctas, ADNI_EINVAL, "conv3d_wgrad_schedule: table too small");
+    for (int c = 0; c < plan.sched.ctas; c++) {
+      table[4 * c + 0] = plan.sched.tile_begin[c];
+      table[4 * c + 1] = plan.sched.box_begin[c];
+      table[4 * c + 2] = plan.sched.tile_last[c];
+      table[4 * c + 3] = plan.sched.box_end[c];
+    }
+  }
   return ADNI_OK;
 }
 

@@ -71,16 +71,21 @@ struct WgradParams {
   float* dw;    // [Cout][K_total] fp32, accumulated with red.add
 };
 
-// Stream-K schedule of wgrad2 (conv_wgrad2.cu): the active (position box x output tile) blocks of all output tiles form
-// one sequence cut into equal ranges.  Tile = mt_outer * n_tiles + nt; CTA b walks tiles tile_begin[b] .. tile_last[b]
-// and, inside its first / last tile, the raw position boxes from box_begin[b] / up to box_end[b].  Partial sums go to
-// dw through red.global.add as in the static schedule, so a tile may be shared by any number of CTAs.
+// Stream-K schedule of wgrad2 (conv_wgrad2.cu): the active (position box x output tile) blocks form one sequence cut
+// into equal ranges.  The sequence is CHUNK-major: the position boxes are split into chunks of `chunk_boxes` (whole
+// samples, sized so that the dY + X slices of one chunk stay L2-resident), and inside a chunk the order is tile-major,
+// so the CTAs running at the same time read the same few samples.  Virtual tile v = chunk * (m_tiles * n_tiles) +
+// mt_outer * n_tiles + nt covers the raw boxes [chunk * chunk_boxes, (chunk + 1) * chunk_boxes); CTA b walks virtual
+// tiles tile_begin[b] .. tile_last[b] and, inside its first / last one, the raw position boxes from box_begin[b] / up
+// to box_end[b].  Partial sums go to dw through red.global.add as in the static schedule, so an output tile may be
+// shared by any number of CTAs.
 struct W2Sched {
   int tile_begin[kSkMaxCtas];
   int box_begin[kSkMaxCtas];
   int tile_last[kSkMaxCtas];
   int box_end[kSkMaxCtas];
   int ctas;
+  int chunk_boxes;
 };
 
 // Halo-resident fprop / dgrad for 3x3x3, stride 1, dilation 1, pad 1 convs with Cin == Cout in {64, 128}

@@ -73,8 +73,9 @@ __device__ __forceinline__ ItemCtx<NG> make_ctx(const WgradParams& p, const Sche
   x.g0 = nt * NG;
   x.ng = min(NG, p.n_groups - x.g0);
   if constexpr (SK) {
-    x.b_begin = item == sk.tile_begin[blockIdx.x] ? sk.box_begin[blockIdx.x] : 0;
-    x.b_end = item == sk.tile_last[blockIdx.x] ? sk.box_end[blockIdx.x] : p.pos_boxes;
+    const int chunk0 = (r / p.m_tiles) * sk.chunk_boxes;   // virtual tile -> position chunk (W2Sched)
+    x.b_begin = item == sk.tile_begin[blockIdx.x] ? sk.box_begin[blockIdx.x] : chunk0;
+    x.b_end = item == sk.tile_last[blockIdx.x] ? sk.box_end[blockIdx.x] : min(chunk0 + sk.chunk_boxes, p.pos_boxes);
   } else {
     const int ks = r / p.m_tiles;
     x.b_begin = ks * p.boxes_per_split;

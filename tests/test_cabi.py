@@ -165,3 +165,85 @@ def test_planner_routes_small_stacks_to_tensor_cores():
                             continue
                         assert kind.value in (1, 2, 3), (chans[i], chans[i + 1], k, pass_, kind.value)
                     ext //= 2
+
+
+def _wgrad_schedule(lib, g):
+    import ctypes
+    header = (ctypes.c_int * 16)()
+    table = (ctypes.c_int * (4 * 160))()
+    rc = lib.adni_conv3d_wgrad_schedule(ctypes.byref(g), header, table, 4 * 160)
+    assert rc == 0, lib.adni_last_error_string()
+    return list(header), list(table)
+
+
+@pytest.mark.parametrize("geom,chunk_mb", [
+    ((32, 16, 16, 16, 512, 512, 3, 1, 4, 4), 48),    # layer4 of the bench workload: 268 MB of operands -> 6 chunks
+    ((32, 16, 16, 16, 256, 256, 3, 1, 2, 2), 48),    # layer3: 3 chunks
+    ((32, 16, 16, 16, 512, 512, 3, 1, 4, 4), 100000),  # one chunk = the plain tile-major sequence
+    ((4, 16, 16, 16, 512, 512, 3, 1, 4, 4), 48),     # the 8-GPU per-rank batch: fits the L2, one chunk
+    ((5, 12, 14, 12, 256, 512, 3, 2, 1, 1), 1),      # strided, ragged extents, tiny chunks (one sample each)
+    ((8, 20, 24, 20, 1024, 256, 1, 1, 0, 1), 16),    # a ResNet-50 1x1x1 conv
+    ((6, 20, 24, 20, 128, 256, 3, 1, 2, 2), 2),      # dilated, box grid not a divisor of the extents
+])
+def test_wgrad_stream_k_schedule_covers_every_active_block_once(geom, chunk_mb, monkeypatch):
+    """Host-side check of the chunk-major stream-K schedule of the tcgen05 wgrad kernel (adni_conv3d_wgrad_schedule, no
+    GPU): replaying the CTA walks exactly as conv_wgrad2.cu does (make_ctx + the box loops) must visit every ACTIVE
+    (output tile, position box) block exactly once - activity recomputed here from the conv geometry alone - and the
+    blocks per CTA must differ by at most one."""
+    lib = _lib.load()
+    monkeypatch.setenv("ADNI_WGRAD_CHUNK_MB", str(chunk_mb))
+    N, D, H, W, Ci, Co, k, s, pad, dil = geom
+    g = _lib.ConvGeom(*geom)
+    h, table = _wgrad_schedule(lib, g)
+    used, ctas, chunk_boxes, pos_boxes, m_tiles, n_tiles, groups, n_groups, cin_blocks, bd, bh, bw, td, th, tw, _ = h
+    assert used == 1 and ctas == 148
+    per_sample = td * th * tw
+    assert pos_boxes == N * per_sample and chunk_boxes % per_sample == 0 and chunk_boxes > 0
+
+    def axis(ext):           # per kernel index: (view extent, box offset) - conv_api.cu fwd_axis_taps / parity_views
+        out = []
+        for kk in range(k):
+            off = kk * dil - pad
+            par = off % s
+            out.append(((ext - par + s - 1) // s, (off - par) // s))
+        return out
+    ad, ah, aw = axis(D), axis(H), axis(W)
+
+    def active(nt, r):       # any 64-column group of N tile nt whose shifted box meets the input (box_active)
+        x, y, z = r % tw, (r // tw) % th, r // (tw * th)
+        for gi in range(nt * groups, min((nt + 1) * groups, n_groups)):
+            t = gi // cin_blocks
+            kd, kh, kw = t // (k * k), (t // k) % k, t % k
+            ok = True
+            for (ext, off), b0, b in ((ad[kd], z * bd, bd), (ah[kh], y * bh, bh), (aw[kw], x * bw, bw)):
+                lo = b0 + off
+                ok = ok and lo + b > 0 and lo < ext
+            if ok:
+                return True
+        return False
+    act = [[active(nt, r) for r in range(per_sample)] for nt in range(n_tiles)]
+    expected = sum(sum(a) for a in act) * m_tiles * N
+    seen = {}
+    loads = []
+    tiles = m_tiles * n_tiles
+    for c in range(ctas):
+        t0, b0, t1, b1 = table[4 * c:4 * c + 4]
+        n = 0
+        for v in range(t0, t1 + 1):
+            nt, mt, chunk = v % n_tiles, (v // n_tiles) % m_tiles, v // tiles
+            lo = b0 if v == t0 else chunk * chunk_boxes
+            hi = b1 if v == t1 else min((chunk + 1) * chunk_boxes, pos_boxes)
+            assert chunk * chunk_boxes <= lo <= hi <= min((chunk + 1) * chunk_boxes, pos_boxes), (c, v, lo, hi)
+            for b in range(lo, hi):
+                if act[nt][b % per_sample]:
+                    key = (mt, nt, b)
+                    assert key not in seen, (key, c, seen[key])
+                    seen[key] = c
+                    n += 1
+        loads.append(n)
+    assert len(seen) == expected
+    assert max(loads) - min(loads) <= 1, (min(loads), max(loads))
+    if chunk_mb >= 100000 or N == 4:
+        assert chunk_boxes == pos_boxes
+    elif geom[:2] == (32, 16) and Ci == 512:
+        assert chunk_boxes == 6 * per_sample          # 8 MB of dY + X per sample -> 6 samples per 48 MB chunk

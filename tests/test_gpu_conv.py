@@ -95,6 +95,32 @@ def test_tc_wgrad(cuda_dev, shape):
     assert_close(g, w_ref.grad, 2e-4, f"wgrad {shape}")
 
 
+@pytest.mark.parametrize("shape,chunk_mb", [
+    ((6, 16, 16, 16, 128, 256, 3, 1, 2, 2), 1),      # 3 MB of dY + X per sample: one sample per chunk, 6 chunks
+    ((5, 12, 14, 12, 256, 512, 3, 2, 1, 1), 1),      # strided (8 parity views), ragged, chunked
+    ((32, 16, 16, 16, 512, 512, 3, 1, 4, 4), 48),    # layer4 at the bench batch: the default budget gives 6 chunks
+])
+def test_tc_wgrad_chunked_stream_k(cuda_dev, shape, chunk_mb, monkeypatch):
+    """The chunk-major stream-K schedule (position chunks sized for the L2, conv_api.cu plan_wgrad_stream_k) against
+    torch and against the single-chunk schedule of the same kernel."""
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    w_ref.requires_grad_(True)
+    ref_y = F.conv3d(x_ref, w_ref, None, s, p, d)
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref_y))
+    ref_y.backward(to_ncdhw_f32(dy_b))
+    monkeypatch.setenv("ADNI_WGRAD_CHUNK_MB", str(chunk_mb))
+    dw, _ = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, engine=TC)
+    g = K.wgrad_to_param_layout(dw, tuple(w.shape))
+    monkeypatch.setenv("ADNI_WGRAD_CHUNK_MB", "1000000")
+    dw1, _ = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, engine=TC)
+    g1 = K.wgrad_to_param_layout(dw1, tuple(w.shape))
+    torch.cuda.synchronize()
+    assert_close(g, w_ref.grad, 2e-4, f"chunked wgrad {shape}")
+    assert_close(g, g1, 2e-5, f"chunked vs single-chunk wgrad {shape}")
+
+
 BNRED_SHAPES = [TC_SHAPES[1], TC_SHAPES[2], TC_SHAPES[4], TC_SHAPES[5], TC_SHAPES[6], TC_SHAPES[9], TC_SHAPES[10],
                 (2, 10, 12, 10, 256, 64, 1, 1, 0, 1)]   # + a Bottleneck 1x1 reduce conv (dx has 256 channels)
 
