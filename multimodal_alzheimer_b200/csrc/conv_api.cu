@@ -502,7 +502,7 @@ double wgrad_executed_fraction(const WgradParams& p, int mt_cfg) {
 // any moment, and once the two tensors exceed the L2 the kernel streams them from HBM once per output tile
 // (profiles/r02_launch_summary.md: 4.0 GB of DRAM reads per layer4 launch against 0.6 GB under the static schedule, i.e.
 // 4.5 TB/s - the kernel had become HBM-bound).  Chunks of whole samples whose dY + X slices fit ADNI_WGRAD_CHUNK_MB
-// (default 48 MB, well inside the 126 MB L2) keep the balance AND the reuse.
+// (default 128 MB = the L2 size; measured A/B in profiles/r02_wgrad_chunk_ab.md: 48 MB chunks cost more in extra accumulator flushes than the reuse returns) keep the balance AND the reuse.
 struct W2Plan {
   bool use = false;
   W2Sched sched;
@@ -511,7 +511,7 @@ struct W2Plan {
 const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
   static std::mutex mu;
   static std::map<std::vector<int>, W2Plan> cache;
-  const int chunk_mb = std::max(1, env_int("ADNI_WGRAD_CHUNK_MB", 48));
+  const int chunk_mb = std::max(1, env_int("ADNI_WGRAD_CHUNK_MB", 128));
   std::vector<int> key = {p.ntaps, p.cin_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.m_tiles, p.n_tiles, mt_cfg, num_sms(),
                           p.cout, chunk_mb};
   for (int t = 0; t < p.ntaps; t++)

@@ -118,7 +118,7 @@ def test_tc_wgrad_chunked_stream_k(cuda_dev, shape, chunk_mb, monkeypatch):
     g1 = K.wgrad_to_param_layout(dw1, tuple(w.shape))
     torch.cuda.synchronize()
     assert_close(g, w_ref.grad, 2e-4, f"chunked wgrad {shape}")
-    assert_close(g, g1, 2e-5, f"chunked vs single-chunk wgrad {shape}")
+    assert_close(g, g1, 1e-4, f"chunked vs single-chunk wgrad {shape}")   # fp32 partial sums in a different order
 
 
 BNRED_SHAPES = [TC_SHAPES[1], TC_SHAPES[2], TC_SHAPES[4], TC_SHAPES[5], TC_SHAPES[6], TC_SHAPES[9], TC_SHAPES[10],
