@@ -8,6 +8,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include <stdio.h>
 
 #include "../../include/adni_b200.h"
@@ -54,7 +56,56 @@ EncodeTiledFn encode_tiled_fn();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, bool swizzle128);
 
+// Programmatic dependent launch is opt-in (ADNI_PDL=1, runtime.cu): measured 0-4 % SLOWER inside the step's CUDA graph.
+bool pdl_enabled();
+
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A training step is ~400 launches, many of them 5-50 us long at the 8-GPU
+// per-rank batch, so the launch-to-launch gap (grid drain, launch latency, barrier / TMEM set-up of the next kernel) is
+// a double-digit share of the step.  With ADNI_PDL=1 every kernel of this library is launched with the programmatic-
+// stream-serialization attribute; every kernel signals `launch_dependents` first thing and executes `griddepcontrol.wait` before its first
+// global-memory access: the next kernel's CTAs are scheduled onto SMs as the current kernel's CTAs retire, run their
+// prologue, and block in `wait` until the current grid has completed and flushed - the stream's data dependencies are
+// unchanged.  (A dependent grid can only start once ALL CTAs of its primary have started, so a waiting grid never
+// keeps an earlier one from being scheduled.)  Stream capture records the attribute as a programmatic graph edge.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+template <typename... KArgs>
+struct PdlLaunch {
+  void (*kern)(KArgs...);
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <typename... Args>
+  void operator()(Args&&... args) const {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface through ADNI_LAUNCH_CHECK
+  }
+};
+
+// kernel<<<grid, block, smem, stream>>>(args...)  ==  pdl_launch(kernel, grid, block, smem, stream)(args...)
+template <typename... KArgs>
+PdlLaunch<KArgs...> pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  return PdlLaunch<KArgs...>{kern, grid, block, smem, stream};
+}
+
 // ------------------------------------------------------------------------------------------------
 // Device helpers
 // ------------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat1
 // TRANSPOSED = true : out[i] = sum_k in[(i + pad - k*dil)/stride] * w[k]      (dgrad; `in` is dy, w is ITO)
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(kThreads) direct_conv_kernel(const DirectParams p) {
+  pdl_enter();
   extern __shared__ float w_s[];  // [taps][ci_chunk][kCoTile]
   const int taps = p.k * p.k * p.k;
   const int co0 = blockIdx.y * kCoTile;
@@ -216,6 +217,7 @@ struct DirectWgradParams {
 };
 
 __global__ void __launch_bounds__(kWgThreads) direct_wgrad_kernel(const DirectWgradParams p) {
+  pdl_enter();
   __shared__ float dy_s[kWgSlab][kWgCoTile];
   __shared__ int pos_s[kWgSlab][4];  // n, id0, ih0, iw0 (input origin of the receptive field) ; n = -1 if inactive
   const int taps = p.k * p.k * p.k;
@@ -299,9 +301,9 @@ int launch_direct(const DirectParams& p0, bool transposed, cudaStream_t stream) 
   const long long npos = (long long)p.N * p.Do * p.Ho * p.Wo;
   dim3 grid((unsigned)((npos + kThreads - 1) / kThreads), (unsigned)((p.Co + kCoTile - 1) / kCoTile));
   if (transposed)
-    direct_conv_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    pdl_launch(direct_conv_kernel<true>, grid, kThreads, smem, stream)(p);
   else
-    direct_conv_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+    pdl_launch(direct_conv_kernel<false>, grid, kThreads, smem, stream)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("direct_conv_kernel");
   return ADNI_OK;
@@ -385,7 +387,7 @@ int direct_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const _
   const int ncols = g.k * g.k * g.k * g.Cin;
   const unsigned zc = (unsigned)std::min((ncols + kWgThreads - 1) / kWgThreads, 8);
   dim3 grid((unsigned)((npos + kWgSlab - 1) / kWgSlab), (unsigned)((p.Co + kWgCoTile - 1) / kWgCoTile), zc);
-  direct_wgrad_kernel<<<grid, kWgThreads, 0, stream>>>(p);
+  pdl_launch(direct_wgrad_kernel, grid, kWgThreads, 0, stream)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("direct_wgrad_kernel");
   return ADNI_OK;

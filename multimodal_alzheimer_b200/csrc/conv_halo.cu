@@ -87,6 +87,7 @@ __device__ __forceinline__ HaloSeg halo_segment(const HaloParams& p, int i, int 
 
 template <int BLOCK_N, int KB, int TPS, int G>
 __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel of the stream may be scheduled once every CTA of this grid has started
   using Cfg = HaloCfg<BLOCK_N, KB, TPS, G>;
   constexpr int RING = Cfg::RING, NBST = Cfg::NBST;
   constexpr int B_TILE = Cfg::B_TILE, STAGE_BYTES = Cfg::STAGE_BYTES, PLANE_BYTES = Cfg::PLANE_BYTES;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and the role split are set up under the previous kernel's tail; global memory only from here on
 
   if (warp == 6) {
     // ===================== halo-plane producer =====================
@@ -543,7 +545,7 @@ int launch_halo_t(const HaloParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = p.total < num_sms() ? p.total : num_sms();
-  kern<<<grid, kHaloThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  pdl_launch(kern, grid, kHaloThreads, Cfg::SMEM_BYTES, stream)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("igemm_halo_kernel");
   return ADNI_OK;

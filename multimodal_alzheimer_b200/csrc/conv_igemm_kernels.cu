@@ -87,6 +87,7 @@ struct IgemmCfg {
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel of the stream may be scheduled once every CTA of this grid has started
   using Cfg = IgemmCfg<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and the role split are set up under the previous kernel's tail; global memory only from here on
 
   // 64-bit mask of the taps whose shifted box intersects the input for this tile (lane t tests taps t, t+32)
   auto tap_mask = [&](const TileCoord& c) -> unsigned long long {
@@ -544,7 +546,7 @@ static int launch_igemm_t(const IgemmParams& p, cudaStream_t stream) {
   }
   const int total_tiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  kern<<<grid, kIgemmThreads, Cfg::SMEM_BYTES, stream>>>(p);
+  pdl_launch(kern, grid, kIgemmThreads, Cfg::SMEM_BYTES, stream)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("igemm_kmajor_kernel");
   return ADNI_OK;

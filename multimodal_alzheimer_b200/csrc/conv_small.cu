@@ -204,6 +204,7 @@ __device__ __forceinline__ void fill_tap_table(const SmallParams& p, bool c1, in
 // =================================================================================================
 template <int NT, int R, bool C1>
 __global__ void __launch_bounds__(kThreads) small_fprop_kernel(const SmallParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   // layout: [B fragments S*NT*32 uint2][tap table Q ints][stats 2*NT*8 doubles][tile][raw (C1)]
   uint2* wfrag = reinterpret_cast<uint2*>(smem);
@@ -377,6 +378,7 @@ struct SmallWgradParams {
 
 template <int MT, int NW, bool C1, int TD>
 __global__ void __launch_bounds__(kThreads) small_wgrad_kernel(const SmallWgradParams wp) {
+  pdl_enter();
   const SmallParams& p = wp.x;
   extern __shared__ __align__(16) uint8_t smem[];
   int* tab = reinterpret_cast<int*>(smem);
@@ -533,7 +535,7 @@ int launch_fprop_t(const SmallParams& p, size_t smem, int ysplit, cudaStream_t s
   const int per_sm = std::max<size_t>(1, std::min<size_t>(4, kSmemLimit / (smem + 1024)));
   const long long want = std::max<long long>(1, static_cast<long long>(num_sms()) * per_sm / ysplit);
   dim3 grid(static_cast<unsigned>(std::min<long long>(p.total_tiles, want)), static_cast<unsigned>(ysplit));
-  kern<<<grid, kThreads, smem, st>>>(p);
+  pdl_launch(kern, grid, kThreads, smem, st)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("small_fprop_kernel");
   return ADNI_OK;
@@ -604,7 +606,7 @@ int launch_wgrad_t(SmallWgradParams& wp, cudaStream_t st) {
   const int per_sm = std::max<size_t>(1, std::min<size_t>(NW <= 4 ? 4 : 2, kSmemLimit / (smem + 1024)));
   const long long want = std::max<long long>(1, static_cast<long long>(num_sms()) * per_sm / ysplit);
   dim3 grid(static_cast<unsigned>(std::min<long long>(p.total_tiles, want)), static_cast<unsigned>(ysplit));
-  kern<<<grid, kThreads, smem, st>>>(wp);
+  pdl_launch(kern, grid, kThreads, smem, st)(wp);
   count_launch();
   ADNI_LAUNCH_CHECK("small_wgrad_kernel");
   return ADNI_OK;

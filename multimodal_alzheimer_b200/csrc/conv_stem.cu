@@ -56,6 +56,7 @@ __device__ __forceinline__ AxisOff axis_off(int kk) {  // input coord = 2*o + kk
 // ------------------------------------------------------------------------------------------------
 __global__ void stem_expand_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int Wo,
                                    __nv_bfloat16* __restrict__ x8) {
+  pdl_enter();
   const long long total = (long long)N * D * H * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -77,6 +78,7 @@ __global__ void stem_expand_kernel(const __nv_bfloat16* __restrict__ x, int N, i
 
 // w_ncdhw fp32 [64][1][7][7][7] -> w2g bf16 [kd*8+kh][co][8] (zero padded kh = 7 and j = 7)
 __global__ void stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w2g) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kTapsP * kCout * 8) return;
   const int j = i & 7, co = (i >> 3) % kCout, t = i / (8 * kCout);
@@ -88,6 +90,7 @@ __global__ void stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 // dw2 fp32 [(kd*8+kh)*8+j][64] -> grad fp32 [64][7][7][7]
 __global__ void stem_wgrad_unpack_kernel(const float* __restrict__ dw2, float* __restrict__ grad) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kCout * kK * kK * kK) return;
   const int kw = i % kK, kh = (i / kK) % kK, kd = (i / (kK * kK)) % kK, co = i / (kK * kK * kK);
@@ -126,6 +129,7 @@ constexpr int kFStatOff = kFBarOff + 256;
 constexpr int kFSmem = kFStatOff + 4 * 2 * kCout * 4 + 1024;
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_kernel(const __grid_constant__ StemParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
@@ -356,6 +360,7 @@ __device__ __forceinline__ StemSeg stem_segment(const StemParams& p, int i, int 
 }
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_plane_kernel(const __grid_constant__ StemParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
@@ -613,6 +618,7 @@ constexpr int kWBarOff = kWStages * kWStageBytes;
 constexpr int kWSmem = kWBarOff + 256 + 1024;
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_wgrad_kernel(const __grid_constant__ StemParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWBarOff);
@@ -761,6 +767,7 @@ constexpr int kWPSmem = kWPBarOff + 512 + 1024;
 constexpr int kWPThreads = 224;
 
 __global__ void __launch_bounds__(kWPThreads, 1) stem_wgrad_plane_kernel(const __grid_constant__ StemParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_p = smem;
@@ -1024,7 +1031,7 @@ int adni_stem_expand(const adni_bf16* x, int N, int D, int H, int W, adni_bf16* 
   const int Wo = (W + 6 - 7) / 2 + 1;
   const long long total = (long long)N * D * H * Wo;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
-  stem_expand_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), N, D, H, W, Wo,
+  pdl_launch(stem_expand_kernel, grid, 256, 0, ST(stream))(reinterpret_cast<const bf16*>(x), N, D, H, W, Wo,
                                                     reinterpret_cast<bf16*>(x8));
   count_launch();
   ADNI_LAUNCH_CHECK("stem_expand_kernel");
@@ -1033,7 +1040,7 @@ int adni_stem_expand(const adni_bf16* x, int N, int D, int H, int W, adni_bf16* 
 
 int adni_stem_weights(const float* w_ncdhw, adni_bf16* w2g, void* stream) {
   ADNI_REQUIRE(w_ncdhw && w2g, ADNI_EINVAL, "stem_weights: null pointer");
-  stem_weights_kernel<<<(kTapsP * kCout * 8 + 255) / 256, 256, 0, ST(stream)>>>(w_ncdhw, reinterpret_cast<bf16*>(w2g));
+  pdl_launch(stem_weights_kernel, (kTapsP * kCout * 8 + 255) / 256, 256, 0, ST(stream))(w_ncdhw, reinterpret_cast<bf16*>(w2g));
   count_launch();
   ADNI_LAUNCH_CHECK("stem_weights_kernel");
   return ADNI_OK;
@@ -1085,7 +1092,7 @@ int adni_stem_fprop(const adni_bf16* x8, int N, int D, int H, int W, const adni_
       ADNI_CUDA_OK(cudaFuncSetAttribute(stem_fprop_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
       attr_p = true;
     }
-    stem_fprop_plane_kernel<<<std::min(p.total, num_sms()), kStemThreads, kPSmem, ST(stream)>>>(p);
+    pdl_launch(stem_fprop_plane_kernel, std::min(p.total, num_sms()), kStemThreads, kPSmem, ST(stream))(p);
     count_launch();
     ADNI_LAUNCH_CHECK("stem_fprop_plane_kernel");
     return ADNI_OK;
@@ -1096,7 +1103,7 @@ int adni_stem_fprop(const adni_bf16* x8, int N, int D, int H, int W, const adni_
     attr = true;
   }
   const int total = N * p.tiles_d * p.tiles_h * p.tiles_w;
-  stem_fprop_kernel<<<std::min(total, num_sms()), kStemThreads, kFSmem, ST(stream)>>>(p);
+  pdl_launch(stem_fprop_kernel, std::min(total, num_sms()), kStemThreads, kFSmem, ST(stream))(p);
   count_launch();
   ADNI_LAUNCH_CHECK("stem_fprop_kernel");
   return ADNI_OK;
@@ -1164,10 +1171,10 @@ int adni_stem_wgrad(const adni_bf16* x8, const adni_bf16* dy, int N, int D, int 
       ADNI_CUDA_OK(cudaFuncSetAttribute(stem_wgrad_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWPSmem));
       attr_p = true;
     }
-    stem_wgrad_plane_kernel<<<std::min(p.total, num_sms()), kWPThreads, kWPSmem, ST(stream)>>>(p);
+    pdl_launch(stem_wgrad_plane_kernel, std::min(p.total, num_sms()), kWPThreads, kWPSmem, ST(stream))(p);
     count_launch();
     ADNI_LAUNCH_CHECK("stem_wgrad_plane_kernel");
-    stem_wgrad_unpack_kernel<<<(kCout * 343 + 255) / 256, 256, 0, ST(stream)>>>(workspace, grad_ncdhw);
+    pdl_launch(stem_wgrad_unpack_kernel, (kCout * 343 + 255) / 256, 256, 0, ST(stream))(workspace, grad_ncdhw);
     count_launch();
     ADNI_LAUNCH_CHECK("stem_wgrad_unpack_kernel");
     return ADNI_OK;
@@ -1178,10 +1185,10 @@ int adni_stem_wgrad(const adni_bf16* x8, const adni_bf16* dy, int N, int D, int 
     attr = true;
   }
   const int total = N * p.tiles_d * p.tiles_h * p.tiles_w;
-  stem_wgrad_kernel<<<std::min(total, num_sms()), kStemThreads, kWSmem, ST(stream)>>>(p);
+  pdl_launch(stem_wgrad_kernel, std::min(total, num_sms()), kStemThreads, kWSmem, ST(stream))(p);
   count_launch();
   ADNI_LAUNCH_CHECK("stem_wgrad_kernel");
-  stem_wgrad_unpack_kernel<<<(kCout * 343 + 255) / 256, 256, 0, ST(stream)>>>(workspace, grad_ncdhw);
+  pdl_launch(stem_wgrad_unpack_kernel, (kCout * 343 + 255) / 256, 256, 0, ST(stream))(workspace, grad_ncdhw);
   count_launch();
   ADNI_LAUNCH_CHECK("stem_wgrad_unpack_kernel");
   return ADNI_OK;

@@ -132,6 +132,7 @@ template <int MT, bool SK>
 __global__ void __launch_bounds__(kThreads, 1)
     wgrad2_kernel(const __grid_constant__ WgradParams p,
                   const __grid_constant__ typename std::conditional<SK, W2Sched, SkNone>::type sk) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel of the stream may be scheduled once every CTA of this grid has started
   using Cfg = W2Cfg<MT>;
   using SchedT = typename std::conditional<SK, W2Sched, SkNone>::type;
   constexpr int NG = Cfg::NG;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and the role split are set up under the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================== TMA producer: lane l issues box l of the stage =====================
@@ -347,7 +349,7 @@ int launch_t(const WgradParams& p, const W2Sched* sk, cudaStream_t stream) {
       ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
       attr_set = true;
     }
-    kern<<<sk->ctas, kThreads, Cfg::SMEM_BYTES, stream>>>(p, *sk);
+    pdl_launch(kern, sk->ctas, kThreads, Cfg::SMEM_BYTES, stream)(p, *sk);
   } else {
     auto kern = wgrad2_kernel<MT, false>;
     static bool attr_set = false;
@@ -357,7 +359,7 @@ int launch_t(const WgradParams& p, const W2Sched* sk, cudaStream_t stream) {
     }
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(p, SkNone{0});
+    pdl_launch(kern, grid, kThreads, Cfg::SMEM_BYTES, stream)(p, SkNone{0});
   }
   count_launch();
   ADNI_LAUNCH_CHECK("wgrad2_kernel");

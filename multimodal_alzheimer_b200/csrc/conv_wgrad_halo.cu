@@ -58,6 +58,7 @@ __device__ __forceinline__ WHUnit wh_decode(const WgradHaloParams& p, int piece)
 __device__ __forceinline__ constexpr int wh_row(int t9) { return (t9 / 3) * kWHPitch + (t9 % 3); }
 
 __global__ void __launch_bounds__(kWHThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel of the stream may be scheduled once every CTA of this grid has started
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWHBarOff);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) wgrad_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and the role split are set up under the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================== TMA producer: lane 0 = input plane, lane 1 = dY piece =====================
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) wgrad_halo_kernel(const __grid_
 
 // [27][64 cin][64 cout] fp32 -> [64 cout][27][64 cin] fp32
 __global__ void wgrad_tic_to_oti_kernel(const float* __restrict__ tic, float* __restrict__ oti) {
+  pdl_enter();
   __shared__ float tile[64][65];
   const int t = blockIdx.x;
   for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) tile[i >> 6][i & 63] = tic[static_cast<long long>(t) * 4096 + i];
@@ -254,10 +257,10 @@ int launch_wgrad_halo(const adni_conv3d_geom& g, const __nv_bfloat16* x, const _
   int grid = num_sms();
   if (grid > 3 * p.total) grid = 3 * p.total;
   if (grid < 3) grid = 3;
-  wgrad_halo_kernel<<<grid, kWHThreads, kWHSmem, stream>>>(p);
+  pdl_launch(wgrad_halo_kernel, grid, kWHThreads, kWHSmem, stream)(p);
   count_launch();
   ADNI_LAUNCH_CHECK("wgrad_halo_kernel");
-  wgrad_tic_to_oti_kernel<<<27, 256, 0, stream>>>(dw_tic, dw_oti);
+  pdl_launch(wgrad_tic_to_oti_kernel, 27, 256, 0, stream)(dw_tic, dw_oti);
   count_launch();
   ADNI_LAUNCH_CHECK("wgrad_tic_to_oti_kernel");
   return ADNI_OK;

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ y, long long n,
                                                            uint32_t thresh24, float scale, unsigned long long seed,
                                                            const long long* __restrict__ offset_dev) {
+  pdl_enter();
   const unsigned long long offset = static_cast<unsigned long long>(*offset_dev);
   const long long nvec = (n + 7) / 8;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                                           uint32_t thresh24, float scale, unsigned long long seed,
                                                           const long long* __restrict__ offset_dev) {
+  pdl_enter();
   const unsigned long long offset = static_cast<unsigned long long>(*offset_dev);
   const long long nvec = (n + 7) / 8;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
@@ -111,10 +113,10 @@ extern "C" int adni_dropout(const void* x, void* y, long long n, int is_f32, dou
   const int grid = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
   auto st = static_cast<cudaStream_t>(stream);
   if (is_f32)
-    dropout_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), n, thresh24, scale,
+    pdl_launch(dropout_f32_kernel, grid, 256, 0, st)(static_cast<const float*>(x), static_cast<float*>(y), n, thresh24, scale,
                                              seed, offset_dev);
   else
-    dropout_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n,
+    pdl_launch(dropout_bf16_kernel, grid, 256, 0, st)(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n,
                                               thresh24, scale, seed, offset_dev);
   count_launch();
   ADNI_LAUNCH_CHECK("dropout_kernel");

@@ -90,6 +90,7 @@ __device__ __forceinline__ BnChannel bn_channel(const double* ssum, const double
 __global__ void bn_finalize_kernel(const double* ssum, const double* ssq, double count, int C, const float* gamma,
                                    const float* beta, float eps, float momentum, float* rmean, float* rvar,
                                    float* mean, float* invstd, float* scale, float* shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const BnChannel ch = bn_channel(ssum, ssq, count, gamma, beta, eps, c);
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ res,
                                                               __nv_bfloat16* __restrict__ out, long long nvec, int vpr,
                                                               int relu) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   // blockDim % vpr == 0  =>  i % vpr is the same for every vector a thread touches: its 8 scale / shift values
   // stay in registers instead of being re-fetched (4 x 16-byte L1 loads per 16-byte data vector otherwise)
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kEwThreads)
                           const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
                           float* __restrict__ rvar, float* __restrict__ bnp, const __nv_bfloat16* __restrict__ res,
                           __nv_bfloat16* __restrict__ out, long long nvec, int vpr, int C, int relu) {
+  pdl_enter();
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const BnChannel ch = bn_channel(ssum, ssq, count, gamma, beta, eps, c);
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(kEwThreads) channel_reduce_kernel(const __nv_b
                                                                     int C, int relu, int slab_rows,
                                                                     double* __restrict__ r0,
                                                                     double* __restrict__ r1) {
+  pdl_enter();
   __shared__ float sm[2][kEwThreads][8];
   const int vpr = C / 8;
   const int rpp = kEwThreads / vpr;  // row lanes per block (vpr <= 256)
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(kEwThreads)
                         const double* __restrict__ red, double inv_count, long long nvec, int vpr, int C, int relu,
                         __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, double pg_scale, int red_form) {
+  pdl_enter();
   // red_form 0: red[C + c] = sum g*xhat;  1: red[C + c] = sum g*y (a conv epilogue produced it, adni_conv3d_dgrad_bnred):
   // sum g*xhat = invstd * (sum g*y - mean * sum g), evaluated in fp64
   auto sum_gx = [&](int c) -> double {
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(kEwThreads)
 
 __global__ void bn_eval_params_kernel(const float* rm, const float* rv, const float* gamma, const float* beta, float eps,
                                       int C, float* scale, float* shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = (gamma ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
@@ -461,6 +467,7 @@ __global__ void bn_eval_params_kernel(const float* rm, const float* rv, const fl
 
 __global__ void __launch_bounds__(kEwThreads) relu_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                               __nv_bfloat16* __restrict__ y, long long nvec) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     Vec8 a = load8(x + i * 8);
@@ -472,6 +479,7 @@ __global__ void __launch_bounds__(kEwThreads) relu_fwd_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(kEwThreads) relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                               const __nv_bfloat16* __restrict__ y,
                                                               __nv_bfloat16* __restrict__ dx, long long nvec) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     Vec8 g = load8(dy + i * 8);
@@ -483,6 +491,7 @@ __global__ void __launch_bounds__(kEwThreads) relu_bwd_kernel(const __nv_bfloat1
 }
 
 __global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, float* dbeta) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dbeta) dbeta[c] = (float)red[c];
@@ -495,6 +504,7 @@ __global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, f
 __global__ void __launch_bounds__(kEwThreads)
     maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int C, int k, int s, int pad,
                        int Do, int Ho, int Wo, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ amax) {
+  pdl_enter();
   const int vpr = C / 8;
   const long long total = (long long)N * Do * Ho * Wo * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -551,6 +561,7 @@ __global__ void __launch_bounds__(kEwThreads)
 __global__ void __launch_bounds__(kEwThreads)
     maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ amax, int N, int D, int H,
                        int W, int C, int k, int s, int pad, int Do, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  pdl_enter();
   const int vpr = C / 8;
   const long long total = (long long)N * D * H * W * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -608,6 +619,7 @@ __global__ void __launch_bounds__(kEwThreads)
     maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ amax, int N, int D, int H,
                              int W, int C, int k, int s, int pad, int Do, int Ho, int Wo, int tiles_d, int tiles_h,
                              int tiles_w, __nv_bfloat16* __restrict__ dx) {
+  pdl_enter();
   __shared__ uint4 s_dy[kMpWMax * kMpWMax * kMpWMax * 8];   // [window][cv] 8 channels bf16
   __shared__ uint2 s_am[kMpWMax * kMpWMax * kMpWMax * 8];   // [window][cv] 8 arg-max bytes
   const int vpr = C / 8;
@@ -680,6 +692,7 @@ __global__ void __launch_bounds__(kEwThreads)
 constexpr int kGapSplit = 8;
 __global__ void __launch_bounds__(kEwThreads)
     gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, float inv_p, float* __restrict__ feat) {
+  pdl_enter();
   // grid: (channel-vector blocks of 32, P splits, N); block = 32 channel vectors x 8 row lanes
   __shared__ float sm[8][32][8];
   const int vpr = C / 8;
@@ -715,6 +728,7 @@ __global__ void __launch_bounds__(kEwThreads)
 __global__ void __launch_bounds__(kEwThreads)
     gap_bwd_kernel(const float* __restrict__ dfeat, int N, long long P, int C, float inv_p,
                    __nv_bfloat16* __restrict__ dx) {
+  pdl_enter();
   const int vpr = C / 8;
   const long long total = (long long)N * P * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -733,10 +747,12 @@ __global__ void __launch_bounds__(kEwThreads)
 // ---------------------------------------------------------------------------------------------
 template <typename TIn>
 __global__ void cast_to_bf16_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn((float)x[i]);
 }
 __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
 }
@@ -747,6 +763,7 @@ __device__ __forceinline__ void store_t(float* p, float v, bool acc) { *p = acc 
 // in [batch][R][Cc] (fp32) -> out [batch][Cc][R]
 template <typename TOut>
 __global__ void transpose_kernel(const float* __restrict__ in, TOut* __restrict__ out, int R, int Cc, bool accumulate) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const long long boff = (long long)blockIdx.z * R * Cc;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -767,7 +784,7 @@ int launch_transpose(const float* in, TOut* out, int batch, int R, int Cc, bool 
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = std::min(batch - b0, 65535);
     dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
-    transpose_kernel<TOut><<<grid, block, 0, stream>>>(in + (long long)b0 * R * Cc, out + (long long)b0 * R * Cc, R, Cc,
+    pdl_launch(transpose_kernel<TOut>, grid, block, 0, stream)(in + (long long)b0 * R * Cc, out + (long long)b0 * R * Cc, R, Cc,
                                                        accumulate);
     count_launch();
   }
@@ -793,6 +810,7 @@ constexpr int kWTile = 16;
 constexpr int kWMaxTaps = 27;
 
 __global__ void __launch_bounds__(256) weights_multi_kernel(const WeightJob* __restrict__ jobs, int n_jobs) {
+  pdl_enter();
   __shared__ float tile[kWTile][kWTile + 1][kWMaxTaps];  // +1: the ITO pass reads with the co index fastest
   int j = 0;
   while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].tile_begin) j++;
@@ -846,7 +864,7 @@ int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double co
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                      float* mean, float* invstd, float* scale, float* shift, void* stream) {
   ADNI_REQUIRE(stat_sum && stat_sqsum && C > 0 && count > 0, ADNI_EINVAL, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stat_sum, stat_sqsum, count, C, gamma, beta, eps,
+  pdl_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, ST(stream))(stat_sum, stat_sqsum, count, C, gamma, beta, eps,
                                                                momentum, running_mean, running_var, mean, invstd,
                                                                scale, shift);
   count_launch();
@@ -856,7 +874,7 @@ int adni_bn_finalize(const double* stat_sum, const double* stat_sqsum, double co
 
 int adni_bn_param_grads(const double* red, int C, float* dgamma, float* dbeta, void* stream) {
   ADNI_REQUIRE(red && C > 0 && (dgamma || dbeta), ADNI_EINVAL, "bn_param_grads: bad arguments");
-  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(red, C, dgamma, dbeta);
+  pdl_launch(bn_param_grads_kernel, (C + 127) / 128, 128, 0, ST(stream))(red, C, dgamma, dbeta);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_param_grads_kernel");
   return ADNI_OK;
@@ -865,7 +883,7 @@ int adni_bn_param_grads(const double* red, int C, float* dgamma, float* dbeta, v
 int adni_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
                         float eps, int C, float* scale, float* shift, void* stream) {
   ADNI_REQUIRE(running_mean && running_var && scale && shift && C > 0, ADNI_EINVAL, "bn_eval_params: bad arguments");
-  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(running_mean, running_var, gamma, beta, eps, C, scale,
+  pdl_launch(bn_eval_params_kernel, (C + 127) / 128, 128, 0, ST(stream))(running_mean, running_var, gamma, beta, eps, C, scale,
                                                                   shift);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_eval_params_kernel");
@@ -874,14 +892,14 @@ int adni_bn_eval_params(const float* running_mean, const float* running_var, con
 
 int adni_relu_fwd(const adni_bf16* x, adni_bf16* y, long long n, void* stream) {
   ADNI_REQUIRE(x && y && n > 0 && n % 8 == 0, ADNI_EINVAL, "relu_fwd: bad arguments");
-  relu_fwd_kernel<<<ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(y), n / 8);
+  pdl_launch(relu_fwd_kernel, ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream))(CBF(x), BF(y), n / 8);
   count_launch();
   ADNI_LAUNCH_CHECK("relu_fwd_kernel");
   return ADNI_OK;
 }
 int adni_relu_bwd(const adni_bf16* dy, const adni_bf16* y, adni_bf16* dx, long long n, void* stream) {
   ADNI_REQUIRE(dy && y && dx && n > 0 && n % 8 == 0, ADNI_EINVAL, "relu_bwd: bad arguments");
-  relu_bwd_kernel<<<ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(dx), n / 8);
+  pdl_launch(relu_bwd_kernel, ew_grid(n / 8, kEwThreads * 4), kEwThreads, 0, ST(stream))(CBF(dy), CBF(y), BF(dx), n / 8);
   count_launch();
   ADNI_LAUNCH_CHECK("relu_bwd_kernel");
   return ADNI_OK;
@@ -893,7 +911,7 @@ int adni_channel_stats(const adni_bf16* x, long long rows, int C, double* sum, d
                C);
   const int slab = red_slab_rows(rows, C);
   const int grid = (int)((rows + slab - 1) / slab);
-  channel_reduce_kernel<0><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr, nullptr,
+  pdl_launch(channel_reduce_kernel<0>, grid, kEwThreads, 0, ST(stream))(CBF(x), nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                  nullptr, rows, C, 0, slab, sum, sqsum);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<0>");
@@ -905,7 +923,7 @@ int adni_bn_apply(const adni_bf16* y, const float* scale, const float* shift, co
   ADNI_REQUIRE(y && scale && shift && out && rows > 0, ADNI_EINVAL, "bn_apply: bad arguments");
   ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_apply: C=%d must be a multiple of 8", C);
   const long long nvec = rows * (C / 8);
-  bn_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(residual),
+  pdl_launch(bn_apply_kernel, ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream))(CBF(y), scale, shift, CBF(residual),
                                                                                  BF(out), nvec, C / 8, relu);
   count_launch();
   ADNI_LAUNCH_CHECK("bn_apply_kernel");
@@ -924,7 +942,7 @@ int adni_bn_bwd_reduce(const adni_bf16* dout, const adni_bf16* out, const adni_b
                C);
   const int slab = red_slab_rows(rows, C);
   const int grid = (int)((rows + slab - 1) / slab);
-  channel_reduce_kernel<1><<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale, shift,
+  pdl_launch(channel_reduce_kernel<1>, grid, kEwThreads, 0, ST(stream))(CBF(dout), CBF(out), CBF(y), mean, invstd, scale, shift,
                                                                  rows, C, relu, slab, red, red + C);
   count_launch();
   ADNI_LAUNCH_CHECK("channel_reduce_kernel<1>");
@@ -943,7 +961,7 @@ int adni_bn_bwd_apply(const adni_bf16* dout, const adni_bf16* out, const adni_bf
   ADNI_REQUIRE(C % 8 == 0 && C >= 8, ADNI_ENOTSUP, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   const long long nvec = rows * (C / 8);
   ADNI_REQUIRE(C <= 2048, ADNI_ENOTSUP, "bn_bwd_apply: C=%d > 2048", C);
-  bn_bwd_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 5 * C * sizeof(float), ST(stream)>>>(
+  pdl_launch(bn_bwd_apply_kernel, ew_grid(nvec, kEwThreads * 4), kEwThreads, 5 * C * sizeof(float), ST(stream))(
       CBF(dout), CBF(out), CBF(y), mean, invstd, gamma, scale, shift, red, 1.0 / count, nvec, C / 8, C, relu, BF(dy),
       BF(dres), dgamma, dbeta, param_grad_scale, red_form);
   count_launch();
@@ -966,7 +984,7 @@ int adni_bn_train_apply(const adni_bf16* y, const double* stat_sum, const double
     return adni_bn_apply(y, bnp + 2 * C, bnp + 3 * C, residual, out, rows, C, relu, nullptr, nullptr, stream);
   }
   const long long nvec = rows * vpr;
-  bn_train_apply_kernel<<<ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(
+  pdl_launch(bn_train_apply_kernel, ew_grid(nvec, kEwThreads * 4), kEwThreads, 0, ST(stream))(
       CBF(y), stat_sum, stat_sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, bnp, CBF(residual),
       BF(out), nvec, vpr, C, relu);
   count_launch();
@@ -982,7 +1000,7 @@ int adni_maxpool3d_fwd(const adni_bf16* x, int N, int D, int H, int W, int C, in
   const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   ADNI_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, ADNI_EINVAL, "maxpool3d_fwd: empty output");
   const long long total = (long long)N * Do * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(x), N, D, H, W, C, k, stride, pad,
+  pdl_launch(maxpool_fwd_kernel, ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream))(CBF(x), N, D, H, W, C, k, stride, pad,
                                                                                  Do, Ho, Wo, BF(y), argmax);
   count_launch();
   ADNI_LAUNCH_CHECK("maxpool_fwd_kernel");
@@ -1003,10 +1021,10 @@ int adni_maxpool3d_bwd(const adni_bf16* dy, const uint8_t* argmax, int N, int D,
   if (wmax <= kMpWMax) {
     const int td = (D + kMpT - 1) / kMpT, th = (H + kMpT - 1) / kMpT, tw = (W + kMpT - 1) / kMpT;
     dim3 grid((unsigned)((long long)N * td * th * tw), (unsigned)((C / 8 + 7) / 8));
-    maxpool_bwd_tiled_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k, stride, pad, Do, Ho,
+    pdl_launch(maxpool_bwd_tiled_kernel, grid, kEwThreads, 0, ST(stream))(CBF(dy), argmax, N, D, H, W, C, k, stride, pad, Do, Ho,
                                                                   Wo, td, th, tw, BF(dx));
   } else {
-    maxpool_bwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream)>>>(CBF(dy), argmax, N, D, H, W, C, k,
+    pdl_launch(maxpool_bwd_kernel, ew_grid(total, kEwThreads), kEwThreads, 0, ST(stream))(CBF(dy), argmax, N, D, H, W, C, k,
                                                                                    stride, pad, Do, Ho, Wo, BF(dx));
   }
   count_launch();
@@ -1020,7 +1038,7 @@ int adni_gap_fwd(const adni_bf16* x, int N, long long P, int C, float* feat, voi
   ADNI_CUDA_OK(cudaMemsetAsync(feat, 0, sizeof(float) * (size_t)N * C, ST(stream)));
   const int split = (int)std::min<long long>(kGapSplit, (P + 63) / 64);
   dim3 grid((C / 8 + 31) / 32, split, N);
-  gap_fwd_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(CBF(x), P, C, 1.0f / (float)P, feat);
+  pdl_launch(gap_fwd_kernel, grid, kEwThreads, 0, ST(stream))(CBF(x), P, C, 1.0f / (float)P, feat);
   count_launch();
   ADNI_LAUNCH_CHECK("gap_fwd_kernel");
   return ADNI_OK;
@@ -1030,7 +1048,7 @@ int adni_gap_bwd(const float* dfeat, int N, long long P, int C, adni_bf16* dx, v
   ADNI_REQUIRE(dfeat && dx && N > 0 && P > 0, ADNI_EINVAL, "gap_bwd: bad arguments");
   ADNI_REQUIRE(C % 8 == 0, ADNI_ENOTSUP, "gap_bwd: C=%d must be a multiple of 8", C);
   const long long total = (long long)N * P * (C / 8);
-  gap_bwd_kernel<<<ew_grid(total, kEwThreads * 4), kEwThreads, 0, ST(stream)>>>(dfeat, N, P, C, 1.0f / (float)P,
+  pdl_launch(gap_bwd_kernel, ew_grid(total, kEwThreads * 4), kEwThreads, 0, ST(stream))(dfeat, N, P, C, 1.0f / (float)P,
                                                                                  BF(dx));
   count_launch();
   ADNI_LAUNCH_CHECK("gap_bwd_kernel");
@@ -1039,21 +1057,21 @@ int adni_gap_bwd(const float* dfeat, int N, long long P, int C, adni_bf16* dx, v
 
 int adni_cast_f32_to_bf16(const float* x, adni_bf16* y, long long n, void* stream) {
   ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
-  cast_to_bf16_kernel<float><<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(x, BF(y), n);
+  pdl_launch(cast_to_bf16_kernel<float>, ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream))(x, BF(y), n);
   count_launch();
   ADNI_LAUNCH_CHECK("cast_to_bf16_kernel");
   return ADNI_OK;
 }
 int adni_cast_f64_to_bf16(const double* x, adni_bf16* y, long long n, void* stream) {
   ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
-  cast_to_bf16_kernel<double><<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(x, BF(y), n);
+  pdl_launch(cast_to_bf16_kernel<double>, ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream))(x, BF(y), n);
   count_launch();
   ADNI_LAUNCH_CHECK("cast_to_bf16_kernel");
   return ADNI_OK;
 }
 int adni_cast_bf16_to_f32(const adni_bf16* x, float* y, long long n, void* stream) {
   ADNI_REQUIRE(x && y && n > 0, ADNI_EINVAL, "cast: bad arguments");
-  cast_bf16_to_f32_kernel<<<ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream)>>>(CBF(x), y, n);
+  pdl_launch(cast_bf16_to_f32_kernel, ew_grid(n, kEwThreads * 8), kEwThreads, 0, ST(stream))(CBF(x), y, n);
   count_launch();
   ADNI_LAUNCH_CHECK("cast_bf16_to_f32_kernel");
   return ADNI_OK;
@@ -1076,7 +1094,7 @@ int adni_weights_multi_job_bytes(void) { return (int)sizeof(WeightJob); }
  * adni_weights_multi_job_bytes and multimodal_alzheimer_b200/kernels.py: WeightArena); total_tiles = sum of tiles. */
 int adni_weights_to_kernel_layout_multi(const void* jobs, int n_jobs, int total_tiles, void* stream) {
   ADNI_REQUIRE(jobs && n_jobs > 0 && total_tiles > 0, ADNI_EINVAL, "weights_to_kernel_layout_multi: bad arguments");
-  weights_multi_kernel<<<total_tiles, 256, 0, ST(stream)>>>(static_cast<const WeightJob*>(jobs), n_jobs);
+  pdl_launch(weights_multi_kernel, total_tiles, 256, 0, ST(stream))(static_cast<const WeightJob*>(jobs), n_jobs);
   count_launch();
   ADNI_LAUNCH_CHECK("weights_multi_kernel");
   return ADNI_OK;

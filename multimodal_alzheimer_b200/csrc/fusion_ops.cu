@@ -25,6 +25,7 @@ inline int grid_for(long long work_items, int per_block) {
 template <typename T, int C>
 __global__ void __launch_bounds__(kThreads) to_ndhwc_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                             int N, long long vox) {
+  pdl_enter();
   const long long total = (long long)N * vox;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / vox, v = i - n * vox;
@@ -54,6 +55,7 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // gradient of a tie - e.g. two post-ReLU zeros - to the first operand, the PET branch)
 __global__ void __launch_bounds__(kThreads) maxout_fwd_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                               uint4* __restrict__ out, long long nvec) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 A = __ldcs(a + i), B = __ldcs(b + i);
     uint4 O;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kThreads) maxout_fwd_kernel(const uint4* __res
 __global__ void __launch_bounds__(kThreads) maxout_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ a,
                                                               const uint4* __restrict__ b, uint4* __restrict__ da,
                                                               uint4* __restrict__ db, long long nvec) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 G = __ldcs(dout + i), A = __ldcs(a + i), B = __ldcs(b + i);
     uint4 DA, DB;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(kThreads) maxout_bwd_kernel(const uint4* __res
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads) concat_kernel(uint4* __restrict__ a, uint4* __restrict__ b,
                                                           uint4* __restrict__ cat, long long rows, int ga, int gb) {
+  pdl_enter();
   const int gc = ga + gb;
   const long long total = rows * gc;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -117,6 +121,7 @@ template <bool CROP, int VEC>
 __global__ void __launch_bounds__(kThreads) pad_high_kernel(const __nv_bfloat16* __restrict__ src,
                                                             __nv_bfloat16* __restrict__ dst, int N, int D, int H, int W,
                                                             int C, int ed, int eh, int ew) {
+  pdl_enter();
   const int cv = C / VEC;
   const int Dd = CROP ? D : D + ed, Hd = CROP ? H : H + eh, Wd = CROP ? W : W + ew;   // destination extents
   const int Ds = CROP ? D + ed : D, Hs = CROP ? H + eh : H, Ws = CROP ? W + ew : W;   // source extents
@@ -153,9 +158,9 @@ static int launch_pad_high(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, 
                            int ew, cudaStream_t st) {
   const long long elems = (long long)N * (CROP ? D : D + ed) * (CROP ? H : H + eh) * (CROP ? W : W + ew) * C;
   if (C % 8 == 0) {
-    pad_high_kernel<CROP, 8><<<grid_for(elems / 8, kThreads * 2), kThreads, 0, st>>>(src, dst, N, D, H, W, C, ed, eh, ew);
+    pdl_launch(pad_high_kernel<CROP, 8>, grid_for(elems / 8, kThreads * 2), kThreads, 0, st)(src, dst, N, D, H, W, C, ed, eh, ew);
   } else {
-    pad_high_kernel<CROP, 1><<<grid_for(elems, kThreads * 4), kThreads, 0, st>>>(src, dst, N, D, H, W, C, ed, eh, ew);
+    pdl_launch(pad_high_kernel<CROP, 1>, grid_for(elems, kThreads * 4), kThreads, 0, st)(src, dst, N, D, H, W, C, ed, eh, ew);
   }
   count_launch();
   ADNI_LAUNCH_CHECK("pad_high_kernel");
@@ -166,9 +171,9 @@ template <typename T>
 static int launch_to_ndhwc(const T* x, int N, int C, long long vox, __nv_bfloat16* out, cudaStream_t st) {
   const int grid = grid_for((long long)N * vox, kThreads * 4);
   switch (C) {
-    case 2: to_ndhwc_kernel<T, 2><<<grid, kThreads, 0, st>>>(x, out, N, vox); break;
-    case 3: to_ndhwc_kernel<T, 3><<<grid, kThreads, 0, st>>>(x, out, N, vox); break;
-    case 4: to_ndhwc_kernel<T, 4><<<grid, kThreads, 0, st>>>(x, out, N, vox); break;
+    case 2: pdl_launch(to_ndhwc_kernel<T, 2>, grid, kThreads, 0, st)(x, out, N, vox); break;
+    case 3: pdl_launch(to_ndhwc_kernel<T, 3>, grid, kThreads, 0, st)(x, out, N, vox); break;
+    case 4: pdl_launch(to_ndhwc_kernel<T, 4>, grid, kThreads, 0, st)(x, out, N, vox); break;
     default:
       set_error("volumes_to_ndhwc: C=%d is not supported (2, 3 or 4 input modalities)", C);
       return ADNI_ENOTSUP;
@@ -206,7 +211,7 @@ int adni_crop_volume_high(const adni_bf16* x_padded, int N, int D, int H, int W,
 int adni_maxout_fwd(const adni_bf16* a, const adni_bf16* b, adni_bf16* out, long long n, void* stream) {
   ADNI_REQUIRE(a && b && out && n > 0, ADNI_EINVAL, "maxout_fwd: bad arguments");
   ADNI_REQUIRE(n % 8 == 0, ADNI_ENOTSUP, "maxout_fwd: n=%lld must be a multiple of 8 (channels are)", n);
-  maxout_fwd_kernel<<<grid_for(n / 8, kThreads * 2), kThreads, 0, ST(stream)>>>(
+  pdl_launch(maxout_fwd_kernel, grid_for(n / 8, kThreads * 2), kThreads, 0, ST(stream))(
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), n / 8);
   count_launch();
   ADNI_LAUNCH_CHECK("maxout_fwd_kernel");
@@ -217,7 +222,7 @@ int adni_maxout_bwd(const adni_bf16* dout, const adni_bf16* a, const adni_bf16* 
                     long long n, void* stream) {
   ADNI_REQUIRE(dout && a && b && (da || db) && n > 0, ADNI_EINVAL, "maxout_bwd: bad arguments");
   ADNI_REQUIRE(n % 8 == 0, ADNI_ENOTSUP, "maxout_bwd: n=%lld must be a multiple of 8 (channels are)", n);
-  maxout_bwd_kernel<<<grid_for(n / 8, kThreads * 2), kThreads, 0, ST(stream)>>>(
+  pdl_launch(maxout_bwd_kernel, grid_for(n / 8, kThreads * 2), kThreads, 0, ST(stream))(
       reinterpret_cast<const uint4*>(dout), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
       reinterpret_cast<uint4*>(da), reinterpret_cast<uint4*>(db), n / 8);
   count_launch();
@@ -229,7 +234,7 @@ int adni_concat_channels(const adni_bf16* a, int Ca, const adni_bf16* b, int Cb,
                          void* stream) {
   ADNI_REQUIRE(a && b && out && rows > 0 && Ca > 0 && Cb > 0, ADNI_EINVAL, "concat_channels: bad arguments");
   ADNI_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, ADNI_ENOTSUP, "concat_channels: Ca=%d, Cb=%d must be multiples of 8", Ca, Cb);
-  concat_kernel<false><<<grid_for(rows * ((Ca + Cb) / 8), kThreads * 2), kThreads, 0, ST(stream)>>>(
+  pdl_launch(concat_kernel<false>, grid_for(rows * ((Ca + Cb) / 8), kThreads * 2), kThreads, 0, ST(stream))(
       reinterpret_cast<uint4*>(const_cast<adni_bf16*>(a)), reinterpret_cast<uint4*>(const_cast<adni_bf16*>(b)),
       reinterpret_cast<uint4*>(out), rows, Ca / 8, Cb / 8);
   count_launch();
@@ -241,7 +246,7 @@ int adni_split_channels(const adni_bf16* dout, int Ca, int Cb, long long rows, a
                         void* stream) {
   ADNI_REQUIRE(dout && (da || db) && rows > 0 && Ca > 0 && Cb > 0, ADNI_EINVAL, "split_channels: bad arguments");
   ADNI_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, ADNI_ENOTSUP, "split_channels: Ca=%d, Cb=%d must be multiples of 8", Ca, Cb);
-  concat_kernel<true><<<grid_for(rows * ((Ca + Cb) / 8), kThreads * 2), kThreads, 0, ST(stream)>>>(
+  pdl_launch(concat_kernel<true>, grid_for(rows * ((Ca + Cb) / 8), kThreads * 2), kThreads, 0, ST(stream))(
       reinterpret_cast<uint4*>(da), reinterpret_cast<uint4*>(db),
       reinterpret_cast<uint4*>(const_cast<adni_bf16*>(dout)), rows, Ca / 8, Cb / 8);
   count_launch();

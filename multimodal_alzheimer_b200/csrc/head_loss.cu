@@ -11,6 +11,7 @@ namespace {
 __global__ void linear_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
                                   const float* __restrict__ bias, float* __restrict__ y, int ldy, int B, int in,
                                   int out, int relu) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * out) return;
@@ -36,6 +37,7 @@ __device__ __forceinline__ float masked_dy(const float* dy, int lddy, const floa
 __global__ void linear_bwd_dx_kernel(const float* __restrict__ W, const float* __restrict__ y, int ldy,
                                      const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
                                      int accumulate, int B, int in, int out, int relu) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * in) return;
   const int b = idx / in, i = idx % in;
@@ -49,6 +51,7 @@ __global__ void linear_bwd_dx_kernel(const float* __restrict__ W, const float* _
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ y, int ldy,
                                      const float* __restrict__ dy, int lddy, float* __restrict__ dW,
                                      float* __restrict__ db, int B, int in, int out, int relu) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)out * (in + 1)) return;
   const int o = (int)(idx / (in + 1)), i = (int)(idx % (in + 1));
@@ -64,12 +67,14 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, int ldx, const
 
 __global__ void relu_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out,
                                 long long n) {
+  pdl_enter();
   // dy == nullptr: out = max(x, 0);  else: out = dy * (x > 0)   (x is the forward OUTPUT in the backward case)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = dy ? (x[i] > 0.f ? dy[i] : 0.f) : fmaxf(x[i], 0.f);
 }
 
 __global__ void rows_stats_kernel(const float* __restrict__ x, int ldx, int B, int C, double* __restrict__ stats) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0, q = 0;
@@ -85,6 +90,7 @@ __global__ void rows_stats_kernel(const float* __restrict__ x, int ldx, int B, i
 __global__ void bn1d_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float* __restrict__ y, int ldy, int B, int C,
                                   int relu) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C) return;
   const int b = idx / C, c = idx % C;
@@ -97,6 +103,7 @@ __global__ void bn1d_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, c
                                        const float* __restrict__ x, int ldx, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, int B, int C, int relu,
                                        double* __restrict__ red) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0, q = 0;
@@ -116,6 +123,7 @@ __global__ void bn1d_bwd_apply_kernel(const float* __restrict__ dy, int lddy, co
                                       const double* __restrict__ red, double inv_count, int B, int C, int relu,
                                       float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C) return;
   const int b = idx / C, c = idx % C;
@@ -145,6 +153,7 @@ template <typename T>
 __global__ void loss_fwd_kernel(const T* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
                                 int C, double gamma, const double* __restrict__ cw, double* __restrict__ partial,
                                 double* __restrict__ coeff) {
+  pdl_enter();
   __shared__ double sm[2][32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double num = 0, nrm = 0;
@@ -192,6 +201,7 @@ template <typename T>
 __global__ void loss_bwd_kernel(const T* __restrict__ logits, int ld, const int64_t* __restrict__ target, int B,
                                 int C, const double* __restrict__ coeff, const double* __restrict__ denom,
                                 const double* __restrict__ upstream, T* __restrict__ dl, int lddl) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const T* z = logits + (long long)i * ld;
@@ -220,7 +230,7 @@ int adni_linear_fwd(const float* x, int ldx, const float* W, const float* b, flo
   ADNI_REQUIRE(x && W && y && B > 0 && in > 0 && out > 0 && ldx >= in && ldy >= out, ADNI_EINVAL,
                "linear_fwd: bad arguments");
   const long long threads = (long long)B * out * 32;
-  linear_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(x, ldx, W, b, y, ldy, B, in, out, relu);
+  pdl_launch(linear_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, ST(stream))(x, ldx, W, b, y, ldy, B, in, out, relu);
   count_launch();
   ADNI_LAUNCH_CHECK("linear_fwd_kernel");
   return ADNI_OK;
@@ -232,14 +242,14 @@ int adni_linear_bwd(const float* x, int ldx, const float* W, const float* y, int
   ADNI_REQUIRE(x && W && dy && B > 0 && in > 0 && out > 0, ADNI_EINVAL, "linear_bwd: bad arguments");
   ADNI_REQUIRE(!relu || y, ADNI_EINVAL, "linear_bwd: relu mask needs the forward output");
   if (dx) {
-    linear_bwd_dx_kernel<<<(B * in + 255) / 256, 256, 0, ST(stream)>>>(W, y, ldy, dy, lddy, dx, lddx, accumulate_dx, B,
+    pdl_launch(linear_bwd_dx_kernel, (B * in + 255) / 256, 256, 0, ST(stream))(W, y, ldy, dy, lddy, dx, lddx, accumulate_dx, B,
                                                                         in, out, relu);
     count_launch();
     ADNI_LAUNCH_CHECK("linear_bwd_dx_kernel");
   }
   if (dW || db) {
     const long long n = (long long)out * (in + 1);
-    linear_bwd_dw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, ldx, y, ldy, dy, lddy, dW, db, B, in,
+    pdl_launch(linear_bwd_dw_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream))(x, ldx, y, ldy, dy, lddy, dW, db, B, in,
                                                                                out, relu);
     count_launch();
     ADNI_LAUNCH_CHECK("linear_bwd_dw_kernel");
@@ -249,7 +259,7 @@ int adni_linear_bwd(const float* x, int ldx, const float* W, const float* y, int
 
 int adni_relu_f32(const float* x, const float* dy, float* out, long long n, void* stream) {
   ADNI_REQUIRE(x && out && n > 0, ADNI_EINVAL, "relu_f32: bad arguments");
-  relu_f32_kernel<<<(unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, ST(stream)>>>(x, dy, out, n);
+  pdl_launch(relu_f32_kernel, (unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, ST(stream))(x, dy, out, n);
   count_launch();
   ADNI_LAUNCH_CHECK("relu_f32_kernel");
   return ADNI_OK;
@@ -257,7 +267,7 @@ int adni_relu_f32(const float* x, const float* dy, float* out, long long n, void
 
 int adni_rows_stats_f32(const float* x, int ldx, int B, int C, double* stats, void* stream) {
   ADNI_REQUIRE(x && stats && B > 0 && C > 0, ADNI_EINVAL, "rows_stats_f32: bad arguments");
-  rows_stats_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(x, ldx, B, C, stats);
+  pdl_launch(rows_stats_kernel, (C + 127) / 128, 128, 0, ST(stream))(x, ldx, B, C, stats);
   count_launch();
   ADNI_LAUNCH_CHECK("rows_stats_kernel");
   return ADNI_OK;
@@ -266,7 +276,7 @@ int adni_rows_stats_f32(const float* x, int ldx, int B, int C, double* stats, vo
 int adni_bn1d_apply(const float* x, int ldx, const float* scale, const float* shift, float* y, int ldy, int B, int C,
                     int relu, void* stream) {
   ADNI_REQUIRE(x && scale && shift && y && B > 0 && C > 0, ADNI_EINVAL, "bn1d_apply: bad arguments");
-  bn1d_apply_kernel<<<(B * C + 255) / 256, 256, 0, ST(stream)>>>(x, ldx, scale, shift, y, ldy, B, C, relu);
+  pdl_launch(bn1d_apply_kernel, (B * C + 255) / 256, 256, 0, ST(stream))(x, ldx, scale, shift, y, ldy, B, C, relu);
   count_launch();
   ADNI_LAUNCH_CHECK("bn1d_apply_kernel");
   return ADNI_OK;
@@ -276,7 +286,7 @@ int adni_bn1d_bwd_reduce(const float* dy, int lddy, const float* y, int ldy, con
                          const float* invstd, int B, int C, int relu, double* red, void* stream) {
   ADNI_REQUIRE(dy && x && mean && invstd && red && B > 0 && C > 0, ADNI_EINVAL, "bn1d_bwd_reduce: bad arguments");
   ADNI_REQUIRE(!relu || y, ADNI_EINVAL, "bn1d_bwd_reduce: relu mask needs the forward output");
-  bn1d_bwd_reduce_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(dy, lddy, y, ldy, x, ldx, mean, invstd, B, C, relu,
+  pdl_launch(bn1d_bwd_reduce_kernel, (C + 127) / 128, 128, 0, ST(stream))(dy, lddy, y, ldy, x, ldx, mean, invstd, B, C, relu,
                                                                    red);
   count_launch();
   ADNI_LAUNCH_CHECK("bn1d_bwd_reduce_kernel");
@@ -289,7 +299,7 @@ int adni_bn1d_bwd_apply(const float* dy, int lddy, const float* y, int ldy, cons
   ADNI_REQUIRE(dy && x && mean && invstd && red && dx && B > 0 && C > 0 && count > 0, ADNI_EINVAL,
                "bn1d_bwd_apply: bad arguments");
   ADNI_REQUIRE(!relu || y, ADNI_EINVAL, "bn1d_bwd_apply: relu mask needs the forward output");
-  bn1d_bwd_apply_kernel<<<(B * C + 255) / 256, 256, 0, ST(stream)>>>(dy, lddy, y, ldy, x, ldx, mean, invstd, gamma, red,
+  pdl_launch(bn1d_bwd_apply_kernel, (B * C + 255) / 256, 256, 0, ST(stream))(dy, lddy, y, ldy, x, ldx, mean, invstd, gamma, red,
                                                                       1.0 / count, B, C, relu, dx, lddx, dgamma, dbeta);
   count_launch();
   ADNI_LAUNCH_CHECK("bn1d_bwd_apply_kernel");
@@ -302,11 +312,11 @@ int adni_loss_fwd(const void* logits, int logits_f64, int ld, const int64_t* tar
   ADNI_REQUIRE(C >= 2 && C <= kMaxClasses && ld >= C, ADNI_ENOTSUP, "loss_fwd: C=%d outside [2,%d]", C, kMaxClasses);
   ADNI_REQUIRE(gamma >= 0, ADNI_EINVAL, "loss_fwd: negative focal gamma");
   if (logits_f64)
-    loss_fwd_kernel<double><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const double*>(logits), ld, target, B,
+    pdl_launch(loss_fwd_kernel<double>, (B + 127) / 128, 128, 0, ST(stream))(static_cast<const double*>(logits), ld, target, B,
                                                                     C, gamma, class_weights, partial,
                                                                     per_sample_coeff);
   else
-    loss_fwd_kernel<float><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(logits), ld, target, B,
+    pdl_launch(loss_fwd_kernel<float>, (B + 127) / 128, 128, 0, ST(stream))(static_cast<const float*>(logits), ld, target, B,
                                                                    C, gamma, class_weights, partial, per_sample_coeff);
   count_launch();
   ADNI_LAUNCH_CHECK("loss_fwd_kernel");
@@ -320,11 +330,11 @@ int adni_loss_bwd(const void* logits, int logits_f64, int ld, const int64_t* tar
                "loss_bwd: bad arguments");
   ADNI_REQUIRE(C >= 2 && C <= kMaxClasses, ADNI_ENOTSUP, "loss_bwd: C=%d outside [2,%d]", C, kMaxClasses);
   if (logits_f64)
-    loss_bwd_kernel<double><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const double*>(logits), ld, target, B,
+    pdl_launch(loss_bwd_kernel<double>, (B + 127) / 128, 128, 0, ST(stream))(static_cast<const double*>(logits), ld, target, B,
                                                                     C, per_sample_coeff, denom, upstream,
                                                                     static_cast<double*>(dlogits), lddl);
   else
-    loss_bwd_kernel<float><<<(B + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(logits), ld, target, B, C,
+    pdl_launch(loss_bwd_kernel<float>, (B + 127) / 128, 128, 0, ST(stream))(static_cast<const float*>(logits), ld, target, B, C,
                                                                    per_sample_coeff, denom, upstream,
                                                                    static_cast<float*>(dlogits), lddl);
   count_launch();

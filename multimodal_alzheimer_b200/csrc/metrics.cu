@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kMetricThreads)
                              const int64_t* __restrict__ idx /* [draws][n] or null = identity */, int n, int C,
                              float* __restrict__ f1_macro, float* __restrict__ f1_class /* [draws][C] */,
                              float* __restrict__ mcc, long long* __restrict__ confmat /* [draws][C][C] */) {
+  pdl_enter();
   __shared__ unsigned int cm[kMaxClasses * kMaxClasses];
   const int draw = blockIdx.x;
   for (int i = threadIdx.x; i < C * C; i += kMetricThreads) cm[i] = 0u;
@@ -101,7 +102,7 @@ int adni_bootstrap_metrics(const double* logits, int ld, const int64_t* labels, 
                            int draws, float* f1_macro, float* f1_class, float* mcc, long long* confmat, void* stream) {
   ADNI_REQUIRE(logits && labels && n > 0 && draws > 0 && ld >= C, ADNI_EINVAL, "bootstrap_metrics: bad arguments");
   ADNI_REQUIRE(C >= 2 && C <= kMaxClasses, ADNI_ENOTSUP, "bootstrap_metrics: %d classes (2..%d supported)", C, kMaxClasses);
-  bootstrap_metrics_kernel<<<draws, kMetricThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl_launch(bootstrap_metrics_kernel, draws, kMetricThreads, 0, static_cast<cudaStream_t>(stream))(
       logits, ld, labels, idx, n, C, f1_macro, f1_class, mcc, confmat);
   count_launch();
   ADNI_LAUNCH_CHECK("bootstrap_metrics_kernel");

@@ -56,6 +56,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kHistThreads) q_hist_kernel(const float* __restrict__ x,
                                                              const uint8_t* __restrict__ mask, long long nvox,
                                                              void* ws) {
+  pdl_enter();
   __shared__ unsigned int h[PASS == 0 ? kBins : 1];
   const int scan = blockIdx.y;
   if (PASS == 0)
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(kHistThreads) q_hist_kernel(const float* __res
 // one block of 4 warps per scan; warp j resolves rank j
 template <int PASS>
 __global__ void __launch_bounds__(128) q_select_kernel(void* ws, double q) {
+  pdl_enter();
   const int scan = blockIdx.x;
   ScanState* st = state_of(ws, scan);
   unsigned int* gh = hist_of(ws, scan);
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(128) q_select_kernel(void* ws, double q) {
 __global__ void __launch_bounds__(256) q_apply_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                       long long nvox, const void* ws, float* __restrict__ of,
                                                       __nv_bfloat16* __restrict__ ob) {
+  pdl_enter();
   const int scan = blockIdx.y;
   const ScanState* st = state_of(const_cast<void*>(ws), scan);
   const double qmax = st->qv[0], qmin = st->qv[1];
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(256) q_apply_kernel(const float* __restrict__ 
 }
 
 __global__ void q_export_kernel(const void* ws, int nscans, long long* info, double* qvals) {
+  pdl_enter();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nscans) return;
   const ScanState* st = state_of(const_cast<void*>(ws), s);
@@ -254,6 +258,7 @@ __global__ void q_export_kernel(const void* ws, int nscans, long long* info, dou
 __global__ void __launch_bounds__(256) standardize_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                           long long n, double mean, double stdv,
                                                           float* __restrict__ of, __nv_bfloat16* __restrict__ ob) {
+  pdl_enter();
   auto norm = [&](float xv, uint8_t mv) -> float {  // the reference's fp64 sequence, rounded to fp32 once
     double v = ((double)xv - mean) / stdv;
     v *= mv ? 1.0 : 0.0;
@@ -310,6 +315,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 // moments[2s] += sum x / nvox ; moments[2s+1] += sum x^2 / nvox
 __global__ void __launch_bounds__(256) scan_moments_kernel(const float* __restrict__ x, long long nvox,
                                                            double* __restrict__ moments) {
+  pdl_enter();
   __shared__ double sm[8];
   const int scan = blockIdx.y;
   const float* xs = x + (long long)scan * nvox;
@@ -334,6 +340,7 @@ template <int PASS>
 __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __restrict__ x,
                                                              const uint8_t* __restrict__ mask, long long nvox,
                                                              double* __restrict__ out) {
+  pdl_enter();
   __shared__ double sm[8];
   const int scan = blockIdx.y;
   const float* xs = x + (long long)scan * nvox;
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __rest
 }
 
 __global__ void masked_finalize_kernel(double* out, int nscans) {
+  pdl_enter();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nscans) return;
   const double n = out[3 * s];
@@ -402,20 +410,20 @@ int adni_quantile_minmax_normalize(const float* x, const uint8_t* mask, int nsca
   cudaStream_t st = ST(stream);
   ADNI_CUDA_OK(cudaMemsetAsync(workspace, 0, adni_quantile_workspace_bytes(nscans), st));
   dim3 grid(scan_blocks(nvox, nscans), nscans);
-  q_hist_kernel<0><<<grid, kHistThreads, 0, st>>>(x, mask, nvox, workspace);
-  q_select_kernel<0><<<nscans, 128, 0, st>>>(workspace, q);
-  q_hist_kernel<1><<<grid, kHistThreads, 0, st>>>(x, mask, nvox, workspace);
-  q_select_kernel<1><<<nscans, 128, 0, st>>>(workspace, q);
-  q_hist_kernel<2><<<grid, kHistThreads, 0, st>>>(x, mask, nvox, workspace);
-  q_select_kernel<2><<<nscans, 128, 0, st>>>(workspace, q);
+  pdl_launch(q_hist_kernel<0>, grid, kHistThreads, 0, st)(x, mask, nvox, workspace);
+  pdl_launch(q_select_kernel<0>, nscans, 128, 0, st)(workspace, q);
+  pdl_launch(q_hist_kernel<1>, grid, kHistThreads, 0, st)(x, mask, nvox, workspace);
+  pdl_launch(q_select_kernel<1>, nscans, 128, 0, st)(workspace, q);
+  pdl_launch(q_hist_kernel<2>, grid, kHistThreads, 0, st)(x, mask, nvox, workspace);
+  pdl_launch(q_select_kernel<2>, nscans, 128, 0, st)(workspace, q);
   for (int i = 0; i < 6; i++) count_launch();
   ADNI_LAUNCH_CHECK("quantile select");
   if (out_f32 || out_bf16) {
-    q_apply_kernel<<<grid, 256, 0, st>>>(x, mask, nvox, workspace, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    pdl_launch(q_apply_kernel, grid, 256, 0, st)(x, mask, nvox, workspace, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
     count_launch();
   }
   if (info || qvals) {
-    q_export_kernel<<<(nscans + 127) / 128, 128, 0, st>>>(workspace, nscans, info, qvals);
+    pdl_launch(q_export_kernel, (nscans + 127) / 128, 128, 0, st)(workspace, nscans, info, qvals);
     count_launch();
   }
   ADNI_LAUNCH_CHECK("quantile apply");
@@ -426,7 +434,7 @@ int adni_standardize(const float* x, const uint8_t* mask, long long n, double me
                      adni_bf16* out_bf16, void* stream) {
   ADNI_REQUIRE(x && n > 0 && (out_f32 || out_bf16), ADNI_EINVAL, "standardize: bad arguments");
   const int grid = (int)std::min<long long>((n + 256 * 16 - 1) / (256 * 16), (long long)num_sms() * 8);
-  standardize_kernel<<<grid, 256, 0, ST(stream)>>>(x, mask, n, mean, std, out_f32,
+  pdl_launch(standardize_kernel, grid, 256, 0, ST(stream))(x, mask, n, mean, std, out_f32,
                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16));
   count_launch();
   ADNI_LAUNCH_CHECK("standardize_kernel");
@@ -436,7 +444,7 @@ int adni_standardize(const float* x, const uint8_t* mask, long long n, double me
 int adni_scan_moments(const float* x, int nscans, long long nvox, double* moments, void* stream) {
   ADNI_REQUIRE(x && moments && nscans > 0 && nscans <= 65535 && nvox > 0, ADNI_EINVAL, "scan_moments: bad arguments");
   dim3 grid(scan_blocks(nvox, nscans), nscans);
-  scan_moments_kernel<<<grid, 256, 0, ST(stream)>>>(x, nvox, moments);
+  pdl_launch(scan_moments_kernel, grid, 256, 0, ST(stream))(x, nvox, moments);
   count_launch();
   ADNI_LAUNCH_CHECK("scan_moments_kernel");
   return ADNI_OK;
@@ -448,9 +456,9 @@ int adni_masked_std_mean(const float* x, const uint8_t* mask, int nscans, long l
   cudaStream_t st = ST(stream);
   ADNI_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * 3 * (size_t)nscans, st));
   dim3 grid(scan_blocks(nvox, nscans), nscans);
-  masked_moments_kernel<0><<<grid, 256, 0, st>>>(x, mask, nvox, out);
-  masked_moments_kernel<1><<<grid, 256, 0, st>>>(x, mask, nvox, out);
-  masked_finalize_kernel<<<(nscans + 127) / 128, 128, 0, st>>>(out, nscans);
+  pdl_launch(masked_moments_kernel<0>, grid, 256, 0, st)(x, mask, nvox, out);
+  pdl_launch(masked_moments_kernel<1>, grid, 256, 0, st)(x, mask, nvox, out);
+  pdl_launch(masked_finalize_kernel, (nscans + 127) / 128, 128, 0, st)(out, nscans);
   for (int i = 0; i < 3; i++) count_launch();
   ADNI_LAUNCH_CHECK("masked_std_mean");
   return ADNI_OK;

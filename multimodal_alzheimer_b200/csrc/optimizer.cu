@@ -57,6 +57,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const __grid_constant__ AdamBatch tb,
                                                                   const AdamScalars s) {
+  pdl_enter();
   // block -> tensor: binary search over the (<= 65 entry) chunk table in the constant bank
   int lo = 0, hi = tb.count - 1;
   while (lo < hi) {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const __grid_c
 }
 
 __global__ void adam_bump_kernel(const __grid_constant__ AdamBatch tb) {
+  pdl_enter();
   const int i = threadIdx.x;
   if (i < tb.count) *tb.step[i] += 1.0f;
 }
@@ -176,10 +178,10 @@ int adni_adam_step_multi(int n_tensors, void* const* params, const void* const* 
     tb.count = cnt;
     tb.hyper = hyper_dev;
     tb.hyper_n = n_tensors;
-    adam_multi_kernel<<<blocks, kAdamThreads, 0, st>>>(tb, s);
+    pdl_launch(adam_multi_kernel, blocks, kAdamThreads, 0, st)(tb, s);
     count_launch();
     ADNI_LAUNCH_CHECK("adam_multi_kernel");
-    adam_bump_kernel<<<1, kAdamMaxTensors, 0, st>>>(tb);
+    pdl_launch(adam_bump_kernel, 1, kAdamMaxTensors, 0, st)(tb);
     count_launch();
     ADNI_LAUNCH_CHECK("adam_bump_kernel");
   }

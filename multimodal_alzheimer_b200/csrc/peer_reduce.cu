@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_f64_kernel(double
                                                                           const unsigned long long* __restrict__ peers,
                                                                           unsigned long long* __restrict__ call_counter,
                                                                           int rank, int world, int max_n) {
+  pdl_enter();
   const unsigned long long call = *call_counter + 1;
   const int par = static_cast<int>(call & 1ull);
   // 1. my vector into slot [par][rank] of every rank's buffer (peer stores travel over NVLink)
@@ -86,7 +87,7 @@ int adni_peer_allreduce_f64(double* data, int n, const void* peers, void* call_c
   ADNI_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, ADNI_EINVAL,
                "peer_allreduce_f64: rank %d / world %d out of range", rank, world);
   ADNI_REQUIRE(n <= max_n, ADNI_ENOTSUP, "peer_allreduce_f64: %d elements exceed the slot size %d", n, max_n);
-  peer_allreduce_f64_kernel<<<1, kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl_launch(peer_allreduce_f64_kernel, 1, kPeerThreads, 0, static_cast<cudaStream_t>(stream))(
       data, n, static_cast<const unsigned long long*>(peers), static_cast<unsigned long long*>(call_counter), rank, world,
       max_n);
   count_launch();

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kThreads) pool_nonoverlap_fwd_kernel(const __n
                                                                        int H, int W, int vpr, int Do, int Ho, int Wo,
                                                                        int relu, __nv_bfloat16* __restrict__ y,
                                                                        uint8_t* __restrict__ am) {
+  pdl_enter();
   const long long total = static_cast<long long>(N) * Do * Ho * Wo * vpr;
   for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kThreads) pool_nonoverlap_bwd_kernel(const __n
                                                                        const __nv_bfloat16* __restrict__ pooled, int N,
                                                                        int D, int H, int W, int vpr, int k, int Do, int Ho,
                                                                        int Wo, __nv_bfloat16* __restrict__ dx) {
+  pdl_enter();
   const long long total = static_cast<long long>(N) * D * H * W * vpr;
   for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
@@ -139,7 +141,7 @@ int launch_pool_nonoverlap_bwd(const __nv_bfloat16* dy, const uint8_t* am, const
                                int W, int C, int k, __nv_bfloat16* dx, cudaStream_t st) {
   const int Do = D / k, Ho = H / k, Wo = W / k;
   const long long total = static_cast<long long>(N) * D * H * W * (C / 8);
-  pool_nonoverlap_bwd_kernel<<<grid_for(total), kThreads, 0, st>>>(dy, am, pooled, N, D, H, W, C / 8, k, Do, Ho, Wo, dx);
+  pdl_launch(pool_nonoverlap_bwd_kernel, grid_for(total), kThreads, 0, st)(dy, am, pooled, N, D, H, W, C / 8, k, Do, Ho, Wo, dx);
   count_launch();
   ADNI_LAUNCH_CHECK("pool_nonoverlap_bwd_kernel");
   return ADNI_OK;
@@ -162,9 +164,9 @@ int adni_relu_maxpool_fwd(const adni_bf16* x, int N, int D, int H, int W, int C,
   auto ys = reinterpret_cast<__nv_bfloat16*>(y);
   auto st = static_cast<cudaStream_t>(stream);
   if (k == 2)
-    pool_nonoverlap_fwd_kernel<2><<<grid_for(total), kThreads, 0, st>>>(xs, N, D, H, W, C / 8, Do, Ho, Wo, relu, ys, argmax);
+    pdl_launch(pool_nonoverlap_fwd_kernel<2>, grid_for(total), kThreads, 0, st)(xs, N, D, H, W, C / 8, Do, Ho, Wo, relu, ys, argmax);
   else
-    pool_nonoverlap_fwd_kernel<3><<<grid_for(total), kThreads, 0, st>>>(xs, N, D, H, W, C / 8, Do, Ho, Wo, relu, ys, argmax);
+    pdl_launch(pool_nonoverlap_fwd_kernel<3>, grid_for(total), kThreads, 0, st)(xs, N, D, H, W, C / 8, Do, Ho, Wo, relu, ys, argmax);
   count_launch();
   ADNI_LAUNCH_CHECK("pool_nonoverlap_fwd_kernel");
   return ADNI_OK;

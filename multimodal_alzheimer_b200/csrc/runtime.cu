@@ -27,6 +27,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ADNI_PDL");   // opt-in: measured slower inside the step's CUDA graph (profiles/r02_pdl_ab.md)
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kThreads)
                             const float* __restrict__ shift, int N, int D, int H, int W, int C, int Do, int Ho, int Wo,
                             int tiles_d, int tiles_h, int tiles_w, __nv_bfloat16* __restrict__ p,
                             uint8_t* __restrict__ amax) {
+  pdl_enter();
   __shared__ uint4 s_a[kFI * kFI * kFI * kFCv];
   const int vpr = C / 8;
   // channel chunks are the fastest-varying block index: the blocks sharing a voxel tile (and its 128-byte lines)
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 3)
                        const float* __restrict__ gamma, const double* __restrict__ red_in, double inv_count, int N,
                        int D, int H, int W, int C, int Do, int Ho, int Wo, int tiles_d, int tiles_h, int tiles_w,
                        double* __restrict__ red_out, __nv_bfloat16* __restrict__ dy) {
+  pdl_enter();
   extern __shared__ float s_g[];  // [512 voxels][kBCv][8]
   __shared__ float s_red[2][kThreads / kBCv][kBCv * 8 + 1];
   const int vpr = C / 8;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
                                    const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho, int Wo,
                                    int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
                                    uint8_t* __restrict__ amax, __nv_bfloat16* __restrict__ yraw) {
+  pdl_enter();
   const int vpr = C / 8;
   __shared__ float s_sc[64], s_sh[64];  // the block's 64 channels
   if (threadIdx.x < 64) {
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(kSFThreads, 3)
                                           const float* __restrict__ shift, int D, int H, int W, int C, int Do, int Ho,
                                           int Wo, int tiles_h, int tiles_w, int dsplit, __nv_bfloat16* __restrict__ p,
                                           uint8_t* __restrict__ amax, __nv_bfloat16* __restrict__ yraw) {
+  pdl_enter();
   const int vpr = C / 8;
   __shared__ float s_sc[64], s_sh[64];
   if (threadIdx.x < 64) {
@@ -610,6 +614,7 @@ __global__ void __launch_bounds__(kGThreads, 3)
                             const float* __restrict__ gamma, const double* __restrict__ red_in, double inv_count, int N,
                             int D, int H, int W, int C, int Do, int Ho, int Wo, double* __restrict__ red_out,
                             __nv_bfloat16* __restrict__ dy) {
+  pdl_enter();
   const int vpr = C / 8;  // power of two <= 32 (checked by the launcher): a thread's channel vector never changes
   const int cv = threadIdx.x & (vpr - 1);
   const int coff = cv * 8;
@@ -773,14 +778,14 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
     const int dsplit = Do >= 16 ? 2 : 1;
     dim3 grid((unsigned)((long long)N * th * tw * dsplit), (unsigned)((C / 8 + 7) / 8));
     if (pool_variant() == 2) {  // experimental packed-compare variant, same results
-      bn_relu_pool_fwd_stream_packed_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(
+      pdl_launch(bn_relu_pool_fwd_stream_packed_kernel, grid, kSFThreads, 0, ST(stream))(
           reinterpret_cast<const bf16*>(y), scale, shift, D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
           reinterpret_cast<bf16*>(p), argmax, reinterpret_cast<bf16*>(y_at_argmax));
       count_launch();
       ADNI_LAUNCH_CHECK("bn_relu_pool_fwd_stream_packed_kernel");
       return ADNI_OK;
     }
-    bn_relu_pool_fwd_stream_kernel<<<grid, kSFThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift,
+    pdl_launch(bn_relu_pool_fwd_stream_kernel, grid, kSFThreads, 0, ST(stream))(reinterpret_cast<const bf16*>(y), scale, shift,
                                                                         D, H, W, C, Do, Ho, Wo, th, tw, dsplit,
                                                                         reinterpret_cast<bf16*>(p), argmax,
                                                                         reinterpret_cast<bf16*>(y_at_argmax));
@@ -791,7 +796,7 @@ int adni_bn_relu_maxpool_fwd(const adni_bf16* y, const float* scale, const float
   ADNI_REQUIRE(y_at_argmax == nullptr, ADNI_ENOTSUP, "bn_relu_maxpool_fwd: y_at_argmax needs a streaming variant (ADNI_POOL_STREAM != 0)");
   const int td = (Do + kFT - 1) / kFT, th = (Ho + kFT - 1) / kFT, tw = (Wo + kFT - 1) / kFT;
   dim3 grid((unsigned)((long long)N * td * th * tw * ((C / 8 + kFCv - 1) / kFCv)));
-  bn_relu_pool_fwd_kernel<<<grid, kThreads, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(y), scale, shift, N, D, H, W,
+  pdl_launch(bn_relu_pool_fwd_kernel, grid, kThreads, 0, ST(stream))(reinterpret_cast<const bf16*>(y), scale, shift, N, D, H, W,
                                                              C, Do, Ho, Wo, td, th, tw, reinterpret_cast<bf16*>(p),
                                                              argmax);
   count_launch();
@@ -806,7 +811,7 @@ int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   if (pool_variant() && pow2_le32(C / 8)) {
-    pool_bn_bwd_cell_kernel<0><<<num_sms() * 3, kGThreads, 0, ST(stream)>>>(
+    pdl_launch(pool_bn_bwd_cell_kernel<0>, num_sms() * 3, kGThreads, 0, ST(stream))(
         reinterpret_cast<const bf16*>(dp), argmax, reinterpret_cast<const bf16*>(y), bnp, nullptr, nullptr, 0.0, N, D, H,
         W, C, Do, Ho, Wo, red, nullptr);
     count_launch();
@@ -821,7 +826,7 @@ int adni_maxpool_bn_bwd_reduce(const adni_bf16* dp, const uint8_t* argmax, const
                                       kBSmemFloats * 4));
     attr0 = true;
   }
-  pool_bn_bwd_kernel<0><<<grid, kThreads, kBSmemFloats * 4, ST(stream)>>>(reinterpret_cast<const bf16*>(dp), argmax,
+  pdl_launch(pool_bn_bwd_kernel<0>, grid, kThreads, kBSmemFloats * 4, ST(stream))(reinterpret_cast<const bf16*>(dp), argmax,
                                                            reinterpret_cast<const bf16*>(y), bnp, nullptr, nullptr, 0.0,
                                                            N, D, H, W, C, Do, Ho, Wo, td, th, tw, red, nullptr);
   count_launch();
@@ -838,7 +843,7 @@ int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const 
   if (rc) return rc;
   const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   if (pool_variant() && pow2_le32(C / 8)) {
-    pool_bn_bwd_cell_kernel<1><<<num_sms() * 3, kGThreads, 0, ST(stream)>>>(
+    pdl_launch(pool_bn_bwd_cell_kernel<1>, num_sms() * 3, kGThreads, 0, ST(stream))(
         reinterpret_cast<const bf16*>(dp), argmax, reinterpret_cast<const bf16*>(y), bnp, gamma, red, 1.0 / count, N, D,
         H, W, C, Do, Ho, Wo, nullptr, reinterpret_cast<bf16*>(dy));
     count_launch();
@@ -853,7 +858,7 @@ int adni_maxpool_bn_bwd_apply(const adni_bf16* dp, const uint8_t* argmax, const 
                                       kBSmemFloats * 4));
     attr1 = true;
   }
-  pool_bn_bwd_kernel<1><<<grid, kThreads, kBSmemFloats * 4, ST(stream)>>>(reinterpret_cast<const bf16*>(dp), argmax,
+  pdl_launch(pool_bn_bwd_kernel<1>, grid, kThreads, kBSmemFloats * 4, ST(stream))(reinterpret_cast<const bf16*>(dp), argmax,
                                                            reinterpret_cast<const bf16*>(y), bnp, gamma, red,
                                                            1.0 / count, N, D, H, W, C, Do, Ho, Wo, td, th, tw, nullptr,
                                                            reinterpret_cast<bf16*>(dy));

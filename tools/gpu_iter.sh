@@ -12,11 +12,14 @@ try:
 except Exception as e: print('no line',e)
 PY
 }
-b b32 --shape-profile gpurun_out/shapes_b32.json
-b r50 --workload mri_r50_160 --steps 4 --warmup 3 --shape-profile gpurun_out/shapes_r50.json
-b b4 --global-batch 4 --steps 20 --shape-profile gpurun_out/shapes_b4.json
-# A/B of the wgrad stream-K position-chunk budget in one process environment (same box, same power cap)
-for mb in 1000000 128 48; do ADNI_WGRAD_CHUNK_MB=$mb b chunk$mb --no-e2e --steps 12; done
-timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_baseline_sizes.py -m gpu -x -q -p no:cacheprovider > gpurun_out/tests_models.log 2>&1; echo "model tests exit $?"; tail -n 3 gpurun_out/tests_models.log
+# A/B of programmatic dependent launch in one call (same box, same power cap)
+for pdl in 0 1 0 1; do
+  ADNI_PDL=$pdl b b32_pdl$pdl --no-e2e --steps 12
+  ADNI_PDL=$pdl b b4_pdl$pdl --no-e2e --global-batch 4 --steps 30
+done
+ADNI_PDL=0 b r50_pdl0 --no-e2e --workload mri_r50_160 --steps 4 --warmup 3
+ADNI_PDL=1 b r50_pdl1 --no-e2e --workload mri_r50_160 --steps 4 --warmup 3
+grep -h "launch_mode" gpurun_out/bench_b4_pdl1.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('launch mode', d['launch_mode'], 'parity', d['parity'])"
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/tests_all.log 2>&1; echo "all gpu tests exit $?"; tail -n 3 gpurun_out/tests_all.log
 [ -n "$1" ] && eval "$@"
 exit 0
