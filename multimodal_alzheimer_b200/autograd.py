@@ -17,6 +17,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import data_parallel as _dp
 from . import kernels as K
 
 BF16 = torch.bfloat16
@@ -192,9 +193,23 @@ def _conv_fwd(x, w, cfg, bias=None, stats=True, need_ito=True):
     return y, st, ito
 
 
+class _WShape(tuple):
+    """A conv weight's shape plus the address of the parameter's storage: the backward pass asks the data-parallel
+    gradient buckets (data_parallel.grad_slot) for the slot this weight's gradient should be written into."""
+    ptr = None
+
+
+def _ws(w):
+    s = _WShape(w.shape)
+    s.ptr = w.data_ptr()
+    return s
+
+
 def _conv_wgrad(x, dy, cfg, wshape, want_dbias=False):
     dw, db = K.conv3d_wgrad(x, dy, cfg.k, cfg.stride, cfg.pad, cfg.dil, want_dbias=want_dbias)
-    return K.wgrad_to_param_layout(dw, tuple(wshape)), db
+    ptr = getattr(wshape, "ptr", None)
+    slot = _dp.grad_slot(ptr) if ptr is not None else None
+    return K.wgrad_to_param_layout(dw, tuple(wshape), dst=slot), db
 
 
 # --------------------------------------------------------------------------------------------- input cast
@@ -291,7 +306,7 @@ class StemFn(torch.autograd.Function):
             yraw = None
         ctx.save_for_backward(xs, y, am, bnp, gamma, yraw)
         ctx.a_shape = a_shape
-        ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, w.shape, tc, tuple(x.shape)
+        ctx.cfg, ctx.pool, ctx.count, ctx.wshape, ctx.tc, ctx.xshape = cfg, pool, count, _ws(w), tc, tuple(x.shape)
         ctx.fused = fused
         return p
 
@@ -342,7 +357,7 @@ class BasicBlockFn(torch.autograd.Function):
             r = x
         out, p2, n2 = _bn_forward(y2, st2, g2, b2, bn2, r, True)
         ctx.save_for_backward(x, y1, a1, y2, out, yd, p1, p2, pd, g1, g2, gd, w1_ito, w2_ito, wd_ito, tail_y, tail_p)
-        ctx.cfg = (c1, c2, cd, n1, n2, nd, w1.shape, w2.shape, None if wd is None else wd.shape, need_dx)
+        ctx.cfg = (c1, c2, cd, n1, n2, nd, _ws(w1), _ws(w2), None if wd is None else _ws(wd), need_dx)
         if p2 is None:
             p2 = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(y2, p2)
@@ -398,7 +413,7 @@ class BottleneckFn(torch.autograd.Function):
         out, p3, n3 = _bn_forward(y3, st3, g3, b3, bn3, r, True)
         ctx.save_for_backward(x, y1, a1, y2, a2, y3, out, yd, p1, p2, p3, pd, g1, g2, g3, gd, w1_ito, w2_ito, w3_ito,
                               wd_ito, tail_y, tail_p)
-        ctx.cfg = (c1, c2, c3, cd, n1, n2, n3, nd, w1.shape, w2.shape, w3.shape, None if wd is None else wd.shape,
+        ctx.cfg = (c1, c2, c3, cd, n1, n2, n3, nd, _ws(w1), _ws(w2), _ws(w3), None if wd is None else _ws(wd),
                    need_dx)
         if p3 is None:
             p3 = torch.empty(0, device=x.device)
@@ -446,7 +461,7 @@ class Conv3dFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         y, st, ito = _conv_fwd(x, w, cfg, bias=bias, stats=want_stats, need_ito=need_dx)
         ctx.save_for_backward(x, ito)
-        ctx.cfg = (cfg, w.shape, bias is not None, need_dx)
+        ctx.cfg = (cfg, _ws(w), bias is not None, need_dx)
         if st is None:
             st = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(st)

@@ -110,37 +110,110 @@ def peer_reducer(channel, device):
     return red
 
 
+# Gradient slots: parameter storage pointer -> (view into a flat bucket buffer, weakref to the parameter, bucket object).
+# The conv autograd Functions ask `grad_slot(w)` where to WRITE a weight gradient: with data-parallel buckets active the
+# wgrad layout kernel stores straight into the bucket (autograd then adopts that view as `.grad`), so that the
+# all-reduce needs neither a flatten nor an unflatten copy of the 265 MB of conv gradients.
+_GRAD_SLOTS = {}
+_GRAD_SLOTS_ON = os.environ.get("ADNI_GRAD_SLOTS", "1") != "0"   # 0: gradients are gathered into the buckets by copy (A/B)
+
+
+def grad_slot(w):
+    """The bucket view a gradient of parameter storage `w` should be written into, or None (no buckets, the
+    parameter already holds a gradient that autograd would accumulate into, or the slot was already handed out in
+    this backward pass - a weight used twice)."""
+    entry = _GRAD_SLOTS.get(w.data_ptr() if isinstance(w, torch.Tensor) else w) if _GRAD_SLOTS_ON else None
+    if entry is None:
+        return None
+    view, pref, owner = entry
+    param = pref()
+    if param is None or param.grad is not None or id(view) in owner._handed_out:
+        return None
+    owner._handed_out.add(id(view))
+    return view.view(param.shape)      # a fresh tensor object: autograd adopts it (use count 1) instead of cloning
+
+
 class GradientBuckets:
     """Sum parameter gradients across ranks in ~bucket_mb buckets, last-produced gradients first (the order the
-    backward pass finishes them), using flat fp32 staging buffers."""
+    backward pass finishes them).  Every bucket owns a persistent flat buffer; a gradient that already lives in its
+    slot (written there by the wgrad kernels through `grad_slot`) is reduced in place, the others are gathered with
+    one multi-tensor copy, and after the all-reduce `p.grad` is REBOUND to the slot view - there is no copy back."""
+
+    ALIGN = 64   # elements: 256-byte slot alignment (the Adam kernel reads gradients as float4)
 
     def __init__(self, params, bucket_mb=64):
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []
-        cur, cur_bytes = [], 0
+        cur, cur_bytes, cur_key = [], 0, None
         for p in reversed(self.params):
+            key = (p.device, p.dtype)
+            if cur and key != cur_key:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+            cur_key = key
             cur.append(p)
-            cur_bytes += p.numel() * 4
+            cur_bytes += p.numel() * p.element_size()
             if cur_bytes >= bucket_mb * (1 << 20):
                 self.buckets.append(cur)
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+        self._views = [None] * len(self.buckets)
+        self._handed_out = set()
+        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self._active:
+            import weakref
+            for bi in range(len(self.buckets)):
+                self._ensure_flat(bi)
+                for p, v in zip(self.buckets[bi], self._views[bi]):
+                    _GRAD_SLOTS[p.data_ptr()] = (v, weakref.ref(p), self)
+
+    def _ensure_flat(self, bi):
+        if self._flat[bi] is None:
+            bucket = self.buckets[bi]
+            offs, total = [], 0
+            for p in bucket:
+                offs.append(total)
+                total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            flat = torch.zeros(total, dtype=bucket[0].dtype, device=bucket[0].device)
+            self._flat[bi] = flat
+            self._views[bi] = [flat[o:o + p.numel()] for o, p in zip(offs, bucket)]
+        return self._flat[bi], self._views[bi]
+
+    def _gather(self, bi):
+        """Bring the bucket's gradients into its flat buffer; returns (flat, [(param, slot view)] of those with a gradient)."""
+        flat, views = self._ensure_flat(bi)
+        have, src, dst = [], [], []
+        for p, v in zip(self.buckets[bi], views):
+            if p.grad is None:
+                continue
+            have.append((p, v))
+            if p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad.reshape(-1))
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        return flat, have
+
+    @staticmethod
+    def _rebind(have):
+        for p, v in have:
+            if p.grad.data_ptr() != v.data_ptr():
+                p.grad = v.view(p.shape)
 
     def all_reduce(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if not self._active:
             return
         works = []
-        for bucket in self.buckets:
-            grads = [p.grad for p in bucket if p.grad is not None]
-            if not grads:
-                continue
-            flat = torch._utils._flatten_dense_tensors(grads)
-            works.append((dist.all_reduce(flat, async_op=True), flat, grads))
-        for work, flat, grads in works:
+        for bi in range(len(self.buckets)):
+            flat, have = self._gather(bi)
+            if have:
+                works.append((dist.all_reduce(flat, async_op=True), have))
+        for work, have in works:
             work.wait()
-            for g, synced in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(synced)
+            self._rebind(have)
+        self._handed_out.clear()
 
 
 class OverlappedGradientBuckets(GradientBuckets):
@@ -161,7 +234,6 @@ class OverlappedGradientBuckets(GradientBuckets):
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 self._bucket_of[id(p)] = bi
-        self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._reset()
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if self._active else []
 
@@ -171,16 +243,16 @@ class OverlappedGradientBuckets(GradientBuckets):
         self._launched = [None] * len(self.buckets)
 
     def _launch(self, bi):
-        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
-        if not grads:
+        if not any(p.grad is not None for p in self.buckets[bi]):
             self._launched[bi] = False
             return
-        if grads[0].is_cuda:
-            cur = torch.cuda.current_stream(grads[0].device)
+        dev = self.buckets[bi][0].device
+        if dev.type == "cuda":
+            cur = torch.cuda.current_stream(dev)
             for ev in self._events[bi]:
                 cur.wait_event(ev)
-        flat = torch._utils._flatten_dense_tensors(grads)
-        self._launched[bi] = (dist.all_reduce(flat, async_op=True), flat, grads)
+        flat, have = self._gather(bi)
+        self._launched[bi] = (dist.all_reduce(flat, async_op=True), have)
 
     def _on_grad(self, p):
         bi = self._bucket_of[id(p)]
@@ -204,10 +276,10 @@ class OverlappedGradientBuckets(GradientBuckets):
         for item in self._launched:
             if not item:
                 continue
-            work, flat, grads = item
+            work, have = item
             work.wait()
-            for g, synced in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(synced)
+            self._rebind(have)
+        self._handed_out.clear()
         self._reset()
 
     def remove_hooks(self):

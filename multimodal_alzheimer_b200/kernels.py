@@ -228,10 +228,17 @@ def register_arena(arena):
     _ARENAS.add(arena)
 
 
-def wgrad_to_param_layout(dw_oti, shape, out=None):
-    """fp32 [Cout, taps, Cin] -> fp32 parameter-shaped gradient [Cout, Cin, kd, kh, kw]."""
+def wgrad_to_param_layout(dw_oti, shape, out=None, dst=None):
+    """fp32 [Cout, taps, Cin] -> fp32 parameter-shaped gradient [Cout, Cin, kd, kh, kw].  `out`: accumulate into it;
+    `dst`: write into it (a slot of a data-parallel gradient bucket, data_parallel.grad_slot)."""
     cout, cin = shape[0], shape[1]
     taps = dw_oti.shape[1]
+    if dst is not None:
+        if taps == 1:
+            dst.copy_(dw_oti.view(shape))
+        else:
+            call("adni_wgrad_to_param_layout", ptr(dw_oti), cout, cin, taps, ptr(dst), 0, stream_ptr())
+        return dst
     if taps == 1 and out is None:      # 1x1x1 convs: [Cout][1][Cin] IS the parameter layout - no copy
         return dw_oti.view(shape)
     accumulate = out is not None

@@ -47,6 +47,67 @@ def _bucket_fn(rank, world):
     return [None if p.grad is None else float(p.grad[0]) for p in params]
 
 
+def _slot_fn(rank, world):
+    """Gradient slots: a gradient produced INSIDE its bucket slot (what the wgrad layout kernel does through
+    data_parallel.grad_slot) is adopted by autograd as `.grad`, reduced in place and never copied; gradients produced
+    elsewhere are gathered; after all_reduce() every `.grad` is a view of the bucket's flat buffer; a parameter that
+    already holds a gradient, or a slot handed out twice in one backward pass, falls back to ordinary allocation."""
+    from multimodal_alzheimer_b200 import data_parallel as dp
+
+    class SlotGrad(torch.autograd.Function):      # stands in for the conv Functions: writes dW where grad_slot says
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.ptr, ctx.shape = w.data_ptr(), w.shape
+            ctx.save_for_backward(x)
+            return (x * w).sum()
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,) = ctx.saved_tensors
+            slot = dp.grad_slot(ctx.ptr)
+            dw = x * g
+            if slot is not None:
+                slot.copy_(dw)
+                dw = slot
+            return None, dw
+
+    torch.manual_seed(0)
+    w_in = torch.nn.Parameter(torch.ones(1000))
+    w_out = torch.nn.Parameter(torch.ones(333))
+    w_twice = torch.nn.Parameter(torch.ones(50))
+    params = [w_in, w_out, w_twice]
+    b = dp.GradientBuckets(params, bucket_mb=0.002)
+    res = {}
+    for step in range(2):
+        x = torch.full((1000,), float(rank + 1 + step))
+        loss = SlotGrad.apply(x, w_in) + (w_out * 2.0 * (rank + 1)).sum() + SlotGrad.apply(x[:50], w_twice) \
+            + SlotGrad.apply(x[:50], w_twice)
+        loss.backward()
+        flat_of = {id(p): (bi, v) for bi in range(len(b.buckets)) for p, v in zip(b.buckets[bi], b._views[bi])}
+        res[f"in_place_before_{step}"] = w_in.grad.data_ptr() == flat_of[id(w_in)][1].data_ptr()
+        b.all_reduce()
+        res[f"views_{step}"] = all(p.grad.data_ptr() == flat_of[id(p)][1].data_ptr() for p in params)
+        res[f"vals_{step}"] = [float(w_in.grad[0]), float(w_out.grad[0]), float(w_twice.grad[0])]
+        for p in params:
+            p.grad = None
+    # a parameter that still holds a gradient gets no slot (autograd would accumulate into it)
+    w_in.grad = torch.zeros_like(w_in)
+    res["slot_with_grad"] = dp.grad_slot(w_in) is None
+    return res
+
+
+def test_gradient_slots_reduce_in_place():
+    out = _run(_slot_fn)
+    for rank in range(2):
+        r = out[rank]
+        for step in range(2):
+            tot = sum(k + 1 + step for k in range(2))
+            assert r[f"in_place_before_{step}"], "autograd did not adopt the slot view as .grad"
+            assert r[f"views_{step}"]
+            assert r[f"vals_{step}"] == [float(tot), 2.0 * 3, 2.0 * tot]
+        assert r["slot_with_grad"]
+
+
 def test_gradient_buckets_sum_across_ranks():
     out = _run(_bucket_fn)
     tot = sum(r + 1 for r in range(2))

@@ -77,11 +77,16 @@ product.to(dev).train()
 raw = W.synth_batch(0, B, volume, w["modalities"])          # the whole global batch on every rank (CPU), sliced below
 raw["label"][0], raw["label"][-1] = 0, 2
 shard = {k: v[lo:hi].to(dev) for k, v in raw.items()}
+params = [p for p in product.parameters() if p.requires_grad]
+buckets = dp.make_gradient_buckets(params)   # before backward: the wgrad kernels write into the bucket slots (dp.grad_slot)
 out = product.general_step(W.normalized_batch_gpu(shard), 0, "train")
 out["loss"].backward()
-params = [p for p in product.parameters() if p.requires_grad]
-dp.make_gradient_buckets(params).all_reduce()
+in_slots = sum(1 for bi in range(len(buckets.buckets)) for p, v in zip(buckets.buckets[bi], buckets._views[bi])
+               if p.grad is not None and p.grad.data_ptr() == v.data_ptr())
+buckets.all_reduce()
 torch.cuda.synchronize()
+if rank == 0:
+    print(f"gradient slots: {in_slots} of {len(params)} gradients were produced inside their bucket slot")
 
 # all ranks must hold bit-identical gradients after the exchange
 flat = torch.cat([p.grad.flatten() for p in params if p.grad is not None])
