@@ -401,6 +401,19 @@ size_t adni_peer_buffer_bytes(int world, int max_n);
 int adni_peer_allreduce_f64(double* data, int n, const void* peers, void* call_counter, int rank, int world, int max_n,
                             void* stream);
 
+/* Two-shot all-reduce (sum, in place) of a range of the fp32 gradient bucket over NVLink peer memory: the gradient
+ * exchange of the data-parallel step (the reference's optimizers see full-batch gradients, anat_cnn.py:111-128,
+ * anat_pet_fusion.py:94-118; it is single-GPU itself).  The bucket of every rank is a symmetric-memory buffer;
+ * `data_peers` / `flag_peers` are DEVICE arrays of `world` pointers (uint64): this process's mappings of every rank's
+ * bucket and of every rank's flag buffer (adni_peer_grad_flag_bytes() bytes, zeroed before the first call).
+ * [elem_offset, elem_offset + n) is the range reduced by this call (multiples of 4 elements).  `call_counter`
+ * (device uint64) and `arrive_counter` (device uint32) are zero-initialised and private to this (rank, flag buffer).
+ * Rank r sums the r-th slice of the range over all ranks in rank order and writes it back to all ranks: results are
+ * bit-identical on every rank and deterministic.  Every rank must issue the same sequence of calls. */
+size_t adni_peer_grad_flag_bytes(void);
+int adni_peer_allreduce_f32(long long elem_offset, long long n, const void* data_peers, const void* flag_peers,
+                            void* call_counter, void* arrive_counter, int rank, int world, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "adni_wgrad_to_param_layout": [_P, _I, _I, _I, _P, _I, _P],
     "adni_peer_buffer_bytes": [_I, _I],
     "adni_peer_allreduce_f64": [_P, _I, _P, _P, _I, _I, _I, _P],
+    "adni_peer_grad_flag_bytes": [],
+    "adni_peer_allreduce_f32": [_LL, _LL, _P, _P, _P, _P, _I, _I, _I, _P],
     "adni_volumes_to_ndhwc_bf16": [_P, _I, _I, _I, _LL, _P, _P],
     "adni_maxout_fwd": [_P, _P, _P, _LL, _P],
     "adni_maxout_bwd": [_P, _P, _P, _P, _P, _LL, _P],
@@ -111,6 +113,7 @@ _RESTYPES = {
     "adni_stem_x8_elems": ctypes.c_longlong,
     "adni_quantile_workspace_bytes": ctypes.c_size_t,
     "adni_peer_buffer_bytes": ctypes.c_size_t,
+    "adni_peer_grad_flag_bytes": ctypes.c_size_t,
     "adni_conv3d_wgrad_scratch_floats": ctypes.c_longlong,
 }
 

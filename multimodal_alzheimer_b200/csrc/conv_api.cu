@@ -16,6 +16,7 @@
 namespace adni {
 
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream);
+int launch_igemm_multi(const IgemmMulti& pm, int block_n, cudaStream_t stream);
 int launch_wgrad2(const WgradParams& p, int mt_cfg, cudaStream_t stream, const W2Sched* sk = nullptr);
 int wgrad2_box_rows(int mt_cfg);
 bool wgrad_halo_supported(const adni_conv3d_geom& g);
@@ -319,6 +320,12 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
       addend ? parity_views(addend, g.D, g.H, g.W, g.Cin, g.stride) : std::vector<View>();
   const std::vector<int> ext_d{Do}, ext_h{Ho}, ext_w{Wo};
 
+  // stride > 1: the parity classes of dx are independent problems with the same tile shape -> ONE launch
+  static const bool multi_on = env_int("ADNI_DGRAD_MULTI", 1) != 0;
+  const bool multi = multi_on && g.stride > 1 && g.stride * g.stride * g.stride <= kMaxMultiProblems;
+  std::vector<IgemmMulti> pm_store(multi ? 1 : 0);
+  IgemmMulti* pm = multi ? pm_store.data() : nullptr;
+  if (pm) pm->ncls = 0;
   int cls = 0;
   for (int pd = 0; pd < g.stride; pd++)
     for (int ph = 0; ph < g.stride; ph++)
@@ -396,9 +403,14 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
           p.stat_sum = red->sum_g;
           p.stat_sq = red->sum_gy;
         }
+        if (pm) {
+          pm->cls[pm->ncls++] = p;
+          continue;
+        }
         rc = launch_igemm(p, block_n, stream);
         if (rc) return rc;
       }
+  if (pm && pm->ncls > 0) return launch_igemm_multi(*pm, block_n, stream);
   return ADNI_OK;
 }
 

@@ -44,6 +44,13 @@ struct IgemmParams {
   int debug;  // diagnostics only (ADNI_DEBUG_MODE): 1 = no MMA issue, 2 = no TMA loads, 3 = no epilogue stores
 };
 
+// up to 8 independent fprop / dgrad problems of one tile shape in one launch (the parity classes of a stride-2 dgrad)
+constexpr int kMaxMultiProblems = 8;
+struct IgemmMulti {
+  IgemmParams cls[kMaxMultiProblems];
+  int ncls;
+};
+
 constexpr int kSkMaxCtas = 160;   // CTAs a stream-K schedule table holds (>= the SM count)
 struct SkNone {
   int unused;

@@ -16,6 +16,8 @@
 // + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bf16 global, fused bias / residual-gradient
 // add / BatchNorm sum & sum-of-squares).  Two TMEM accumulators let the epilogue of tile i overlap the
 // mainloop of tile i+1.
+#include <algorithm>
+
 #include "conv_igemm.cuh"
 
 namespace adni {
@@ -86,7 +88,7 @@ struct IgemmCfg {
 };
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+__device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
   pdl_trigger();   // PDL (common.cuh): the next kernel of the stream may be scheduled once every CTA of this grid has started
   using Cfg = IgemmCfg<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -530,6 +532,20 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
   }
 }
 
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+  igemm_kmajor_body<BLOCK_N, STAGES>(p);
+}
+
+// Several independent problems of one shape family in ONE launch: blockIdx.y selects the problem, the CTAs of a row
+// walk that problem's tiles.  A stride-2 dgrad is 8 such problems (the parity classes of dx, each with its own tap
+// subset and output view); as 8 launches of ~15 us each they cost 0.25 ms per layer2.0-type block at the 8-GPU per-rank
+// batch whatever the batch size (profiles/r02_b4_launch_summary.md).
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_multi_kernel(const __grid_constant__ IgemmMulti pm) {
+  igemm_kmajor_body<BLOCK_N, STAGES>(pm.cls[blockIdx.y]);
+}
+
 // =================================================================================================
 // Launchers
 // =================================================================================================
@@ -550,6 +566,41 @@ static int launch_igemm_t(const IgemmParams& p, cudaStream_t stream) {
   count_launch();
   ADNI_LAUNCH_CHECK("igemm_kmajor_kernel");
   return ADNI_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_igemm_multi_t(const IgemmMulti& pm, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N, STAGES>;
+  auto kern = igemm_kmajor_multi_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADNI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int max_tiles = 1;
+  for (int c = 0; c < pm.ncls; c++) {
+    const IgemmParams& p = pm.cls[c];
+    max_tiles = std::max(max_tiles, p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles);
+  }
+  const int per_cls = std::max(1, std::min(max_tiles, num_sms() / pm.ncls));   // one resident wave over all problems
+  pdl_launch(kern, dim3(per_cls, pm.ncls, 1), kIgemmThreads, Cfg::SMEM_BYTES, stream)(pm);
+  count_launch();
+  ADNI_LAUNCH_CHECK("igemm_kmajor_multi_kernel");
+  return ADNI_OK;
+}
+
+int launch_igemm_multi(const IgemmMulti& pm, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 64:
+      return launch_igemm_multi_t<64, 8>(pm, stream);
+    case 128:
+      return launch_igemm_multi_t<128, 6>(pm, stream);
+    case 256:
+      return launch_igemm_multi_t<256, 4>(pm, stream);
+    default:
+      set_error("igemm: unsupported BLOCK_N %d", block_n);
+      return ADNI_ENOTSUP;
+  }
 }
 
 int launch_igemm(const IgemmParams& p, int block_n, cudaStream_t stream) {

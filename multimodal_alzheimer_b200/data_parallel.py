@@ -133,59 +133,113 @@ def grad_slot(w):
     return view.view(param.shape)      # a fresh tensor object: autograd adopts it (use count 1) instead of cloning
 
 
+class _PeerArena:
+    """A flat fp32 gradient arena in symmetric memory plus the flag buffer / counters of csrc/peer_reduce.cu's two-shot
+    NVLink all-reduce (adni_peer_allreduce_f32).  Construction is collective (all ranks, same order)."""
+
+    def __init__(self, numel, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.flat = symm.empty(numel, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.flags = symm.empty(int(lib.adni_peer_grad_flag_bytes()) // 8, dtype=torch.int64, device=device)
+        self.flags.zero_()
+        self._h_data = symm.rendezvous(self.flat, dist.group.WORLD)
+        self._h_flags = symm.rendezvous(self.flags, dist.group.WORLD)
+        self.data_peers = torch.tensor([int(p) for p in self._h_data.buffer_ptrs], dtype=torch.int64, device=device)
+        self.flag_peers = torch.tensor([int(p) for p in self._h_flags.buffer_ptrs], dtype=torch.int64, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+        self.arrive = torch.zeros(1, dtype=torch.int32, device=device)
+        # CTAs of 256 threads: two per SM keep (world x 4) float4 loads per thread in flight on every SM (measured on
+        # 2 x B200: 16 / 32 / 64 CTAs = 9.64 / 8.90 / 8.60 ms per step at 4 pairs per rank - the kernel is latency-bound)
+        self.ctas = int(os.environ.get("ADNI_PEER_GRAD_CTAS", str(2 * torch.cuda.get_device_properties(device).multi_processor_count)))
+        torch.cuda.synchronize(device)
+        dist.barrier()  # every buffer is zeroed before any rank touches a peer
+
+    def all_reduce_range(self, start, end):
+        from . import _lib
+        _lib.call("adni_peer_allreduce_f32", start, end - start, _lib.ptr(self.data_peers), _lib.ptr(self.flag_peers),
+                  _lib.ptr(self.counter), _lib.ptr(self.arrive), self.rank, self.world, self.ctas, _lib.stream_ptr())
+
+
+# ADNI_PEER_GRADS: "1" (default) = gradient buckets live in symmetric memory and are summed by our own two-shot NVLink
+# kernel; if symmetric memory cannot be set up the exchange goes through NCCL with a warning on every rank's stderr
+# and `gradient_exchange_status()` says so; "require" = raise instead; "0" = NCCL.
+_PEER_GRADS_MODE = os.environ.get("ADNI_PEER_GRADS", "1")
+_GRAD_STATUS = {"mode": "unused", "error": None}
+
+
+def gradient_exchange_status():
+    return dict(_GRAD_STATUS)
+
+
 class GradientBuckets:
     """Sum parameter gradients across ranks in ~bucket_mb buckets, last-produced gradients first (the order the
-    backward pass finishes them).  Every bucket owns a persistent flat buffer; a gradient that already lives in its
-    slot (written there by the wgrad kernels through `grad_slot`) is reduced in place, the others are gathered with
-    one multi-tensor copy, and after the all-reduce `p.grad` is REBOUND to the slot view - there is no copy back."""
+    backward pass finishes them).  All gradients of a (device, dtype) group share one persistent flat ARENA (in
+    symmetric memory when the NVLink kernel is used); a bucket is a contiguous range of it.  A gradient that already
+    lives in its slot (written there by the wgrad kernels through `grad_slot`) is reduced in place, the others are
+    gathered with one multi-tensor copy, and after the all-reduce `p.grad` is REBOUND to the slot view - there is no
+    copy back."""
 
     ALIGN = 64   # elements: 256-byte slot alignment (the Adam kernel reads gradients as float4)
 
     def __init__(self, params, bucket_mb=64):
         self.params = [p for p in params if p.requires_grad]
-        self.buckets = []
-        cur, cur_bytes, cur_key = [], 0, None
-        for p in reversed(self.params):
-            key = (p.device, p.dtype)
-            if cur and key != cur_key:
-                self.buckets.append(cur)
-                cur, cur_bytes = [], 0
-            cur_key = key
-            cur.append(p)
-            cur_bytes += p.numel() * p.element_size()
-            if cur_bytes >= bucket_mb * (1 << 20):
-                self.buckets.append(cur)
-                cur, cur_bytes = [], 0
-        if cur:
-            self.buckets.append(cur)
-        self._flat = [None] * len(self.buckets)
-        self._views = [None] * len(self.buckets)
-        self._handed_out = set()
         self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if self._active:
-            import weakref
-            for bi in range(len(self.buckets)):
-                self._ensure_flat(bi)
-                for p, v in zip(self.buckets[bi], self._views[bi]):
-                    _GRAD_SLOTS[p.data_ptr()] = (v, weakref.ref(p), self)
-
-    def _ensure_flat(self, bi):
-        if self._flat[bi] is None:
-            bucket = self.buckets[bi]
+        self.buckets, self._views, self._ranges, self._arenas = [], [], [], []
+        self._handed_out = set()
+        groups = {}
+        for p in reversed(self.params):
+            groups.setdefault((p.device, p.dtype), []).append(p)
+        for (device, dtype), plist in groups.items():
             offs, total = [], 0
-            for p in bucket:
+            for p in plist:
                 offs.append(total)
                 total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-            flat = torch.zeros(total, dtype=bucket[0].dtype, device=bucket[0].device)
-            self._flat[bi] = flat
-            self._views[bi] = [flat[o:o + p.numel()] for o, p in zip(offs, bucket)]
-        return self._flat[bi], self._views[bi]
+            ai = len(self._arenas)
+            self._arenas.append(self._make_arena(total, dtype, device) if self._active else None)
+            limit = bucket_mb * (1 << 20) / plist[0].element_size()
+            cur, start = [], 0
+            for i, (p, o) in enumerate(zip(plist, offs)):
+                cur.append((p, o))
+                end = offs[i + 1] if i + 1 < len(plist) else total
+                if end - start >= limit or i + 1 == len(plist):
+                    self.buckets.append([q for q, _ in cur])
+                    self._ranges.append((ai, start, end))
+                    flat = self._arenas[ai]["flat"] if self._arenas[ai] else None
+                    self._views.append([flat[oo:oo + q.numel()] for q, oo in cur] if flat is not None else None)
+                    cur, start = [], end
+        if self._active:
+            import weakref
+            for bucket, views in zip(self.buckets, self._views):
+                for p, v in zip(bucket, views):
+                    _GRAD_SLOTS[p.data_ptr()] = (v, weakref.ref(p), self)
+
+    @staticmethod
+    def _make_arena(numel, dtype, device):
+        if device.type == "cuda" and dtype == torch.float32 and _PEER_GRADS_MODE != "0" and not _GRAD_STATUS.get("disabled"):
+            try:
+                peer = _PeerArena(numel, device)
+                _GRAD_STATUS["mode"] = "peer (two-shot NVLink kernel)"
+                return {"flat": peer.flat, "peer": peer}
+            except Exception as e:  # noqa: BLE001 - reported, never silent
+                if _PEER_GRADS_MODE == "require":
+                    raise
+                _GRAD_STATUS.update(mode=f"nccl (peer gradient all-reduce unavailable: {type(e).__name__})", error=str(e),
+                                    disabled=True)
+                import sys
+                print(f"[adni_b200 rank {dist.get_rank()}] WARNING: NVLink gradient all-reduce unavailable "
+                      f"({type(e).__name__}: {e}); gradient buckets go through NCCL", file=sys.stderr, flush=True)
+        if _GRAD_STATUS["mode"] == "unused":
+            _GRAD_STATUS["mode"] = "nccl" if device.type == "cuda" else str(dist.get_backend())
+        return {"flat": torch.zeros(numel, dtype=dtype, device=device), "peer": None}
 
     def _gather(self, bi):
-        """Bring the bucket's gradients into its flat buffer; returns (flat, [(param, slot view)] of those with a gradient)."""
-        flat, views = self._ensure_flat(bi)
+        """Bring the bucket's gradients into its slots; returns [(param, slot view)] of those with a gradient."""
         have, src, dst = [], [], []
-        for p, v in zip(self.buckets[bi], views):
+        for p, v in zip(self.buckets[bi], self._views[bi]):
             if p.grad is None:
                 continue
             have.append((p, v))
@@ -194,7 +248,16 @@ class GradientBuckets:
                 dst.append(v)
         if dst:
             torch._foreach_copy_(dst, src)
-        return flat, have
+        return have
+
+    def _reduce(self, bi):
+        """Start the all-reduce of bucket bi (its gradients are gathered); returns a work handle or None (stream-ordered)."""
+        ai, start, end = self._ranges[bi]
+        arena = self._arenas[ai]
+        if arena["peer"] is not None:
+            arena["peer"].all_reduce_range(start, end)
+            return None
+        return dist.all_reduce(arena["flat"][start:end], async_op=True)
 
     @staticmethod
     def _rebind(have):
@@ -207,13 +270,24 @@ class GradientBuckets:
             return
         works = []
         for bi in range(len(self.buckets)):
-            flat, have = self._gather(bi)
+            have = self._gather(bi)
             if have:
-                works.append((dist.all_reduce(flat, async_op=True), have))
+                works.append((self._reduce(bi), have))
         for work, have in works:
-            work.wait()
+            if work is not None:
+                work.wait()
             self._rebind(have)
         self._handed_out.clear()
+
+
+class _EventWork:
+    """work.wait() for a stream-ordered exchange issued on a side stream: the current stream waits for its event."""
+
+    def __init__(self, event, device):
+        self.event, self.device = event, device
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_event(self.event)
 
 
 class OverlappedGradientBuckets(GradientBuckets):
@@ -234,6 +308,7 @@ class OverlappedGradientBuckets(GradientBuckets):
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 self._bucket_of[id(p)] = bi
+        self._side = {}
         self._reset()
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if self._active else []
 
@@ -247,12 +322,29 @@ class OverlappedGradientBuckets(GradientBuckets):
             self._launched[bi] = False
             return
         dev = self.buckets[bi][0].device
+        ai = self._ranges[bi][0]
+        if dev.type == "cuda" and self._arenas[ai]["peer"] is not None:
+            # NVLink kernel: stream-ordered, so it runs on a SIDE stream - the backward kernels of the producing
+            # streams go on while the bucket crosses the links (the kernel has no shared memory and co-resides with
+            # the persistent conv grids); all_reduce() joins the side stream
+            side = self._side.get(dev.index)
+            if side is None:
+                side = self._side[dev.index] = torch.cuda.Stream(device=dev)
+            for ev in self._events[bi]:
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                have = self._gather(bi)
+                self._reduce(bi)
+                done = torch.cuda.Event()
+                done.record(side)
+            self._launched[bi] = (_EventWork(done, dev), have)
+            return
         if dev.type == "cuda":
             cur = torch.cuda.current_stream(dev)
             for ev in self._events[bi]:
                 cur.wait_event(ev)
-        flat, have = self._gather(bi)
-        self._launched[bi] = (dist.all_reduce(flat, async_op=True), have)
+        have = self._gather(bi)
+        self._launched[bi] = (self._reduce(bi), have)
 
     def _on_grad(self, p):
         bi = self._bucket_of[id(p)]
@@ -277,7 +369,8 @@ class OverlappedGradientBuckets(GradientBuckets):
             if not item:
                 continue
             work, have = item
-            work.wait()
+            if work is not None:
+                work.wait()
             self._rebind(have)
         self._handed_out.clear()
         self._reset()
