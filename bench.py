@@ -233,7 +233,7 @@ def run_b200(args):
     opt = model.configure_optimizers()          # the reference's per-tensor groups -> csrc/optimizer.cu
     opt = opt["optimizer"] if isinstance(opt, dict) else opt
     params = [p for p in model.parameters() if p.requires_grad]
-    buckets = dp.make_gradient_buckets(params)
+    buckets = dp.make_gradient_buckets(params, overlap=True)   # one backward pass per step: exchange during backward
 
     host_data = W.synth_batch(lo, n_local, volume, w["modalities"])   # this rank's shard of the fixed global batch
     data = {k: v.to(dev) for k, v in host_data.items()}

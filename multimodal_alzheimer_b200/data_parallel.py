@@ -291,8 +291,9 @@ class _EventWork:
 
 
 class OverlappedGradientBuckets(GradientBuckets):
-    """EXPERIMENTAL (opt-in, ADNI_OVERLAP_GRADS=1 in bench.py; not yet measured on GPUs): the same buckets, but a
-    bucket's all-reduce starts as soon as the backward pass has produced its last gradient
+    """The same buckets, but a bucket's all-reduce starts as soon as the backward pass has produced its last gradient
+    (bench.py's choice; measured +1.3 % at 8 GPUs with the NVLink kernel on a side stream, and SLOWER with NCCL, whose
+    CTAs take whole SMs away from the persistent conv grids):
     (`register_post_accumulate_grad_hook`), so that the 265 MB of gradient traffic of the two-encoder model overlaps
     the remaining dgrad / wgrad kernels instead of following them.  `all_reduce()` after `backward()` then only
     launches what is still pending (parameters without a gradient), waits and copies back.
@@ -381,8 +382,15 @@ class OverlappedGradientBuckets(GradientBuckets):
         self._handles = []
 
 
-def make_gradient_buckets(params, bucket_mb=64):
-    """GradientBuckets, or the overlapped variant when ADNI_OVERLAP_GRADS=1."""
-    if os.environ.get("ADNI_OVERLAP_GRADS", "0") == "1":
+def make_gradient_buckets(params, bucket_mb=64, overlap=None):
+    """GradientBuckets, or the variant that starts a bucket's exchange from the backward pass (one backward pass per
+    optimizer step: no gradient accumulation across backward calls).  `overlap=None`: ADNI_OVERLAP_GRADS decides
+    (default off); ADNI_OVERLAP_GRADS=0 / 1 overrides the argument.  Measured on 8 x B200 (profiles/r02_bench_dp8*.json):
+    NCCL after backward 9.22 ms per step, NVLink kernel after backward 9.15, NVLink kernel on a side stream during
+    backward 9.04."""
+    env = os.environ.get("ADNI_OVERLAP_GRADS")
+    if env is not None:
+        overlap = env == "1"
+    if overlap:
         return OverlappedGradientBuckets(params, bucket_mb)
     return GradientBuckets(params, bucket_mb)
