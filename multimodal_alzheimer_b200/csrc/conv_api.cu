@@ -42,6 +42,16 @@ int direct_conv_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const 
 int direct_conv_wgrad(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
                       float* dbias, cudaStream_t stream);
 
+void finish_igemm_params(IgemmParams& p) {
+  const long long total = static_cast<long long>(p.N) * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int d[4] = {p.n_tiles, p.tiles_w, p.tiles_h, p.tiles_d};
+  p.fd_ok = 1;
+  for (int i = 0; i < 4; i++) {
+    if (d[i] <= 0 || total * d[i] >= (1LL << 32)) p.fd_ok = 0;
+    p.fd_mul[i] = d[i] <= 1 ? 0u : static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned long long>(d[i])) + 1u;
+  }
+}
+
 namespace {
 
 struct View {  // a strided 5-D (N, D, H, W, C) view of an NDHWC bf16 tensor
@@ -216,8 +226,84 @@ int tc_halo(const adni_conv3d_geom& g, const __nv_bfloat16* a, const __nv_bfloat
   return launch_igemm_halo(p, C, stream);
 }
 
+// 1x1x1 stride-1 convs are plain GEMMs over the flattened positions: out[M, n_out] = a[M, k_in] * w[n_out, k_in]^T
+// (+ addend).  The flat path of the tap-per-box kernel: 128 consecutive positions per tile, TMA-store epilogue.
+bool flat_1x1(const adni_conv3d_geom& g, const float* bias) {
+  static const bool on = env_int("ADNI_FLAT_1X1", 1) != 0;
+  const long long m = static_cast<long long>(g.N) * g.D * g.H * g.W;
+  return on && g.k == 1 && g.stride == 1 && g.pad == 0 && bias == nullptr && m < (1LL << 31);
+}
+
+int tc_flat_gemm(long long m_rows, int k_in, int n_out, const __nv_bfloat16* a, const __nv_bfloat16* w, const __nv_bfloat16* addend,
+                 __nv_bfloat16* out, double* ssum, double* ssq, cudaStream_t stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int M = static_cast<int>(m_rows);
+  View v;
+  v.base = a;
+  v.D = 1;
+  v.H = 1;
+  v.W = M;
+  v.sw = k_in;
+  v.sh = v.sd = v.sn = static_cast<long long>(M) * k_in;
+  const Box b{1, 1, 128};
+  int rc = encode_view(&p.a_maps[0], v, k_in, b, 1);
+  if (rc) return rc;
+  p.a_ext[0][0] = 1;
+  p.a_ext[0][1] = 1;
+  p.a_ext[0][2] = M;
+  const int block_n = pick_block_n(n_out);
+  {
+    const uint64_t dims[2] = {uint64_t(k_in), uint64_t(n_out)};
+    const uint64_t strides[2] = {1, uint64_t(k_in)};
+    const uint32_t box[2] = {64, uint32_t(block_n)};
+    rc = make_tmap_bf16(&p.b_map, w, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(n_out), uint64_t(M)};
+    const uint64_t strides[2] = {1, uint64_t(n_out)};
+    const uint32_t box[2] = {64, 32};
+    rc = make_tmap_bf16(&p.out_map, out, 2, dims, strides, box, true);
+    if (rc) return rc;
+    if (addend != nullptr) {
+      rc = make_tmap_bf16(&p.add_map, addend, 2, dims, strides, box, true);
+      if (rc) return rc;
+    }
+  }
+  p.taps[0].map = 0;
+  p.taps[0].dd = p.taps[0].dh = p.taps[0].dw = 0;
+  p.taps[0].kofs = 0;
+  p.ntaps = 1;
+  p.kc_blocks = k_in / 64;
+  p.N = 1;
+  p.Do = p.Ho = 1;
+  p.Wo = M;
+  p.bd = p.bh = 1;
+  p.bw = 128;
+  p.tiles_d = p.tiles_h = 1;
+  p.tiles_w = (M + 127) / 128;
+  p.n_tiles = n_out / block_n;
+  p.n_total = n_out;
+  p.out_sw = n_out;
+  p.out_sh = p.out_sd = p.out_sn = static_cast<long long>(M) * n_out;
+  p.out = out;
+  p.addend = addend;
+  p.stat_sum = ssum;
+  p.stat_sq = ssq;
+  p.flat = 1;
+  {
+    const char* dbg = getenv("ADNI_DEBUG_MODE");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  finish_igemm_params(p);
+  return launch_igemm(p, block_n, stream);
+}
+
 int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloat16* w_oti, const float* bias,
              __nv_bfloat16* y, double* ssum, double* ssq, cudaStream_t stream) {
+  if (flat_1x1(g, bias))
+    return tc_flat_gemm(static_cast<long long>(g.N) * g.D * g.H * g.W, g.Cin, g.Cout, x, w_oti, nullptr, y, ssum, ssq, stream);
   if (halo_supported(g)) {
     const int rc = tc_halo(g, x, w_oti, false, bias, nullptr, y, ssum, ssq, stream);
     if (rc != ADNI_ENOTSUP) return rc;
@@ -291,12 +377,15 @@ int tc_fprop(const adni_conv3d_geom& g, const __nv_bfloat16* x, const __nv_bfloa
     const char* dbg = getenv("ADNI_DEBUG_MODE");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  finish_igemm_params(p);
   return launch_igemm(p, block_n, stream);
 }
 
 // dx = sum_k dy[(i + pad - k*dil)/stride] * w[k]^T, one launch per parity class of dx when stride > 1.
 int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w_ito,
              const __nv_bfloat16* addend, __nv_bfloat16* dx, cudaStream_t stream, const BnReduceEpilogue* red = nullptr) {
+  if (red == nullptr && flat_1x1(g, nullptr))   // dx[M, Cin] = dy[M, Cout] * w_ito[Cin, Cout]^T (+ addend)
+    return tc_flat_gemm(static_cast<long long>(g.N) * g.D * g.H * g.W, g.Cout, g.Cin, dy, w_ito, addend, dx, nullptr, nullptr, stream);
   if (halo_supported(g)) {
     const int rc = tc_halo(g, dy, w_ito, true, nullptr, addend, dx, nullptr, nullptr, stream, red);
     if (rc != ADNI_ENOTSUP) return rc;
@@ -403,6 +492,7 @@ int tc_dgrad(const adni_conv3d_geom& g, const __nv_bfloat16* dy, const __nv_bflo
           p.stat_sum = red->sum_g;
           p.stat_sq = red->sum_gy;
         }
+        finish_igemm_params(p);
         if (pm) {
           pm->cls[pm->ncls++] = p;
           continue;

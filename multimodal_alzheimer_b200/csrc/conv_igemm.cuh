@@ -42,7 +42,20 @@ struct IgemmParams {
   const float* red_scale;         // [N_total], nullable
   const float* red_shift;
   int debug;  // diagnostics only (ADNI_DEBUG_MODE): 1 = no MMA issue, 2 = no TMA loads, 3 = no epilogue stores
+  // tile-index decoding without divisions: fd_mul[i] = floor(2^32 / d_i) + 1 (0 for d_i == 1) for d = (n_tiles, tiles_w,
+  // tiles_h, tiles_d); fd_ok = the products stay below 2^32 (set by finish_igemm_params)
+  uint32_t fd_mul[4];
+  int fd_ok;
+  // 1x1x1 stride-1 problems are plain GEMMs over the flattened positions (`flat` = 1: N = D = H = 1, W = all positions,
+  // box = 128 consecutive rows): the epilogue stages 32-row x 64-channel bf16 blocks per warp and hands them to TMA
+  // (out_map / add_map: 2-D (channels, positions) views of out / addend, box (64, 32), 128-byte swizzle).
+  int flat;
+  CUtensorMap out_map;
+  CUtensorMap add_map;
 };
+
+// host: fills fd_mul / fd_ok from the tile counts (call after every other field is set)
+void finish_igemm_params(IgemmParams& p);
 
 // up to 8 independent fprop / dgrad problems of one tile shape in one launch (the parity classes of a stride-2 dgrad)
 constexpr int kMaxMultiProblems = 8;

@@ -47,17 +47,37 @@ struct TileCoord {
   int n, d0, h0, w0, n0;
 };
 
+// n / d with the host-side multiplier floor(2^32 / d) + 1 (0 for d == 1): exact while n * d < 2^32 (IgemmParams::fd_mul)
+__device__ __forceinline__ int fdiv(int n, uint32_t mul) {
+  return mul ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul)) : n;
+}
+
 template <int BLOCK_N>
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord c;
-  const int nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
-  const int tw = m % p.tiles_w;
-  m /= p.tiles_w;
-  const int th = m % p.tiles_h;
-  m /= p.tiles_h;
-  const int td = m % p.tiles_d;
-  c.n = m / p.tiles_d;
+  int m, nt, tw, th, td;
+  if (p.fd_ok) {   // four divisions by run-time constants per tile and warp are ~80 instructions as real divisions
+    m = fdiv(tile, p.fd_mul[0]);
+    nt = tile - m * p.n_tiles;
+    int q = fdiv(m, p.fd_mul[1]);
+    tw = m - q * p.tiles_w;
+    m = q;
+    q = fdiv(m, p.fd_mul[2]);
+    th = m - q * p.tiles_h;
+    m = q;
+    q = fdiv(m, p.fd_mul[3]);
+    td = m - q * p.tiles_d;
+    c.n = q;
+  } else {
+    nt = tile % p.n_tiles;
+    m = tile / p.n_tiles;
+    tw = m % p.tiles_w;
+    m /= p.tiles_w;
+    th = m % p.tiles_h;
+    m /= p.tiles_h;
+    td = m % p.tiles_d;
+    c.n = m / p.tiles_d;
+  }
   c.d0 = td * p.bd;
   c.h0 = th * p.bh;
   c.w0 = tw * p.bw;
@@ -74,18 +94,211 @@ struct IgemmCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  // epilogue staging right after the stages (1024-byte aligned: the TMA-store blocks of the flat path are 128-byte
+  // swizzled); the fp32 staging of the box path and the four 4 KB bf16 blocks of the flat path share it
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STG_PITCH = 36;
+  static constexpr int STG_BYTES = 19 * 1024;   // >= 4 * 32 * STG_PITCH * 4 = 18432 and >= 4 * 4096
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int STAT_OFF = BAR_OFF + 256;
   static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 4;
   // epilogue staging: one 32-row x 32-column fp32 chunk per epilogue warp.  Pitch 36 floats keeps the three access
   // patterns conflict-free: STS.128 of a thread's own row, LDS.32 down a column (BatchNorm sums), LDS.128 of the
   // 8-column pieces of the coalesced store mapping.
-  static constexpr int STG_OFF = STAT_OFF + STAT_BYTES;
-  static constexpr int STG_PITCH = 36;
-  static constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;
-  static constexpr int SMEM_BYTES = STG_OFF + STG_BYTES + 1024;  // + slack for manual 1024-B alignment
+  static constexpr int SMEM_BYTES = STAT_OFF + STAT_BYTES + 1024;  // + slack for manual 1024-B alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
+
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One 32-column chunk of the staged epilogue, common case (accumulator present, no bias): `v` = this thread's row.
+template <int BLOCK_N, int PITCH, bool STATS, bool ADDEND>
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&v)[32], const uint4 (&ad)[4], int chunk, uint32_t stg, uint32_t stat0,
+                                               int lane, bool all_valid, bool row_valid, unsigned sval_mask,
+                                               __nv_bfloat16* const (&optr)[4]) {
+  const uint32_t own = stg + static_cast<uint32_t>(lane * PITCH * 4);
+  if (all_valid) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4++) sts_u4(own + j4 * 16, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+  } else {   // rows outside the output are staged as zeros: they must not count in the statistics (and are never stored)
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4++)
+      sts_u4(own + j4 * 16, row_valid ? v[j4 * 4] : 0u, row_valid ? v[j4 * 4 + 1] : 0u, row_valid ? v[j4 * 4 + 2] : 0u,
+             row_valid ? v[j4 * 4 + 3] : 0u);
+  }
+  __syncwarp();
+  if (STATS) {
+    float cs1 = 0.f, cs2 = 0.f, cs1b = 0.f, cs2b = 0.f;   // two chains: the 32 loads are independent
+    const uint32_t colp = stg + static_cast<uint32_t>(lane * 4);
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      const float x0 = lds_f1(colp + r * PITCH * 4);
+      const float x1 = lds_f1(colp + (r + 1) * PITCH * 4);
+      cs1 += x0;
+      cs2 = fmaf(x0, x0, cs2);
+      cs1b += x1;
+      cs2b = fmaf(x1, x1, cs2b);
+    }
+    sts_f1(stat0 + static_cast<uint32_t>(chunk * 128), cs1 + cs1b);
+    sts_f1(stat0 + static_cast<uint32_t>(BLOCK_N * 4 + chunk * 128), cs2 + cs2b);
+  }
+  const uint32_t rowp = stg + static_cast<uint32_t>(((lane >> 2) * PITCH + (lane & 3) * 8) * 4);
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    if (sval_mask & (1u << it)) {
+      const float4 a = lds_f4(rowp + it * 8 * PITCH * 4);
+      const float4 b = lds_f4(rowp + it * 8 * PITCH * 4 + 16);
+      float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      if (ADDEND) {
+        const uint32_t aw[4] = {ad[it].x, ad[it].y, ad[it].z, ad[it].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          o[e * 2 + 0] += bf16_lo(aw[e]);
+          o[e * 2 + 1] += bf16_hi(aw[e]);
+        }
+      }
+      *reinterpret_cast<uint4*>(optr[it] + chunk * 32) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+  __syncwarp();   // the staging block is rewritten by the next chunk
+}
+
+// One accumulator tile through the staged epilogue: two register sets alternate (the TMEM load of chunk c + 1 and its
+// addend rows are in flight while chunk c is processed), the TMEM buffer is handed back after the last load.
+template <int BLOCK_N, int PITCH, bool STATS, bool ADDEND>
+__device__ __forceinline__ void epi_tile_fast(uint32_t t_row, uint32_t stg, uint32_t stat0, int lane, bool all_valid, bool row_valid,
+                                              unsigned sval_mask, __nv_bfloat16* const (&optr)[4], const __nv_bfloat16* const (&aptr)[4],
+                                              uint64_t* tfull_bar, uint32_t tfull_phase, uint64_t* tempty_bar) {
+  constexpr int NCH = BLOCK_N / 32;
+  static_assert(NCH % 2 == 0, "chunks are processed in pairs");
+  uint4 ad_a[4], ad_b[4];
+  auto addend_prefetch = [&](uint4 (&ad)[4], int chunk) {
+    if (ADDEND) {
+#pragma unroll
+      for (int it = 0; it < 4; it++)
+        if (sval_mask & (1u << it)) ad[it] = __ldg(reinterpret_cast<const uint4*>(aptr[it] + chunk * 32));
+    }
+  };
+  addend_prefetch(ad_a, 0);   // does not depend on the accumulator
+  mbar_wait_spin(tfull_bar, tfull_phase, 2217);
+  tc_fence_after();
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32(t_row, va);
+#pragma unroll 1
+  for (int chunk = 0; chunk < NCH; chunk += 2) {
+    tmem_ld_wait();
+    tmem_ld_32x32(t_row + static_cast<uint32_t>((chunk + 1) * 32), vb);
+    addend_prefetch(ad_b, chunk + 1);
+    epi_chunk_fast<BLOCK_N, PITCH, STATS, ADDEND>(va, ad_a, chunk, stg, stat0, lane, all_valid, row_valid, sval_mask, optr);
+    tmem_ld_wait();
+    if (chunk + 2 < NCH) {
+      tmem_ld_32x32(t_row + static_cast<uint32_t>((chunk + 2) * 32), va);
+      addend_prefetch(ad_a, chunk + 2);
+    } else {   // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    epi_chunk_fast<BLOCK_N, PITCH, STATS, ADDEND>(vb, ad_b, chunk + 1, stg, stat0, lane, all_valid, row_valid, sval_mask, optr);
+  }
+}
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Flat (1x1x1, stride 1) epilogue of one accumulator tile, one warp = 32 consecutive positions.  Per 64-channel group:
+// [addend block by TMA into the warp's staging block] -> two TMEM loads -> (+ addend) -> bf16 -> swizzled STS of the own
+// row -> TMA store of the 32 x 64 block; the BatchNorm sums are column sums of the STAGED (stored) values, two columns
+// per lane.  TMEM reads (64 B / clk / SM) and the ~1000 shared-memory wavefronts per tile are what is left of the
+// ~4000 LSU wavefronts per tile of the register -> fp32 staging -> 16-byte global stores path, which held the
+// ResNet-50 1x1x1 convs at 10-13 k cycles per tile whatever the MMA / TMA / store traffic (tools/k1_probe.py).
+template <int BLOCK_N, bool STATS, bool ADDEND>
+__device__ __forceinline__ void epi_tile_flat(const IgemmParams& p, uint32_t t_row, uint32_t buf, uint32_t stat0, int lane, int row0,
+                                              int n0, uint64_t* tfull_bar, uint32_t tfull_phase, uint64_t* tempty_bar,
+                                              uint64_t* add_bar, uint32_t& add_phase) {
+  constexpr int NG = BLOCK_N / 64;
+  const uint32_t own = buf + static_cast<uint32_t>(lane * 128);
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  mbar_wait_spin(tfull_bar, tfull_phase, 2217);
+  tc_fence_after();
+#pragma unroll 1
+  for (int g = 0; g < NG; g++) {
+    const int col0 = n0 + g * 64;
+    if (lane == 0) tma_store_wait_read();   // the previous block has left the staging buffer
+    __syncwarp();
+    if (ADDEND) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(add_bar, 32 * 128);
+        tma_load_2d_u32(buf, &p.add_map, add_bar, col0, row0);
+      }
+    }
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32(t_row + static_cast<uint32_t>(g * 64), v0);
+    tmem_ld_32x32(t_row + static_cast<uint32_t>(g * 64 + 32), v1);
+    tmem_ld_wait();
+    if (g + 1 == NG) {   // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    if (ADDEND) {
+      mbar_wait_spin(add_bar, add_phase, 2218);
+      add_phase ^= 1u;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t a = own + ((static_cast<uint32_t>(j) ^ sw) << 4);
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) f[e] = __uint_as_float(j < 4 ? v0[j * 8 + e] : v1[(j - 4) * 8 + e]);
+      if (ADDEND) {
+        const uint4 ad = lds_u4(a);
+        const uint32_t aw[4] = {ad.x, ad.y, ad.z, ad.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          f[e * 2 + 0] += bf16_lo(aw[e]);
+          f[e * 2 + 1] += bf16_hi(aw[e]);
+        }
+      }
+      sts_u4(a, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && p.debug != 3) {
+      tma_store_2d_u32(&p.out_map, buf, col0, row0);
+      tma_store_commit();
+    }
+    if (STATS) {
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      const uint32_t colw = buf + static_cast<uint32_t>((lane & 3) * 4);
+      const uint32_t ch = static_cast<uint32_t>(lane >> 2);
+#pragma unroll
+      for (int r = 0; r < 32; r++) {
+        const uint32_t w = lds_u1(colw + static_cast<uint32_t>(r * 128) + ((ch ^ static_cast<uint32_t>(r & 7)) << 4));
+        const float lo = bf16_lo(w), hi = bf16_hi(w);
+        s0 += lo;
+        q0 = fmaf(lo, lo, q0);
+        s1 += hi;
+        q1 = fmaf(hi, hi, q1);
+      }
+      // columns g*64 + 2*lane, + 1 of this warp's partial sums
+      const uint32_t sa = stat0 + static_cast<uint32_t>((g * 64 + lane) * 4);   // stat0 already carries + lane * 4
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(s0), "f"(s1) : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa + static_cast<uint32_t>(BLOCK_N * 4)), "f"(q0), "f"(q1) : "memory");
+    }
+  }
+}
 
 template <int BLOCK_N, int STAGES>
 __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
@@ -99,7 +312,8 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* abar = tempty + 2;   // per epilogue warp: addend block landed (flat path)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(abar + 4);
   float* stat_smem = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);
 
   const int warp = threadIdx.x >> 5;
@@ -115,6 +329,7 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
     }
+    for (int i = 0; i < 4; i++) mbar_init(&abar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -250,13 +465,19 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
     const int rd = row / (p.bw * p.bh);
     const int srow = lane >> 2, scol = (lane & 3) * 8;
     int sw_[4], sh_[4], sd_[4];
+    long long srel[4];   // offset of the four stored rows relative to the tile origin (tile independent)
 #pragma unroll
     for (int it = 0; it < 4; it++) {
       const int rr = q * 32 + it * 8 + srow;
       sw_[it] = rr % p.bw;
       sh_[it] = (rr / p.bw) % p.bh;
       sd_[it] = rr / (p.bw * p.bh);
+      srel[it] = sd_[it] * p.out_sd + sh_[it] * p.out_sh + sw_[it] * p.out_sw + scol;
     }
+    const bool fast_ok = p.bias == nullptr && p.debug != 3;
+    const uint32_t flat_buf = smem_u32(smem + Cfg::STG_OFF) + static_cast<uint32_t>(ew * 4096);
+    uint32_t add_phase = 0;
+    const uint32_t stat0 = stat_u32 + static_cast<uint32_t>((ew * 2 * BLOCK_N + lane) * 4);
     double acc_s[NCOL], acc_q[NCOL];
 #pragma unroll
     for (int i = 0; i < NCOL; i++) acc_s[i] = acc_q[i] = 0.0;
@@ -286,7 +507,20 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
         acc_n0 = c.n0;
       }
 
-      if (do_red) {
+      if (p.flat) {
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+        const int row0 = c.w0 + q * 32;
+        if (do_stats) {
+          epi_tile_flat<BLOCK_N, true, false>(p, t_row, flat_buf, stat0, lane, row0, c.n0, &tfull[acc], accph, &tempty[acc], &abar[ew],
+                                              add_phase);
+        } else if (p.addend != nullptr) {
+          epi_tile_flat<BLOCK_N, false, true>(p, t_row, flat_buf, stat0, lane, row0, c.n0, &tfull[acc], accph, &tempty[acc], &abar[ew],
+                                              add_phase);
+        } else {
+          epi_tile_flat<BLOCK_N, false, false>(p, t_row, flat_buf, stat0, lane, row0, c.n0, &tfull[acc], accph, &tempty[acc], &abar[ew],
+                                               add_phase);
+        }
+      } else if (do_red) {
         // fused BatchNorm-backward sums: the y / mask rows of chunk c+1 are in flight while chunk c is processed, and
         // those of chunk 0 while this thread still waits for the accumulator (they do not depend on the MMA result)
         uint4 y_nxt[4], m_nxt[4];
@@ -396,6 +630,31 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+      } else if (fast_ok && has_k) {
+        // common case: accumulator present, no bias -> the specialised staged epilogue (no run-time switches inside)
+        const long long tile_off = c.n * p.out_sn + c.d0 * p.out_sd + c.h0 * p.out_sh + c.w0 * p.out_sw + c.n0;
+        const int lim_d = min(p.bd, p.Do - c.d0), lim_h = p.Ho - c.h0, lim_w = p.Wo - c.w0;
+        unsigned sval_mask = 0;
+        __nv_bfloat16* optr[4];
+        const __nv_bfloat16* aptr[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          if (sd_[it] < lim_d && sh_[it] < lim_h && sw_[it] < lim_w) sval_mask |= 1u << it;
+          optr[it] = p.out + tile_off + srel[it];
+          aptr[it] = p.addend + tile_off + srel[it];
+        }
+        const bool all_valid = __all_sync(0xffffffffu, valid);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+        if (do_stats) {
+          epi_tile_fast<BLOCK_N, PITCH, true, false>(t_row, stg, stat0, lane, all_valid, valid, sval_mask, optr, aptr, &tfull[acc],
+                                                     accph, &tempty[acc]);
+        } else if (p.addend != nullptr) {
+          epi_tile_fast<BLOCK_N, PITCH, false, true>(t_row, stg, stat0, lane, all_valid, valid, sval_mask, optr, aptr, &tfull[acc],
+                                                     accph, &tempty[acc]);
+        } else {
+          epi_tile_fast<BLOCK_N, PITCH, false, false>(t_row, stg, stat0, lane, all_valid, valid, sval_mask, optr, aptr, &tfull[acc],
+                                                      accph, &tempty[acc]);
+        }
       } else {
         long long soff[4];
         bool sval[4];
@@ -511,8 +770,8 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int w4 = 0; w4 < 4; w4++) {
-              a += stat_smem[(w4 * 2 + 0) * BLOCK_N + col];
-              b += stat_smem[(w4 * 2 + 1) * BLOCK_N + col];
+              a += lds_f1(stat_u32 + static_cast<uint32_t>(((w4 * 2 + 0) * BLOCK_N + col) * 4));
+              b += lds_f1(stat_u32 + static_cast<uint32_t>(((w4 * 2 + 1) * BLOCK_N + col) * 4));
             }
             acc_s[i] += static_cast<double>(a);
             acc_q[i] += static_cast<double>(b);
@@ -522,6 +781,7 @@ __device__ __forceinline__ void igemm_kmajor_body(const IgemmParams& p) {
       }
     }
     if (do_stats || do_red) flush_sums();
+    if (p.flat && lane == 0) tma_store_wait_all();   // the staged blocks must outlive the bulk stores that read them
   }
 
   tc_fence_before();

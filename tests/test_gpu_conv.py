@@ -25,6 +25,10 @@ TC_SHAPES = [
     (20, 33, 16, 8, 64, 64, 3, 1, 1, 1),    # halo engine: long columns, odd depth (unpaired last piece), many CTAs
     (9, 21, 16, 16, 128, 128, 3, 1, 1, 1),  # halo engine, two K blocks, several pieces per CTA
     (1, 5, 40, 20, 64, 64, 3, 1, 1, 1),     # halo engine: three H tiles (ragged), more CTAs than planes per column
+    (2, 10, 12, 10, 256, 64, 1, 1, 0, 1),   # flat 1x1x1 path: 2400 positions (ragged last tile), K = 256, N = 64
+    (3, 5, 6, 7, 64, 512, 1, 1, 0, 1),      # flat path: two 256-channel tiles, 630 positions
+    (1, 4, 4, 4, 128, 128, 1, 1, 0, 1),     # flat path: fewer positions than one tile
+    (2, 9, 10, 11, 1024, 256, 1, 1, 0, 1),  # flat path: 16 K blocks per tile (ResNet-50 layer3 reduce conv)
 ]
 # feature maps smaller than one tile: the fusion conv of PET_MRI_FMF (anat_pet_featuremapfusion.py:75-81) sees 8^3 maps
 # for 128^3 inputs, 5x6x5 for the MNI 91x109x91 grid and 2^3 for the 32^3 test volumes
@@ -59,6 +63,13 @@ def test_tc_fprop(cuda_dev, shape):
     assert_close(to_ncdhw_f32(y), ref, 6e-3, f"fprop {shape}")
     ssum = ref.sum(dim=(0, 2, 3, 4)).double()
     ssq = (ref.double() ** 2).sum(dim=(0, 2, 3, 4))
+    if k == 1 and s == 1:
+        # flat 1x1x1 path: the fused statistics are the sums of the STORED bf16 tensor (what BatchNorm then normalises)
+        stored = to_ncdhw_f32(y).double()
+        assert_close(st[0], stored.sum(dim=(0, 2, 3, 4)), 1e-5, f"fprop stats sum of the stored tensor {shape}")
+        assert_close(st[1], (stored ** 2).sum(dim=(0, 2, 3, 4)), 1e-5, f"fprop stats sqsum of the stored tensor {shape}")
+        assert_close(st[1], ssq, 1e-3, f"fprop stats sqsum {shape}")
+        return
     assert_close(st[0], ssum, 1e-3, f"fprop stats sum {shape}") if float(ssum.norm()) > 1 else None
     assert_close(st[1], ssq, 1e-4, f"fprop stats sqsum {shape}")
 

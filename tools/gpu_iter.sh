@@ -12,15 +12,12 @@ try:
 except Exception as e: print('no line',e)
 PY
 }
-# A/B of the single-launch strided dgrad in one call (same box)
-for m in 0 1 0 1; do
-  ADNI_DGRAD_MULTI=$m b b4_multi$m --no-e2e --global-batch 4 --steps 30
-done
-ADNI_DGRAD_MULTI=0 b b32_multi0 --no-e2e --steps 12
-ADNI_DGRAD_MULTI=1 b b32_multi1 --steps 12 --shape-profile gpurun_out/shapes_b32.json
-ADNI_DGRAD_MULTI=0 b r50_multi0 --no-e2e --workload mri_r50_160 --steps 4 --warmup 3
-ADNI_DGRAD_MULTI=1 b r50_multi1 --no-e2e --workload mri_r50_160 --steps 4 --warmup 3
-grep -h "launch_mode" gpurun_out/bench_b4_multi1.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('launch mode', d['launch_mode'], 'parity', d['parity'])"
+python tools/k1_probe.py child > gpurun_out/k1_flat.txt 2>&1; cat gpurun_out/k1_flat.txt
+ADNI_FLAT_1X1=0 b r50_box --no-e2e --workload mri_r50_160 --steps 4 --warmup 3
+b r50 --workload mri_r50_160 --steps 4 --warmup 3 --shape-profile gpurun_out/shapes_r50.json
+b b32 --steps 12 --shape-profile gpurun_out/shapes_b32.json
+b b4 --no-e2e --global-batch 4 --steps 30
+grep -h "launch_mode" gpurun_out/bench_b4.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('launch mode', d['launch_mode'], 'parity', d['parity'])"
 timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/tests_all.log 2>&1; echo "all gpu tests exit $?"; tail -n 3 gpurun_out/tests_all.log
 [ -n "$1" ] && eval "$@"
 exit 0
