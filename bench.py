@@ -470,8 +470,32 @@ def run_b200(args):
                   "launches_per_step": d["n"] / args.steps, "kernel_ms_per_step": d["ms"] / args.steps}
         for tag, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if tag.startswith("hbm_")}
     roofline["hbm_peak_gbs"] = hbm_peak
-    roofline["traffic_note"] = ("dram bytes per launch are a profiler quantity (ncu --set full) and are not measured inside "
-                                "this run: see profiles/r02_traffic.json for the committed capture of this workload")
+    # DRAM bytes per launch are a profiler quantity: they come from the committed ncu capture of THIS command line
+    # (tools/gpu_profile.sh -> profiles/r02_traffic.json), and only for the configuration that capture ran
+    # (default workload, 32 pairs on one GPU); everything else reports null
+    traffic_path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if (args.workload == "pet_mri_fusion_r18" and world == 1 and global_batch == 32 and depth == 18
+            and volume == (128, 128, 128) and dominant is tc and os.path.exists(traffic_path)):
+        with open(traffic_path) as f:
+            cap = json.load(f)
+        roofline["traffic"] = cap.get("dram_bytes_per_launch")
+        # algorithmic bytes of the same launches: activations in + out (+ addend) and the weights, once each, bf16
+        import re as _re
+        alg, nl = 0.0, 0
+        for key, rec in getattr(K.PROFILE, "shapes", {}).items():
+            mm = _re.match(r"tc_kmajor (fprop|dgrad\S*) N(\d+) (\d+)x(\d+)x(\d+) (\d+)->(\d+) k(\d+) s(\d+) d\d+", key)
+            if not mm:
+                continue
+            n_, d_, h_, w_, ci, co, k_, s_ = (int(v) for v in mm.groups()[1:])
+            pos_in, pos_out = n_ * d_ * h_ * w_, n_ * d_ * h_ * w_ // (s_ ** 3)
+            alg += rec["n"] * 2.0 * (pos_in * ci + pos_out * co + co * ci * k_ ** 3)
+            nl += rec["n"]
+        roofline["traffic_algorithmic_bytes_per_launch"] = alg / nl if nl else None
+        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per igemm_kmajor launch, averaged over the "
+                                    "launches of one step, from the committed ncu capture of this command line: " + cap.get("source", ""))
+    else:
+        roofline["traffic_note"] = ("dram bytes per launch are a profiler quantity (ncu) captured for the default workload at 32 "
+                                    "pairs on one GPU only (profiles/r02_traffic.json): null here")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cstep, cvols, threads = cpu_reference_step_fn(args, args.cpu_sample_pairs)

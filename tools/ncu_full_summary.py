@@ -8,7 +8,7 @@ src, dst, title = sys.argv[1], sys.argv[2], sys.argv[3]
 rows = list(csv.reader(open(src)))
 hdr, data = rows[0], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
-cols = [("time ms", "gpu__time_duration.sum", 1.0, "{:.3f}"),
+cols = [("time us", "gpu__time_duration.sum", 1.0, "{:.1f}"),
         ("tensor pipe active %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 1.0, "{:.1f}"),
         ("utcmma bf16 % of peak", "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", 1.0, "{:.1f}"),
         ("L2 %", "lts__throughput.avg.pct_of_peak_sustained_elapsed", 1.0, "{:.1f}"),
