@@ -566,6 +566,10 @@ int plan_wgrad_geometry(const adni_conv3d_geom& g, WgradParams& p, Box& b) {
   int splits = (4 * num_sms() + base_items - 1) / base_items;
   splits = std::min(splits, std::max(1, p.pos_boxes * box_rows / 1024));
   splits = std::max(splits, 1);
+  // ADNI_WGRAD_DETERMINISTIC=1: one CTA per output tile over ALL positions (no split-K, no stream-K): every element of dW
+  // receives exactly one red.add onto the zeroed buffer, the MMA order inside a CTA is fixed -> bit-identical runs, at
+  // the price of the schedule's balance (108 tiles on 148 SMs for layer4)
+  if (env_int("ADNI_WGRAD_DETERMINISTIC", 0) != 0) splits = 1;
   p.boxes_per_split = (p.pos_boxes + splits - 1) / splits;
   p.splits = (p.pos_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
   p.cout = g.Cout;
@@ -615,7 +619,7 @@ const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
   static std::map<std::vector<int>, W2Plan> cache;
   const int chunk_mb = std::max(1, env_int("ADNI_WGRAD_CHUNK_MB", 128));
   std::vector<int> key = {p.ntaps, p.cin_blocks, p.N, p.Do, p.Ho, p.Wo, p.bd, p.bh, p.bw, p.m_tiles, p.n_tiles, mt_cfg, num_sms(),
-                          p.cout, chunk_mb};
+                          p.cout, chunk_mb, env_int("ADNI_WGRAD_DETERMINISTIC", 0), env_int("ADNI_STREAM_K_WGRAD", 1)};
   for (int t = 0; t < p.ntaps; t++)
     key.push_back((int(p.taps[t].map) << 24) ^ ((p.taps[t].dd & 0xff) << 16) ^ ((p.taps[t].dh & 0xff) << 8) ^ (p.taps[t].dw & 0xff));
   for (int m = 0; m < kMaxMaps; m++)
@@ -625,7 +629,7 @@ const W2Plan& plan_wgrad_stream_k(const WgradParams& p, int mt_cfg) {
   if (it != cache.end()) return it->second;
   W2Plan plan;
   memset(&plan.sched, 0, sizeof(plan.sched));
-  static const int enabled = env_int("ADNI_STREAM_K_WGRAD", 1);
+  const int enabled = env_int("ADNI_STREAM_K_WGRAD", 1) != 0 && env_int("ADNI_WGRAD_DETERMINISTIC", 0) == 0;
   const int groups = 8 / mt_cfg;
   const int per_sample = p.tiles_d * p.tiles_h * p.tiles_w;
   const int G = std::min(num_sms(), kSkMaxCtas);

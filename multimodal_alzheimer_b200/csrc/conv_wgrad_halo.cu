@@ -219,7 +219,9 @@ __global__ void wgrad_tic_to_oti_kernel(const float* __restrict__ tic, float* __
 
 bool wgrad_halo_supported(const adni_conv3d_geom& g) {
   const char* e = getenv("ADNI_WGRAD_HALO");
-  return g.k == 3 && g.stride == 1 && g.dil == 1 && g.pad == 1 && g.Cin == 64 && g.Cout == 64 && !(e && atoi(e) == 0);
+  const char* det = getenv("ADNI_WGRAD_DETERMINISTIC");   // its CTAs share the scratch accumulator through red.add
+  return g.k == 3 && g.stride == 1 && g.dil == 1 && g.pad == 1 && g.Cin == 64 && g.Cout == 64 && !(e && atoi(e) == 0) &&
+         !(det && atoi(det) != 0);
 }
 
 // dw_tic: zeroed fp32 scratch [27][64][64]; dw_oti: output [64][27][64] (overwritten)

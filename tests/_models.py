@@ -58,6 +58,13 @@ CASES = [
      (48, 64, 48), ("mri", "pet1451")),
     ("fmf", dict(fusion_mode="maxout", filter_size_fusion=5, n_classes=2), 3, (32, 32, 32), ("mri", "pet1451")),
     ("fmf", dict(fusion_mode="concatenate", filter_size_fusion=4), 4, (48, 48, 64), ("mri", "pet1451")),   # even kernel
+    # better-conditioned twins of the tiny-batch cases above (the per-tensor rule, not the widened one,
+    # should carry the fusion and Bottleneck paths): batch 6 keeps BatchNorm's backward away from the catastrophic
+    # cancellation a batch of 2 produces in bf16 for torch's own autocast as well
+    ("anat_pet_2resnet", dict(depth=10), 6, (48, 48, 48), ("mri", "pet1451")),
+    ("all", dict(depth=10), 6, (48, 48, 48), ("mri", "pet1451", "tabular")),
+    ("anat", dict(depth=50, fl_gamma=1), 6, (40, 48, 40), ("mri",)),
+    ("pet_resnet", dict(depth=18), 6, (48, 48, 48), ("pet1451",)),
 ]
 CASE_IDS = [f"{c[0]}-{i}" for i, c in enumerate(CASES)]
 

@@ -132,6 +132,31 @@ def test_tc_wgrad_chunked_stream_k(cuda_dev, shape, chunk_mb, monkeypatch):
     assert_close(g, g1, 1e-4, f"chunked vs single-chunk wgrad {shape}")   # fp32 partial sums in a different order
 
 
+@pytest.mark.parametrize("shape", [(6, 16, 16, 16, 128, 256, 3, 1, 2, 2), (4, 16, 16, 16, 64, 64, 3, 1, 1, 1),
+                                   (32, 16, 16, 16, 512, 512, 3, 1, 4, 4)])
+def test_tc_wgrad_deterministic_option(cuda_dev, shape, monkeypatch):
+    """ADNI_WGRAD_DETERMINISTIC=1 (one CTA per output tile over all positions; layer1 leaves the halo-plane kernel): two
+    runs are bit-identical and agree with torch; the default stream-K schedule accumulates through red.add in an
+    order that varies from run to run."""
+    from multimodal_alzheimer_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k, s, p, d = shape
+    x_b, x_ref, w, w_ref = _mk(shape, cuda_dev)
+    w_ref.requires_grad_(True)
+    ref_y = F.conv3d(x_ref, w_ref, None, s, p, d)
+    dy_b = to_ndhwc_bf16(torch.randn_like(ref_y))
+    ref_y.backward(to_ncdhw_f32(dy_b))
+    monkeypatch.setenv("ADNI_WGRAD_DETERMINISTIC", "1")
+    K._PLAN_CACHE.clear()
+    runs = []
+    for _ in range(3):
+        dw, _ = K.conv3d_wgrad(x_b, dy_b, k, s, p, d, engine=TC)
+        runs.append(K.wgrad_to_param_layout(dw, tuple(w.shape)).clone())
+    torch.cuda.synchronize()
+    K._PLAN_CACHE.clear()
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    assert_close(runs[0], w_ref.grad, 2e-4, f"deterministic wgrad {shape}")
+
+
 BNRED_SHAPES = [TC_SHAPES[1], TC_SHAPES[2], TC_SHAPES[4], TC_SHAPES[5], TC_SHAPES[6], TC_SHAPES[9], TC_SHAPES[10],
                 (2, 10, 12, 10, 256, 64, 1, 1, 0, 1)]   # + a Bottleneck 1x1 reduce conv (dx has 256 channels)
 
