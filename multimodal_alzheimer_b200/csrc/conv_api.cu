@@ -606,9 +606,12 @@ double wgrad_executed_fraction(const WgradParams& p, int mt_cfg) {
 // red.global.add, so cutting tiles at arbitrary box boundaries needs no fix-up pass.
 // The sequence is chunk-major (W2Sched): a plain tile-major sequence spreads the 148 CTAs over ALL positions of dY / X at
 // any moment, and once the two tensors exceed the L2 the kernel streams them from HBM once per output tile
-// (profiles/r02_launch_summary.md: 4.0 GB of DRAM reads per layer4 launch against 0.6 GB under the static schedule, i.e.
-// 4.5 TB/s - the kernel had become HBM-bound).  Chunks of whole samples whose dY + X slices fit ADNI_WGRAD_CHUNK_MB
-// (default 128 MB = the L2 size; measured A/B in profiles/r02_wgrad_chunk_ab.md: 48 MB chunks cost more in extra accumulator flushes than the reuse returns) keep the balance AND the reuse.
+// (profiles/r02_launch_summary.md: 4.0 GB of DRAM reads per layer4 launch against 0.6 GB under the static schedule).
+// Chunks of whole samples whose dY + X slices fit ADNI_WGRAD_CHUNK_MB restore the reuse, but every extra chunk costs each
+// CTA one more un-overlapped accumulator flush (256 KB of red.add; the CTA owns all 512 TMEM columns), and the kernel is
+// tensor-bound either way (0.98 of the burst peak in executed FLOPs): measured 53.04 ms per step with 48 MB chunks,
+// 52.31 with the default of 128 MB (two chunks for layers 3 / 4 at 32 pairs, traffic unchanged), 52.52 with one chunk
+// (profiles/r02_wgrad_chunk_ab.md).  The knob stays for boxes whose HBM is the scarcer resource.
 struct W2Plan {
   bool use = false;
   W2Sched sched;
