@@ -1,17 +1,22 @@
 // One-shot all-reduce over NVLink peer memory for the tiny fp64 messages of synchronised BatchNorm (sum x, sum x^2
 // forward; sum g, sum g*xhat backward; the loss normaliser): 2 x C doubles, 84 + 84 times per two-encoder step.
 // A NCCL all-reduce of 1-8 KB is pure launch + protocol latency; here every rank stores its vector straight into a
-// slot of every peer's symmetric buffer, raises a flag there, waits for the world's flags in its own buffer and sums
-// the slots in RANK ORDER (so all ranks obtain bit-identical sums).  One CTA, no host involvement, graph-capturable.
+// slot of every peer's symmetric buffer and sums the world's slots in RANK ORDER (so all ranks obtain bit-identical
+// sums).  One CTA, no host involvement, graph-capturable.
+//
+// Low-latency cells (round 2): a double travels as two 8-byte packets {32 data bits | 32-bit call number}; an 8-byte
+// store is single-copy atomic over NVLink, so every packet validates itself and the receiver simply polls the cells it
+// needs.  The first version wrote plain doubles, then `__threadfence_system()` (a full NVLink round trip until every
+// remote store is acknowledged), then a flag per peer - two traversals plus the fence on the critical path of each of
+// the 168 exchanges of a step, which at 8 ranks had become the larger part of the data-parallel overhead.
 //
 // The reference is single-GPU; this is the exchange that makes N ranks on shards of a
 // batch reproduce its full-batch BatchNorm.
 //
 // Symmetric buffer layout per rank (allocated and exchanged by the host: torch symmetric memory = plumbing):
-//   [0, 1024)            flags   uint64 [2 parities][64 ranks]   (monotonic call numbers)
-//   [1024, ...)          slots   double [2 parities][world][max_n]
+//   cells  ulonglong2 [2 parities][world][max_n]      (zero-initialised: call numbers start at 1)
 // Call k (k = 1, 2, ...) uses parity k & 1.  A peer can be at most one call ahead of a rank that is still reading its
-// slots (it needs that rank's flag for call k+1 to finish k+1), so two parities are enough and nothing is ever reset.
+// cells (it needs that rank's packets of call k+1 to finish k+1), so two parities are enough and nothing is ever reset.
 #include "common.cuh"
 
 namespace adni {
@@ -20,7 +25,6 @@ namespace {
 
 constexpr int kPeerThreads = 256;
 constexpr int kPeerMaxWorld = 64;
-constexpr size_t kPeerFlagBytes = 2 * kPeerMaxWorld * sizeof(unsigned long long);
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -30,6 +34,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_cell(ulonglong2* p, unsigned long long lo, unsigned long long hi) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_cell(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_f64_kernel(double* __restrict__ data, int n,
                                                                           const unsigned long long* __restrict__ peers,
@@ -37,36 +49,37 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_f64_kernel(double
                                                                           int rank, int world, int max_n) {
   pdl_enter();
   const unsigned long long call = *call_counter + 1;
-  const int par = static_cast<int>(call & 1ull);
-  // 1. my vector into slot [par][rank] of every rank's buffer (peer stores travel over NVLink)
-  for (int r = 0; r < world; r++) {
-    double* dst = reinterpret_cast<double*>(peers[r] + kPeerFlagBytes) + (static_cast<size_t>(par) * world + rank) * max_n;
-    for (int i = threadIdx.x; i < n; i += kPeerThreads) dst[i] = data[i];
+  const unsigned long long tag = (call & 0xffffffffull) << 32;
+  const size_t par_off = static_cast<size_t>(call & 1ull) * world * max_n;
+  // 1. my vector into cell block [par][rank] of every rank's buffer (peer stores travel over NVLink); every thread
+  //    handles the same elements i in both phases, so data[i] is read before it is overwritten
+  for (int i = threadIdx.x; i < n; i += kPeerThreads) {
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(data[i]));
+    const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
+    for (int r = 0; r < world; r++)
+      st_cell(reinterpret_cast<ulonglong2*>(peers[r]) + par_off + static_cast<size_t>(rank) * max_n + i, lo, hi);
   }
-  __threadfence_system();
-  __syncthreads();
-  // 2. raise my flag in every rank's buffer, 3. wait for every rank's flag in mine
-  if (threadIdx.x < world) {
-    unsigned long long* remote = reinterpret_cast<unsigned long long*>(peers[threadIdx.x]) + par * kPeerMaxWorld + rank;
-    st_release_sys(remote, call);
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers[rank]) + par * kPeerMaxWorld + threadIdx.x;
-    const uint64_t t0 = global_timer_ns();
-    uint32_t spins = 0;
-    while (ld_acquire_sys(mine) < call) {
-      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 8000000000ull) {  // 8 s: a peer is gone
-        printf("adni_b200: peer all-reduce timeout rank %d waiting for rank %d call %llu\n", rank, threadIdx.x, call);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-  // 4. sum the world's slots in rank order (L1 is bypassed: the lines were written by peers)
-  const double* slots = reinterpret_cast<const double*>(peers[rank] + kPeerFlagBytes) + static_cast<size_t>(par) * world * max_n;
+  // 2. sum the world's cells in rank order as they arrive
+  const ulonglong2* cells = reinterpret_cast<const ulonglong2*>(peers[rank]) + par_off;
+  const uint64_t t0 = global_timer_ns();
   for (int i = threadIdx.x; i < n; i += kPeerThreads) {
     double s = 0.0;
-    for (int r = 0; r < world; r++) s += __ldcg(slots + static_cast<size_t>(r) * max_n + i);
+    for (int r = 0; r < world; r++) {
+      const ulonglong2* c = cells + static_cast<size_t>(r) * max_n + i;
+      ulonglong2 v = ld_cell(c);
+      uint32_t spins = 0;
+      while ((v.x & 0xffffffff00000000ull) != tag || (v.y & 0xffffffff00000000ull) != tag) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 8000000000ull) {  // 8 s: a peer is gone
+          printf("adni_b200: peer all-reduce timeout rank %d waiting for rank %d call %llu\n", rank, r, call);
+          __trap();
+        }
+        v = ld_cell(c);
+      }
+      s += __longlong_as_double(static_cast<long long>((v.y << 32) | (v.x & 0xffffffffull)));
+    }
     data[i] = s;
   }
+  __syncthreads();
   if (threadIdx.x == 0) *call_counter = call;
 }
 
@@ -185,7 +198,7 @@ using namespace adni;
 extern "C" {
 
 size_t adni_peer_buffer_bytes(int world, int max_n) {
-  return kPeerFlagBytes + sizeof(double) * 2 * static_cast<size_t>(world) * static_cast<size_t>(max_n);
+  return sizeof(ulonglong2) * 2 * static_cast<size_t>(world) * static_cast<size_t>(max_n);
 }
 
 int adni_peer_allreduce_f64(double* data, int n, const void* peers, void* call_counter, int rank, int world, int max_n,
