@@ -252,3 +252,36 @@ def test_three_stage_construction_from_checkpoint_paths(tmp_path):
         ref_keys = list(json.load(f)["cases"]["all-11"]["state_dict"].keys())
     assert list(m.state_dict().keys()) == ref_keys          # == the reference's All_Modalities_Fusion.state_dict()
     assert len(m.model_anat_pet.model_fuse) == 1             # all_modalities_fusion.py:29-31 applied after loading
+
+
+def test_tile_decode_multiplier_is_exact_in_its_domain():
+    """conv_igemm_kernels.cu decodes tile indices with q = umulhi(n, floor(2^32 / d) + 1) instead of divisions
+    (IgemmParams::fd_mul); conv_api.cu: finish_igemm_params only enables it while n * d < 2^32.  Exactness on that
+    domain, checked in integer arithmetic."""
+    import random
+    rng = random.Random(15)
+    for d in list(range(2, 600)) + [4095, 4096, 4097, 65535, 65536, 100003, (1 << 20) + 7]:
+        mul = (1 << 32) // d + 1
+        nmax = ((1 << 32) - 1) // d
+        for n in [0, 1, d - 1, d, d + 1, nmax - 1, nmax, nmax // 2] + [rng.randrange(0, nmax + 1) for _ in range(40)]:
+            if 0 <= n <= nmax:
+                assert (n * mul) >> 32 == n // d, (n, d)
+
+
+def test_gradient_bucket_factory_switches(monkeypatch):
+    """make_gradient_buckets: the argument chooses, ADNI_OVERLAP_GRADS overrides it either way; without a process group
+    both variants are inert (no arena, all_reduce() returns)."""
+    import torch
+    from multimodal_alzheimer_b200 import data_parallel as dp
+    params = [torch.nn.Parameter(torch.zeros(10))]
+    monkeypatch.delenv("ADNI_OVERLAP_GRADS", raising=False)
+    assert type(dp.make_gradient_buckets(params)) is dp.GradientBuckets
+    assert type(dp.make_gradient_buckets(params, overlap=True)) is dp.OverlappedGradientBuckets
+    monkeypatch.setenv("ADNI_OVERLAP_GRADS", "0")
+    assert type(dp.make_gradient_buckets(params, overlap=True)) is dp.GradientBuckets
+    monkeypatch.setenv("ADNI_OVERLAP_GRADS", "1")
+    b = dp.make_gradient_buckets(params)
+    assert type(b) is dp.OverlappedGradientBuckets
+    params[0].grad = torch.ones(10)
+    b.all_reduce()
+    assert dp.grad_slot(params[0]) is None and float(params[0].grad.sum()) == 10.0
