@@ -291,12 +291,12 @@ class _EventWork:
 
 
 class OverlappedGradientBuckets(GradientBuckets):
-    """The same buckets, but a bucket's all-reduce starts as soon as the backward pass has produced its last gradient
-    (bench.py's choice; measured +1.3 % at 8 GPUs with the NVLink kernel on a side stream, and SLOWER with NCCL, whose
-    CTAs take whole SMs away from the persistent conv grids):
+    """The same buckets, but a bucket's exchange starts as soon as the backward pass has produced its last gradient
     (`register_post_accumulate_grad_hook`), so that the 265 MB of gradient traffic of the two-encoder model overlaps
-    the remaining dgrad / wgrad kernels instead of following them.  `all_reduce()` after `backward()` then only
-    launches what is still pending (parameters without a gradient), waits and copies back.
+    the remaining dgrad / wgrad kernels instead of following them.  bench.py's choice: +1.3 % at 8 GPUs with the NVLink
+    kernel on a side stream; SLOWER with NCCL, whose CTAs take whole SMs away from the persistent conv grids.
+    `all_reduce()` after `backward()` then only launches what is still pending (parameters without a gradient), joins
+    the exchanges and rebinds `p.grad` to the bucket slots.
 
     Stream safety: a hook runs on the stream its gradient was produced on (the two encoder branches use two streams);
     every hook records an event, and the stream that launches a bucket first waits for the events of all of the
